@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200 (BASELINE.json).
+
+Workload (configs[1]): miccai2012_v1 inference of one synthetic 256^3 T1 + synthetic 15-channel
+atlas priors, full brain (speedup_segmentation=False: every voxel is a candidate).  One "step" =
+one whole volume from "volume + atlas resident in HBM" to "label volume resident in HBM"
+(sc_segment_volume: dense dilated formulation of the three-branch CNN + atlas-fused FC head).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size 256]
+
+N > 1 (launched by torchrun, one rank per GPU): every rank segments its own volume (configs[2]:
+volumes sharded across GPUs, no collective) -> weak scaling; value = N * voxels * K / max-over-ranks time.
+--impl reference: the reference's CPU path (oracle restatement: numpy gather + torch-CPU forward in
+nolearn-sized minibatches of 128) timed on this box's host cores on a bounded sample of the same volume.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "sub-cortical_segmentation_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "voxels_per_sec_full_volume_inference"
+UNIT = "voxels/s"
+WEIGHTS = os.path.join(ROOT, "nets", "miccai2012_v1", "miccai2012_v1.pkl")
+FLOP_PATCHWISE = 35407800       # algorithmic forward FLOPs per voxel, patchwise form
+# dense-form algorithmic FLOPs per voxel per kernel class (2 x MAC, three views), SURVEY.md 8f-1
+FLOP_DENSE = {"conv1": 3 * 2 * 180, "conv2": 3 * 2 * 3600, "conv3": 3 * 2 * 7200, "conv4": 3 * 2 * 14400,
+              "conv5": 3 * 2 * 21600, "gemm_d1": 3 * 2 * 97200, "gemm_fc1": 2 * 291600, "gemm_fc2": 2 * 149850,
+              "out_softmax": 2 * 4050}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tflops_burst": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_volume(size, seed):
+    """strictly positive T1 (every voxel a candidate) normalised like base.py:358, + atlas."""
+    from cnn_cort import synthetic
+    shape = (size, size, size)
+    t1 = synthetic.make_t1(shape, seed)
+    nz = t1[np.nonzero(t1)]
+    norm = ((t1 - nz.mean()) / nz.std()).astype(np.float32)
+    atlas, _, _ = synthetic.make_atlas(shape, seed)
+    return t1, norm, atlas
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle restatement of the reference's mode=cpu path (test infrastructure used
+# here ONLY as the thing timed for the baseline, never on the product path).
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(norm, atlas, n_voxels, repeats=1, seed=0):
+    import torch
+    from oracle import gather as og, network as on
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = on.load_params(WEIGHTS)
+    rng = np.random.RandomState(seed)
+    shape = norm.shape
+    start = rng.randint(0, norm.size - n_voxels)
+    lin = np.arange(start, start + n_voxels)                       # consecutive C-order candidates, as test_scan sees them
+    cen = np.stack(np.unravel_index(lin, shape), 1)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for ax, co, sa, av, _c in og.patch_batches(norm, atlas, cen, 100000):
+            on.predict(P, ax, co, sa, av, dtype=torch.float32, minibatch=128)
+        times.append(time.perf_counter() - t0)
+    return n_voxels / min(times), times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    size = args.size
+    _, norm, atlas = synthetic_volume(size, 1234)
+    sample = args.ref_sample
+    for _ in range(args.warmup):
+        cpu_reference_rate(norm, atlas, min(256, sample))
+    t0 = time.perf_counter()
+    rates = [cpu_reference_rate(norm, atlas, sample, seed=s)[0] for s in range(args.steps)]
+    total = time.perf_counter() - t0
+    value = sample * args.steps / total
+    cores = os.cpu_count() or 1
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "miccai2012_v1 inference, one synthetic %d^3 T1 + atlas priors, full brain" % size,
+                      "note": "oracle port of the reference's mode=cpu path (Theano stack absent); each step = %d consecutive "
+                              "candidate voxels (numpy gather + torch-CPU fp32 forward, minibatch 128), extrapolates linearly" % sample},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "%d steps x %d voxels of the %d^3 volume" % (args.steps, sample, size)},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "per_step_rates": rates}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--gemm", type=int, default=-1, help="-1 library default, 0 SIMT fp32, 1 tcgen05 TF32")
+    ap.add_argument("--ref-sample", type=int, default=2048)
+    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from cnn_cort import _native, nets
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = load_peaks()
+    size = args.size
+    nvox = size ** 3
+    t1, norm, atlas = synthetic_volume(size, 1234 + rank)
+    ctx = _native.Context(local_rank)
+    import pickle
+    with open(WEIGHTS, "rb") as f:
+        ctx.load_weights(nets.pack_params(pickle.load(f, encoding="latin1")))
+    if args.gemm >= 0:
+        ctx.set_option("gemm", args.gemm)
+    backend = "tcgen05-tf32" if ctx.counter("gemm") == 1 else "simt-fp32"
+
+    d_vol = torch.from_numpy(norm).cuda()
+    d_atlas = torch.from_numpy(atlas).cuda()
+    d_mask = torch.from_numpy((t1 != 0).view(np.uint8)).cuda()      # base.py:372 candidates = non-zero voxels of the raw T1
+    d_lab = torch.zeros((size,) * 3, dtype=torch.uint8, device="cuda")
+    n_cand = int(d_mask.sum())
+
+    def step():
+        ctx.segment_volume(d_vol, d_atlas, cand_mask=d_mask, label_vol=d_lab)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    ctx.set_option("profile", 1)
+    ctx.profile_read()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.counter("launches")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.counter("launches") - l0
+    prof = ctx.profile_read()
+    ctx.set_option("profile", 0)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n_cand * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call: pinned host volume + atlas in, labels out ----
+    h_vol = torch.from_numpy(norm).pin_memory()
+    h_atlas = torch.from_numpy(atlas).pin_memory()
+    h_mask = torch.from_numpy((t1 != 0).view(np.uint8)).pin_memory()
+    h_lab = torch.zeros((size,) * 3, dtype=torch.uint8).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        ctx.segment_volume_host(h_vol.numpy(), h_atlas.numpy(), cand_mask=h_mask.numpy(), label_out=h_lab.numpy())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_cand * e2e_steps / (float(t.item()) * 1e-3)
+    agree = float((torch.from_numpy(h_lab.numpy()).cuda() == d_lab).float().mean())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class (CUDA-event times measured over the timed region) ----
+    table = {}
+    for name, (kms, cnt) in prof.items():
+        fl = FLOP_DENSE.get(name, 0) * nvox * args.steps
+        table[name] = {"ms_per_step": kms / args.steps, "launches_per_step": cnt / args.steps,
+                       "share": kms / max(ms, 1e-9), "algorithmic_tflops": fl / (kms * 1e-3) / 1e12 if kms > 0 and fl else None}
+    dom = max(table, key=lambda k: table[k]["ms_per_step"])
+    dk = table[dom]
+    flops_per_launch = FLOP_DENSE.get(dom, 0) * nvox / max(dk["launches_per_step"], 1e-9)
+    dur_s = dk["ms_per_step"] * 1e-3 / max(dk["launches_per_step"], 1e-9)
+    achieved = flops_per_launch / dur_s / 1e12 if dur_s > 0 else 0.0
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tflops"], "traffic": None,
+                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json); TF32 dense peak is half of it" % peaks["source"],
+                "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": dur_s * 1e3,
+                "patchwise_equivalent_tflops": value * FLOP_PATCHWISE / 1e12,
+                "dense_executed_tflops": value * sum(FLOP_DENSE.values()) / 1e12}
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, times = cpu_reference_rate(norm, atlas, args.cpu_sample)
+        cpu_base = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                    "sample": "%d consecutive candidate voxels of the same %d^3 volume: numpy gather + torch-CPU fp32 forward, "
+                              "minibatch 128 (%.1f s); extrapolates linearly to the volume" % (args.cpu_sample, size, min(times))}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+           "ms_per_step": ms_max / args.steps, "seconds_per_volume": ms_max / args.steps * 1e-3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if backend.startswith("tcgen05") else "f32",
+           "data": "synthetic",
+           "config": {"workload": "miccai2012_v1 inference on B200, one synthetic %d^3 T1 + synthetic atlas priors per GPU, full brain "
+                                  "(speedup_segmentation=False, all %d voxels)" % (size, n_cand),
+                      "path": "sc_segment_volume (dense dilated formulation == patchwise network at every voxel)",
+                      "gemm_backend": backend, "l2": "inputs + activations (>> 126 MB) exceed L2; no explicit flush",
+                      "parallelism": "volumes sharded across %d GPU(s), no collective" % world},
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(norm.nbytes + atlas.nbytes + nvox),
+                   "d2h_bytes_per_step": int(nvox), "steps": e2e_steps, "label_agreement_with_device_path": agree,
+                   "call": "sc_segment_volume_host (pinned host volume + atlas + mask in, uint8 label volume out)"},
+           "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernels": table}
+    if cpu_base:
+        out["cpu_baseline"] = cpu_base
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,164 @@
+/* subcort_b200 -- C-ABI of the B200-native voxelwise hot path.
+ *
+ * The reference (sergivalverde/sub-cortical_segmentation) has NO FFI of its own: its
+ * native arithmetic is generated at run time by Theano behind nolearn's NeuralNet
+ * (cnn_cort/nets.py:233-246) and its data layer is numpy (cnn_cort/base.py).  Each entry
+ * point below therefore names the reference *Python* interface it replaces; the
+ * Python-side binding a maintainer adds is the ctypes stub shown in INTEGRATION.md
+ * (implemented in sub-cortical_segmentation_b200/cnn_cort/_native.py).
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every call returns 0 on success or
+ * a negative sc_status, with a human-readable message in sc_last_error() (thread-local);
+ * no exceptions cross the boundary.  Pointers named *_dev are CUDA device pointers on the
+ * context's device (e.g. torch tensors' data_ptr()); *_host are host pointers (pinned
+ * memory makes the copies asynchronous).  `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream).  One sc_ctx per device per thread; contexts are
+ * independent.  There is no CPU fallback: without a CUDA device sc_create fails.
+ *
+ * Coordinates are (x, y, z) int32 triples, volumes are C-ordered [X][Y][Z] (z fastest),
+ * the atlas is [X][Y][Z][15] float32 -- the layouts cnn_cort/base.py uses after nibabel.
+ */
+#ifndef SUBCORT_B200_H
+#define SUBCORT_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SC_API __attribute__((visibility("default")))
+#else
+#define SC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sc_ctx sc_ctx;
+
+typedef enum {
+  SC_OK = 0,
+  SC_ERR_CUDA = -1,        /* a CUDA runtime/driver call failed */
+  SC_ERR_ARG = -2,         /* bad argument (null pointer, negative size, unsupported patch size ...) */
+  SC_ERR_STATE = -3,       /* call order violated (e.g. forward before sc_load_weights) */
+  SC_ERR_NOMEM = -4,       /* device workspace could not be allocated */
+  SC_ERR_UNSUPPORTED = -5  /* device is not sm_100 */
+} sc_status;
+
+#define SC_NUM_CLASSES 15
+#define SC_PATCH 32
+#define SC_PARAM_FLOATS 883455   /* floats in nets/<name>/<name>.pkl, pickle order */
+#define SC_NUM_ARRAYS 107        /* non-empty arrays in that pickle */
+
+/* ---- context ------------------------------------------------------------------------ */
+SC_API int sc_version(void);
+SC_API const char* sc_last_error(void);
+/* replaces: THEANO_FLAGS device selection, cnn_cort/load_options.py:54-57 */
+SC_API int sc_create(int device, sc_ctx** out);
+SC_API int sc_destroy(sc_ctx* ctx);
+/* knobs: "gemm" = 0 SIMT fp32 | 1 tcgen05 TF32 (default when available);
+ *        "chunk_voxels" = voxels per head chunk in sc_segment_volume; "profile" = 0 | 1. */
+SC_API int sc_set_option(sc_ctx* ctx, const char* key, int64_t value);
+SC_API int64_t sc_get_counter(sc_ctx* ctx, const char* key); /* "launches": kernels launched so far */
+/* per-kernel-class device times: after sc_set_option(ctx, "profile", 1) every launch is bracketed by
+ * CUDA events on its stream; sc_profile_read synchronises, returns summed ms and launch counts per
+ * class (arrays of at least sc_profile_classes() entries) and resets the accumulators. */
+SC_API int sc_profile_classes(void);
+SC_API const char* sc_profile_name(int cls);
+SC_API int sc_profile_read(sc_ctx* ctx, double* ms_out, int64_t* launches_out, int n);
+
+/* ---- parameters ----------------------------------------------------------------------
+ * replaces: nolearn NeuralNet.load_params_from / save_params_to (call site nets.py:251).
+ * `blob_host` is the concatenation of the 107 arrays of the OrderedDict in pickle order
+ * (SC_PARAM_FLOATS floats).  The library keeps that master copy on the device and derives
+ * the inference layouts (filter flip for flip_filters=True, BN folded to scale/shift,
+ * transposed / padded / TF32-rounded GEMM operands). */
+SC_API int sc_load_weights(sc_ctx* ctx, const float* blob_host, int64_t n_floats);
+SC_API int sc_get_params(sc_ctx* ctx, float* blob_host, int64_t n_floats);
+
+/* ---- candidate voxels ----------------------------------------------------------------
+ * replaces: get_mask_voxels(mask) cnn_cort/base.py:310-331 (np.nonzero order, C-order).
+ * elem_bytes: 1 (uint8/bool mask) or 4 (float32/int32 image, tested != 0).
+ * Writes up to `capacity` triples; *n_out_host receives the total count (synchronises). */
+SC_API int sc_nonzero_coords(sc_ctx* ctx, const void* vol_dev, int elem_bytes, const int32_t dims[3],
+                      int32_t* xyz_dev, int64_t capacity, int64_t* n_out_host, void* stream);
+
+/* ---- orthogonal patch gather ---------------------------------------------------------
+ * replaces: get_patches x3 views (base.py:272-308) + the atlas vector with background fix
+ * (base.py:387-394) of one load_patch_batch batch.  Outputs are [n][1][32][32] float32 per
+ * view and [n][15] float32; any output pointer may be NULL to skip it.  bg_fix=1 applies
+ * "row sums to 0 -> row[14] = 1" (test path); 0 leaves rows untouched (train path, Q4). */
+SC_API int sc_gather_patches(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3],
+                      const float* atlas_dev, int bg_fix, const int32_t* xyz_dev, int64_t n,
+                      float* axial_dev, float* coronal_dev, float* saggital_dev,
+                      float* atlas_out_dev, void* stream);
+/* the same windows of an integer label volume (load_patch_vectors, base.py:156-160);
+ * only the centre pixel is ever consumed (base.py:85), so this returns labels[n] uint8. */
+SC_API int sc_gather_center_labels(sc_ctx* ctx, const uint8_t* labels_dev, const int32_t dims[3],
+                            const int32_t* xyz_dev, int64_t n, uint8_t* y_dev, void* stream);
+
+/* ---- network forward (patchwise) -----------------------------------------------------
+ * replaces: net.predict_proba / net.predict on {'in1','in2','in3','in4'}
+ * (call sites base.py:425-428, 435-438).  proba_dev [n][15] and/or label_dev [n] may be
+ * NULL.  Deterministic mode (stored BN statistics, no dropout). */
+SC_API int sc_forward(sc_ctx* ctx, const float* in1_dev, const float* in2_dev, const float* in3_dev,
+               const float* in4_dev, int64_t n, float* proba_dev, int32_t* label_dev, void* stream);
+/* host-buffer form of the same call: H2D of the four inputs and D2H of the results inside. */
+SC_API int sc_forward_host(sc_ctx* ctx, const float* in1_host, const float* in2_host, const float* in3_host,
+                    const float* in4_host, int64_t n, float* proba_host, int32_t* label_host, void* stream);
+/* gather + forward without materialising patches on the host: one test_scan batch
+ * (base.py:421-428) from a device-resident volume. */
+SC_API int sc_forward_from_volume(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3],
+                           const float* atlas_dev, const int32_t* xyz_dev, int64_t n,
+                           float* proba_dev, int32_t* label_dev, void* stream);
+
+/* ---- whole-volume inference (dense dilated formulation) -----------------------------
+ * replaces: the body of test_scan (base.py:421-440) when the candidates are (nearly) all
+ * voxels of a box: per view the branch runs as dilated convolutions over whole slices,
+ * which is exactly the patchwise network evaluated at every pixel.
+ * box = {x0,x1,y0,y1,z0,z1} half-open (NULL = whole volume).  cand_mask_dev (uint8
+ * [X][Y][Z], NULL = every voxel of the box) selects which voxels are written; the others
+ * keep whatever label_vol/proba_vol held.  label_vol_dev uint8 [X][Y][Z];
+ * proba_vol_dev float32 [X][Y][Z][15] or NULL. */
+SC_API int sc_segment_volume(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3],
+                      const float* atlas_dev, const int32_t* box, const uint8_t* cand_mask_dev,
+                      uint8_t* label_vol_dev, float* proba_vol_dev, void* stream);
+/* host-buffer form: copies volume + atlas (+mask) in and the label (+proba) volume out. */
+SC_API int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dims[3],
+                           const float* atlas_host, const int32_t* box, const uint8_t* cand_mask_host,
+                           uint8_t* label_vol_host, float* proba_vol_host, void* stream);
+
+/* ---- scatter -------------------------------------------------------------------------
+ * replaces: image[x,y,z] = y_pred and image_proba[x,y,z,c] = proba[:,c] (base.py:430-440) */
+SC_API int sc_scatter(sc_ctx* ctx, const int32_t* xyz_dev, int64_t n, const int32_t* label_dev,
+               const float* proba_dev, const int32_t dims[3], uint8_t* label_vol_dev,
+               float* proba_vol_dev, void* stream);
+
+/* ---- training ------------------------------------------------------------------------
+ * replaces: one minibatch of nolearn's train_fn inside net.fit (nets.py:233-246):
+ * training-mode forward (BN batch statistics, dropout p=.5), categorical cross-entropy,
+ * backward.  Gradients land in the context's flat gradient buffer (parameter layout);
+ * BN running statistics are updated in the master parameters.  drop_masks_dev: NULL to
+ * draw masks from `seed`, or [n][3*540 + 540 + 540] uint8 keep-masks (tests inject them).
+ * loss_dev: 1 float (sum of -log p over the batch divided by `n_global`). */
+SC_API int sc_train_forward_backward(sc_ctx* ctx, const float* in1_dev, const float* in2_dev,
+                              const float* in3_dev, const float* in4_dev, const uint8_t* y_dev,
+                              int64_t n, int64_t n_global, uint64_t seed,
+                              const uint8_t* drop_masks_dev, float* loss_dev, void* stream);
+/* device pointers to the flat gradient / parameter buffers (SC_PARAM_FLOATS floats) so the
+ * caller can all-reduce gradients in place (NCCL via torch.distributed). */
+SC_API int sc_grad_buffer(sc_ctx* ctx, float** grads_dev);
+SC_API int sc_param_buffer(sc_ctx* ctx, float** params_dev);
+/* replaces: lasagne.updates.adam (nets.py:236-237): a_t = lr*sqrt(1-b2^t)/(1-b1^t);
+ * p -= a_t * m / (sqrt(v) + eps), over the trainable entries; grad_scale multiplies the
+ * gradient first (1/world_size after a sum all-reduce).  Refreshes the inference layouts. */
+SC_API int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+SC_API int sc_reset_optimizer(sc_ctx* ctx);
+/* evaluation pass of nolearn's eval_fn: mean CE loss and accuracy numerators over a batch
+ * in deterministic mode; out2_dev = {sum of -log p[y], number of correct argmax}. */
+SC_API int sc_eval_batch(sc_ctx* ctx, const float* in1_dev, const float* in2_dev, const float* in3_dev,
+                  const float* in4_dev, const uint8_t* y_dev, int64_t n, float* out2_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUBCORT_B200_H */

@@ -1,0 +1,262 @@
+"""ctypes binding of libsubcort_b200.so (the stub INTEGRATION.md shows).
+
+PyTorch is used only as glue: device memory (torch tensors' ``data_ptr()``), the current
+CUDA stream and, for multi-GPU training, ``torch.distributed``.  Every compute call goes
+through the C-ABI declared in ``include/subcort_b200.h``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsubcort_b200.so")
+PARAM_FLOATS = 883455
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _p(t):
+    return ctypes.POINTER(t)
+
+
+_c_f, _c_i32, _c_u8, _c_i64 = ctypes.c_float, ctypes.c_int32, ctypes.c_uint8, ctypes.c_int64
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/subcort_b200.h one to one
+PROTOTYPES = {
+    "sc_version": (ctypes.c_int, []),
+    "sc_last_error": (ctypes.c_char_p, []),
+    "sc_create": (ctypes.c_int, [ctypes.c_int, _p(_vp)]),
+    "sc_destroy": (ctypes.c_int, [_vp]),
+    "sc_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, _c_i64]),
+    "sc_get_counter": (_c_i64, [_vp, ctypes.c_char_p]),
+    "sc_profile_classes": (ctypes.c_int, []),
+    "sc_profile_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "sc_profile_read": (ctypes.c_int, [_vp, _p(ctypes.c_double), _p(_c_i64), ctypes.c_int]),
+    "sc_load_weights": (ctypes.c_int, [_vp, _vp, _c_i64]),
+    "sc_get_params": (ctypes.c_int, [_vp, _vp, _c_i64]),
+    "sc_nonzero_coords": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _c_i64, _p(_c_i64), _vp]),
+    "sc_gather_patches": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, ctypes.c_int, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp]),
+    "sc_gather_center_labels": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _c_i64, _vp, _vp]),
+    "sc_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp]),
+    "sc_forward_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp]),
+    "sc_forward_from_volume": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _vp, _c_i64, _vp, _vp, _vp]),
+    "sc_segment_volume": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _p(_c_i32), _vp, _vp, _vp, _vp]),
+    "sc_segment_volume_host": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _p(_c_i32), _vp, _vp, _vp, _vp]),
+    "sc_scatter": (ctypes.c_int, [_vp, _vp, _c_i64, _vp, _vp, _p(_c_i32), _vp, _vp, _vp]),
+    "sc_train_forward_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, ctypes.c_uint64, _vp, _vp, _vp]),
+    "sc_grad_buffer": (ctypes.c_int, [_vp, _p(_vp)]),
+    "sc_param_buffer": (ctypes.c_int, [_vp, _p(_vp)]),
+    "sc_adam_step": (ctypes.c_int, [_vp, _c_f, _c_f, _c_f, _c_f, _c_f, _vp]),
+    "sc_reset_optimizer": (ctypes.c_int, [_vp]),
+    "sc_eval_batch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp]),
+}
+
+
+def load_library():
+    """dlopen the in-tree library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "%s is missing: build it with `python __graft_entry__.py` (or `make -C "
+            "sub-cortical_segmentation_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _check(status):
+    if status != 0:
+        raise NativeError("subcort_b200 error %d: %s" % (status, load_library().sc_last_error().decode("utf-8", "replace")))
+
+
+def _dims(shape):
+    return (_c_i32 * 3)(*[int(s) for s in shape[:3]])
+
+
+def _ptr(t):
+    """device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        assert t.flags["C_CONTIGUOUS"]
+        return t.ctypes.data
+    assert t.is_contiguous()
+    return t.data_ptr()
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Context(object):
+    """One sc_ctx (one GPU).  Methods take torch CUDA tensors unless named *_host."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _vp()
+        _check(self.lib.sc_create(int(device), ctypes.byref(h)))
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- options / counters ---------------------------------------------------------------
+    def set_option(self, key, value):
+        _check(self.lib.sc_set_option(self.h, key.encode(), int(value)))
+
+    def counter(self, key):
+        return int(self.lib.sc_get_counter(self.h, key.encode()))
+
+    def profile_read(self):
+        """{kernel class: (summed ms, launches)} since the last read (needs set_option('profile', 1))."""
+        n = self.lib.sc_profile_classes()
+        ms = (ctypes.c_double * n)()
+        cnt = (_c_i64 * n)()
+        _check(self.lib.sc_profile_read(self.h, ms, cnt, n))
+        return {self.lib.sc_profile_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
+
+    # -- parameters -------------------------------------------------------------------------
+    def load_weights(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        _check(self.lib.sc_load_weights(self.h, blob.ctypes.data, blob.size))
+
+    def get_params(self):
+        out = np.empty(PARAM_FLOATS, np.float32)
+        _check(self.lib.sc_get_params(self.h, out.ctypes.data, out.size))
+        return out
+
+    # -- data layer ---------------------------------------------------------------------------
+    def nonzero_coords(self, vol):
+        """vol: CUDA tensor [X,Y,Z] (uint8/bool or float32/int32) -> int32 CUDA tensor [N,3], C-order."""
+        import torch
+        eb = vol.element_size()
+        n = _c_i64(0)
+        _check(self.lib.sc_nonzero_coords(self.h, _ptr(vol), eb, _dims(vol.shape), None, 0, ctypes.byref(n), _stream()))
+        xyz = torch.empty((n.value, 3), dtype=torch.int32, device=vol.device)
+        if n.value:
+            _check(self.lib.sc_nonzero_coords(self.h, _ptr(vol), eb, _dims(vol.shape), _ptr(xyz), n.value, None, _stream()))
+        return xyz
+
+    def gather_patches(self, vol, xyz, atlas=None, bg_fix=True, views=(True, True, True)):
+        import torch
+        n = xyz.shape[0]
+        outs = [torch.empty((n, 1, 32, 32), dtype=torch.float32, device=vol.device) if v else None for v in views]
+        at = torch.empty((n, 15), dtype=torch.float32, device=vol.device) if atlas is not None else None
+        _check(self.lib.sc_gather_patches(self.h, _ptr(vol), _dims(vol.shape), _ptr(atlas), int(bool(bg_fix)), _ptr(xyz), n,
+                                          _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(at), _stream()))
+        return outs[0], outs[1], outs[2], at
+
+    def gather_center_labels(self, labels, xyz):
+        import torch
+        y = torch.empty((xyz.shape[0],), dtype=torch.uint8, device=labels.device)
+        _check(self.lib.sc_gather_center_labels(self.h, _ptr(labels), _dims(labels.shape), _ptr(xyz), xyz.shape[0], _ptr(y), _stream()))
+        return y
+
+    # -- network ------------------------------------------------------------------------------
+    def forward(self, in1, in2, in3, in4, want_proba=True, want_label=True):
+        import torch
+        n = in1.shape[0]
+        proba = torch.empty((n, 15), dtype=torch.float32, device=in1.device) if want_proba else None
+        label = torch.empty((n,), dtype=torch.int32, device=in1.device) if want_label else None
+        _check(self.lib.sc_forward(self.h, _ptr(in1), _ptr(in2), _ptr(in3), _ptr(in4), n, _ptr(proba), _ptr(label), _stream()))
+        return proba, label
+
+    def forward_host(self, in1, in2, in3, in4, want_proba=True, want_label=True):
+        n = in1.shape[0]
+        proba = np.empty((n, 15), np.float32) if want_proba else None
+        label = np.empty((n,), np.int32) if want_label else None
+        _check(self.lib.sc_forward_host(self.h, _ptr(in1), _ptr(in2), _ptr(in3), _ptr(in4), n, _ptr(proba), _ptr(label), _stream()))
+        return proba, label
+
+    def forward_from_volume(self, vol, atlas, xyz, want_proba=True, want_label=True):
+        import torch
+        n = xyz.shape[0]
+        proba = torch.empty((n, 15), dtype=torch.float32, device=vol.device) if want_proba else None
+        label = torch.empty((n,), dtype=torch.int32, device=vol.device) if want_label else None
+        _check(self.lib.sc_forward_from_volume(self.h, _ptr(vol), _dims(vol.shape), _ptr(atlas), _ptr(xyz), n,
+                                               _ptr(proba), _ptr(label), _stream()))
+        return proba, label
+
+    def segment_volume(self, vol, atlas, box=None, cand_mask=None, label_vol=None, proba_vol=None):
+        cbox = (_c_i32 * 6)(*[int(b) for b in box]) if box is not None else None
+        _check(self.lib.sc_segment_volume(self.h, _ptr(vol), _dims(vol.shape), _ptr(atlas), cbox, _ptr(cand_mask),
+                                          _ptr(label_vol), _ptr(proba_vol), _stream()))
+
+    def segment_volume_host(self, vol, atlas, box=None, cand_mask=None, want_proba=False, label_out=None):
+        """numpy (or pinned torch CPU) in -> numpy uint8 label volume (+ float32 proba volume)."""
+        shape = tuple(int(s) for s in vol.shape[:3])
+        label = label_out if label_out is not None else np.zeros(shape, np.uint8)
+        proba = np.zeros(shape + (15,), np.float32) if want_proba else None
+        cbox = (_c_i32 * 6)(*[int(b) for b in box]) if box is not None else None
+        _check(self.lib.sc_segment_volume_host(self.h, _ptr(vol), _dims(shape), _ptr(atlas), cbox, _ptr(cand_mask),
+                                               _ptr(label), _ptr(proba), _stream()))
+        return label, proba
+
+    def scatter(self, xyz, dims, label=None, proba=None, label_vol=None, proba_vol=None):
+        _check(self.lib.sc_scatter(self.h, _ptr(xyz), xyz.shape[0], _ptr(label), _ptr(proba), _dims(dims),
+                                   _ptr(label_vol), _ptr(proba_vol), _stream()))
+
+    # -- training -----------------------------------------------------------------------------
+    def train_forward_backward(self, in1, in2, in3, in4, y, n_global=None, seed=0, drop_masks=None, loss_out=None):
+        import torch
+        n = in1.shape[0]
+        loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=in1.device)
+        _check(self.lib.sc_train_forward_backward(self.h, _ptr(in1), _ptr(in2), _ptr(in3), _ptr(in4), _ptr(y), n,
+                                                  int(n_global or n), int(seed), _ptr(drop_masks), _ptr(loss), _stream()))
+        return loss
+
+    def _buffer(self, fn):
+        import torch
+        p = _vp()
+        _check(fn(self.h, ctypes.byref(p)))
+        return p.value
+
+    def grad_tensor(self):
+        """torch view (no copy) of the flat gradient buffer, for torch.distributed.all_reduce."""
+        return _as_tensor(self._buffer(self.lib.sc_grad_buffer), PARAM_FLOATS, self.device)
+
+    def param_tensor(self):
+        return _as_tensor(self._buffer(self.lib.sc_param_buffer), PARAM_FLOATS, self.device)
+
+    def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+        _check(self.lib.sc_adam_step(self.h, lr, beta1, beta2, eps, grad_scale, _stream()))
+
+    def reset_optimizer(self):
+        _check(self.lib.sc_reset_optimizer(self.h))
+
+    def eval_batch(self, in1, in2, in3, in4, y):
+        import torch
+        out = torch.zeros(2, dtype=torch.float32, device=in1.device)
+        _check(self.lib.sc_eval_batch(self.h, _ptr(in1), _ptr(in2), _ptr(in3), _ptr(in4), _ptr(y), in1.shape[0], _ptr(out), _stream()))
+        return out
+
+
+class _CudaArrayHolder(object):
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _as_tensor(ptr, n, device):
+    import torch
+    return torch.as_tensor(_CudaArrayHolder(ptr, n), device="cuda:%d" % device)

@@ -1,0 +1,384 @@
+// extern "C" surface of libsubcort_b200.so (declared in include/subcort_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sc {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ensure_ws(Workspace& ws, size_t bytes) {
+  if (ws.bytes >= bytes) return SC_OK;
+  if (ws.ptr) {
+    cudaDeviceSynchronize();
+    cudaFree(ws.ptr);
+    ws.ptr = nullptr;
+    ws.bytes = 0;
+  }
+  bytes = (bytes + ((size_t)64 << 20) - 1) & ~(((size_t)64 << 20) - 1);
+  cudaError_t e = cudaMalloc(&ws.ptr, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("workspace allocation of %zu MiB failed: %s", bytes >> 20, cudaGetErrorString(e));
+    ws.ptr = nullptr;
+    return SC_ERR_NOMEM;
+  }
+  ws.bytes = bytes;
+  return SC_OK;
+}
+
+static int need_weights(sc_ctx* ctx, const char* who) {
+  SC_CHECK(ctx != nullptr, SC_ERR_ARG, "%s: null context", who);
+  SC_CHECK(ctx->weights_loaded, SC_ERR_STATE, "%s: call sc_load_weights first", who);
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return SC_OK;
+}
+
+// inference entry points call this: re-derive the folded layouts after optimiser steps
+static int fresh_weights(sc_ctx* ctx, const char* who, cudaStream_t st) {
+  SC_TRY(need_weights(ctx, who));
+  if (ctx->derived_dirty) {
+    SC_TRY(derive_weights(ctx, st));
+    ctx->derived_dirty = false;
+  }
+  return SC_OK;
+}
+
+}  // namespace sc
+
+using namespace sc;
+
+extern "C" {
+
+int sc_version(void) { return 100; }
+const char* sc_last_error(void) { return sc::g_err; }
+
+int sc_create(int device, sc_ctx** out) {
+  SC_CHECK(out != nullptr, SC_ERR_ARG, "sc_create: null out pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    set_error("sc_create: no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return SC_ERR_CUDA;
+  }
+  SC_CHECK(device >= 0 && device < count, SC_ERR_ARG, "sc_create: device %d out of range [0,%d)", device, count);
+  SC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SC_CUDA(cudaGetDeviceProperties(&prop, device));
+  SC_CHECK(prop.major == 10, SC_ERR_UNSUPPORTED, "sc_create: device %d is sm_%d%d; this library is built for sm_100a only",
+           device, prop.major, prop.minor);
+  sc_ctx* ctx = new sc_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->off = make_param_off();
+  if (ctx->off.total != SC_PARAM_FLOATS) {
+    set_error("internal: parameter table has %d floats", ctx->off.total);
+    delete ctx;
+    return SC_ERR_STATE;
+  }
+  const size_t pb = sizeof(float) * SC_PARAM_FLOATS;
+  SC_CUDA(cudaMalloc(&ctx->params, pb));
+  SC_CUDA(cudaMalloc(&ctx->grads, pb));
+  SC_CUDA(cudaMalloc(&ctx->adam_m, pb));
+  SC_CUDA(cudaMalloc(&ctx->adam_v, pb));
+  SC_CUDA(cudaMalloc(&ctx->trainable, SC_PARAM_FLOATS));
+  SC_CUDA(cudaMemset(ctx->grads, 0, pb));
+  SC_CUDA(cudaMemset(ctx->adam_m, 0, pb));
+  SC_CUDA(cudaMemset(ctx->adam_v, 0, pb));
+  {
+    std::vector<uint8_t> t(SC_PARAM_FLOATS, 1);
+    for (int b = 0; b < 3; ++b)
+      for (int l = 0; l < 5; ++l)
+        for (int k = 2; k < 4; ++k)
+          for (int c = 0; c < kConvCout[l]; ++c) t[ctx->off.br[b].bn[l][k] + c] = 0;  // BN mean / inv_std are state
+    SC_CUDA(cudaMemcpy(ctx->trainable, t.data(), SC_PARAM_FLOATS, cudaMemcpyHostToDevice));
+  }
+  SC_CUDA(cudaMalloc(&ctx->d_count, sizeof(int64_t)));
+  SC_CUDA(cudaMallocHost(&ctx->h_count, sizeof(int64_t)));
+  ctx->gemm_backend = tc_init(ctx) == SC_OK ? 1 : 0;
+  *out = ctx;
+  return SC_OK;
+}
+
+int sc_destroy(sc_ctx* ctx) {
+  if (!ctx) return SC_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  tc_destroy(ctx);
+  cudaFree(ctx->params); cudaFree(ctx->grads); cudaFree(ctx->adam_m); cudaFree(ctx->adam_v);
+  cudaFree(ctx->trainable); cudaFree(ctx->derived); cudaFree(ctx->ws.ptr); cudaFree(ctx->ws_train.ptr);
+  cudaFree(ctx->d_count); cudaFreeHost(ctx->h_count);
+  for (auto& ev : ctx->prof_live) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  for (auto& ev : ctx->prof_free) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  delete ctx;
+  return SC_OK;
+}
+
+int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
+  SC_CHECK(ctx && key, SC_ERR_ARG, "sc_set_option: null argument");
+  if (!strcmp(key, "gemm")) {
+    SC_CHECK(value == 0 || value == 1, SC_ERR_ARG, "sc_set_option: gemm must be 0 (SIMT) or 1 (tcgen05)");
+    SC_CHECK(value == 0 || ctx->tc_state != nullptr, SC_ERR_UNSUPPORTED, "sc_set_option: tcgen05 back-end unavailable");
+    ctx->gemm_backend = (int)value;
+    return SC_OK;
+  }
+  if (!strcmp(key, "profile")) {
+    ctx->profile = value != 0;
+    return SC_OK;
+  }
+  if (!strcmp(key, "chunk_voxels")) {
+    SC_CHECK(value >= 1024, SC_ERR_ARG, "sc_set_option: chunk_voxels must be >= 1024");
+    ctx->chunk_voxels = value;
+    return SC_OK;
+  }
+  set_error("sc_set_option: unknown key '%s'", key);
+  return SC_ERR_ARG;
+}
+
+int64_t sc_get_counter(sc_ctx* ctx, const char* key) {
+  if (!ctx || !key) return -1;
+  if (!strcmp(key, "launches")) return ctx->launches;
+  if (!strcmp(key, "gemm")) return ctx->gemm_backend;
+  if (!strcmp(key, "adam_t")) return ctx->adam_t;
+  if (!strcmp(key, "workspace_bytes")) return (int64_t)ctx->ws.bytes;
+  return -1;
+}
+
+static const char* kProfNames[PC_COUNT] = {"gather", "nonzero", "scatter", "patch_branch", "conv1", "conv2", "conv3",
+                                           "conv4", "conv5", "gemm_d1", "gemm_fc1", "gemm_fc2", "atlas", "out_softmax",
+                                           "train_fwd", "train_bwd", "adam"};
+int sc_profile_classes(void) { return PC_COUNT; }
+const char* sc_profile_name(int cls) { return cls >= 0 && cls < PC_COUNT ? kProfNames[cls] : ""; }
+int sc_profile_read(sc_ctx* ctx, double* ms_out, int64_t* launches_out, int n) {
+  SC_CHECK(ctx && ms_out && launches_out && n >= PC_COUNT, SC_ERR_ARG, "sc_profile_read: bad argument");
+  SC_CUDA(cudaSetDevice(ctx->device));
+  SC_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < n; ++i) { ms_out[i] = 0.0; launches_out[i] = 0; }
+  for (auto& ev : ctx->prof_live) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { ms_out[ev.cls] += ms; launches_out[ev.cls]++; }
+    ctx->prof_free.push_back(ev);
+  }
+  cudaGetLastError();
+  ctx->prof_live.clear();
+  return SC_OK;
+}
+
+int sc_load_weights(sc_ctx* ctx, const float* blob_host, int64_t n_floats) {
+  SC_CHECK(ctx && blob_host, SC_ERR_ARG, "sc_load_weights: null argument");
+  SC_CHECK(n_floats == SC_PARAM_FLOATS, SC_ERR_ARG, "sc_load_weights: expected %d floats, got %lld", SC_PARAM_FLOATS,
+           (long long)n_floats);
+  SC_CUDA(cudaSetDevice(ctx->device));
+  SC_CUDA(cudaMemcpy(ctx->params, blob_host, sizeof(float) * SC_PARAM_FLOATS, cudaMemcpyHostToDevice));
+  SC_TRY(derive_weights(ctx, nullptr));
+  ctx->weights_loaded = true;
+  ctx->derived_dirty = false;
+  return SC_OK;
+}
+
+int sc_get_params(sc_ctx* ctx, float* blob_host, int64_t n_floats) {
+  SC_TRY(need_weights(ctx, "sc_get_params"));
+  SC_CHECK(blob_host && n_floats == SC_PARAM_FLOATS, SC_ERR_ARG, "sc_get_params: bad buffer");
+  SC_CUDA(cudaDeviceSynchronize());
+  SC_CUDA(cudaMemcpy(blob_host, ctx->params, sizeof(float) * SC_PARAM_FLOATS, cudaMemcpyDeviceToHost));
+  return SC_OK;
+}
+
+static int check_dims(const int32_t* dims, const char* who) {
+  SC_CHECK(dims && dims[0] > 0 && dims[1] > 0 && dims[2] > 0, SC_ERR_ARG, "%s: bad volume dims", who);
+  SC_CHECK((int64_t)dims[0] * dims[1] * dims[2] < (1ll << 31), SC_ERR_ARG, "%s: volume too large", who);
+  return SC_OK;
+}
+
+int sc_nonzero_coords(sc_ctx* ctx, const void* vol_dev, int elem_bytes, const int32_t dims[3], int32_t* xyz_dev,
+                      int64_t capacity, int64_t* n_out_host, void* stream) {
+  SC_CHECK(ctx && vol_dev, SC_ERR_ARG, "sc_nonzero_coords: null argument");
+  SC_TRY(check_dims(dims, "sc_nonzero_coords"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return launch_nonzero(ctx, vol_dev, elem_bytes, dims, xyz_dev, capacity, n_out_host, (cudaStream_t)stream);
+}
+
+int sc_gather_patches(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3], const float* atlas_dev, int bg_fix,
+                      const int32_t* xyz_dev, int64_t n, float* axial_dev, float* coronal_dev, float* saggital_dev,
+                      float* atlas_out_dev, void* stream) {
+  SC_CHECK(ctx && vol_dev && (xyz_dev || n == 0) && n >= 0, SC_ERR_ARG, "sc_gather_patches: bad argument");
+  SC_TRY(check_dims(dims, "sc_gather_patches"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return launch_gather(ctx, vol_dev, dims, atlas_dev, bg_fix, xyz_dev, n, axial_dev, coronal_dev, saggital_dev,
+                       atlas_out_dev, (cudaStream_t)stream);
+}
+
+int sc_gather_center_labels(sc_ctx* ctx, const uint8_t* labels_dev, const int32_t dims[3], const int32_t* xyz_dev,
+                            int64_t n, uint8_t* y_dev, void* stream) {
+  SC_CHECK(ctx && labels_dev && (xyz_dev || n == 0) && (y_dev || n == 0) && n >= 0, SC_ERR_ARG, "sc_gather_center_labels: bad argument");
+  SC_TRY(check_dims(dims, "sc_gather_center_labels"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return launch_center_labels(ctx, labels_dev, dims, xyz_dev, n, y_dev, (cudaStream_t)stream);
+}
+
+int sc_forward(sc_ctx* ctx, const float* in1_dev, const float* in2_dev, const float* in3_dev, const float* in4_dev,
+               int64_t n, float* proba_dev, int32_t* label_dev, void* stream) {
+  SC_TRY(fresh_weights(ctx, "sc_forward", (cudaStream_t)stream));
+  SC_CHECK(n >= 0, SC_ERR_ARG, "sc_forward: negative batch");
+  if (n == 0) return SC_OK;
+  SC_CHECK(in1_dev && in2_dev && in3_dev && in4_dev, SC_ERR_ARG, "sc_forward: null input");
+  return forward_patches(ctx, in1_dev, in2_dev, in3_dev, in4_dev, n, proba_dev, label_dev, (cudaStream_t)stream);
+}
+
+int sc_forward_host(sc_ctx* ctx, const float* in1_host, const float* in2_host, const float* in3_host,
+                    const float* in4_host, int64_t n, float* proba_host, int32_t* label_host, void* stream) {
+  SC_TRY(fresh_weights(ctx, "sc_forward_host", (cudaStream_t)stream));
+  SC_CHECK(n >= 0, SC_ERR_ARG, "sc_forward_host: negative batch");
+  if (n == 0) return SC_OK;
+  SC_CHECK(in1_host && in2_host && in3_host && in4_host, SC_ERR_ARG, "sc_forward_host: null input");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t chunk = 32768;
+  const int64_t cmax = n < chunk ? n : chunk;
+  const size_t pb = (size_t)cmax * 1024 * sizeof(float);
+  const size_t bytes = 3 * pb + (size_t)cmax * (15 + 15 + 1) * sizeof(float);
+  SC_TRY(ensure_ws(ctx->ws_train, bytes));  // staging lives in the second arena; forward_patches uses ctx->ws
+  char* base = reinterpret_cast<char*>(ctx->ws_train.ptr);
+  float* d_in[3] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + pb), reinterpret_cast<float*>(base + 2 * pb)};
+  float* d_at = reinterpret_cast<float*>(base + 3 * pb);
+  float* d_pr = d_at + cmax * 15;
+  int32_t* d_lb = reinterpret_cast<int32_t*>(d_pr + cmax * 15);
+  const float* h_in[3] = {in1_host, in2_host, in3_host};
+  for (int64_t s = 0; s < n; s += chunk) {
+    const int64_t m = n - s < chunk ? n - s : chunk;
+    for (int b = 0; b < 3; ++b)
+      SC_CUDA(cudaMemcpyAsync(d_in[b], h_in[b] + s * 1024, (size_t)m * 4096, cudaMemcpyHostToDevice, st));
+    SC_CUDA(cudaMemcpyAsync(d_at, in4_host + s * 15, (size_t)m * 60, cudaMemcpyHostToDevice, st));
+    SC_TRY(forward_patches(ctx, d_in[0], d_in[1], d_in[2], d_at, m, d_pr, d_lb, st));
+    if (proba_host) SC_CUDA(cudaMemcpyAsync(proba_host + s * 15, d_pr, (size_t)m * 60, cudaMemcpyDeviceToHost, st));
+    if (label_host) SC_CUDA(cudaMemcpyAsync(label_host + s, d_lb, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+  }
+  SC_CUDA(cudaStreamSynchronize(st));
+  return SC_OK;
+}
+
+int sc_forward_from_volume(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3], const float* atlas_dev,
+                           const int32_t* xyz_dev, int64_t n, float* proba_dev, int32_t* label_dev, void* stream) {
+  SC_TRY(fresh_weights(ctx, "sc_forward_from_volume", (cudaStream_t)stream));
+  SC_CHECK(n >= 0, SC_ERR_ARG, "sc_forward_from_volume: negative batch");
+  if (n == 0) return SC_OK;
+  SC_CHECK(vol_dev && atlas_dev && xyz_dev, SC_ERR_ARG, "sc_forward_from_volume: null input");
+  SC_TRY(check_dims(dims, "sc_forward_from_volume"));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t chunk = 32768;
+  const int64_t cmax = n < chunk ? n : chunk;
+  const size_t pb = (size_t)cmax * 1024 * sizeof(float);
+  SC_TRY(ensure_ws(ctx->ws_train, 3 * pb + (size_t)cmax * 15 * sizeof(float)));
+  char* base = reinterpret_cast<char*>(ctx->ws_train.ptr);
+  float* d_in[3] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + pb), reinterpret_cast<float*>(base + 2 * pb)};
+  float* d_at = reinterpret_cast<float*>(base + 3 * pb);
+  for (int64_t s = 0; s < n; s += chunk) {
+    const int64_t m = n - s < chunk ? n - s : chunk;
+    SC_TRY(launch_gather(ctx, vol_dev, dims, atlas_dev, 1, xyz_dev + s * 3, m, d_in[0], d_in[1], d_in[2], d_at, st));
+    SC_TRY(forward_patches(ctx, d_in[0], d_in[1], d_in[2], d_at, m, proba_dev ? proba_dev + s * 15 : nullptr,
+                           label_dev ? label_dev + s : nullptr, st));
+  }
+  return SC_OK;
+}
+
+int sc_segment_volume(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3], const float* atlas_dev,
+                      const int32_t* box, const uint8_t* cand_mask_dev, uint8_t* label_vol_dev, float* proba_vol_dev,
+                      void* stream) {
+  SC_TRY(fresh_weights(ctx, "sc_segment_volume", (cudaStream_t)stream));
+  SC_CHECK(vol_dev && atlas_dev && (label_vol_dev || proba_vol_dev), SC_ERR_ARG, "sc_segment_volume: null argument");
+  SC_TRY(check_dims(dims, "sc_segment_volume"));
+  return segment_volume(ctx, vol_dev, dims, atlas_dev, box, cand_mask_dev, label_vol_dev, proba_vol_dev, (cudaStream_t)stream);
+}
+
+int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dims[3], const float* atlas_host,
+                           const int32_t* box, const uint8_t* cand_mask_host, uint8_t* label_vol_host,
+                           float* proba_vol_host, void* stream) {
+  SC_TRY(fresh_weights(ctx, "sc_segment_volume_host", (cudaStream_t)stream));
+  SC_CHECK(vol_host && atlas_host && (label_vol_host || proba_vol_host), SC_ERR_ARG, "sc_segment_volume_host: null argument");
+  SC_TRY(check_dims(dims, "sc_segment_volume_host"));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nvox = (size_t)dims[0] * dims[1] * dims[2];
+  const size_t vb = (nvox * 4 + 255) & ~(size_t)255, ab = (nvox * 60 + 255) & ~(size_t)255, mb = (nvox + 255) & ~(size_t)255;
+  const size_t pb = proba_vol_host ? ab : 0;
+  SC_TRY(ensure_ws(ctx->ws_train, vb + ab + 2 * mb + pb));
+  char* base = reinterpret_cast<char*>(ctx->ws_train.ptr);
+  float* d_vol = reinterpret_cast<float*>(base);
+  float* d_atlas = reinterpret_cast<float*>(base + vb);
+  uint8_t* d_mask = reinterpret_cast<uint8_t*>(base + vb + ab);
+  uint8_t* d_lab = d_mask + mb;
+  float* d_proba = proba_vol_host ? reinterpret_cast<float*>(base + vb + ab + 2 * mb) : nullptr;
+  SC_CUDA(cudaMemcpyAsync(d_vol, vol_host, nvox * 4, cudaMemcpyHostToDevice, st));
+  SC_CUDA(cudaMemcpyAsync(d_atlas, atlas_host, nvox * 60, cudaMemcpyHostToDevice, st));
+  if (cand_mask_host) SC_CUDA(cudaMemcpyAsync(d_mask, cand_mask_host, nvox, cudaMemcpyHostToDevice, st));
+  SC_CUDA(cudaMemsetAsync(d_lab, 0, nvox, st));
+  if (d_proba) SC_CUDA(cudaMemsetAsync(d_proba, 0, nvox * 60, st));
+  SC_TRY(segment_volume(ctx, d_vol, dims, d_atlas, box, cand_mask_host ? d_mask : nullptr, d_lab, d_proba, st));
+  if (label_vol_host) SC_CUDA(cudaMemcpyAsync(label_vol_host, d_lab, nvox, cudaMemcpyDeviceToHost, st));
+  if (proba_vol_host) SC_CUDA(cudaMemcpyAsync(proba_vol_host, d_proba, nvox * 60, cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaStreamSynchronize(st));
+  return SC_OK;
+}
+
+int sc_scatter(sc_ctx* ctx, const int32_t* xyz_dev, int64_t n, const int32_t* label_dev, const float* proba_dev,
+               const int32_t dims[3], uint8_t* label_vol_dev, float* proba_vol_dev, void* stream) {
+  SC_CHECK(ctx && (xyz_dev || n == 0) && n >= 0, SC_ERR_ARG, "sc_scatter: bad argument");
+  SC_TRY(check_dims(dims, "sc_scatter"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return launch_scatter(ctx, xyz_dev, n, label_dev, proba_dev, dims, label_vol_dev, proba_vol_dev, (cudaStream_t)stream);
+}
+
+int sc_train_forward_backward(sc_ctx* ctx, const float* in1_dev, const float* in2_dev, const float* in3_dev,
+                              const float* in4_dev, const uint8_t* y_dev, int64_t n, int64_t n_global, uint64_t seed,
+                              const uint8_t* drop_masks_dev, float* loss_dev, void* stream) {
+  SC_TRY(need_weights(ctx, "sc_train_forward_backward"));
+  SC_CHECK(n > 0 && n_global >= n, SC_ERR_ARG, "sc_train_forward_backward: bad batch size");
+  SC_CHECK(in1_dev && in2_dev && in3_dev && in4_dev && y_dev && loss_dev, SC_ERR_ARG, "sc_train_forward_backward: null argument");
+  return train_forward_backward(ctx, in1_dev, in2_dev, in3_dev, in4_dev, y_dev, n, n_global, seed, drop_masks_dev,
+                                loss_dev, (cudaStream_t)stream);
+}
+
+int sc_grad_buffer(sc_ctx* ctx, float** grads_dev) {
+  SC_CHECK(ctx && grads_dev, SC_ERR_ARG, "sc_grad_buffer: null argument");
+  *grads_dev = ctx->grads;
+  return SC_OK;
+}
+
+int sc_param_buffer(sc_ctx* ctx, float** params_dev) {
+  SC_CHECK(ctx && params_dev, SC_ERR_ARG, "sc_param_buffer: null argument");
+  *params_dev = ctx->params;
+  return SC_OK;
+}
+
+int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  SC_TRY(need_weights(ctx, "sc_adam_step"));
+  return adam_step(ctx, lr, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
+}
+
+int sc_reset_optimizer(sc_ctx* ctx) {
+  SC_CHECK(ctx, SC_ERR_ARG, "sc_reset_optimizer: null context");
+  SC_CUDA(cudaSetDevice(ctx->device));
+  SC_CUDA(cudaDeviceSynchronize());
+  SC_CUDA(cudaMemset(ctx->adam_m, 0, sizeof(float) * SC_PARAM_FLOATS));
+  SC_CUDA(cudaMemset(ctx->adam_v, 0, sizeof(float) * SC_PARAM_FLOATS));
+  ctx->adam_t = 0;
+  return SC_OK;
+}
+
+int sc_eval_batch(sc_ctx* ctx, const float* in1_dev, const float* in2_dev, const float* in3_dev, const float* in4_dev,
+                  const uint8_t* y_dev, int64_t n, float* out2_dev, void* stream) {
+  SC_TRY(fresh_weights(ctx, "sc_eval_batch", (cudaStream_t)stream));
+  SC_CHECK(n > 0 && in1_dev && in2_dev && in3_dev && in4_dev && y_dev && out2_dev, SC_ERR_ARG, "sc_eval_batch: bad argument");
+  return eval_batch(ctx, in1_dev, in2_dev, in3_dev, in4_dev, y_dev, n, out2_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+// Shared declarations of the subcort_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/subcort_b200.h"
+
+namespace sc {
+
+void set_error(const char* fmt, ...);
+
+#define SC_CUDA(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      sc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));   \
+      return SC_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define SC_CHECK(cond, code, ...)   \
+  do {                              \
+    if (!(cond)) {                  \
+      sc::set_error(__VA_ARGS__);   \
+      return code;                  \
+    }                               \
+  } while (0)
+
+#define SC_TRY(expr)           \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != SC_OK) return _s;\
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Parameter table: offsets (in floats) into the flat pickle-ordered blob
+// (nets/<name>/<name>.pkl; graph order of cnn_cort/nets.py:170-231).
+// ---------------------------------------------------------------------------------------
+constexpr int kConvCin[5] = {1, 20, 20, 40, 40};
+constexpr int kConvCout[5] = {20, 20, 40, 40, 60};
+
+struct BranchOff {
+  int convW[5];   // (Cout, Cin, 3, 3)
+  int bn[5][4];   // beta, gamma, mean, inv_std
+  int alpha[5];   // PReLU
+  int d1W, d1b, d1alpha;  // (540,180), (180), (180)
+};
+struct ParamOff {
+  BranchOff br[3];
+  int fc1W, fc1b, a1;   // (540,540) (540) (540)
+  int fc2W, fc2b, a2;   // (555,270) (270) (270)
+  int outW, outb;       // (270,15) (15)
+  int total;
+};
+inline ParamOff make_param_off() {
+  ParamOff P;
+  int o = 0;
+  for (int b = 0; b < 3; ++b) {
+    for (int l = 0; l < 5; ++l) {
+      P.br[b].convW[l] = o; o += kConvCout[l] * kConvCin[l] * 9;
+      for (int k = 0; k < 4; ++k) { P.br[b].bn[l][k] = o; o += kConvCout[l]; }
+      P.br[b].alpha[l] = o; o += kConvCout[l];
+    }
+    P.br[b].d1W = o; o += 540 * 180;
+    P.br[b].d1b = o; o += 180;
+    P.br[b].d1alpha = o; o += 180;
+  }
+  P.fc1W = o; o += 540 * 540; P.fc1b = o; o += 540; P.a1 = o; o += 540;
+  P.fc2W = o; o += 555 * 270; P.fc2b = o; o += 270; P.a2 = o; o += 270;
+  P.outW = o; o += 270 * 15; P.outb = o; o += 15;
+  P.total = o;
+  return P;
+}
+
+// ---------------------------------------------------------------------------------------
+// Derived inference layouts (device)
+// ---------------------------------------------------------------------------------------
+// GEMM operand geometry (padded so that K is a multiple of 32 floats = one 128 B swizzle row)
+constexpr int kFeat = 540;       // concat of the three d1 outputs
+constexpr int kFeatLd = 544;     // row stride of the feature buffer (K of FC1)
+constexpr int kH1 = 555;         // FC1 out (540) + atlas (15)
+constexpr int kH1Ld = 576;       // row stride (K of fc_2)
+constexpr int kH2 = 270;
+constexpr int kH2Ld = 272;
+constexpr int kC5Ld = 64;        // conv5 output channels padded 60 -> 64 (NHWC)
+constexpr int kD1K = 9 * kC5Ld;  // 576: K of d1 as a 3x3 dilation-4 conv over conv5 output
+
+struct GemmW {      // one dense layer prepared for both GEMM back-ends
+  float* w_kn;      // [Kpad][Npad] row-major (SIMT path), zero padded
+  float* w_nk;      // [Npad][Kpad] K-major, TF32-rounded (tcgen05 path), zero padded
+  float* bias;      // [Npad]
+  float* alpha;     // [Npad] (PReLU; 1 where identity)
+  int K, N, Kpad, Npad;
+};
+
+struct BranchW {
+  float* c1_w;          // [9][20]  flipped taps, tap = ky*3+kx
+  float* conv_w[5];     // l=1..4 used: [Cin][9][Cout] flipped (conv2..conv5)
+  float* scale[5];      // BN folded: gamma*inv_std
+  float* shift[5];      // beta - mean*scale
+  float* alpha[5];
+  GemmW d1;             // patchwise: K=540 (c*9+h*3+w order)
+  GemmW d1_dense;       // dense: K=576 (tap*64+ci), same N
+};
+
+struct Workspace {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+// per-kernel-class timing with CUDA events on the launching stream (sc_set_option "profile")
+enum ProfClass {
+  PC_GATHER = 0, PC_NONZERO, PC_SCATTER, PC_PATCH_BRANCH, PC_CONV1, PC_CONV2, PC_CONV3, PC_CONV4, PC_CONV5,
+  PC_GEMM_D1, PC_GEMM_FC1, PC_GEMM_FC2, PC_ATLAS, PC_OUT, PC_TRAIN_FWD, PC_TRAIN_BWD, PC_ADAM, PC_COUNT
+};
+struct ProfEvent { int cls; cudaEvent_t a, b; };
+
+}  // namespace sc
+
+struct sc_ctx {
+  int device = 0;
+  int sm_count = 0;
+  bool weights_loaded = false;
+  int gemm_backend = 0;          // 0 SIMT, 1 tcgen05
+  int64_t chunk_voxels = 1 << 20;
+  int64_t launches = 0;
+  sc::ParamOff off;
+  float* params = nullptr;       // master copy, pickle order
+  float* grads = nullptr;        // same layout
+  float* adam_m = nullptr;
+  float* adam_v = nullptr;
+  uint8_t* trainable = nullptr;  // 1 where the entry is trainable
+  int64_t adam_t = 0;
+  float* derived = nullptr;      // arena for the derived layouts
+  size_t derived_floats = 0;
+  sc::BranchW br[3];
+  sc::GemmW fc1, fc2;
+  float* out_w = nullptr;        // [270][16]
+  float* out_b = nullptr;        // [16]
+  sc::Workspace ws;              // inference scratch (grow-only)
+  sc::Workspace ws_train;        // training scratch
+  int64_t* d_count = nullptr;    // device scalar for stream compaction
+  int64_t* h_count = nullptr;    // pinned
+  void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
+  bool profile = false;
+  std::vector<sc::ProfEvent> prof_live;
+  std::vector<sc::ProfEvent> prof_free;
+  bool derived_dirty = false;    // master parameters changed since the inference layouts were derived
+};
+
+namespace sc {
+int ensure_ws(Workspace& ws, size_t bytes);
+
+struct ProfScope {
+  sc_ctx* ctx; cudaStream_t st; ProfEvent ev; bool on;
+  ProfScope(sc_ctx* c, int cls, cudaStream_t s) : ctx(c), st(s), on(c->profile) {
+    if (!on) return;
+    if (!ctx->prof_free.empty()) { ev = ctx->prof_free.back(); ctx->prof_free.pop_back(); }
+    else { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
+    ev.cls = cls;
+    cudaEventRecord(ev.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(ev.b, st);
+    ctx->prof_live.push_back(ev);
+  }
+};
+
+// gather.cu
+int launch_gather(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, int bg_fix,
+                  const int32_t* xyz, int64_t n, float* ax, float* co, float* sa, float* atlas_out, cudaStream_t st);
+int launch_center_labels(sc_ctx* ctx, const uint8_t* lab, const int32_t* dims, const int32_t* xyz, int64_t n,
+                         uint8_t* y, cudaStream_t st);
+int launch_nonzero(sc_ctx* ctx, const void* vol, int elem_bytes, const int32_t* dims, int32_t* xyz,
+                   int64_t capacity, int64_t* n_out_host, cudaStream_t st);
+int launch_scatter(sc_ctx* ctx, const int32_t* xyz, int64_t n, const int32_t* label, const float* proba,
+                   const int32_t* dims, uint8_t* label_vol, float* proba_vol, cudaStream_t st);
+
+// weights.cu
+int derive_weights(sc_ctx* ctx, cudaStream_t st);
+
+// gemm_simt.cu : C = prelu(A*W + b), implicit-GEMM with taps
+struct GemmProblem {
+  const float* A;       // A(m, y, z, tap, k) = A[z*a_zs + y*a_ys + m*lda + tap_off[tap] + k]
+  int64_t lda, a_ys, a_zs;
+  int ntaps;            // 1 (dense layer) or 9 (3x3 conv)
+  int64_t tap_off[9];
+  int kc;               // K per tap (multiple of 4)
+  float* C;             // C(m, y, z, n) = C[z*c_zs + y*c_ys + m*ldc + n]
+  int64_t ldc, c_ys, c_zs;
+  int M, Y, Z;          // rows per (y,z) line, lines, planes
+  int prof_cls;         // ProfClass of this launch
+  int n_store;          // columns written (<= w.Npad)
+  int round_tf32;       // round outputs to TF32 (they feed a tensor-core GEMM)
+};
+int launch_gemm(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
+// rows of h2 -> softmax / argmax.  geo == nullptr: row m writes proba[m], label32[m].
+// geo != nullptr: row m is voxel (ix,iy,iz) of a box slab; results go to the volume-shaped
+// outputs (label8 / proba) at that voxel, skipped where mask[voxel] == 0.
+struct OutGeo { int x0, y0, z0, by, bz, Y, Z; };
+int launch_out_softmax(sc_ctx* ctx, const float* h2, int64_t n, float* proba, int32_t* label32, uint8_t* label8,
+                       const uint8_t* mask, const OutGeo* geo, cudaStream_t st);
+
+// gemm_tc.cu : tcgen05 / TMEM / TMA back-end for the same problem
+int tc_init(sc_ctx* ctx);
+void tc_destroy(sc_ctx* ctx);
+int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
+
+// patch_forward.cu
+int launch_branch_patches(sc_ctx* ctx, int branch, const float* patches, int64_t n, float* c5_out /*[n][540]*/,
+                          cudaStream_t st);
+int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, int64_t n,
+                    float* proba, int32_t* label, cudaStream_t st);
+
+// dense.cu
+int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, const int32_t* box,
+                   const uint8_t* cand, uint8_t* label_vol, float* proba_vol, cudaStream_t st);
+
+// train.cu
+int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4,
+                           const uint8_t* y, int64_t n, int64_t n_global, uint64_t seed, const uint8_t* masks,
+                           float* loss, cudaStream_t st);
+int adam_step(sc_ctx* ctx, float lr, float b1, float b2, float eps, float gscale, cudaStream_t st);
+int eval_batch(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, const uint8_t* y,
+               int64_t n, float* out2, cudaStream_t st);
+
+__device__ __forceinline__ float prelu(float x, float a) { return x > 0.f ? x : a * x; }
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+}  // namespace sc

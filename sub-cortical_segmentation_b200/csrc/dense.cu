@@ -1,0 +1,413 @@
+// Whole-volume inference in the dense dilated formulation.
+//
+// The reference evaluates the branch of cnn_cort/nets.py:170-180 on one 32x32 patch per
+// candidate voxel (base.py:421-428).  Evaluated at EVERY pixel of a slice that is the same
+// as running, on the slice zero-padded by (16 before, 15 after):
+//   conv1 d=1 -> conv2 d=1 -> maxpool(2, stride 1) -> conv3 d=2 -> conv4 d=2 ->
+//   maxpool(2, stride 1, dilation 2) -> conv5 d=4 -> d1 as a 3x3 dilation-4 conv (540 -> 180)
+// (oracle/network.py:dense_branch proves the identity in fp64).  20x fewer FLOPs than the
+// patchwise form and no patch materialisation at all.
+//
+// Coordinates: every layer buffer of a view shares the origin (r0, c0) of the requested
+// output box in padded-slice coordinates; layer L covers rows [r0, r1 + ext_L):
+//   ext: conv1 29, conv2 27, conv3 22, conv4 18, conv5 8, d1 0.
+// The 2x2 stride-1 pools are folded into the load stage of conv3 / conv5.
+// Layouts: conv1..conv4 planar [slice][C][rows][ld]; conv5 NHWC-64 [slice][rows][cols][64]
+// (the A operand of the d1 implicit GEMM, K = tap*64 + c).
+#include "common.cuh"
+
+namespace sc {
+
+struct ViewGeo {
+  int64_t ss, rs, cs;   // element strides of slice / row / col in the [X][Y][Z] volume
+  int s0, ns;           // slice range of the box along the view's slice axis
+  int r0, c0;           // box origin inside the slice
+  int br, bc;           // box extent (rows, cols)
+  int R, C;             // full slice extent (zero outside)
+};
+
+__host__ __device__ inline int round8(int v) { return (v + 7) & ~7; }
+
+// ---------------------------------------------------------------------------------------
+// conv1 (1 -> 20) straight from the volume, zero padding implicit.  4 pixels x 20 channels
+// per thread; planar output.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_conv1_kernel(const float* __restrict__ vol, ViewGeo g, int sbeg, int ns,
+                                                          const float* __restrict__ w, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, const float* __restrict__ alpha,
+                                                          float* __restrict__ out, int outR, int ld) {
+  __shared__ float sw[9 * 20], ssc[20], ssh[20], sal[20];
+  for (int i = threadIdx.x; i < 180; i += 256) sw[i] = w[i];
+  if (threadIdx.x < 20) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; sal[threadIdx.x] = alpha[threadIdx.x]; }
+  __syncthreads();
+  const int quads = ld >> 2;
+  const int64_t total = (int64_t)ns * outR * quads;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int q = (int)(e % quads);
+    const int i = (int)((e / quads) % outR);
+    const int s = (int)(e / ((int64_t)quads * outR));
+    const int j0 = q * 4;
+    float x[3][6];
+    const float* base = vol + (int64_t)(g.s0 + sbeg + s) * g.ss;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int rr = g.r0 + i + ky - 16;
+      const bool rin = rr >= 0 && rr < g.R;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+        const int cc = g.c0 + j0 + t - 16;
+        x[ky][t] = (rin && cc >= 0 && cc < g.C) ? __ldg(base + (int64_t)rr * g.rs + (int64_t)cc * g.cs) : 0.f;
+      }
+    }
+    float* o = out + (((int64_t)s * 20) * outR + i) * ld + j0;
+    const int64_t plane = (int64_t)outR * ld;
+#pragma unroll 4
+    for (int co = 0; co < 20; ++co) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float wv = sw[(ky * 3 + kx) * 20 + co];
+          a0 = fmaf(x[ky][kx + 0], wv, a0); a1 = fmaf(x[ky][kx + 1], wv, a1);
+          a2 = fmaf(x[ky][kx + 2], wv, a2); a3 = fmaf(x[ky][kx + 3], wv, a3);
+        }
+      const float sc_ = ssc[co], sh = ssh[co], al = sal[co];
+      float4 v;
+      v.x = prelu(fmaf(a0, sc_, sh), al); v.y = prelu(fmaf(a1, sc_, sh), al);
+      v.z = prelu(fmaf(a2, sc_, sh), al); v.w = prelu(fmaf(a3, sc_, sh), al);
+      *reinterpret_cast<float4*>(o + co * plane) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// conv2..conv5: 3x3 dilated conv + BN affine + PReLU over planar slices, fp32 FFMA.
+// CTA = 320 threads = 64 pixel groups (16 rows x 4 segments of 8 columns) x 5 channel groups.
+// Input channels stream through shared memory in chunks of 10 together with their taps.
+// ---------------------------------------------------------------------------------------
+template <int CIN, int COUT, int DIL, int POOLD, bool NHWC_OUT>
+struct ConvCfg {
+  static constexpr int TH = 16, TW = 32, CHUNK = 10;
+  static constexpr int CO_T = COUT / 5;
+  static constexpr int IH = TH + 2 * DIL;
+  static constexpr int NV = (8 + 2 * DIL + 3) / 4;            // float4 loads per thread per input row
+  static constexpr int IW = 24 + NV * 4;                      // widest column any thread reads
+  static constexpr int IWP = (IW % 8 == 4) ? IW : IW + 4;     // row stride == 4 (mod 8): conflict-free LDS.128
+  static constexpr int IN_FLOATS = CHUNK * IH * IWP;
+  static constexpr int W_FLOATS = CHUNK * 9 * COUT;
+  static constexpr size_t SMEM = (size_t)(IN_FLOATS + W_FLOATS) * sizeof(float);
+};
+
+struct ConvArgs {
+  const float* in; int inR, inLd;       // planar [ns][CIN][inR][inLd] (raw, before the folded pool)
+  float* out; int outR, outC, outLd;    // planar [ns][COUT][outR][outLd] or NHWC [ns][outR][outC][64]
+  const float* w;                       // [CIN][9][COUT]
+  const float* scale; const float* shift; const float* alpha;
+  int ns; int round_out;
+};
+
+template <int CIN, int COUT, int DIL, int POOLD, bool NHWC_OUT>
+__global__ void __launch_bounds__(320) dense_conv_kernel(const ConvArgs a) {
+  using Cfg = ConvCfg<CIN, COUT, DIL, POOLD, NHWC_OUT>;
+  extern __shared__ __align__(16) float smem[];
+  float* s_in = smem;
+  float* s_w = smem + Cfg::IN_FLOATS;
+  const int tid = threadIdx.x;
+  const int cg = tid >> 6, pg = tid & 63, prow = pg >> 2, pseg = pg & 3;
+  const int tr0 = blockIdx.y * Cfg::TH, tc0 = blockIdx.x * Cfg::TW;
+  const int s = blockIdx.z;
+  const float* in_s = a.in + (int64_t)s * CIN * a.inR * a.inLd;
+
+  float acc[8][Cfg::CO_T];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int c = 0; c < Cfg::CO_T; ++c) acc[p][c] = 0.f;
+
+  for (int ci0 = 0; ci0 < CIN; ci0 += Cfg::CHUNK) {
+    __syncthreads();
+    // stage CHUNK input planes (with the stride-1 max-pool of the previous layer folded in)
+    for (int e = tid; e < Cfg::CHUNK * Cfg::IH * Cfg::IW; e += 320) {
+      const int col = e % Cfg::IW;
+      const int row = (e / Cfg::IW) % Cfg::IH;
+      const int ci = e / (Cfg::IW * Cfg::IH);
+      const int gr = tr0 + row, gc = tc0 + col;
+      float v = 0.f;
+      if (gr + POOLD < a.inR && gc + POOLD < a.inLd) {
+        const float* p = in_s + ((int64_t)(ci0 + ci) * a.inR + gr) * a.inLd + gc;
+        v = __ldg(p);
+        if (POOLD > 0) {
+          v = fmaxf(v, __ldg(p + POOLD));
+          v = fmaxf(v, fmaxf(__ldg(p + (int64_t)POOLD * a.inLd), __ldg(p + (int64_t)POOLD * a.inLd + POOLD)));
+        }
+      }
+      s_in[(ci * Cfg::IH + row) * Cfg::IWP + col] = v;
+    }
+    for (int e = tid; e < Cfg::W_FLOATS / 4; e += 320)
+      reinterpret_cast<float4*>(s_w)[e] = __ldg(reinterpret_cast<const float4*>(a.w + (int64_t)ci0 * 9 * COUT) + e);
+    __syncthreads();
+
+#pragma unroll 1
+    for (int ci = 0; ci < Cfg::CHUNK; ++ci) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        float x[Cfg::NV * 4];
+        const float4* src = reinterpret_cast<const float4*>(s_in + (ci * Cfg::IH + prow + ky * DIL) * Cfg::IWP + pseg * 8);
+#pragma unroll
+        for (int v = 0; v < Cfg::NV; ++v) {
+          const float4 t = src[v];
+          x[v * 4 + 0] = t.x; x[v * 4 + 1] = t.y; x[v * 4 + 2] = t.z; x[v * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          float wv[Cfg::CO_T];
+          const float4* wsrc = reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * COUT + cg * Cfg::CO_T);
+#pragma unroll
+          for (int v = 0; v < Cfg::CO_T / 4; ++v) {
+            const float4 t = wsrc[v];
+            wv[v * 4 + 0] = t.x; wv[v * 4 + 1] = t.y; wv[v * 4 + 2] = t.z; wv[v * 4 + 3] = t.w;
+          }
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+#pragma unroll
+            for (int c = 0; c < Cfg::CO_T; ++c) acc[p][c] = fmaf(x[kx * DIL + p], wv[c], acc[p][c]);
+        }
+      }
+    }
+  }
+
+  const int orow = tr0 + prow, ocol = tc0 + pseg * 8;
+  if (orow >= a.outR) return;
+  if (!NHWC_OUT) {
+    if (ocol >= a.outLd) return;
+#pragma unroll
+    for (int c = 0; c < Cfg::CO_T; ++c) {
+      const int co = cg * Cfg::CO_T + c;
+      const float sc_ = __ldg(a.scale + co), sh = __ldg(a.shift + co), al = __ldg(a.alpha + co);
+      float r[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) r[p] = prelu(fmaf(acc[p][c], sc_, sh), al);
+      float* o = a.out + (((int64_t)s * COUT + co) * a.outR + orow) * a.outLd + ocol;
+      *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+  } else {
+    float sc_[Cfg::CO_T], sh[Cfg::CO_T], al[Cfg::CO_T];
+#pragma unroll
+    for (int c = 0; c < Cfg::CO_T; ++c) {
+      const int co = cg * Cfg::CO_T + c;
+      sc_[c] = __ldg(a.scale + co); sh[c] = __ldg(a.shift + co); al[c] = __ldg(a.alpha + co);
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      if (ocol + p >= a.outC) break;
+      float* o = a.out + (((int64_t)s * a.outR + orow) * a.outC + ocol + p) * kC5Ld + cg * Cfg::CO_T;
+#pragma unroll
+      for (int v = 0; v < Cfg::CO_T / 4; ++v) {
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          r[k] = prelu(fmaf(acc[p][v * 4 + k], sc_[v * 4 + k], sh[v * 4 + k]), al[v * 4 + k]);
+          if (a.round_out) r[k] = round_tf32(r[k]);
+        }
+        *reinterpret_cast<float4*>(o + v * 4) = make_float4(r[0], r[1], r[2], r[3]);
+      }
+      if (cg == 4 && COUT < kC5Ld) *reinterpret_cast<float4*>(o + Cfg::CO_T) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+template <int CIN, int COUT, int DIL, int POOLD, bool NHWC_OUT>
+static int launch_dense_conv(sc_ctx* ctx, const ConvArgs& a, int prof_cls, cudaStream_t st) {
+  using Cfg = ConvCfg<CIN, COUT, DIL, POOLD, NHWC_OUT>;
+  auto kern = dense_conv_kernel<CIN, COUT, DIL, POOLD, NHWC_OUT>;
+  static bool configured = false;
+  if (!configured) {
+    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    configured = true;
+  }
+  const int width = NHWC_OUT ? a.outC : a.outLd;
+  dim3 grid((width + Cfg::TW - 1) / Cfg::TW, (a.outR + Cfg::TH - 1) / Cfg::TH, a.ns);
+  ProfScope prof(ctx, prof_cls, st);
+  kern<<<grid, 320, Cfg::SMEM, st>>>(a);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// atlas prior (with the background fix of base.py:392-394) -> columns 540..575 of the h1 rows
+__global__ void dense_atlas_kernel(const float* __restrict__ atlas, OutGeo g, int ix0, int64_t rows, float* __restrict__ h1) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const int64_t plane = (int64_t)g.by * g.bz;
+  const int ix = (int)(m / plane);
+  const int rem = (int)(m - (int64_t)ix * plane);
+  const int iy = rem / g.bz, iz = rem - iy * g.bz;
+  const int64_t v = ((int64_t)(g.x0 + ix0 + ix) * g.Y + (g.y0 + iy)) * g.Z + (g.z0 + iz);
+  float a[16];
+#pragma unroll
+  for (int c = 0; c < 15; ++c) a[c] = __ldg(atlas + v * 15 + c);
+  float s = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])),
+                      __fadd_rn(__fadd_rn(a[4], a[5]), __fadd_rn(a[6], a[7])));
+#pragma unroll
+  for (int k = 8; k < 15; ++k) s = __fadd_rn(s, a[k]);
+  if (s == 0.f) a[14] = 1.f;
+  a[15] = 0.f;
+  float4* o = reinterpret_cast<float4*>(h1 + m * kH1Ld + 540);
+  o[0] = make_float4(a[0], a[1], a[2], a[3]);
+  o[1] = make_float4(a[4], a[5], a[6], a[7]);
+  o[2] = make_float4(a[8], a[9], a[10], a[11]);
+  o[3] = make_float4(a[12], a[13], a[14], a[15]);
+#pragma unroll
+  for (int k = 4; k < 9; ++k) o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, const int32_t* box,
+                   const uint8_t* cand, uint8_t* label_vol, float* proba_vol, cudaStream_t st) {
+  const int X = dims[0], Y = dims[1], Z = dims[2];
+  int b[6] = {0, X, 0, Y, 0, Z};
+  if (box) for (int i = 0; i < 6; ++i) b[i] = box[i];
+  SC_CHECK(b[0] >= 0 && b[1] <= X && b[2] >= 0 && b[3] <= Y && b[4] >= 0 && b[5] <= Z, SC_ERR_ARG, "sc_segment_volume: box outside the volume");
+  const int bx = b[1] - b[0], by = b[3] - b[2], bz = b[5] - b[4];
+  if (bx <= 0 || by <= 0 || bz <= 0) return SC_OK;
+  const int64_t YZ = (int64_t)Y * Z;
+  const bool tc = ctx->gemm_backend == 1;
+
+  ViewGeo vg[3];
+  // axial: slices along z, rows x, cols y  (patch axes (dx, dy), base.py:291-292)
+  vg[0] = {1, YZ, Z, b[4], bz, b[0], b[2], bx, by, X, Y};
+  // coronal: slices along y, rows x, cols z
+  vg[1] = {Z, YZ, 1, b[2], by, b[0], b[4], bx, bz, X, Z};
+  // saggital: slices along x, rows y, cols z
+  vg[2] = {YZ, Z, 1, b[0], bx, b[2], b[4], by, bz, Y, Z};
+
+  // ---- workspace carve-up ----------------------------------------------------------------
+  size_t a5_off[3], a5_bytes = 0;
+  for (int v = 0; v < 3; ++v) {
+    a5_off[v] = a5_bytes;
+    a5_bytes += align256((size_t)vg[v].ns * (vg[v].br + 8) * (vg[v].bc + 8) * kC5Ld * sizeof(float));
+  }
+  size_t per_slice_max = 0;
+  for (int v = 0; v < 3; ++v) {
+    const size_t br = vg[v].br, bc = vg[v].bc;
+    size_t f = 20 * (br + 29) * round8(bc + 29) + 20 * (br + 27) * round8(bc + 27) + 40 * (br + 22) * round8(bc + 22) +
+               40 * (br + 18) * round8(bc + 18);
+    per_slice_max = f > per_slice_max ? f : per_slice_max;
+  }
+  const size_t scratch_budget = (size_t)1536 << 20;
+  int group = (int)(scratch_budget / (per_slice_max * sizeof(float) + 1024));
+  if (group < 1) group = 1;
+  if (group > 64) group = 64;
+  const size_t scratch_bytes = align256((per_slice_max * sizeof(float) + 1024) * group);
+  const int64_t plane = (int64_t)by * bz;
+  int slab = (int)(ctx->chunk_voxels / plane);
+  if (slab < 1) slab = 1;
+  if (slab > bx) slab = bx;
+  const size_t rows_max = (size_t)slab * plane;
+  const size_t feat_bytes = align256(rows_max * kFeatLd * sizeof(float));
+  const size_t h1_bytes = align256(rows_max * kH1Ld * sizeof(float));
+  const size_t h2_bytes = align256(rows_max * kH2Ld * sizeof(float));
+  const size_t total = a5_bytes + scratch_bytes + feat_bytes + h1_bytes + h2_bytes;
+  SC_TRY(ensure_ws(ctx->ws, total));
+  char* wsb = reinterpret_cast<char*>(ctx->ws.ptr);
+  float* a5[3] = {reinterpret_cast<float*>(wsb + a5_off[0]), reinterpret_cast<float*>(wsb + a5_off[1]),
+                  reinterpret_cast<float*>(wsb + a5_off[2])};
+  char* scratch = wsb + a5_bytes;
+  float* feats = reinterpret_cast<float*>(scratch + scratch_bytes);
+  float* h1 = reinterpret_cast<float*>(reinterpret_cast<char*>(feats) + feat_bytes);
+  float* h2 = reinterpret_cast<float*>(reinterpret_cast<char*>(h1) + h1_bytes);
+
+  // ---- phase 1: conv1..conv5 per view, slices in groups ------------------------------------
+  for (int v = 0; v < 3; ++v) {
+    const ViewGeo& g = vg[v];
+    const BranchW& W = ctx->br[v];
+    const int r1 = g.br + 29, l1 = round8(g.bc + 29);
+    const int r2 = g.br + 27, l2 = round8(g.bc + 27);
+    const int r3 = g.br + 22, l3 = round8(g.bc + 22);
+    const int r4 = g.br + 18, l4 = round8(g.bc + 18);
+    const int r5 = g.br + 8, c5 = g.bc + 8;
+    for (int sb = 0; sb < g.ns; sb += group) {
+      const int ns = g.ns - sb < group ? g.ns - sb : group;
+      float* c1 = reinterpret_cast<float*>(scratch);
+      float* c2 = c1 + align256((size_t)ns * 20 * r1 * l1 * 4) / 4;
+      float* c3 = c2 + align256((size_t)ns * 20 * r2 * l2 * 4) / 4;
+      float* c4 = c3 + align256((size_t)ns * 40 * r3 * l3 * 4) / 4;
+      {
+        const int64_t work = (int64_t)ns * r1 * (l1 / 4);
+        const int64_t blocks = (work + 255) / 256;
+        const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
+        ProfScope prof(ctx, PC_CONV1, st);
+        dense_conv1_kernel<<<grid, 256, 0, st>>>(vol, g, sb, ns, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], c1, r1, l1);
+        ctx->launches++;
+        SC_CUDA(cudaGetLastError());
+      }
+      ConvArgs a;
+      a.ns = ns; a.round_out = 0;
+      a.in = c1; a.inR = r1; a.inLd = l1; a.out = c2; a.outR = r2; a.outC = g.bc + 27; a.outLd = l2;
+      a.w = W.conv_w[1]; a.scale = W.scale[1]; a.shift = W.shift[1]; a.alpha = W.alpha[1];
+      SC_TRY((launch_dense_conv<20, 20, 1, 0, false>(ctx, a, PC_CONV2, st)));
+      a.in = c2; a.inR = r2; a.inLd = l2; a.out = c3; a.outR = r3; a.outC = g.bc + 22; a.outLd = l3;
+      a.w = W.conv_w[2]; a.scale = W.scale[2]; a.shift = W.shift[2]; a.alpha = W.alpha[2];
+      SC_TRY((launch_dense_conv<20, 40, 2, 1, false>(ctx, a, PC_CONV3, st)));
+      a.in = c3; a.inR = r3; a.inLd = l3; a.out = c4; a.outR = r4; a.outC = g.bc + 18; a.outLd = l4;
+      a.w = W.conv_w[3]; a.scale = W.scale[3]; a.shift = W.shift[3]; a.alpha = W.alpha[3];
+      SC_TRY((launch_dense_conv<40, 40, 2, 0, false>(ctx, a, PC_CONV4, st)));
+      a.in = c4; a.inR = r4; a.inLd = l4; a.out = a5[v] + (size_t)sb * r5 * c5 * kC5Ld; a.outR = r5; a.outC = c5; a.outLd = c5;
+      a.w = W.conv_w[4]; a.scale = W.scale[4]; a.shift = W.shift[4]; a.alpha = W.alpha[4];
+      a.round_out = tc ? 1 : 0;
+      SC_TRY((launch_dense_conv<40, 60, 4, 2, true>(ctx, a, PC_CONV5, st)));
+    }
+  }
+
+  // ---- phase 2: d1 (x3) + FC head per slab of x-planes -------------------------------------
+  OutGeo og = {b[0], b[2], b[4], by, bz, Y, Z};
+  for (int ix0 = 0; ix0 < bx; ix0 += slab) {
+    const int nx = bx - ix0 < slab ? bx - ix0 : slab;
+    const int64_t rows = (int64_t)nx * plane;
+    for (int v = 0; v < 3; ++v) {
+      const ViewGeo& g = vg[v];
+      const int64_t c5 = g.bc + 8, r5 = g.br + 8;
+      GemmProblem p;
+      p.lda = kC5Ld; p.a_ys = c5 * kC5Ld; p.a_zs = r5 * c5 * kC5Ld;
+      p.ntaps = 9; p.kc = kC5Ld;
+      for (int t = 0; t < 9; ++t) p.tap_off[t] = ((int64_t)(t / 3) * 4 * c5 + (t % 3) * 4) * kC5Ld;
+      p.ldc = 0; p.round_tf32 = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
+      p.n_store = v == 2 ? 184 : 180;
+      if (v == 0) {        // m = y, lines = x (slab), planes = z
+        p.A = a5[0] + (int64_t)ix0 * p.a_ys; p.M = by; p.Y = nx; p.Z = bz;
+        p.ldc = (int64_t)bz * kFeatLd; p.c_ys = plane * kFeatLd; p.c_zs = kFeatLd;
+      } else if (v == 1) { // m = z, lines = x (slab), planes = y
+        p.A = a5[1] + (int64_t)ix0 * p.a_ys; p.M = bz; p.Y = nx; p.Z = by;
+        p.ldc = kFeatLd; p.c_ys = plane * kFeatLd; p.c_zs = (int64_t)bz * kFeatLd;
+      } else {             // m = z, lines = y, planes = x (slab)
+        p.A = a5[2] + (int64_t)ix0 * p.a_zs; p.M = bz; p.Y = by; p.Z = nx;
+        p.ldc = kFeatLd; p.c_ys = (int64_t)bz * kFeatLd; p.c_zs = plane * kFeatLd;
+      }
+      p.C = feats + v * 180;
+      SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->br[v].d1_dense, st) : launch_gemm(ctx, p, ctx->br[v].d1_dense, st));
+    }
+    { ProfScope prof(ctx, PC_ATLAS, st);
+      dense_atlas_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(atlas, og, ix0, rows, h1); }
+    ctx->launches++;
+    SC_CUDA(cudaGetLastError());
+    GemmProblem p;
+    p.ntaps = 1; p.tap_off[0] = 0; p.a_ys = p.a_zs = p.c_ys = p.c_zs = 0; p.Y = p.Z = 1;
+    SC_CHECK(rows < (1ll << 31), SC_ERR_ARG, "sc_segment_volume: chunk too large");
+    p.M = (int)rows;
+    p.A = feats; p.lda = kFeatLd; p.kc = kFeatLd; p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.round_tf32 = tc ? 1 : 0;
+    p.prof_cls = PC_GEMM_FC1;
+    SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
+    p.A = h1; p.lda = kH1Ld; p.kc = kH1Ld; p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.round_tf32 = 0;
+    p.prof_cls = PC_GEMM_FC2;
+    SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc2, st) : launch_gemm(ctx, p, ctx->fc2, st));
+    OutGeo og2 = og;
+    og2.x0 = b[0] + ix0;
+    SC_TRY(launch_out_softmax(ctx, h2, rows, proba_vol, nullptr, label_vol, cand, &og2, st));
+  }
+  return SC_OK;
+}
+
+}  // namespace sc

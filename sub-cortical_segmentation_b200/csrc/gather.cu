@@ -1,0 +1,297 @@
+// K1: orthogonal patch gather + atlas vectors; candidate-voxel compaction; result scatter.
+// Integer / byte work, HBM-write bound: no tensor cores here, only coalesced 128 B rows.
+//
+// Reference behaviour (paths relative to /root/reference):
+//   get_patches        cnn_cort/base.py:272-308   window [c-16, c+16) on the two in-plane axes, zeros outside
+//   atlas + bg-fix     cnn_cort/base.py:387-394   atlas[x,y,z,:]; if the row sums to 0 -> row[14] = 1
+//   get_mask_voxels    cnn_cort/base.py:310-331   np.nonzero order (x slowest, z fastest)
+//   scatter            cnn_cort/base.py:430-440
+#include "common.cuh"
+
+namespace sc {
+
+constexpr int kGroup = 32;  // candidates per CTA
+
+// One CTA (256 threads) gathers the three 32x32 views of kGroup candidates.
+//  coronal  [dx][dz] at y and saggital [dy][dz] at x: a patch row is contiguous along z, so one
+//           warp copies one row (lane = column): 128 B coalesced read (unaligned start) -> 128 B store.
+//  axial    [dx][dy] at z: no contiguous in-plane axis.  Lanes run over the CANDIDATES instead
+//           (consecutive candidates of np.nonzero order are consecutive in z => one 128 B line),
+//           a 32x33 shared tile transposes so that the store is again one full patch row per warp.
+__global__ void __launch_bounds__(256) gather_patches_kernel(
+    const float* __restrict__ vol, int X, int Y, int Z, const float* __restrict__ atlas, int bg_fix,
+    const int32_t* __restrict__ xyz, int64_t n, float* __restrict__ ax, float* __restrict__ co,
+    float* __restrict__ sa, float* __restrict__ atlas_out) {
+  __shared__ int sx[kGroup], sy[kGroup], sz[kGroup];
+  __shared__ float tile[32][33];
+  __shared__ float satl[kGroup][16];
+  const int64_t base = (int64_t)blockIdx.x * kGroup;
+  const int cnt = (int)min((int64_t)kGroup, n - base);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kGroup) {
+    int64_t c = base + min(tid, cnt - 1);
+    sx[tid] = xyz[c * 3 + 0];
+    sy[tid] = xyz[c * 3 + 1];
+    sz[tid] = xyz[c * 3 + 2];
+  }
+  __syncthreads();
+  const int64_t YZ = (int64_t)Y * Z;
+
+  // ---- coronal and saggital: row copies ------------------------------------------------
+  for (int job = warp; job < cnt * 32; job += 8) {
+    const int c = job >> 5, i = job & 31;
+    const int x = sx[c], y = sy[c], z = sz[c];
+    const int zz = z - 16 + lane;
+    const bool zin = (zz >= 0) && (zz < Z);
+    const int64_t o = (base + c) * 1024 + i * 32 + lane;
+    if (co) {
+      const int xx = x - 16 + i;
+      float v = 0.f;
+      if (zin && xx >= 0 && xx < X) v = __ldg(vol + (int64_t)xx * YZ + (int64_t)y * Z + zz);
+      __stcs(co + o, v);
+    }
+    if (sa) {
+      const int yy = y - 16 + i;
+      float v = 0.f;
+      if (zin && yy >= 0 && yy < Y) v = __ldg(vol + (int64_t)x * YZ + (int64_t)yy * Z + zz);
+      __stcs(sa + o, v);
+    }
+  }
+
+  // ---- axial: lanes over candidates, transposed through shared memory --------------------
+  if (ax) {
+    const int x = sx[lane], y = sy[lane], z = sz[lane];
+    for (int i = 0; i < 32; ++i) {
+      const int xx = x - 16 + i;
+      const bool xin = (xx >= 0) && (xx < X) && (lane < cnt);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = warp * 4 + jj;
+        const int yy = y - 16 + j;
+        float v = 0.f;
+        if (xin && yy >= 0 && yy < Y) v = __ldg(vol + (int64_t)xx * YZ + (int64_t)yy * Z + z);
+        tile[j][lane] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = warp * 4 + cc;
+        if (c < cnt) __stcs(ax + (base + c) * 1024 + i * 32 + lane, tile[lane][c]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- atlas prior vector (+ background fix) ---------------------------------------------
+  if (atlas_out) {
+    for (int e = tid; e < cnt * 15; e += 256) {
+      const int c = e / 15, ch = e - c * 15;
+      const int64_t v = (int64_t)sx[c] * YZ + (int64_t)sy[c] * Z + sz[c];
+      satl[c][ch] = __ldg(atlas + v * 15 + ch);
+    }
+    __syncthreads();
+    if (bg_fix && tid < cnt) {
+      // np.sum of a contiguous float32[15]: numpy's pairwise kernel keeps 8 partial sums for the
+      // first 8 elements, combines them as a tree, then adds the remaining 7 in order.
+      const float* a = satl[tid];
+      float s = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])),
+                          __fadd_rn(__fadd_rn(a[4], a[5]), __fadd_rn(a[6], a[7])));
+#pragma unroll
+      for (int k = 8; k < 15; ++k) s = __fadd_rn(s, a[k]);
+      if (s == 0.f) satl[tid][14] = 1.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < cnt * 15; e += 256) atlas_out[base * 15 + e] = satl[e / 15][e % 15];
+  }
+}
+
+int launch_gather(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, int bg_fix,
+                  const int32_t* xyz, int64_t n, float* ax, float* co, float* sa, float* atlas_out,
+                  cudaStream_t st) {
+  if (n == 0) return SC_OK;
+  SC_CHECK(!atlas_out || atlas, SC_ERR_ARG, "sc_gather_patches: atlas output requested without an atlas");
+  const int64_t blocks = (n + kGroup - 1) / kGroup;
+  SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "sc_gather_patches: too many candidates in one call");
+  ProfScope prof(ctx, PC_GATHER, st);
+  gather_patches_kernel<<<(unsigned)blocks, 256, 0, st>>>(vol, dims[0], dims[1], dims[2], atlas, bg_fix, xyz, n, ax,
+                                                          co, sa, atlas_out);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+__global__ void center_labels_kernel(const uint8_t* __restrict__ lab, int Y, int Z, const int32_t* __restrict__ xyz,
+                                     int64_t n, uint8_t* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = ((int64_t)xyz[i * 3] * Y + xyz[i * 3 + 1]) * Z + xyz[i * 3 + 2];
+  y[i] = lab[v];
+}
+
+int launch_center_labels(sc_ctx* ctx, const uint8_t* lab, const int32_t* dims, const int32_t* xyz, int64_t n,
+                         uint8_t* y, cudaStream_t st) {
+  if (n == 0) return SC_OK;
+  center_labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lab, dims[1], dims[2], xyz, n, y);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Ordered stream compaction: count per 4096-element block, scan the block counts, emit.
+// ---------------------------------------------------------------------------------------
+constexpr int kNzPerThread = 16;
+constexpr int kNzBlock = 256 * kNzPerThread;
+
+template <int EB>
+__device__ __forceinline__ bool nz_at(const void* vol, int64_t i) {
+  if (EB == 1) return reinterpret_cast<const uint8_t*>(vol)[i] != 0;
+  // float32 / int32: any non-zero bit pattern except -0.0f (numpy: -0.0 is False)
+  uint32_t u = reinterpret_cast<const uint32_t*>(vol)[i];
+  return (u & 0x7fffffffu) != 0;
+}
+
+template <int EB>
+__global__ void __launch_bounds__(256) nz_count_kernel(const void* __restrict__ vol, int64_t total,
+                                                       int32_t* __restrict__ counts) {
+  const int64_t start = (int64_t)blockIdx.x * kNzBlock + (int64_t)threadIdx.x * kNzPerThread;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < kNzPerThread; ++k)
+    if (start + k < total && nz_at<EB>(vol, start + k)) ++c;
+  __shared__ int wsum[8];
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < 8; ++w) s += wsum[w];
+    counts[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) nz_scan_kernel(const int32_t* __restrict__ counts, int nblocks,
+                                                       int64_t* __restrict__ offsets, int64_t* __restrict__ total) {
+  __shared__ int64_t wsum[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    int64_t v = i < nblocks ? counts[i] : 0, inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int64_t w = wsum[threadIdx.x], winc = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (threadIdx.x >= o) winc += t;
+      }
+      wsum[threadIdx.x] = winc - w;
+    }
+    __syncthreads();
+    const int64_t excl = carry + wsum[threadIdx.x >> 5] + inc - v;
+    if (i < nblocks) offsets[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+template <int EB>
+__global__ void __launch_bounds__(256) nz_emit_kernel(const void* __restrict__ vol, int64_t total, int Y, int Z,
+                                                      const int64_t* __restrict__ offsets, int32_t* __restrict__ xyz,
+                                                      int64_t capacity) {
+  const int64_t start = (int64_t)blockIdx.x * kNzBlock + (int64_t)threadIdx.x * kNzPerThread;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < kNzPerThread; ++k)
+    if (start + k < total && nz_at<EB>(vol, start + k)) bits |= 1u << k;
+  const int c = __popc(bits);
+  int inc = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += t;
+  }
+  __shared__ int wsum[8];
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += wsum[w];
+  int64_t o = offsets[blockIdx.x] + wbase + inc - c;
+  const int64_t YZ = (int64_t)Y * Z;
+  while (bits) {
+    const int k = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int64_t v = start + k;
+    if (o < capacity) {
+      const int x = (int)(v / YZ);
+      const int64_t r = v - (int64_t)x * YZ;
+      xyz[o * 3 + 0] = x;
+      xyz[o * 3 + 1] = (int)(r / Z);
+      xyz[o * 3 + 2] = (int)(r % Z);
+    }
+    ++o;
+  }
+}
+
+int launch_nonzero(sc_ctx* ctx, const void* vol, int elem_bytes, const int32_t* dims, int32_t* xyz, int64_t capacity,
+                   int64_t* n_out_host, cudaStream_t st) {
+  SC_CHECK(elem_bytes == 1 || elem_bytes == 4, SC_ERR_ARG, "sc_nonzero_coords: elem_bytes must be 1 or 4");
+  const int64_t total = (int64_t)dims[0] * dims[1] * dims[2];
+  if (total == 0) {
+    if (n_out_host) *n_out_host = 0;
+    return SC_OK;
+  }
+  const int nblocks = (int)((total + kNzBlock - 1) / kNzBlock);
+  SC_TRY(ensure_ws(ctx->ws, (size_t)nblocks * 12 + 64));
+  int32_t* counts = reinterpret_cast<int32_t*>(ctx->ws.ptr);
+  int64_t* offsets = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(ctx->ws.ptr) + (((size_t)nblocks * 4 + 15) & ~(size_t)15));
+  if (elem_bytes == 1) nz_count_kernel<1><<<nblocks, 256, 0, st>>>(vol, total, counts);
+  else nz_count_kernel<4><<<nblocks, 256, 0, st>>>(vol, total, counts);
+  nz_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, offsets, ctx->d_count);
+  if (xyz && capacity > 0) {
+    if (elem_bytes == 1) nz_emit_kernel<1><<<nblocks, 256, 0, st>>>(vol, total, dims[1], dims[2], offsets, xyz, capacity);
+    else nz_emit_kernel<4><<<nblocks, 256, 0, st>>>(vol, total, dims[1], dims[2], offsets, xyz, capacity);
+    ctx->launches++;
+  }
+  ctx->launches += 2;
+  SC_CUDA(cudaGetLastError());
+  if (n_out_host) {
+    SC_CUDA(cudaMemcpyAsync(ctx->h_count, ctx->d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaStreamSynchronize(st));
+    *n_out_host = *ctx->h_count;
+  }
+  return SC_OK;
+}
+
+__global__ void scatter_kernel(const int32_t* __restrict__ xyz, int64_t n, const int32_t* __restrict__ label,
+                               const float* __restrict__ proba, int Y, int Z, uint8_t* __restrict__ label_vol,
+                               float* __restrict__ proba_vol) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t v = ((int64_t)xyz[i * 3] * Y + xyz[i * 3 + 1]) * Z + xyz[i * 3 + 2];
+  if (label_vol && label) label_vol[v] = (uint8_t)label[i];
+  if (proba_vol && proba) {
+#pragma unroll
+    for (int c = 0; c < 15; ++c) proba_vol[v * 15 + c] = proba[i * 15 + c];
+  }
+}
+
+int launch_scatter(sc_ctx* ctx, const int32_t* xyz, int64_t n, const int32_t* label, const float* proba,
+                   const int32_t* dims, uint8_t* label_vol, float* proba_vol, cudaStream_t st) {
+  if (n == 0) return SC_OK;
+  ProfScope prof(ctx, PC_SCATTER, st);
+  scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, n, label, proba, dims[1], dims[2], label_vol,
+                                                              proba_vol);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+}  // namespace sc
