@@ -111,6 +111,13 @@ SC_API int sc_forward_from_volume(sc_ctx* ctx, const float* vol_dev, const int32
                            const float* atlas_dev, const int32_t* xyz_dev, int64_t n,
                            float* proba_dev, int32_t* label_dev, void* stream);
 
+/* one dense layer of the head on its own (parity tests of the GEMM back-ends): which = 0..2 the
+ * d1 layer of the axial / coronal / saggital branch (in [n][544] flattened conv5 maps -> out [n][192],
+ * columns 0..179 valid), 3 = FC1 (in [n][544] -> out [n][576], columns 0..539 written), 4 = fc_2
+ * (in [n][576] = FC1 output | atlas | zero pad -> out [n][272]).  backend: 0 SIMT fp32, 1 tcgen05 TF32.
+ * replaces: DenseLayer + PReLU, cnn_cort/nets.py:179-180, 217-218, 227-228. */
+SC_API int sc_dense_layer(sc_ctx* ctx, int which, const float* in_dev, int64_t n, float* out_dev, int backend, void* stream);
+
 /* ---- whole-volume inference (dense dilated formulation) -----------------------------
  * replaces: the body of test_scan (base.py:421-440) when the candidates are (nearly) all
  * voxels of a box: per view the branch runs as dilated convolutions over whole slices,

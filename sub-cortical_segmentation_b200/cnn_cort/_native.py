@@ -45,6 +45,7 @@ PROTOTYPES = {
     "sc_gather_center_labels": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _c_i64, _vp, _vp]),
     "sc_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp]),
     "sc_forward_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp]),
+    "sc_dense_layer": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _c_i64, _vp, ctypes.c_int, _vp]),
     "sc_forward_from_volume": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _vp, _c_i64, _vp, _vp, _vp]),
     "sc_segment_volume": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _p(_c_i32), _vp, _vp, _vp, _vp]),
     "sc_segment_volume_host": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _p(_c_i32), _vp, _vp, _vp, _vp]),
@@ -188,6 +189,14 @@ class Context(object):
         label = np.empty((n,), np.int32) if want_label else None
         _check(self.lib.sc_forward_host(self.h, _ptr(in1), _ptr(in2), _ptr(in3), _ptr(in4), n, _ptr(proba), _ptr(label), _stream()))
         return proba, label
+
+    def dense_layer(self, which, x, backend):
+        """one head layer on its own: which 0..2 = d1 of a branch, 3 = FC1, 4 = fc_2 (see subcort_b200.h)"""
+        import torch
+        width = {0: 192, 1: 192, 2: 192, 3: 576, 4: 272}[which]
+        out = torch.zeros((x.shape[0], width), dtype=torch.float32, device=x.device)
+        _check(self.lib.sc_dense_layer(self.h, which, _ptr(x), x.shape[0], _ptr(out), backend, _stream()))
+        return out
 
     def forward_from_volume(self, vol, atlas, xyz, want_proba=True, want_label=True):
         import torch

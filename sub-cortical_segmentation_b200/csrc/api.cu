@@ -329,6 +329,29 @@ int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dim
   return SC_OK;
 }
 
+int sc_dense_layer(sc_ctx* ctx, int which, const float* in_dev, int64_t n, float* out_dev, int backend, void* stream) {
+  SC_TRY(fresh_weights(ctx, "sc_dense_layer", (cudaStream_t)stream));
+  SC_CHECK(which >= 0 && which <= 4 && in_dev && out_dev && n > 0 && n < (1ll << 31), SC_ERR_ARG, "sc_dense_layer: bad argument");
+  SC_CHECK(backend == 0 || (backend == 1 && ctx->tc_state), SC_ERR_UNSUPPORTED, "sc_dense_layer: back-end %d unavailable", backend);
+  GemmProblem p;
+  const GemmW* w;
+  if (which < 3) {
+    w = &ctx->br[which].d1;
+    gemm_problem_rows(p, in_dev, kFeatLd, kFeatLd, (int)n);
+    p.C = out_dev; p.ldc = 192; p.n_store = 192; p.prof_cls = PC_GEMM_D1;
+  } else if (which == 3) {
+    w = &ctx->fc1;
+    gemm_problem_rows(p, in_dev, kFeatLd, kFeatLd, (int)n);
+    p.C = out_dev; p.ldc = kH1Ld; p.n_store = 540; p.prof_cls = PC_GEMM_FC1;
+  } else {
+    w = &ctx->fc2;
+    gemm_problem_rows(p, in_dev, kH1Ld, kH1Ld, (int)n);
+    p.C = out_dev; p.ldc = kH2Ld; p.n_store = kH2Ld; p.prof_cls = PC_GEMM_FC2;
+  }
+  p.round_tf32 = 0;
+  return backend == 1 ? launch_gemm_tc(ctx, p, *w, (cudaStream_t)stream) : launch_gemm(ctx, p, *w, (cudaStream_t)stream);
+}
+
 int sc_scatter(sc_ctx* ctx, const int32_t* xyz_dev, int64_t n, const int32_t* label_dev, const float* proba_dev,
                const int32_t dims[3], uint8_t* label_vol_dev, float* proba_vol_dev, void* stream) {
   SC_CHECK(ctx && (xyz_dev || n == 0) && n >= 0, SC_ERR_ARG, "sc_scatter: bad argument");

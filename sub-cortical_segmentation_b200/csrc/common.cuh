@@ -193,11 +193,26 @@ struct GemmProblem {
   float* C;             // C(m, y, z, n) = C[z*c_zs + y*c_ys + m*ldc + n]
   int64_t ldc, c_ys, c_zs;
   int M, Y, Z;          // rows per (y,z) line, lines, planes
+  // tcgen05 back-end: the same A described for a 4-D TMA tensor map (k, pixel, line, plane)
+  const float* a_base;  // start of the whole buffer (16 B aligned)
+  int64_t a_dims[4];    // extents: k, pixels per line, lines, planes
+  int64_t a_strides[3]; // element strides of pixel, line, plane
+  int tap_dx[9], tap_dy[9];  // tap shifts in pixels / lines
+  int a_y0, a_z0;       // line / plane offset of this launch inside the buffer
   int prof_cls;         // ProfClass of this launch
   int n_store;          // columns written (<= w.Npad)
   int round_tf32;       // round outputs to TF32 (they feed a tensor-core GEMM)
 };
 int launch_gemm(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
+// plain [M][lda] row-major A, one tap: fills both the pointer form and the tensor-map form
+inline void gemm_problem_rows(GemmProblem& p, const float* A, int64_t lda, int kc, int M) {
+  p.A = A; p.lda = lda; p.a_ys = p.a_zs = 0; p.ntaps = 1; p.tap_off[0] = 0; p.kc = kc;
+  p.M = M; p.Y = p.Z = 1; p.c_ys = p.c_zs = 0;
+  p.a_base = A; p.a_dims[0] = kc; p.a_dims[1] = M; p.a_dims[2] = p.a_dims[3] = 1;
+  p.a_strides[0] = lda; p.a_strides[1] = p.a_strides[2] = (int64_t)M * lda;
+  for (int t = 0; t < 9; ++t) p.tap_dx[t] = p.tap_dy[t] = 0;
+  p.a_y0 = p.a_z0 = 0;
+}
 // rows of h2 -> softmax / argmax.  geo == nullptr: row m writes proba[m], label32[m].
 // geo != nullptr: row m is voxel (ix,iy,iz) of a box slab; results go to the volume-shaped
 // outputs (label8 / proba) at that voxel, skipped where mask[voxel] == 0.

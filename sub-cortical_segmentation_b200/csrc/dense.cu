@@ -373,7 +373,13 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       GemmProblem p;
       p.lda = kC5Ld; p.a_ys = c5 * kC5Ld; p.a_zs = r5 * c5 * kC5Ld;
       p.ntaps = 9; p.kc = kC5Ld;
-      for (int t = 0; t < 9; ++t) p.tap_off[t] = ((int64_t)(t / 3) * 4 * c5 + (t % 3) * 4) * kC5Ld;
+      for (int t = 0; t < 9; ++t) {
+        p.tap_off[t] = ((int64_t)(t / 3) * 4 * c5 + (t % 3) * 4) * kC5Ld;
+        p.tap_dx[t] = (t % 3) * 4; p.tap_dy[t] = (t / 3) * 4;
+      }
+      p.a_base = a5[v]; p.a_dims[0] = kC5Ld; p.a_dims[1] = c5; p.a_dims[2] = r5; p.a_dims[3] = g.ns;
+      p.a_strides[0] = kC5Ld; p.a_strides[1] = c5 * kC5Ld; p.a_strides[2] = r5 * c5 * kC5Ld;
+      p.a_y0 = v == 2 ? 0 : ix0; p.a_z0 = v == 2 ? ix0 : 0;
       p.ldc = 0; p.round_tf32 = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
       p.n_store = v == 2 ? 184 : 180;
       if (v == 0) {        // m = y, lines = x (slab), planes = z
@@ -394,13 +400,13 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     ctx->launches++;
     SC_CUDA(cudaGetLastError());
     GemmProblem p;
-    p.ntaps = 1; p.tap_off[0] = 0; p.a_ys = p.a_zs = p.c_ys = p.c_zs = 0; p.Y = p.Z = 1;
     SC_CHECK(rows < (1ll << 31), SC_ERR_ARG, "sc_segment_volume: chunk too large");
-    p.M = (int)rows;
-    p.A = feats; p.lda = kFeatLd; p.kc = kFeatLd; p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.round_tf32 = tc ? 1 : 0;
+    gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)rows);
+    p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.round_tf32 = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
-    p.A = h1; p.lda = kH1Ld; p.kc = kH1Ld; p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.round_tf32 = 0;
+    gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)rows);
+    p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.round_tf32 = 0;
     p.prof_cls = PC_GEMM_FC2;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc2, st) : launch_gemm(ctx, p, ctx->fc2, st));
     OutGeo og2 = og;

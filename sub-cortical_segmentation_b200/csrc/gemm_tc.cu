@@ -1,10 +1,316 @@
-// tcgen05 / TMEM / TMA back-end (placeholder until the kernel lands)
+// tcgen05 / TMEM / TMA back-end of the dense-layer / implicit-GEMM problem (sm_100a).
+//
+//   C[m, n] = prelu( sum_tap sum_k A[pixel m shifted by tap, k] * W[n, tap*kc + k] + bias[n] )
+//
+// used for d1 (as a 3x3 dilation-4 conv over the NHWC-64 conv5 map), FC1 and fc_2
+// (reference: DenseLayer + PReLU at cnn_cort/nets.py:179-180, 217-218, 227-228).
+// Operands are fp32 bit patterns consumed as TF32 (kind::tf32, fp32 accumulate in TMEM);
+// every producer rounds its outputs to TF32 (cvt.rna) and the weights are rounded at load,
+// so the tensor core's implicit truncation never discards set bits.
+//
+// One CTA = one 128-row x BN-column output tile, 192 threads:
+//   warp 0   TMA producer: per k-block (32 floats = one 128 B swizzle row) one 4-D tiled load of
+//            A (box 32 x 128 pixels, tap shift applied to the pixel coordinates, zero fill outside)
+//            and one 2-D load of W (box 32 x BN) into a ring of shared-memory stages
+//   warp 1   allocates TMEM, issues 4 x tcgen05.mma (M=128, N=BN, K=8) per stage from one lane,
+//            tcgen05.commit releases the stage / signals the accumulator
+//   warps 2-5 epilogue: tcgen05.ld 32x32b.x16 -> bias + PReLU (+ TF32 rounding) -> global
+// Two CTAs are co-resident per SM (<= 256 TMEM columns and <= 113 KB shared memory each) so that
+// one tile's epilogue and prologue overlap the other's main loop.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace sc {
-int tc_init(sc_ctx*) { return SC_ERR_UNSUPPORTED; }
-void tc_destroy(sc_ctx*) {}
-int launch_gemm_tc(sc_ctx*, const GemmProblem&, const GemmW&, cudaStream_t) {
-  set_error("tcgen05 back-end not built");
-  return SC_ERR_UNSUPPORTED;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+  EncodeTiledFn encode;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;               // floats per k-block = 128 B
+constexpr int TC_A_STAGE = TC_BM * 128;  // bytes
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 256;
+
+struct TcArgs {
+  int kpt;            // k-blocks per tap (kc / 32)
+  int nkb;            // total k-blocks
+  int stages;
+  int bn;             // tile columns (multiple of 16, <= 192)
+  int nt, mt;         // tiles along n, along m (per line)
+  int Y;              // lines per plane
+  int M;              // rows per line
+  int n_store, npad;
+  int a_y0, a_z0;     // coordinate offsets of line / plane in the A tensor map
+  int tap_dx[9], tap_dy[9];
+  float* C;
+  long long ldc, c_ys, c_zs;
+  const float* bias;
+  const float* alpha;
+  int round_tf32;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // carve: [stages x A][stages x B][barriers][tmem ptr][bias][alpha]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_stage = a.bn * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + a.stages * TC_A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + a.stages * b_stage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + a.stages;
+  uint64_t* accum = bars + 2 * a.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_alpha = s_bias + 192;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long bid = blockIdx.x;
+  const int n_tile = (int)(bid % a.nt); bid /= a.nt;
+  const int m_tile = (int)(bid % a.mt); bid /= a.mt;
+  const int y = (int)(bid % a.Y);
+  const int z = (int)(bid / a.Y);
+  const int m0 = m_tile * TC_BM, n0 = n_tile * a.bn;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < a.bn; i += TC_THREADS) {
+    s_bias[i] = n0 + i < a.npad ? __ldg(a.bias + n0 + i) : 0.f;
+    s_alpha[i] = n0 + i < a.npad ? __ldg(a.alpha + n0 + i) : 1.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+      const uint32_t bytes = TC_A_STAGE + b_stage;
+      for (int kb = 0; kb < a.nkb; ++kb) {
+        const int s = kb % a.stages, it = kb / a.stages;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        mbar_expect_tx(&full[s], bytes);
+        const int tap = kb / a.kpt, kk = (kb - tap * a.kpt) * TC_BK;
+        tma_load_4d(&mapA, &full[s], sA + s * TC_A_STAGE, kk, m0 + a.tap_dx[tap], y + a.a_y0 + a.tap_dy[tap], z + a.a_z0);
+        tma_load_2d(&mapB, &full[s], sB + s * b_stage, kb * TC_BK, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=TF32, both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < a.nkb; ++kb) {
+        const int s = kb % a.stages, it = kb / a.stages;
+        mbar_wait(&full[s], it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = umma_desc(smem_u32(sA + s * TC_A_STAGE));
+        const uint64_t db = umma_desc(smem_u32(sB + s * b_stage));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)  // 4 x K=8 floats (32 B) inside the 128 B swizzle row
+          umma_tf32(tmem_base, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), idesc, (kb | j) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+    __syncwarp();
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    mbar_wait(accum, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + q * 32 + lane;
+    float* crow = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys + (long long)m * a.ldc + n0;
+    const bool row_ok = m < a.M;
+    for (int c0 = 0; c0 < a.bn; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n0 + c0 + g * 4;
+          if (n < a.n_store) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = c0 + g * 4 + k;
+              float x = __uint_as_float(r[g * 4 + k]) + s_bias[c];
+              x = prelu(x, s_alpha[c]);
+              v[k] = a.round_tf32 ? round_tf32(x) : x;
+            }
+            *reinterpret_cast<float4*>(crow + c0 + g * 4) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+int tc_init(sc_ctx* ctx) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    cudaGetLastError();
+    set_error("tcgen05 back-end: cuTensorMapEncodeTiled unavailable");
+    return SC_ERR_UNSUPPORTED;
+  }
+  TcState* s = new TcState();
+  s->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  ctx->tc_state = s;
+  return SC_OK;
+}
+
+void tc_destroy(sc_ctx* ctx) {
+  delete reinterpret_cast<TcState*>(ctx->tc_state);
+  ctx->tc_state = nullptr;
+}
+
+static int pick_bn(int n_store) {
+  // widest tile <= 192 (two CTAs x 256 TMEM columns per SM) that wastes the fewest columns
+  int best = 16, best_cost = 1 << 30;
+  for (int bn = 192; bn >= 64; bn -= 16) {
+    const int tiles = (n_store + bn - 1) / bn;
+    const int cost = tiles * bn * 4 + tiles * 128;  // padded columns + A re-reads
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st) {
+  TcState* s = reinterpret_cast<TcState*>(ctx->tc_state);
+  SC_CHECK(s != nullptr, SC_ERR_UNSUPPORTED, "tcgen05 back-end not initialised");
+  if (p.M <= 0 || p.Y <= 0 || p.Z <= 0) return SC_OK;
+  SC_CHECK(p.kc % TC_BK == 0 && p.ntaps * p.kc == w.Kpad && p.n_store % 4 == 0 && p.n_store <= w.Npad, SC_ERR_ARG,
+           "gemm_tc: bad geometry kc=%d ntaps=%d Kpad=%d n_store=%d", p.kc, p.ntaps, w.Kpad, p.n_store);
+  TcArgs a;
+  a.kpt = p.kc / TC_BK;
+  a.nkb = p.ntaps * a.kpt;
+  a.bn = pick_bn(p.n_store);
+  a.nt = (p.n_store + a.bn - 1) / a.bn;
+  a.mt = (p.M + TC_BM - 1) / TC_BM;
+  a.Y = p.Y; a.M = p.M; a.n_store = p.n_store; a.npad = w.Npad;
+  a.a_y0 = p.a_y0; a.a_z0 = p.a_z0;
+  for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; }
+  a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
+  a.bias = w.bias; a.alpha = w.alpha; a.round_tf32 = p.round_tf32;
+  const int stage_bytes = TC_A_STAGE + a.bn * 128;
+  a.stages = (110 * 1024) / stage_bytes;
+  if (a.stages > 6) a.stages = 6;
+  SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: tile too wide for two stages");
+  const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 2 * 192 * 4;
+
+  CUtensorMap mapA, mapB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p.a_dims[0], (cuuint64_t)p.a_dims[1], (cuuint64_t)p.a_dims[2], (cuuint64_t)p.a_dims[3]};
+    cuuint64_t strides[3] = {(cuuint64_t)p.a_strides[0] * 4, (cuuint64_t)p.a_strides[1] * 4, (cuuint64_t)p.a_strides[2] * 4};
+    cuuint32_t box[4] = {TC_BK, TC_BM, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = s->encode(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.a_base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled(A) failed with %d (dims %llu %llu %llu %llu)", (int)r,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3]);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)w.Kpad, (cuuint64_t)w.Npad};
+    cuuint64_t strides[1] = {(cuuint64_t)w.Kpad * 4};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)a.bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = s->encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.w_nk, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  static bool configured = false;
+  if (!configured) {
+    SC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    configured = true;
+  }
+  SC_CHECK(smem <= 113 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
+  const long long blocks = (long long)a.mt * a.nt * p.Y * p.Z;
+  SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
+  ProfScope prof(ctx, p.prof_cls, st);
+  gemm_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, st>>>(mapA, mapB, a);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
 }  // namespace sc

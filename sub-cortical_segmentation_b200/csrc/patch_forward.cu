@@ -258,8 +258,8 @@ int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float
       float* c5b = c5 + (size_t)b * cmax * kFeatLd;
       SC_TRY(launch_branch_patches(ctx, b, ins[b] + s * 1024, m, c5b, st));
       GemmProblem p;
-      p.ntaps = 1; p.tap_off[0] = 0; p.a_ys = p.a_zs = p.c_ys = p.c_zs = 0; p.Y = p.Z = 1; p.M = (int)m;
-      p.A = c5b; p.lda = kFeatLd; p.kc = kFeatLd; p.C = feats + b * 180; p.ldc = kFeatLd;
+      gemm_problem_rows(p, c5b, kFeatLd, kFeatLd, (int)m);
+      p.C = feats + b * 180; p.ldc = kFeatLd;
       p.n_store = b == 2 ? 184 : 180; p.round_tf32 = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
       SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->br[b].d1, st) : launch_gemm(ctx, p, ctx->br[b].d1, st));
     }
@@ -268,11 +268,12 @@ int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float
     ctx->launches++;
     SC_CUDA(cudaGetLastError());
     GemmProblem p;
-    p.ntaps = 1; p.tap_off[0] = 0; p.a_ys = p.a_zs = p.c_ys = p.c_zs = 0; p.Y = p.Z = 1; p.M = (int)m;
-    p.A = feats; p.lda = kFeatLd; p.kc = kFeatLd; p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.round_tf32 = tc ? 1 : 0;
+    gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)m);
+    p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.round_tf32 = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
-    p.A = h1; p.lda = kH1Ld; p.kc = kH1Ld; p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.round_tf32 = 0;
+    gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)m);
+    p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.round_tf32 = 0;
     p.prof_cls = PC_GEMM_FC2;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc2, st) : launch_gemm(ctx, p, ctx->fc2, st));
     SC_TRY(launch_out_softmax(ctx, h2, m, proba ? proba + s * 15 : nullptr, label ? label + s : nullptr, nullptr,
