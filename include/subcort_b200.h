@@ -55,7 +55,7 @@ SC_API const char* sc_last_error(void);
 /* replaces: THEANO_FLAGS device selection, cnn_cort/load_options.py:54-57 */
 SC_API int sc_create(int device, sc_ctx** out);
 SC_API int sc_destroy(sc_ctx* ctx);
-/* knobs: "gemm" = 0 SIMT fp32 | 1 tcgen05 TF32 (default when available);
+/* knobs: "gemm" = 0 SIMT fp32 | 1 tcgen05 bf16x3 (default when available);
  *        "chunk_voxels" = voxels per head chunk in sc_segment_volume; "profile" = 0 | 1. */
 SC_API int sc_set_option(sc_ctx* ctx, const char* key, int64_t value);
 SC_API int64_t sc_get_counter(sc_ctx* ctx, const char* key); /* "launches": kernels launched so far */
@@ -71,7 +71,7 @@ SC_API int sc_profile_read(sc_ctx* ctx, double* ms_out, int64_t* launches_out, i
  * `blob_host` is the concatenation of the 107 arrays of the OrderedDict in pickle order
  * (SC_PARAM_FLOATS floats).  The library keeps that master copy on the device and derives
  * the inference layouts (filter flip for flip_filters=True, BN folded to scale/shift,
- * transposed / padded / TF32-rounded GEMM operands). */
+ * transposed / padded / split-bf16 GEMM operands). */
 SC_API int sc_load_weights(sc_ctx* ctx, const float* blob_host, int64_t n_floats);
 SC_API int sc_get_params(sc_ctx* ctx, float* blob_host, int64_t n_floats);
 
@@ -112,9 +112,9 @@ SC_API int sc_forward_from_volume(sc_ctx* ctx, const float* vol_dev, const int32
                            float* proba_dev, int32_t* label_dev, void* stream);
 
 /* one dense layer of the head on its own (parity tests of the GEMM back-ends): which = 0..2 the
- * d1 layer of the axial / coronal / saggital branch (in [n][544] flattened conv5 maps -> out [n][192],
- * columns 0..179 valid), 3 = FC1 (in [n][544] -> out [n][576], columns 0..539 written), 4 = fc_2
- * (in [n][576] = FC1 output | atlas | zero pad -> out [n][272]).  backend: 0 SIMT fp32, 1 tcgen05 TF32.
+ * d1 layer of the axial / coronal / saggital branch (in [n][576] flattened conv5 maps, 540 used -> out [n][192],
+ * columns 0..179 valid), 3 = FC1 (in [n][576] -> out [n][576], columns 0..539 written), 4 = fc_2
+ * (in [n][576] = FC1 output | atlas | zero pad -> out [n][272]).  backend: 0 SIMT fp32, 1 tcgen05 split-bf16 (three MMAs).
  * replaces: DenseLayer + PReLU, cnn_cort/nets.py:179-180, 217-218, 227-228. */
 SC_API int sc_dense_layer(sc_ctx* ctx, int which, const float* in_dev, int64_t n, float* out_dev, int backend, void* stream);
 

@@ -348,8 +348,14 @@ int sc_dense_layer(sc_ctx* ctx, int which, const float* in_dev, int64_t n, float
     gemm_problem_rows(p, in_dev, kH1Ld, kH1Ld, (int)n);
     p.C = out_dev; p.ldc = kH2Ld; p.n_store = kH2Ld; p.prof_cls = PC_GEMM_FC2;
   }
-  p.round_tf32 = 0;
-  return backend == 1 ? launch_gemm_tc(ctx, p, *w, (cudaStream_t)stream) : launch_gemm(ctx, p, *w, (cudaStream_t)stream);
+  if (backend == 1) {  // the tcgen05 back-end consumes split bf16 hi|lo rows
+    SC_TRY(ensure_ws(ctx->ws, (size_t)n * kFeatLd * sizeof(float)));
+    float* tmp = reinterpret_cast<float*>(ctx->ws.ptr);
+    SC_TRY(launch_split_rows(ctx, in_dev, n, tmp, (cudaStream_t)stream));
+    p.A = p.a_base = tmp;
+    return launch_gemm_tc(ctx, p, *w, (cudaStream_t)stream);
+  }
+  return launch_gemm(ctx, p, *w, (cudaStream_t)stream);
 }
 
 int sc_scatter(sc_ctx* ctx, const int32_t* xyz_dev, int64_t n, const int32_t* label_dev, const float* proba_dev,

@@ -1,5 +1,6 @@
 // Shared declarations of the subcort_b200 library (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -78,9 +79,12 @@ inline ParamOff make_param_off() {
 // ---------------------------------------------------------------------------------------
 // Derived inference layouts (device)
 // ---------------------------------------------------------------------------------------
-// GEMM operand geometry (padded so that K is a multiple of 32 floats = one 128 B swizzle row)
+// GEMM operand geometry: every K is padded to 576 = 9 blocks of 64.  Activation rows are 576 floats
+// wide in both modes: plain fp32 (SIMT back-end), or -- for the tcgen05 back-end -- per 64-wide block
+// 64 bf16 "hi" values followed by 64 bf16 "lo" values (x = hi + lo to ~2^-17): the split-precision
+// operands of the three-MMA bf16x3 product (xh*wh + xh*wl + xl*wh), same bytes as fp32.
 constexpr int kFeat = 540;       // concat of the three d1 outputs
-constexpr int kFeatLd = 544;     // row stride of the feature buffer (K of FC1)
+constexpr int kFeatLd = 576;     // row stride of the feature buffer (K of FC1)
 constexpr int kH1 = 555;         // FC1 out (540) + atlas (15)
 constexpr int kH1Ld = 576;       // row stride (K of fc_2)
 constexpr int kH2 = 270;
@@ -89,8 +93,8 @@ constexpr int kC5Ld = 64;        // conv5 output channels padded 60 -> 64 (NHWC)
 constexpr int kD1K = 9 * kC5Ld;  // 576: K of d1 as a 3x3 dilation-4 conv over conv5 output
 
 struct GemmW {      // one dense layer prepared for both GEMM back-ends
-  float* w_kn;      // [Kpad][Npad] row-major (SIMT path), zero padded
-  float* w_nk;      // [Npad][Kpad] K-major, TF32-rounded (tcgen05 path), zero padded
+  float* w_kn;      // [Kpad][Npad] row-major fp32 (SIMT path), zero padded
+  float* w_nk;      // [Npad][Kpad] K-major split bf16 hi|lo blocks (tcgen05 path), zero padded
   float* bias;      // [Npad]
   float* alpha;     // [Npad] (PReLU; 1 where identity)
   int K, N, Kpad, Npad;
@@ -201,11 +205,13 @@ struct GemmProblem {
   int a_y0, a_z0;       // line / plane offset of this launch inside the buffer
   int prof_cls;         // ProfClass of this launch
   int n_store;          // columns written (<= w.Npad)
-  int round_tf32;       // round outputs to TF32 (they feed a tensor-core GEMM)
+  int c_col0;           // first output column inside the C row (C points at the row start)
+  int out_split;        // write C rows in the split bf16 hi|lo block layout (they feed a tcgen05 GEMM)
 };
 int launch_gemm(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
 // plain [M][lda] row-major A, one tap: fills both the pointer form and the tensor-map form
 inline void gemm_problem_rows(GemmProblem& p, const float* A, int64_t lda, int kc, int M) {
+  p.c_col0 = 0; p.out_split = 0;
   p.A = A; p.lda = lda; p.a_ys = p.a_zs = 0; p.ntaps = 1; p.tap_off[0] = 0; p.kc = kc;
   p.M = M; p.Y = p.Z = 1; p.c_ys = p.c_zs = 0;
   p.a_base = A; p.a_dims[0] = kc; p.a_dims[1] = M; p.a_dims[2] = p.a_dims[3] = 1;
@@ -224,6 +230,7 @@ int launch_out_softmax(sc_ctx* ctx, const float* h2, int64_t n, float* proba, in
 int tc_init(sc_ctx* ctx);
 void tc_destroy(sc_ctx* ctx);
 int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
+int launch_split_rows(sc_ctx* ctx, const float* in, int64_t rows, float* out, cudaStream_t st);  // [rows][576] plain -> split
 
 // patch_forward.cu
 int launch_branch_patches(sc_ctx* ctx, int branch, const float* patches, int64_t n, float* c5_out /*[n][540]*/,
@@ -244,9 +251,29 @@ int eval_batch(sc_ctx* ctx, const float* in1, const float* in2, const float* in3
                int64_t n, float* out2, cudaStream_t st);
 
 __device__ __forceinline__ float prelu(float x, float a) { return x > 0.f ? x : a * x; }
-__device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// split-precision store of 4 consecutive logical columns n..n+3 (n % 4 == 0) of one activation row
+__device__ __forceinline__ void store_split4(float* row, int n, float v0, float v1, float v2, float v3) {
+  __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(row) + (n >> 6) * 128 + (n & 63);
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1), h2 = __float2bfloat16_rn(v2), h3 = __float2bfloat16_rn(v3);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+  const __nv_bfloat16 l2 = __float2bfloat16_rn(v2 - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v3 - __bfloat162float(h3));
+  uint2 hp, lp;
+  hp.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hp.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  lp.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  lp.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  *reinterpret_cast<uint2*>(r) = hp;
+  *reinterpret_cast<uint2*>(r + 64) = lp;
+}
+__device__ __forceinline__ void store_row1(float* row, int n, int split, float v) {
+  if (!split) { row[n] = v; return; }
+  __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(row) + (n >> 6) * 128 + (n & 63);
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  r[0] = h;
+  r[64] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ void store_row4(float* row, int n, int split, float v0, float v1, float v2, float v3) {
+  if (split) store_split4(row, n, v0, v1, v2, v3);
+  else *reinterpret_cast<float4*>(row + n) = make_float4(v0, v1, v2, v3);
 }
 }  // namespace sc

@@ -104,7 +104,7 @@ struct ConvArgs {
   float* out; int outR, outC, outLd;    // planar [ns][COUT][outR][outLd] or NHWC [ns][outR][outC][64]
   const float* w;                       // [CIN][9][COUT]
   const float* scale; const float* shift; const float* alpha;
-  int ns; int round_out;
+  int ns; int round_out;   // round_out: write the NHWC map in the split bf16 hi|lo layout
 };
 
 template <int CIN, int COUT, int DIL, int POOLD, bool NHWC_OUT>
@@ -202,18 +202,15 @@ __global__ void __launch_bounds__(320) dense_conv_kernel(const ConvArgs a) {
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
       if (ocol + p >= a.outC) break;
-      float* o = a.out + (((int64_t)s * a.outR + orow) * a.outC + ocol + p) * kC5Ld + cg * Cfg::CO_T;
+      float* o = a.out + (((int64_t)s * a.outR + orow) * a.outC + ocol + p) * kC5Ld;   // this pixel's 64-channel row
 #pragma unroll
       for (int v = 0; v < Cfg::CO_T / 4; ++v) {
         float r[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          r[k] = prelu(fmaf(acc[p][v * 4 + k], sc_[v * 4 + k], sh[v * 4 + k]), al[v * 4 + k]);
-          if (a.round_out) r[k] = round_tf32(r[k]);
-        }
-        *reinterpret_cast<float4*>(o + v * 4) = make_float4(r[0], r[1], r[2], r[3]);
+        for (int k = 0; k < 4; ++k) r[k] = prelu(fmaf(acc[p][v * 4 + k], sc_[v * 4 + k], sh[v * 4 + k]), al[v * 4 + k]);
+        store_row4(o, cg * Cfg::CO_T + v * 4, a.round_out, r[0], r[1], r[2], r[3]);
       }
-      if (cg == 4 && COUT < kC5Ld) *reinterpret_cast<float4*>(o + Cfg::CO_T) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cg == 4 && COUT < kC5Ld) store_row4(o, COUT, a.round_out, 0.f, 0.f, 0.f, 0.f);
     }
   }
 }
@@ -236,8 +233,10 @@ static int launch_dense_conv(sc_ctx* ctx, const ConvArgs& a, int prof_cls, cudaS
   return SC_OK;
 }
 
-// atlas prior (with the background fix of base.py:392-394) -> columns 540..575 of the h1 rows
-__global__ void dense_atlas_kernel(const float* __restrict__ atlas, OutGeo g, int ix0, int64_t rows, float* __restrict__ h1) {
+// atlas prior (with the background fix of base.py:392-394) -> columns 540..575 of the h1 rows;
+// also clears the K padding (columns 540..575) of the feature rows.
+__global__ void dense_atlas_kernel(const float* __restrict__ atlas, OutGeo g, int ix0, int64_t rows, float* __restrict__ h1,
+                                   float* __restrict__ feats, int split) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= rows) return;
   const int64_t plane = (int64_t)g.by * g.bz;
@@ -254,13 +253,14 @@ __global__ void dense_atlas_kernel(const float* __restrict__ atlas, OutGeo g, in
   for (int k = 8; k < 15; ++k) s = __fadd_rn(s, a[k]);
   if (s == 0.f) a[14] = 1.f;
   a[15] = 0.f;
-  float4* o = reinterpret_cast<float4*>(h1 + m * kH1Ld + 540);
-  o[0] = make_float4(a[0], a[1], a[2], a[3]);
-  o[1] = make_float4(a[4], a[5], a[6], a[7]);
-  o[2] = make_float4(a[8], a[9], a[10], a[11]);
-  o[3] = make_float4(a[12], a[13], a[14], a[15]);
+  float* hr = h1 + m * kH1Ld;
+  float* fr = feats + m * kFeatLd;
 #pragma unroll
-  for (int k = 4; k < 9; ++k) o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < 9; ++q) {
+    if (q < 4) store_row4(hr, 540 + 4 * q, split, a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+    else store_row4(hr, 540 + 4 * q, split, 0.f, 0.f, 0.f, 0.f);
+    store_row4(fr, 540 + 4 * q, split, 0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -380,8 +380,8 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       p.a_base = a5[v]; p.a_dims[0] = kC5Ld; p.a_dims[1] = c5; p.a_dims[2] = r5; p.a_dims[3] = g.ns;
       p.a_strides[0] = kC5Ld; p.a_strides[1] = c5 * kC5Ld; p.a_strides[2] = r5 * c5 * kC5Ld;
       p.a_y0 = v == 2 ? 0 : ix0; p.a_z0 = v == 2 ? ix0 : 0;
-      p.ldc = 0; p.round_tf32 = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
-      p.n_store = v == 2 ? 184 : 180;
+      p.ldc = 0; p.out_split = tc ? 1 : 0; p.c_col0 = v * 180; p.prof_cls = PC_GEMM_D1;
+      p.n_store = 180;
       if (v == 0) {        // m = y, lines = x (slab), planes = z
         p.A = a5[0] + (int64_t)ix0 * p.a_ys; p.M = by; p.Y = nx; p.Z = bz;
         p.ldc = (int64_t)bz * kFeatLd; p.c_ys = plane * kFeatLd; p.c_zs = kFeatLd;
@@ -392,21 +392,21 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
         p.A = a5[2] + (int64_t)ix0 * p.a_zs; p.M = bz; p.Y = by; p.Z = nx;
         p.ldc = kFeatLd; p.c_ys = (int64_t)bz * kFeatLd; p.c_zs = plane * kFeatLd;
       }
-      p.C = feats + v * 180;
+      p.C = feats;
       SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->br[v].d1_dense, st) : launch_gemm(ctx, p, ctx->br[v].d1_dense, st));
     }
     { ProfScope prof(ctx, PC_ATLAS, st);
-      dense_atlas_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(atlas, og, ix0, rows, h1); }
+      dense_atlas_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(atlas, og, ix0, rows, h1, feats, tc ? 1 : 0); }
     ctx->launches++;
     SC_CUDA(cudaGetLastError());
     GemmProblem p;
     SC_CHECK(rows < (1ll << 31), SC_ERR_ARG, "sc_segment_volume: chunk too large");
     gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)rows);
-    p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.round_tf32 = tc ? 1 : 0;
+    p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
     gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)rows);
-    p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.round_tf32 = 0;
+    p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.out_split = 0;
     p.prof_cls = PC_GEMM_FC2;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc2, st) : launch_gemm(ctx, p, ctx->fc2, st));
     OutGeo og2 = og;

@@ -87,8 +87,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs a) {
     v.y = prelu(acc[i][1] + bias.y, al.y);
     v.z = prelu(acc[i][2] + bias.z, al.z);
     v.w = prelu(acc[i][3] + bias.w, al.w);
-    if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-    *reinterpret_cast<float4*>(Cbase + (int64_t)m * p.ldc + n) = v;
+    *reinterpret_cast<float4*>(Cbase + (int64_t)m * p.ldc + p.c_col0 + n) = v;
   }
 }
 
@@ -96,6 +95,7 @@ int launch_gemm(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t 
   if (p.M <= 0 || p.Y <= 0 || p.Z <= 0) return SC_OK;
   SC_CHECK(p.kc % BK == 0 && p.n_store % 4 == 0 && p.n_store <= w.Npad, SC_ERR_ARG, "gemm: bad geometry kc=%d n_store=%d", p.kc, p.n_store);
   SC_CHECK(p.ntaps * p.kc == w.Kpad, SC_ERR_ARG, "gemm: K mismatch %d*%d vs %d", p.ntaps, p.kc, w.Kpad);
+  SC_CHECK(!p.out_split && p.c_col0 % 4 == 0, SC_ERR_ARG, "gemm: the SIMT back-end writes plain fp32 rows only");
   GemmArgs a;
   a.p = p; a.W = w.w_kn; a.bias = w.bias; a.alpha = w.alpha; a.Npad = w.Npad;
   a.mt = (p.M + BM - 1) / BM;

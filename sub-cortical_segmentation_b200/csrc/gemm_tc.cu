@@ -4,19 +4,22 @@
 //
 // used for d1 (as a 3x3 dilation-4 conv over the NHWC-64 conv5 map), FC1 and fc_2
 // (reference: DenseLayer + PReLU at cnn_cort/nets.py:179-180, 217-218, 227-228).
-// Operands are fp32 bit patterns consumed as TF32 (kind::tf32, fp32 accumulate in TMEM);
-// every producer rounds its outputs to TF32 (cvt.rna) and the weights are rounded at load,
-// so the tensor core's implicit truncation never discards set bits.
+//
+// Precision: single-pass TF32 / fp16 misses the 1e-3 softmax tolerance on unsaturated inputs
+// (measured: 1.4e-3), so the product is the three-MMA split  xh*wh + xh*wl + xl*wh  of bf16 pairs
+// (x = xh + xl to ~2^-17, kind::f16 with fp32 accumulation in TMEM; oracle emulation: 1.8e-5).
+// Activations and weights are stored per 64-wide k block as 64 bf16 hi | 64 bf16 lo, i.e. exactly
+// the bytes of the fp32 row, so one 128 B swizzle row holds one block half.
 //
 // One CTA = one 128-row x BN-column output tile, 192 threads:
-//   warp 0   TMA producer: per k-block (32 floats = one 128 B swizzle row) one 4-D tiled load of
-//            A (box 32 x 128 pixels, tap shift applied to the pixel coordinates, zero fill outside)
-//            and one 2-D load of W (box 32 x BN) into a ring of shared-memory stages
-//   warp 1   allocates TMEM, issues 4 x tcgen05.mma (M=128, N=BN, K=8) per stage from one lane,
+//   warp 0   TMA producer: per k block four tiled loads into one shared-memory stage -- A hi and
+//            A lo (4-D box 64 bf16 x 128 pixels, tap shift applied to the pixel/line coordinates,
+//            zero fill outside) and W hi and W lo (2-D box 64 x BN)
+//   warp 1   allocates TMEM; one lane issues 12 x tcgen05.mma (M=128, N=BN, K=16) per stage,
 //            tcgen05.commit releases the stage / signals the accumulator
-//   warps 2-5 epilogue: tcgen05.ld 32x32b.x16 -> bias + PReLU (+ TF32 rounding) -> global
-// Two CTAs are co-resident per SM (<= 256 TMEM columns and <= 113 KB shared memory each) so that
-// one tile's epilogue and prologue overlap the other's main loop.
+//   warps 2-5 epilogue: tcgen05.ld 32x32b.x16 -> bias + PReLU -> plain fp32 or split bf16 rows
+// Two CTAs are co-resident per SM (<= 256 TMEM columns and <= 112 KB shared memory each) so that
+// one tile's loads / epilogue overlap the other's MMAs.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -32,27 +35,27 @@ struct TcState {
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;               // floats per k-block = 128 B
-constexpr int TC_A_STAGE = TC_BM * 128;  // bytes
+constexpr int TC_BK = 64;                    // logical k per block (64 bf16 = one 128 B swizzle row)
+constexpr int TC_A_HALF = TC_BM * 128;       // bytes of the hi (or lo) half of an A stage
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;
 
 struct TcArgs {
-  int kpt;            // k-blocks per tap (kc / 32)
+  int kpt;            // k-blocks per tap (kc / 64)
   int nkb;            // total k-blocks
   int stages;
   int bn;             // tile columns (multiple of 16, <= 192)
   int nt, mt;         // tiles along n, along m (per line)
   int Y;              // lines per plane
   int M;              // rows per line
-  int n_store, npad;
+  int n_store, npad, c_col0;
   int a_y0, a_z0;     // coordinate offsets of line / plane in the A tensor map
   int tap_dx[9], tap_dy[9];
   float* C;
   long long ldc, c_ys, c_zs;
   const float* bias;
   const float* alpha;
-  int round_tf32;
+  int out_split;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,12 +94,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -106,12 +109,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  // carve: [stages x A][stages x B][barriers][tmem ptr][bias][alpha]
+  // carve: [stages x (A hi | A lo | W hi | W lo)][barriers][tmem ptr][bias][alpha]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_stage = a.bn * 128;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + a.stages * TC_A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + a.stages * b_stage);
+  const int b_half = a.bn * 128;
+  const int stage_bytes = 2 * TC_A_HALF + 2 * b_half;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + a.stages;
   uint64_t* accum = bars + 2 * a.stages;
@@ -149,30 +151,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
-      const uint32_t bytes = TC_A_STAGE + b_stage;
       for (int kb = 0; kb < a.nkb; ++kb) {
         const int s = kb % a.stages, it = kb / a.stages;
         if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-        mbar_expect_tx(&full[s], bytes);
-        const int tap = kb / a.kpt, kk = (kb - tap * a.kpt) * TC_BK;
-        tma_load_4d(&mapA, &full[s], sA + s * TC_A_STAGE, kk, m0 + a.tap_dx[tap], y + a.a_y0 + a.tap_dy[tap], z + a.a_z0);
-        tma_load_2d(&mapB, &full[s], sB + s * b_stage, kb * TC_BK, n0);
+        mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+        uint8_t* st = smem + s * stage_bytes;
+        const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;   // bf16 element offset of the block's hi half
+        const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
+        tma_load_4d(&mapA, &full[s], st, ka, px, ln, pl);
+        tma_load_4d(&mapA, &full[s], st + TC_A_HALF, ka + TC_BK, px, ln, pl);
+        tma_load_2d(&mapB, &full[s], st + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
+        tma_load_2d(&mapB, &full[s], st + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=TF32, both K-major, N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // instruction descriptor: D=F32, A=B=BF16, both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < a.nkb; ++kb) {
         const int s = kb % a.stages, it = kb / a.stages;
         mbar_wait(&full[s], it & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = umma_desc(smem_u32(sA + s * TC_A_STAGE));
-        const uint64_t db = umma_desc(smem_u32(sB + s * b_stage));
+        const uint32_t st = smem_u32(smem + s * stage_bytes);
+        const uint64_t ah = umma_desc(st), al = umma_desc(st + TC_A_HALF);
+        const uint64_t wh = umma_desc(st + 2 * TC_A_HALF), wl = umma_desc(st + 2 * TC_A_HALF + b_half);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)  // 4 x K=8 floats (32 B) inside the 128 B swizzle row
-          umma_tf32(tmem_base, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), idesc, (kb | j) != 0);
+        for (int j = 0; j < 4; ++j) {  // 4 x K=16 bf16 (32 B) inside the 128 B swizzle row; small terms first
+          const uint64_t o = (uint64_t)(j * 2);
+          umma_bf16(tmem_base, al + o, wh + o, idesc, (kb | j) != 0);
+          umma_bf16(tmem_base, ah + o, wl + o, idesc, 1);
+          umma_bf16(tmem_base, ah + o, wh + o, idesc, 1);
+        }
         umma_commit(&empty[s]);
       }
       umma_commit(accum);
@@ -184,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     mbar_wait(accum, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = m0 + q * 32 + lane;
-    float* crow = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys + (long long)m * a.ldc + n0;
+    float* crow = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys + (long long)m * a.ldc;
     const bool row_ok = m < a.M;
     for (int c0 = 0; c0 < a.bn; c0 += 16) {
       uint32_t r[16];
@@ -204,11 +214,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int c = c0 + g * 4 + k;
-              float x = __uint_as_float(r[g * 4 + k]) + s_bias[c];
-              x = prelu(x, s_alpha[c]);
-              v[k] = a.round_tf32 ? round_tf32(x) : x;
+              v[k] = prelu(__uint_as_float(r[g * 4 + k]) + s_bias[c], s_alpha[c]);
             }
-            *reinterpret_cast<float4*>(crow + c0 + g * 4) = make_float4(v[0], v[1], v[2], v[3]);
+            store_row4(crow, a.c_col0 + n, a.out_split, v[0], v[1], v[2], v[3]);
           }
         }
       }
@@ -220,6 +228,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
+}
+
+// plain fp32 [rows][576] -> split bf16 hi|lo blocks (test entry sc_dense_layer only)
+__global__ void split_rows_kernel(const float* __restrict__ in, int64_t rows, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (kFeatLd / 4)) return;
+  const int64_t m = i / (kFeatLd / 4);
+  const int n = (int)(i - m * (kFeatLd / 4)) * 4;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(in + m * kFeatLd + n));
+  store_split4(out + m * kFeatLd, n, v.x, v.y, v.z, v.w);
+}
+int launch_split_rows(sc_ctx* ctx, const float* in, int64_t rows, float* out, cudaStream_t st) {
+  const int64_t work = rows * (kFeatLd / 4);
+  split_rows_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(in, rows, out);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
 }
 
 int tc_init(sc_ctx* ctx) {
@@ -261,6 +286,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
            "gemm_tc: bad geometry kc=%d ntaps=%d Kpad=%d n_store=%d", p.kc, p.ntaps, w.Kpad, p.n_store);
   TcArgs a;
   a.kpt = p.kc / TC_BK;
+  a.c_col0 = p.c_col0;
   a.nkb = p.ntaps * a.kpt;
   a.bn = pick_bn(p.n_store);
   a.nt = (p.n_store + a.bn - 1) / a.bn;
@@ -269,41 +295,43 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.a_y0 = p.a_y0; a.a_z0 = p.a_z0;
   for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; }
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
-  a.bias = w.bias; a.alpha = w.alpha; a.round_tf32 = p.round_tf32;
-  const int stage_bytes = TC_A_STAGE + a.bn * 128;
-  a.stages = (110 * 1024) / stage_bytes;
-  if (a.stages > 6) a.stages = 6;
-  SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: tile too wide for two stages");
+  a.bias = w.bias; a.alpha = w.alpha; a.out_split = p.out_split;
+  SC_CHECK(p.c_col0 % 4 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 4");
+  const int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
+  a.stages = (108 * 1024) / stage_bytes;
+  if (a.stages > 4) a.stages = 4;
+  SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
   const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 2 * 192 * 4;
 
   CUtensorMap mapA, mapB;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)p.a_dims[0], (cuuint64_t)p.a_dims[1], (cuuint64_t)p.a_dims[2], (cuuint64_t)p.a_dims[3]};
+    // a row of kc logical columns is 2*kc bf16 (hi | lo per 64-wide block)
+    cuuint64_t dims[4] = {(cuuint64_t)p.a_dims[0] * 2, (cuuint64_t)p.a_dims[1], (cuuint64_t)p.a_dims[2], (cuuint64_t)p.a_dims[3]};
     cuuint64_t strides[3] = {(cuuint64_t)p.a_strides[0] * 4, (cuuint64_t)p.a_strides[1] * 4, (cuuint64_t)p.a_strides[2] * 4};
     cuuint32_t box[4] = {TC_BK, TC_BM, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = s->encode(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.a_base), dims, strides, box, es,
+    CUresult r = s->encode(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<float*>(p.a_base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled(A) failed with %d (dims %llu %llu %llu %llu)", (int)r,
              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3]);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)w.Kpad, (cuuint64_t)w.Npad};
+    cuuint64_t dims[2] = {(cuuint64_t)w.Kpad * 2, (cuuint64_t)w.Npad};
     cuuint64_t strides[1] = {(cuuint64_t)w.Kpad * 4};
     cuuint32_t box[2] = {TC_BK, (cuuint32_t)a.bn};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = s->encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.w_nk, dims, strides, box, es,
+    CUresult r = s->encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w_nk, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
   static bool configured = false;
   if (!configured) {
-    SC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    SC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  SC_CHECK(smem <= 113 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
+  SC_CHECK(smem <= 112 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
   const long long blocks = (long long)a.mt * a.nt * p.Y * p.Z;
   SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
   ProfScope prof(ctx, p.prof_cls, st);

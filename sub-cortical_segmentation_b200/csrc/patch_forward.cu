@@ -201,12 +201,11 @@ __global__ void __launch_bounds__(256) branch_patch_kernel(const float* __restri
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int co = cgp * 4 + c;
-      float v = prelu(fmaf(acc[c], __ldg(W.scale[4] + co), __ldg(W.shift[4] + co)), __ldg(W.alpha[4] + co));
-      if (round_out) v = round_tf32(v);
-      out[co * 9 + px] = v;
+      const float v = prelu(fmaf(acc[c], __ldg(W.scale[4] + co), __ldg(W.shift[4] + co)), __ldg(W.alpha[4] + co));
+      store_row1(out, co * 9 + px, round_out, v);
     }
-  } else if (tid >= 252) {
-    out[540 + (tid - 252)] = 0.f;
+  } else if (tid >= 220) {
+    store_row1(out, 540 + (tid - 220), round_out, 0.f);   // K padding 540..575
   }
 }
 
@@ -231,13 +230,20 @@ int launch_branch_patches(sc_ctx* ctx, int b, const float* patches, int64_t n, f
   return SC_OK;
 }
 
-// [n][15] atlas rows -> columns 540..575 of h1 (no background fix here: the caller's in4 already has it)
-__global__ void atlas_rows_kernel(const float* __restrict__ in4, int64_t n, float* __restrict__ h1) {
+// [n][15] atlas rows -> columns 540..575 of h1 (no background fix here: the caller's in4 already has it);
+// also clears the K padding (columns 540..575) of the feature rows.
+__global__ void atlas_rows_kernel(const float* __restrict__ in4, int64_t n, float* __restrict__ h1, float* __restrict__ feats,
+                                  int split) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * 36) return;
-  const int64_t m = i / 36;
-  const int c = (int)(i - m * 36);
-  h1[m * kH1Ld + 540 + c] = c < 15 ? __ldg(in4 + m * 15 + c) : 0.f;
+  if (i >= n * 9) return;
+  const int64_t m = i / 9;
+  const int q = (int)(i - m * 9);
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (q * 4 + k < 15) a[k] = __ldg(in4 + m * 15 + q * 4 + k);
+  store_row4(h1 + m * kH1Ld, 540 + 4 * q, split, a[0], a[1], a[2], a[3]);
+  store_row4(feats + m * kFeatLd, 540 + 4 * q, split, 0.f, 0.f, 0.f, 0.f);
 }
 
 int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, int64_t n,
@@ -259,21 +265,21 @@ int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float
       SC_TRY(launch_branch_patches(ctx, b, ins[b] + s * 1024, m, c5b, st));
       GemmProblem p;
       gemm_problem_rows(p, c5b, kFeatLd, kFeatLd, (int)m);
-      p.C = feats + b * 180; p.ldc = kFeatLd;
-      p.n_store = b == 2 ? 184 : 180; p.round_tf32 = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
+      p.C = feats; p.ldc = kFeatLd; p.c_col0 = b * 180;
+      p.n_store = 180; p.out_split = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
       SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->br[b].d1, st) : launch_gemm(ctx, p, ctx->br[b].d1, st));
     }
     { ProfScope prof(ctx, PC_ATLAS, st);
-    atlas_rows_kernel<<<(unsigned)((m * 36 + 255) / 256), 256, 0, st>>>(in4 + s * 15, m, h1); }
+    atlas_rows_kernel<<<(unsigned)((m * 9 + 255) / 256), 256, 0, st>>>(in4 + s * 15, m, h1, feats, tc ? 1 : 0); }
     ctx->launches++;
     SC_CUDA(cudaGetLastError());
     GemmProblem p;
     gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)m);
-    p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.round_tf32 = tc ? 1 : 0;
+    p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
     gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)m);
-    p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.round_tf32 = 0;
+    p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.out_split = 0;
     p.prof_cls = PC_GEMM_FC2;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc2, st) : launch_gemm(ctx, p, ctx->fc2, st));
     SC_TRY(launch_out_softmax(ctx, h2, m, proba ? proba + s * 15 : nullptr, label ? label + s : nullptr, nullptr,

@@ -12,11 +12,15 @@
 
 namespace sc {
 
-static float tf32_rna(float x) {
+static uint16_t bf16_rn(float x) {  // round to nearest even, like __float2bfloat16_rn
   uint32_t u;
   memcpy(&u, &x, 4);
-  if ((u & 0x7f800000u) == 0x7f800000u) return x;
-  u = (u + 0x1000u) & ~0x1fffu;
+  if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static float bf16_to_float(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
   float r;
   memcpy(&r, &u, 4);
   return r;
@@ -45,7 +49,11 @@ static GemmOff make_gemm(Arena& A, GemmW& g, int K, int N, int Kpad, int Npad) {
 }
 static void set_w(Arena& A, const GemmOff& o, const GemmW& g, int k, int n, float v) {
   A.host[o.kn + (size_t)k * g.Npad + n] = v;
-  A.host[o.nk + (size_t)n * g.Kpad + k] = tf32_rna(v);
+  // split bf16 row: per 64-wide k block, 64 hi then 64 lo (2 bf16 per float slot of the arena)
+  uint16_t* row = reinterpret_cast<uint16_t*>(&A.host[o.nk + (size_t)n * g.Kpad]);
+  const uint16_t hi = bf16_rn(v);
+  row[(k >> 6) * 128 + (k & 63)] = hi;
+  row[(k >> 6) * 128 + 64 + (k & 63)] = bf16_rn(v - bf16_to_float(hi));
 }
 static void bind(GemmW& g, const GemmOff& o, float* base) {
   g.w_kn = base + o.kn; g.w_nk = base + o.nk; g.bias = base + o.bias; g.alpha = base + o.alpha;
@@ -101,10 +109,10 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
       A.host[bo[b].d1.alpha + n] = A.host[bo[b].d1d.alpha + n] = al;
     }
   }
-  fc1o = make_gemm(A, ctx->fc1, 540, 540, kFeatLd, 544);
+  fc1o = make_gemm(A, ctx->fc1, 540, 540, kFeatLd, 576);
   for (int k = 0; k < 540; ++k)
     for (int n = 0; n < 540; ++n) set_w(A, fc1o, ctx->fc1, k, n, h[P.fc1W + (size_t)k * 540 + n]);
-  for (int n = 0; n < 544; ++n) {
+  for (int n = 0; n < 576; ++n) {
     A.host[fc1o.bias + n] = n < 540 ? h[P.fc1b + n] : 0.f;
     A.host[fc1o.alpha + n] = n < 540 ? h[P.a1 + n] : 1.f;
   }

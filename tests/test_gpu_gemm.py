@@ -1,4 +1,4 @@
-"""K3 pieces: each dense layer of the head through both GEMM back-ends (SIMT fp32, tcgen05 TF32)
+"""K3 pieces: each dense layer of the head through both GEMM back-ends (SIMT fp32, tcgen05 bf16x3)
 vs a float64 numpy product on the committed weights."""
 import numpy as np
 import pytest
@@ -43,7 +43,7 @@ def _ref(P, which, x):
 @pytest.mark.parametrize("n", [1, 128, 333, 4097])
 def test_dense_layer_backends(ctx, P, which, n):
     rng = np.random.RandomState(which * 100 + n)
-    width_in = 576 if which == 4 else 544
+    width_in = 576
     k = 555 if which == 4 else 540
     x = np.zeros((n, width_in), np.float32)
     x[:, :k] = rng.randn(n, k).astype(np.float32)
@@ -53,10 +53,6 @@ def test_dense_layer_backends(ctx, P, which, n):
     got0 = ctx.dense_layer(which, dev(x), 0).cpu().numpy()[:, :ncol]
     assert np.abs(got0 - ref).max() < 2e-5 * max(1.0, scale)
     if ctx.counter("gemm") == 1:
-        xt = torch.from_numpy(x).cuda()
-        xr = ((xt.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)     # producers round to TF32
-        got1 = ctx.dense_layer(which, xr.contiguous(), 1).cpu().numpy()[:, :ncol]
-        ref_r = _ref(P, which, xr.cpu().numpy())
-        # single-pass TF32: relative 2^-11 per operand, accumulated over K <= 555 random-sign terms
-        assert np.abs(got1 - ref_r).max() < 3e-3 * max(1.0, scale), np.abs(got1 - ref_r).max()
-        assert np.abs(got1 - got0).max() < 4e-3 * max(1.0, scale)
+        got1 = ctx.dense_layer(which, dev(x), 1).cpu().numpy()[:, :ncol]
+        # split bf16 (hi + lo, three MMAs): ~2^-16 relative per product, K <= 555 random-sign terms
+        assert np.abs(got1 - ref).max() < 1e-4 * max(1.0, scale), np.abs(got1 - ref).max()
