@@ -143,9 +143,10 @@ SC_API int sc_scatter(sc_ctx* ctx, const int32_t* xyz_dev, int64_t n, const int3
 /* ---- training ------------------------------------------------------------------------
  * replaces: one minibatch of nolearn's train_fn inside net.fit (nets.py:233-246):
  * training-mode forward (BN batch statistics, dropout p=.5), categorical cross-entropy,
- * backward.  Gradients land in the context's flat gradient buffer (parameter layout);
- * BN running statistics are updated in the master parameters.  drop_masks_dev: NULL to
- * draw masks from `seed`, or [n][3*540 + 540 + 540] uint8 keep-masks (tests inject them).
+ * backward.  Gradients land in the context's flat gradient buffer (parameter layout); the
+ * slots of the BN running statistics receive this batch's mean / inv_std (applied by
+ * sc_adam_step).  drop_masks_dev: NULL to draw masks from `seed`, or [n][3*540 + 540 + 540]
+ * uint8 keep-masks per sample (axial|coronal|saggital l1drop in (c,h,w) order, f1_drop, f2_drop).
  * loss_dev: 1 float (sum of -log p over the batch divided by `n_global`). */
 SC_API int sc_train_forward_backward(sc_ctx* ctx, const float* in1_dev, const float* in2_dev,
                               const float* in3_dev, const float* in4_dev, const uint8_t* y_dev,
@@ -156,9 +157,11 @@ SC_API int sc_train_forward_backward(sc_ctx* ctx, const float* in1_dev, const fl
 SC_API int sc_grad_buffer(sc_ctx* ctx, float** grads_dev);
 SC_API int sc_param_buffer(sc_ctx* ctx, float** params_dev);
 /* replaces: lasagne.updates.adam (nets.py:236-237): a_t = lr*sqrt(1-b2^t)/(1-b1^t);
- * p -= a_t * m / (sqrt(v) + eps), over the trainable entries; grad_scale multiplies the
- * gradient first (1/world_size after a sum all-reduce).  Refreshes the inference layouts. */
-SC_API int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+ * p -= a_t * m / (sqrt(v) + eps) over the trainable entries, gradient multiplied by grad_scale first.
+ * The slots of the BN running statistics in the gradient buffer carry the batch mean / inv_std
+ * (summed over ranks by the all-reduce): s <- 0.9 s + 0.1 * slot * stat_scale (stat_scale = 1/world).
+ * Marks the inference layouts stale; they are re-derived lazily by the next inference call. */
+SC_API int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, float stat_scale, void* stream);
 SC_API int sc_reset_optimizer(sc_ctx* ctx);
 /* evaluation pass of nolearn's eval_fn: mean CE loss and accuracy numerators over a batch
  * in deterministic mode; out2_dev = {sum of -log p[y], number of correct argmax}. */

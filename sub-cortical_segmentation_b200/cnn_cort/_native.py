@@ -53,7 +53,7 @@ PROTOTYPES = {
     "sc_train_forward_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, ctypes.c_uint64, _vp, _vp, _vp]),
     "sc_grad_buffer": (ctypes.c_int, [_vp, _p(_vp)]),
     "sc_param_buffer": (ctypes.c_int, [_vp, _p(_vp)]),
-    "sc_adam_step": (ctypes.c_int, [_vp, _c_f, _c_f, _c_f, _c_f, _c_f, _vp]),
+    "sc_adam_step": (ctypes.c_int, [_vp, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _vp]),
     "sc_reset_optimizer": (ctypes.c_int, [_vp]),
     "sc_eval_batch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp]),
 }
@@ -248,8 +248,8 @@ class Context(object):
     def param_tensor(self):
         return _as_tensor(self._buffer(self.lib.sc_param_buffer), PARAM_FLOATS, self.device)
 
-    def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
-        _check(self.lib.sc_adam_step(self.h, lr, beta1, beta2, eps, grad_scale, _stream()))
+    def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, stat_scale=1.0):
+        _check(self.lib.sc_adam_step(self.h, lr, beta1, beta2, eps, grad_scale, stat_scale, _stream()))
 
     def reset_optimizer(self):
         _check(self.lib.sc_reset_optimizer(self.h))

@@ -251,7 +251,7 @@ class Net(object):
                 if world > 1:
                     dist.all_reduce(grads)
                     dist.all_reduce(loss_buf)
-                ctx.adam_step(lr=self.update_learning_rate)
+                ctx.adam_step(lr=self.update_learning_rate, stat_scale=1.0 / world)
                 losses.append(loss_buf.clone())
                 sizes.append(len(gidx))
             train_loss = float(np.average(torch.cat(losses).cpu().numpy(), weights=sizes)) if losses else float('nan')

@@ -388,9 +388,9 @@ int sc_param_buffer(sc_ctx* ctx, float** params_dev) {
   return SC_OK;
 }
 
-int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, float stat_scale, void* stream) {
   SC_TRY(need_weights(ctx, "sc_adam_step"));
-  return adam_step(ctx, lr, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
+  return adam_step(ctx, lr, beta1, beta2, eps, grad_scale, stat_scale, (cudaStream_t)stream);
 }
 
 int sc_reset_optimizer(sc_ctx* ctx) {

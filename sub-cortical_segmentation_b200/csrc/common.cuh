@@ -239,6 +239,16 @@ int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float
                     float* proba, int32_t* label, cudaStream_t st);
 
 // dense.cu
+struct ConvArgs {
+  const float* in; int inR, inLd;       // planar [ns][CIN][inR][inLd] (raw, before the folded pool)
+  float* out; int outR, outC, outLd;    // planar [ns][COUT][outR][outLd] or NHWC [ns][outR][outC][64]
+  const float* w;                       // [CIN][9][COUT]
+  const float* scale; const float* shift; const float* alpha;
+  int ns; int round_out;                // round_out: write the NHWC map in the split bf16 hi|lo layout
+};
+int launch_conv3x3(sc_ctx* ctx, int cin, int cout, const ConvArgs& a, int prof_cls, cudaStream_t st);
+int launch_conv1_patches(sc_ctx* ctx, const float* patches, int n, const float* w, const float* scale, const float* shift,
+                         const float* alpha, float* out, cudaStream_t st);
 int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, const int32_t* box,
                    const uint8_t* cand, uint8_t* label_vol, float* proba_vol, cudaStream_t st);
 
@@ -246,7 +256,7 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
 int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4,
                            const uint8_t* y, int64_t n, int64_t n_global, uint64_t seed, const uint8_t* masks,
                            float* loss, cudaStream_t st);
-int adam_step(sc_ctx* ctx, float lr, float b1, float b2, float eps, float gscale, cudaStream_t st);
+int adam_step(sc_ctx* ctx, float lr, float b1, float b2, float eps, float gscale, float sscale, cudaStream_t st);
 int eval_batch(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, const uint8_t* y,
                int64_t n, float* out2, cudaStream_t st);
 

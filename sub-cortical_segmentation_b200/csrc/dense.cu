@@ -99,14 +99,6 @@ struct ConvCfg {
   static constexpr size_t SMEM = (size_t)(IN_FLOATS + W_FLOATS) * sizeof(float);
 };
 
-struct ConvArgs {
-  const float* in; int inR, inLd;       // planar [ns][CIN][inR][inLd] (raw, before the folded pool)
-  float* out; int outR, outC, outLd;    // planar [ns][COUT][outR][outLd] or NHWC [ns][outR][outC][64]
-  const float* w;                       // [CIN][9][COUT]
-  const float* scale; const float* shift; const float* alpha;
-  int ns; int round_out;   // round_out: write the NHWC map in the split bf16 hi|lo layout
-};
-
 template <int CIN, int COUT, int DIL, int POOLD, bool NHWC_OUT>
 __global__ void __launch_bounds__(320) dense_conv_kernel(const ConvArgs a) {
   using Cfg = ConvCfg<CIN, COUT, DIL, POOLD, NHWC_OUT>;
@@ -228,6 +220,33 @@ static int launch_dense_conv(sc_ctx* ctx, const ConvArgs& a, int prof_cls, cudaS
   dim3 grid((width + Cfg::TW - 1) / Cfg::TW, (a.outR + Cfg::TH - 1) / Cfg::TH, a.ns);
   ProfScope prof(ctx, prof_cls, st);
   kern<<<grid, 320, Cfg::SMEM, st>>>(a);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// plain (dilation 1, no folded pool, planar) 3x3 valid conv over [n][CIN][R][ld] maps: the training
+// forward convs and -- with the roles of the channel axes swapped and raw taps -- their dgrads.
+int launch_conv3x3(sc_ctx* ctx, int cin, int cout, const ConvArgs& a, int prof_cls, cudaStream_t st) {
+  if (cin == 20 && cout == 20) return launch_dense_conv<20, 20, 1, 0, false>(ctx, a, prof_cls, st);
+  if (cin == 20 && cout == 40) return launch_dense_conv<20, 40, 1, 0, false>(ctx, a, prof_cls, st);
+  if (cin == 40 && cout == 40) return launch_dense_conv<40, 40, 1, 0, false>(ctx, a, prof_cls, st);
+  if (cin == 40 && cout == 60) return launch_dense_conv<40, 60, 1, 0, false>(ctx, a, prof_cls, st);
+  if (cin == 60 && cout == 40) return launch_dense_conv<60, 40, 1, 0, false>(ctx, a, prof_cls, st);
+  if (cin == 40 && cout == 20) return launch_dense_conv<40, 20, 1, 0, false>(ctx, a, prof_cls, st);
+  set_error("launch_conv3x3: unsupported channel pair %d -> %d", cin, cout);
+  return SC_ERR_ARG;
+}
+
+// conv1 (1 -> 20) over [n][32][32] patches -> planar [n][20][30][32]
+int launch_conv1_patches(sc_ctx* ctx, const float* patches, int n, const float* w, const float* scale, const float* shift,
+                         const float* alpha, float* out, cudaStream_t st) {
+  ViewGeo g = {1024, 32, 1, 0, n, 16, 16, 30, 30, 32, 32};  // origin 16 cancels the dense path's zero-pad offset
+  const int64_t work = (int64_t)n * 30 * 8;
+  const int64_t blocks = (work + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
+  ProfScope prof(ctx, PC_TRAIN_FWD, st);
+  dense_conv1_kernel<<<grid, 256, 0, st>>>(patches, g, 0, n, w, scale, shift, alpha, out, 30, 32);
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
   return SC_OK;

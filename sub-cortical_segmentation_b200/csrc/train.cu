@@ -1,18 +1,612 @@
-// training step (placeholder until the kernels land)
+// Training step: nolearn's train_fn / eval_fn inside net.fit (cnn_cort/nets.py:233-246).
+//
+//   forward (training mode)  conv -> BatchNorm with BATCH statistics (biased variance, eps 1e-4) -> PReLU,
+//                            pools after conv2 / conv4, dropout p=.5 (rescaled by 2) at *_l1drop, f1_drop, f2_drop,
+//                            dense layers + PReLU, softmax, categorical cross-entropy (mean over the GLOBAL batch)
+//   backward                 every parameter the reference trains: conv W, BN beta/gamma, PReLU alpha, dense W/b
+//   output                   the context's flat gradient buffer (pickle layout).  The slots of the non-trainable BN
+//                            running statistics carry this batch's mean / inv_std so that one all-reduce moves both;
+//                            sc_adam_step applies Lasagne's Adam to the trainable entries and
+//                            s <- 0.9 s + 0.1 batch (mean AND inv_std, Lasagne BatchNormLayer) to the statistics.
+//
+// BatchNorm's batch statistics force a grid-wide reduction between each conv and its activation, so the training
+// forward is per-layer kernels.  The 3x3 convolutions (forward and dgrad) reuse the planar conv kernel of dense.cu
+// with an identity epilogue; everything else is here.  All arithmetic fp32 FFMA; per-channel reductions accumulate
+// in fp64 atomics.
 #include "common.cuh"
+
 namespace sc {
-int train_forward_backward(sc_ctx*, const float*, const float*, const float*, const float*, const uint8_t*, int64_t,
-                           int64_t, uint64_t, const uint8_t*, float*, cudaStream_t) {
-  set_error("training kernels not built");
-  return SC_ERR_UNSUPPORTED;
+
+constexpr float kBnEps = 1e-4f;
+constexpr int kH[5] = {30, 28, 12, 10, 3};      // conv output size per layer
+constexpr int kLd[5] = {32, 32, 16, 16, 8};     // row stride of the conv output maps
+constexpr int kInH[5] = {32, 30, 14, 12, 5};    // conv input size
+constexpr int kInLd[5] = {32, 32, 16, 16, 8};
+
+__host__ __device__ inline uint32_t hash3(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 16);
 }
-int adam_step(sc_ctx*, float, float, float, float, float, cudaStream_t) {
-  set_error("training kernels not built");
-  return SC_ERR_UNSUPPORTED;
+
+// ---- parameter repacking ------------------------------------------------------------------------
+// fwd: out[ci][t][co] = W[co][ci][8-t] (true convolution -> correlation taps);  dgrad: out[co][t][ci] = W[co][ci][t]
+__global__ void repack_conv_kernel(const float* __restrict__ W, int cout, int cin, float* __restrict__ fwd, float* __restrict__ dgrad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cin * 9) return;
+  const int t = i % 9, ci = (i / 9) % cin, co = i / (9 * cin);
+  const float v = W[i];
+  fwd[(ci * 9 + (8 - t)) * cout + co] = v;
+  if (dgrad) dgrad[(co * 9 + t) * cin + ci] = v;
 }
-int eval_batch(sc_ctx*, const float*, const float*, const float*, const float*, const uint8_t*, int64_t, float*,
-               cudaStream_t) {
-  set_error("training kernels not built");
-  return SC_ERR_UNSUPPORTED;
+
+// ---- BatchNorm statistics --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int n, int C, int H, int W, int ld,
+                                                       double* __restrict__ sums /*[C][2]*/) {
+  const int c = blockIdx.x;
+  const int64_t per = (int64_t)H * W, total = (int64_t)n * per;
+  double s = 0.0, q = 0.0;
+  for (int64_t e = (int64_t)blockIdx.y * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.y * 256) {
+    const int i = (int)(e / per);
+    const int r = (int)(e - (int64_t)i * per);
+    const int h = r / W, w = r - h * W;
+    const float v = x[(((int64_t)i * C + c) * H + h) * ld + w];
+    s += v; q += (double)v * v;
+  }
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  __shared__ double ss[8], sq[8];
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { s += ss[w]; q += sq[w]; }
+    atomicAdd(&sums[c * 2], s);
+    atomicAdd(&sums[c * 2 + 1], q);
+  }
 }
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count, float* __restrict__ mean,
+                                   float* __restrict__ istd, float* __restrict__ g_mean_slot, float* __restrict__ g_istd_slot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c * 2] / count;
+  double var = sums[c * 2 + 1] / count - m * m;
+  if (var < 0) var = 0;
+  const float is = (float)(1.0 / sqrt(var + (double)kBnEps));
+  mean[c] = (float)m; istd[c] = is;
+  g_mean_slot[c] = (float)m; g_istd_slot[c] = is;   // carried to the optimiser through the gradient buffer
+}
+
+// y = (x-mean)*gamma*istd + beta; a = prelu(y); optional 2x2/2 max-pool with arg-max record
+__global__ void bn_act_kernel(const float* __restrict__ x, int n, int C, int H, int W, int ld, const float* __restrict__ mean,
+                              const float* __restrict__ istd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              const float* __restrict__ alpha, int pool, float* __restrict__ out, int oH, int oW, int old,
+                              uint8_t* __restrict__ idx) {
+  const int64_t total = (int64_t)n * C * oH * oW;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(e % oW);
+    const int h = (int)((e / oW) % oH);
+    const int c = (int)((e / ((int64_t)oW * oH)) % C);
+    const int i = (int)(e / ((int64_t)oW * oH * C));
+    const float sc_ = gamma[c] * istd[c], sh = beta[c] - mean[c] * sc_, al = alpha[c];
+    const float* xp = x + (((int64_t)i * C + c) * H) * ld;
+    float r;
+    if (!pool) {
+      r = prelu(fmaf(xp[h * ld + w], sc_, sh), al);
+    } else {
+      int best = 0;
+      r = prelu(fmaf(xp[(2 * h) * ld + 2 * w], sc_, sh), al);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        const float v = prelu(fmaf(xp[(2 * h + (k >> 1)) * ld + 2 * w + (k & 1)], sc_, sh), al);
+        if (v > r) { r = v; best = k; }
+      }
+      idx[(((int64_t)i * C + c) * oH + h) * old + w] = (uint8_t)best;
+    }
+    out[(((int64_t)i * C + c) * oH + h) * old + w] = r;
+  }
+}
+
+// ---- dropout ------------------------------------------------------------------------------------------
+// mask layout per sample: [3][540] branch (c*9+h*3+w) | [540] f1_drop | [540] f2_drop
+__global__ void make_masks_kernel(uint8_t* __restrict__ m, int64_t total, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) m[i] = (uint8_t)(hash3(seed, (uint64_t)i) & 1u);
+}
+
+// conv5 activation [n][60][3][ld=8] -> F5 [n][540] with dropout
+__global__ void flatten_drop_kernel(const float* __restrict__ a5, int n, const uint8_t* __restrict__ mask /*+b*540*/, float* __restrict__ f5) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n * 540) return;
+  const int i = (int)(e / 540), k = (int)(e - (int64_t)i * 540);
+  const int c = k / 9, r = k - c * 9, h = r / 3, w = r - h * 3;
+  const float v = a5[(((int64_t)i * 60 + c) * 3 + h) * 8 + w];
+  f5[e] = mask[(int64_t)i * 2700 + k] ? 2.f * v : 0.f;
+}
+// d(F5) [n][540] -> d(A5) [n][60][3][8]
+__global__ void unflatten_drop_kernel(const float* __restrict__ df5, int n, const uint8_t* __restrict__ mask, float* __restrict__ da5) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n * 540) return;
+  const int i = (int)(e / 540), k = (int)(e - (int64_t)i * 540);
+  const int c = k / 9, r = k - c * 9, h = r / 3, w = r - h * 3;
+  da5[(((int64_t)i * 60 + c) * 3 + h) * 8 + w] = mask[(int64_t)i * 2700 + k] ? 2.f * df5[e] : 0.f;
+}
+
+// ---- generic small SGEMM with guards: C[M][N] (+)= op(A)[M][K] * op(B)[K][N] ------------------------
+// TA: A stored [K][M] (lda = M-stride);  TB: B stored [N][K].  beta0: overwrite, else accumulate (C += ...).
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                    float* __restrict__ C, int ldc, int M, int N, int K,
+                                                    const float* __restrict__ bias, int accumulate) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+      int kk, mm;
+      if (TA) { mm = e & 63; kk = e >> 6; } else { kk = e & 15; mm = e >> 4; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? (TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk]) : 0.f;
+      int nn;
+      if (TB) { kk = e & 15; nn = e >> 4; } else { nn = e & 63; kk = e >> 6; }
+      const int gn = n0 + nn; const int gk2 = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk2 < K) ? (TB ? B[(int64_t)gn * ldb + gk2] : B[(int64_t)gk2 * ldb + gn]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (accumulate) v += C[(int64_t)m * ldc + n];
+      C[(int64_t)m * ldc + n] = v;
+    }
+  }
+}
+
+template <bool TA, bool TB>
+static int sgemm(sc_ctx* ctx, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                 const float* bias, int accumulate, int cls, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  ProfScope prof(ctx, cls, st);
+  sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, accumulate);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// dense PReLU forward: out[m][col0+j] = prelu(z[m][j], alpha[j]) * (mask ? 2*mask : 1)
+__global__ void dense_act_kernel(const float* __restrict__ z, int M, int N, const float* __restrict__ alpha,
+                                 const uint8_t* __restrict__ mask, int mask_ld, float* __restrict__ out, int out_ld, int col0) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)M * N) return;
+  const int m = (int)(e / N), j = (int)(e - (int64_t)m * N);
+  float v = prelu(z[e], alpha[j]);
+  if (mask) v = mask[(int64_t)m * mask_ld + j] ? 2.f * v : 0.f;
+  out[(int64_t)m * out_ld + col0 + j] = v;
+}
+// dense PReLU backward: dz = dy*(mask*2)*(z>0?1:alpha); galpha[j] += sum_m dyd*z*[z<=0]; gbias[j] += sum_m dz
+__global__ void __launch_bounds__(256) dense_act_bwd_kernel(const float* __restrict__ dy, int dy_ld, int col0, const float* __restrict__ z,
+                                                            int M, int N, const float* __restrict__ alpha, const uint8_t* __restrict__ mask,
+                                                            int mask_ld, float* __restrict__ dz, float* __restrict__ galpha,
+                                                            float* __restrict__ gbias) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r0 = threadIdx.x >> 5;
+  float sa = 0.f, sb = 0.f;
+  if (j < N) {
+    const float al = alpha[j];
+    for (int m = blockIdx.y * 8 + r0; m < M; m += gridDim.y * 8) {
+      float g = dy[(int64_t)m * dy_ld + col0 + j];
+      if (mask) g = mask[(int64_t)m * mask_ld + j] ? 2.f * g : 0.f;
+      const float zz = z[(int64_t)m * N + j];
+      const float d = zz > 0.f ? g : al * g;
+      dz[(int64_t)m * N + j] = d;
+      if (zz <= 0.f) sa += g * zz;
+      sb += d;
+    }
+  }
+  __shared__ float ra[8][33], rb[8][33];
+  ra[r0][threadIdx.x & 31] = sa; rb[r0][threadIdx.x & 31] = sb;
+  __syncthreads();
+  if (r0 == 0 && j < N) {
+    for (int k = 1; k < 8; ++k) { sa += ra[k][threadIdx.x & 31]; sb += rb[k][threadIdx.x & 31]; }
+    atomicAdd(&galpha[j], sa);
+    atomicAdd(&gbias[j], sb);
+  }
+}
+__global__ void colsum_kernel(const float* __restrict__ x, int M, int N, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float s = 0.f;
+  for (int m = blockIdx.y; m < M; m += gridDim.y) s += x[(int64_t)m * N + j];
+  atomicAdd(&out[j], s);
+}
+
+// softmax + cross-entropy: dz = (p - onehot)/n_global, loss += sum(-log p[y])/n_global
+__global__ void softmax_ce_kernel(const float* __restrict__ z, const uint8_t* __restrict__ y, int n, float inv_global,
+                                  float* __restrict__ dz, float* __restrict__ loss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (i < n) {
+    float v[15], mx = -INFINITY, s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 15; ++c) { v[c] = z[i * 15 + c]; mx = fmaxf(mx, v[c]); }
+#pragma unroll
+    for (int c = 0; c < 15; ++c) { v[c] = expf(v[c] - mx); s += v[c]; }
+    const int t = y[i];
+    l = -(logf(v[t] / s)) * inv_global;
+#pragma unroll
+    for (int c = 0; c < 15; ++c) dz[i * 15 + c] = (v[c] / s - (c == t ? 1.f : 0.f)) * inv_global;
+  }
+  for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss, l);
+}
+
+// ---- conv block backward ------------------------------------------------------------------------------
+// incoming gradient da: at pooled resolution (pool=1, routed through idx) or full resolution.
+// pass 1: s[c] = {sum dy, sum dy*xhat, sum da*y*[y<=0]}   with y = xhat*gamma+beta, dy = da*(y>0?1:alpha)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ da, const uint8_t* __restrict__ idx,
+                                                            int n, int C, int H, int W, int ld, int pool, int pld,
+                                                            const float* __restrict__ mean, const float* __restrict__ istd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ alpha, double* __restrict__ sums /*[C][3]*/) {
+  const int c = blockIdx.x;
+  const int64_t per = (int64_t)H * W, total = (int64_t)n * per;
+  const float mu = mean[c], is = istd[c], ga = gamma[c], be = beta[c], al = alpha[c];
+  double s1 = 0, s2 = 0, s3 = 0;
+  for (int64_t e = (int64_t)blockIdx.y * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.y * 256) {
+    const int i = (int)(e / per);
+    const int r = (int)(e - (int64_t)i * per);
+    const int h = r / W, w = r - h * W;
+    float g;
+    if (pool) {
+      const int64_t po = (((int64_t)i * C + c) * (H / 2) + (h >> 1)) * pld + (w >> 1);
+      g = idx[po] == ((h & 1) * 2 + (w & 1)) ? da[po] : 0.f;
+    } else {
+      g = da[(((int64_t)i * C + c) * H + h) * ld + w];
+    }
+    const float xh = (x[(((int64_t)i * C + c) * H + h) * ld + w] - mu) * is;
+    const float yv = fmaf(xh, ga, be);
+    const float dy = yv > 0.f ? g : al * g;
+    s1 += dy; s2 += (double)dy * xh;
+    if (yv <= 0.f) s3 += (double)g * yv;
+  }
+  for (int o = 16; o; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  __shared__ double sh[8][3];
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = s1; sh[threadIdx.x >> 5][1] = s2; sh[threadIdx.x >> 5][2] = s3; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { s1 += sh[w][0]; s2 += sh[w][1]; s3 += sh[w][2]; }
+    atomicAdd(&sums[c * 3], s1); atomicAdd(&sums[c * 3 + 1], s2); atomicAdd(&sums[c * 3 + 2], s3);
+  }
+}
+__global__ void bn_bwd_params_kernel(const double* __restrict__ sums, int C, float* __restrict__ gbeta, float* __restrict__ ggamma,
+                                     float* __restrict__ galpha) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  gbeta[c] = (float)sums[c * 3]; ggamma[c] = (float)sums[c * 3 + 1]; galpha[c] = (float)sums[c * 3 + 2];
+}
+// pass 2: dx = gamma*istd*(dy - s1/m - xhat*s2/m), written (a) compact [n][C][H][ld] for wgrad and
+// (b) zero-padded by 2 [n][C][H+4][pld2] for the dgrad convolution (borders pre-zeroed).
+__global__ void bn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ da, const uint8_t* __restrict__ idx, int n, int C,
+                                 int H, int W, int ld, int pool, int pld, const float* __restrict__ mean, const float* __restrict__ istd,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha,
+                                 const double* __restrict__ sums, double count, float* __restrict__ dx, float* __restrict__ dxpad, int pld2) {
+  const int64_t total = (int64_t)n * C * H * W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(e % W);
+    const int h = (int)((e / W) % H);
+    const int c = (int)((e / ((int64_t)W * H)) % C);
+    const int i = (int)(e / ((int64_t)W * H * C));
+    float g;
+    if (pool) {
+      const int64_t po = (((int64_t)i * C + c) * (H / 2) + (h >> 1)) * pld + (w >> 1);
+      g = idx[po] == ((h & 1) * 2 + (w & 1)) ? da[po] : 0.f;
+    } else {
+      g = da[(((int64_t)i * C + c) * H + h) * ld + w];
+    }
+    const float is = istd[c], ga = gamma[c];
+    const int64_t xo = (((int64_t)i * C + c) * H + h) * ld + w;
+    const float xh = (x[xo] - mean[c]) * is;
+    const float yv = fmaf(xh, ga, beta[c]);
+    const float dy = yv > 0.f ? g : alpha[c] * g;
+    const float r = ga * is * (dy - (float)(sums[c * 3] / count) - xh * (float)(sums[c * 3 + 1] / count));
+    dx[xo] = r;
+    if (dxpad) dxpad[(((int64_t)i * C + c) * (H + 4) + h + 2) * pld2 + w + 2] = r;
+  }
+}
+// wgrad: gW[co][ci][ky][kx] = sum_{n,y,x} dx[n][co][y][x] * in[n][ci][y+2-ky][x+2-kx]
+// one CTA per (co, ci, sample chunk); 9 taps per thread, block reduction, atomicAdd
+__global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict__ in, int Cin, int inH, int inLd, const float* __restrict__ dx,
+                                                         int Cout, int H, int W, int ld, int n, float* __restrict__ gW) {
+  const int co = blockIdx.x, ci = blockIdx.y;
+  const int per = H * W;
+  float acc[9] = {};
+  for (int i = blockIdx.z; i < n; i += gridDim.z) {
+    const float* dp = dx + ((int64_t)i * Cout + co) * H * ld;
+    const float* ip = in + ((int64_t)i * Cin + ci) * inH * inLd;
+    for (int e = threadIdx.x; e < per; e += 128) {
+      const int y = e / W, xx = e - y * W;
+      const float d = dp[y * ld + xx];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(d, ip[(y + 2 - ky) * inLd + xx + 2 - kx], acc[ky * 3 + kx]);
+    }
+  }
+  __shared__ float red[4][9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float v = acc[t];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    const float v = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    atomicAdd(&gW[((int64_t)co * Cin + ci) * 9 + threadIdx.x], v);
+  }
+}
+
+// ---- optimiser -------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            const uint8_t* __restrict__ trainable, int n, float a_t, float b1, float b2, float eps, float gscale,
+                            float sscale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (trainable[i]) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - a_t * mi / (sqrtf(vi) + eps);
+  } else {
+    p[i] = 0.9f * p[i] + 0.1f * (g[i] * sscale);   // BN running mean / inv_std (Lasagne alpha = 0.1)
+  }
+}
+
+int adam_step(sc_ctx* ctx, float lr, float b1, float b2, float eps, float gscale, float sscale, cudaStream_t st) {
+  ctx->adam_t += 1;
+  const double t = (double)ctx->adam_t;
+  const float a_t = (float)(lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  ProfScope prof(ctx, PC_ADAM, st);
+  adam_kernel<<<(SC_PARAM_FLOATS + 255) / 256, 256, 0, st>>>(ctx->params, ctx->grads, ctx->adam_m, ctx->adam_v, ctx->trainable,
+                                                             SC_PARAM_FLOATS, a_t, b1, b2, eps, gscale, sscale);
+  ctx->launches++;
+  ctx->derived_dirty = true;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// ---- the step ------------------------------------------------------------------------------------------------
+struct Bump {
+  char* base; size_t off;
+  template <class T> T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += (count * sizeof(T) + 255) & ~(size_t)255;
+    return p;
+  }
+};
+
+static unsigned ew_grid(int64_t total) { return (unsigned)((total + 255) / 256 < 65535 * 8 ? (total + 255) / 256 : 65535 * 8); }
+
+int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, const uint8_t* y,
+                           int64_t n64, int64_t n_global, uint64_t seed, const uint8_t* masks_in, float* loss, cudaStream_t st) {
+  SC_CHECK(n64 <= 16384, SC_ERR_ARG, "sc_train_forward_backward: per-GPU batch %lld too large (max 16384)", (long long)n64);
+  const int n = (int)n64;
+  const ParamOff& O = ctx->off;
+  float* P = ctx->params;
+  float* G = ctx->grads;
+  const float* ins[3] = {in1, in2, in3};
+
+  // ---- workspace (two passes over the same carve-up: size, then pointers) ----
+  struct BranchBuf {
+    float* X[5]; float* A[5]; uint8_t* idx[2]; float* mean[5]; float* istd[5];
+    float* F5; float* Z1;
+    float* wf[5]; float* wd[5];
+  } bb[3];
+  float *CAT, *ZF1, *CAT2, *ZF2, *H2, *ZO, *dZO, *dH2, *dZF2, *dCAT2, *dZF1, *dCAT, *dZ1, *dF5, *dA, *dX, *dXpad, *ones, *zeros;
+  uint8_t* masks;
+  double* sums;
+  auto carve = [&](Bump& B) {
+    for (int b = 0; b < 3; ++b) {
+      for (int l = 0; l < 5; ++l) {
+        bb[b].X[l] = B.take<float>((size_t)n * kConvCout[l] * kH[l] * kLd[l]);
+        const int oh = (l == 1 || l == 3) ? kH[l] / 2 : kH[l];
+        const int old = (l == 1) ? 16 : (l == 3) ? 8 : kLd[l];
+        bb[b].A[l] = B.take<float>((size_t)n * kConvCout[l] * oh * old);
+        bb[b].mean[l] = B.take<float>(64); bb[b].istd[l] = B.take<float>(64);
+        bb[b].wf[l] = B.take<float>((size_t)kConvCout[l] * kConvCin[l] * 9);
+        bb[b].wd[l] = l > 0 ? B.take<float>((size_t)kConvCout[l] * kConvCin[l] * 9) : nullptr;
+      }
+      bb[b].idx[0] = B.take<uint8_t>((size_t)n * 20 * 14 * 16);
+      bb[b].idx[1] = B.take<uint8_t>((size_t)n * 40 * 5 * 8);
+      bb[b].F5 = B.take<float>((size_t)n * 540);
+      bb[b].Z1 = B.take<float>((size_t)n * 180);
+    }
+    CAT = B.take<float>((size_t)n * 540);     // [D1_ax | D1_cor | D1_sag], f1_drop applied
+    ZF1 = B.take<float>((size_t)n * 540);
+    CAT2 = B.take<float>((size_t)n * 555);    // [prelu(ZF1) with f2_drop | atlas]
+    ZF2 = B.take<float>((size_t)n * 270);
+    H2 = B.take<float>((size_t)n * 270);
+    ZO = B.take<float>((size_t)n * 15);
+    dZO = B.take<float>((size_t)n * 15);
+    dH2 = B.take<float>((size_t)n * 270);
+    dZF2 = B.take<float>((size_t)n * 270);
+    dCAT2 = B.take<float>((size_t)n * 555);
+    dZF1 = B.take<float>((size_t)n * 540);
+    dCAT = B.take<float>((size_t)n * 540);
+    dZ1 = B.take<float>((size_t)n * 180);
+    dF5 = B.take<float>((size_t)n * 540);
+    dA = B.take<float>((size_t)n * 20 * 30 * 32);      // incoming activation gradient of the current layer
+    dX = B.take<float>((size_t)n * 20 * 30 * 32);      // compact conv-output gradient
+    dXpad = B.take<float>((size_t)n * 20 * 34 * 32);   // zero-padded copy for dgrad
+    masks = B.take<uint8_t>((size_t)n * 2700);
+    sums = B.take<double>(64 * 3);
+    ones = B.take<float>(64);
+    zeros = B.take<float>(64);
+  };
+  Bump sizing{nullptr, 0};
+  carve(sizing);
+  SC_TRY(ensure_ws(ctx->ws_train, sizing.off + 4096));
+  Bump B{reinterpret_cast<char*>(ctx->ws_train.ptr), 0};
+  carve(B);
+
+  SC_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * SC_PARAM_FLOATS, st));
+  SC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  SC_CUDA(cudaMemsetAsync(zeros, 0, 64 * 4, st));
+  {
+    float h1[64];
+    for (int i = 0; i < 64; ++i) h1[i] = 1.f;
+    SC_CUDA(cudaMemcpyAsync(ones, h1, sizeof(h1), cudaMemcpyHostToDevice, st));
+  }
+  if (masks_in) SC_CUDA(cudaMemcpyAsync(masks, masks_in, (size_t)n * 2700, cudaMemcpyDeviceToDevice, st));
+  else { make_masks_kernel<<<ew_grid((int64_t)n * 2700), 256, 0, st>>>(masks, (int64_t)n * 2700, seed); ctx->launches++; }
+
+  // ================= forward =================
+  for (int b = 0; b < 3; ++b) {
+    const BranchOff& Ob = O.br[b];
+    for (int l = 0; l < 5; ++l) {
+      const int co = kConvCout[l], ci = kConvCin[l];
+      repack_conv_kernel<<<(co * ci * 9 + 255) / 256, 256, 0, st>>>(P + Ob.convW[l], co, ci, bb[b].wf[l], bb[b].wd[l]);
+      ctx->launches++;
+      if (l == 0) {
+        SC_TRY(launch_conv1_patches(ctx, ins[b], n, bb[b].wf[0], ones, zeros, ones, bb[b].X[0], st));
+      } else {
+        ConvArgs a;
+        a.in = bb[b].A[l - 1]; a.inR = kInH[l]; a.inLd = kInLd[l];
+        a.out = bb[b].X[l]; a.outR = kH[l]; a.outC = kH[l]; a.outLd = kLd[l];
+        a.w = bb[b].wf[l]; a.scale = ones; a.shift = zeros; a.alpha = ones; a.ns = n; a.round_out = 0;
+        SC_TRY(launch_conv3x3(ctx, ci, co, a, PC_TRAIN_FWD, st));
+      }
+      SC_CUDA(cudaMemsetAsync(sums, 0, 64 * 3 * sizeof(double), st));
+      bn_stats_kernel<<<dim3(co, 32), 256, 0, st>>>(bb[b].X[l], n, co, kH[l], kH[l], kLd[l], sums);
+      bn_finalize_kernel<<<1, 64, 0, st>>>(sums, co, (double)n * kH[l] * kH[l], bb[b].mean[l], bb[b].istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3]);
+      const int pool = (l == 1 || l == 3);
+      const int oh = pool ? kH[l] / 2 : kH[l];
+      const int old = (l == 1) ? 16 : (l == 3) ? 8 : kLd[l];
+      bn_act_kernel<<<ew_grid((int64_t)n * co * oh * oh), 256, 0, st>>>(bb[b].X[l], n, co, kH[l], kH[l], kLd[l], bb[b].mean[l], bb[b].istd[l],
+                                                                      P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], pool, bb[b].A[l], oh, oh, old,
+                                                                      pool ? bb[b].idx[l == 1 ? 0 : 1] : nullptr);
+      ctx->launches += 3;
+    }
+    flatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, st>>>(bb[b].A[4], n, masks + b * 540, bb[b].F5);
+    ctx->launches++;
+    SC_TRY((sgemm<false, false>(ctx, bb[b].F5, 540, P + Ob.d1W, 180, bb[b].Z1, 180, n, 180, 540, P + Ob.d1b, 0, PC_TRAIN_FWD, st)));
+    dense_act_kernel<<<ew_grid((int64_t)n * 180), 256, 0, st>>>(bb[b].Z1, n, 180, P + Ob.d1alpha, masks + 1620 + b * 180, 2700, CAT, 540, b * 180);
+    ctx->launches++;
+  }
+  SC_TRY((sgemm<false, false>(ctx, CAT, 540, P + O.fc1W, 540, ZF1, 540, n, 540, 540, P + O.fc1b, 0, PC_TRAIN_FWD, st)));
+  dense_act_kernel<<<ew_grid((int64_t)n * 540), 256, 0, st>>>(ZF1, n, 540, P + O.a1, masks + 2160, 2700, CAT2, 555, 0);
+  SC_CUDA(cudaMemcpy2DAsync(CAT2 + 540, 555 * 4, in4, 15 * 4, 15 * 4, n, cudaMemcpyDeviceToDevice, st));
+  SC_TRY((sgemm<false, false>(ctx, CAT2, 555, P + O.fc2W, 270, ZF2, 270, n, 270, 555, P + O.fc2b, 0, PC_TRAIN_FWD, st)));
+  dense_act_kernel<<<ew_grid((int64_t)n * 270), 256, 0, st>>>(ZF2, n, 270, P + O.a2, nullptr, 0, H2, 270, 0);
+  SC_TRY((sgemm<false, false>(ctx, H2, 270, P + O.outW, 15, ZO, 15, n, 15, 270, P + O.outb, 0, PC_TRAIN_FWD, st)));
+  softmax_ce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ZO, y, n, 1.f / (float)n_global, dZO, loss);
+  ctx->launches += 3;
+
+  // ================= backward =================
+  // out layer
+  SC_TRY((sgemm<true, false>(ctx, H2, 270, dZO, 15, G + O.outW, 15, 270, 15, n, nullptr, 0, PC_TRAIN_BWD, st)));
+  colsum_kernel<<<dim3(1, 32), 32, 0, st>>>(dZO, n, 15, G + O.outb);
+  SC_TRY((sgemm<false, true>(ctx, dZO, 15, P + O.outW, 15, dH2, 270, n, 270, 15, nullptr, 0, PC_TRAIN_BWD, st)));
+  // fc_2
+  dense_act_bwd_kernel<<<dim3((270 + 31) / 32, 16), 256, 0, st>>>(dH2, 270, 0, ZF2, n, 270, P + O.a2, nullptr, 0, dZF2, G + O.a2, G + O.fc2b);
+  SC_TRY((sgemm<true, false>(ctx, CAT2, 555, dZF2, 270, G + O.fc2W, 270, 555, 270, n, nullptr, 0, PC_TRAIN_BWD, st)));
+  SC_TRY((sgemm<false, true>(ctx, dZF2, 270, P + O.fc2W, 270, dCAT2, 555, n, 555, 270, nullptr, 0, PC_TRAIN_BWD, st)));
+  // FC1 (dropout f2_drop sits on its activation)
+  dense_act_bwd_kernel<<<dim3((540 + 31) / 32, 16), 256, 0, st>>>(dCAT2, 555, 0, ZF1, n, 540, P + O.a1, masks + 2160, 2700, dZF1, G + O.a1, G + O.fc1b);
+  SC_TRY((sgemm<true, false>(ctx, CAT, 540, dZF1, 540, G + O.fc1W, 540, 540, 540, n, nullptr, 0, PC_TRAIN_BWD, st)));
+  SC_TRY((sgemm<false, true>(ctx, dZF1, 540, P + O.fc1W, 540, dCAT, 540, n, 540, 540, nullptr, 0, PC_TRAIN_BWD, st)));
+  ctx->launches += 3;
+
+  for (int b = 0; b < 3; ++b) {
+    const BranchOff& Ob = O.br[b];
+    // d1 (dropout f1_drop sits on the concatenated d1 activations)
+    dense_act_bwd_kernel<<<dim3((180 + 31) / 32, 16), 256, 0, st>>>(dCAT, 540, b * 180, bb[b].Z1, n, 180, P + Ob.d1alpha, masks + 1620 + b * 180, 2700,
+                                                                   dZ1, G + Ob.d1alpha, G + Ob.d1b);
+    SC_TRY((sgemm<true, false>(ctx, bb[b].F5, 540, dZ1, 180, G + Ob.d1W, 180, 540, 180, n, nullptr, 0, PC_TRAIN_BWD, st)));
+    SC_TRY((sgemm<false, true>(ctx, dZ1, 180, P + Ob.d1W, 180, dF5, 540, n, 540, 180, nullptr, 0, PC_TRAIN_BWD, st)));
+    unflatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, st>>>(dF5, n, masks + b * 540, dA);
+    ctx->launches += 2;
+    for (int l = 4; l >= 0; --l) {
+      const int co = kConvCout[l], ci = kConvCin[l], H = kH[l], ld = kLd[l];
+      const int pool = (l == 1 || l == 3);
+      const int pld = (l == 1) ? 16 : 8;
+      const uint8_t* idx = pool ? bb[b].idx[l == 1 ? 0 : 1] : nullptr;
+      const double count = (double)n * H * H;
+      SC_CUDA(cudaMemsetAsync(sums, 0, 64 * 3 * sizeof(double), st));
+      bn_bwd_reduce_kernel<<<dim3(co, 32), 256, 0, st>>>(bb[b].X[l], dA, idx, n, co, H, H, ld, pool, pld, bb[b].mean[l], bb[b].istd[l],
+                                                         P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], sums);
+      bn_bwd_params_kernel<<<1, 64, 0, st>>>(sums, co, G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l]);
+      const int pld2 = kInLd[l];   // padded map has the size of this layer's input (H+4 >= inH, same row stride)
+      if (l > 0) SC_CUDA(cudaMemsetAsync(dXpad, 0, (size_t)n * co * (H + 4) * pld2 * 4, st));
+      bn_bwd_dx_kernel<<<ew_grid((int64_t)n * co * H * H), 256, 0, st>>>(bb[b].X[l], dA, idx, n, co, H, H, ld, pool, pld, bb[b].mean[l], bb[b].istd[l],
+                                                                        P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], sums, count, dX,
+                                                                        l > 0 ? dXpad : nullptr, pld2);
+      // wgrad against this layer's input (the previous activation, or the patches for conv1)
+      const float* lin = l == 0 ? ins[b] : bb[b].A[l - 1];
+      int zc = n < 32 ? n : 32;
+      conv_wgrad_kernel<<<dim3(co, ci, zc), 128, 0, st>>>(lin, ci, kInH[l], kInLd[l], dX, co, H, H, ld, n, G + Ob.convW[l]);
+      ctx->launches += 4;
+      if (l > 0) {
+        // dgrad: d(input) = valid conv of the zero-padded dx with the raw taps, channel roles swapped
+        ConvArgs a;
+        a.in = dXpad; a.inR = H + 4; a.inLd = pld2;
+        a.out = dA; a.outR = kInH[l]; a.outC = kInH[l]; a.outLd = kInLd[l];
+        a.w = bb[b].wd[l]; a.scale = ones; a.shift = zeros; a.alpha = ones; a.ns = n; a.round_out = 0;
+        SC_TRY(launch_conv3x3(ctx, co, ci, a, PC_TRAIN_BWD, st));
+      }
+    }
+  }
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// eval_fn: deterministic forward, sum of -log p[y] and number of correct arg-max
+__global__ void eval_reduce_kernel(const float* __restrict__ proba, const uint8_t* __restrict__ y, int n, float* __restrict__ out2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f, c = 0.f;
+  if (i < n) {
+    const float* p = proba + (int64_t)i * 15;
+    int best = 0;
+    for (int k = 1; k < 15; ++k) if (p[k] > p[best]) best = k;
+    l = -logf(fmaxf(p[y[i]], 1e-38f));
+    c = best == y[i] ? 1.f : 0.f;
+  }
+  for (int o = 16; o; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out2, l); atomicAdd(out2 + 1, c); }
+}
+
+int eval_batch(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, const uint8_t* y, int64_t n,
+               float* out2, cudaStream_t st) {
+  SC_TRY(ensure_ws(ctx->ws_train, (size_t)n * 15 * sizeof(float) + 256));
+  float* proba = reinterpret_cast<float*>(ctx->ws_train.ptr);
+  SC_TRY(forward_patches(ctx, in1, in2, in3, in4, n, proba, nullptr, st));
+  SC_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(float), st));
+  eval_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(proba, y, (int)n, out2);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
 }  // namespace sc
