@@ -79,7 +79,7 @@ def pack_params(P):
     """OrderedDict -> flat float32 blob in pickle order (the C-ABI's parameter layout)."""
     out = []
     for name, shapes in layer_table():
-        arrs = P[name]
+        arrs = P[name] if name in P else []      # parameter-less layers may be absent
         if len(arrs) != len(shapes):
             raise ValueError("layer %s: expected %d arrays, got %d" % (name, len(shapes), len(arrs)))
         for a, s in zip(arrs, shapes):

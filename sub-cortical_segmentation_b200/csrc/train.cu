@@ -248,10 +248,11 @@ __global__ void softmax_ce_kernel(const float* __restrict__ z, const uint8_t* __
     float v[15], mx = -INFINITY, s = 0.f;
 #pragma unroll
     for (int c = 0; c < 15; ++c) { v[c] = z[i * 15 + c]; mx = fmaxf(mx, v[c]); }
+    const int t = y[i];
+    const float zt = z[i * 15 + t] - mx;
 #pragma unroll
     for (int c = 0; c < 15; ++c) { v[c] = expf(v[c] - mx); s += v[c]; }
-    const int t = y[i];
-    l = -(logf(v[t] / s)) * inv_global;
+    l = (logf(s) - zt) * inv_global;   // -log softmax[t], stable for saturated outputs
 #pragma unroll
     for (int c = 0; c < 15; ++c) dz[i * 15 + c] = (v[c] / s - (c == t ? 1.f : 0.f)) * inv_global;
   }
