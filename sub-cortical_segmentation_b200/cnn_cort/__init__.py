@@ -9,4 +9,4 @@ sm_100a CUDA kernels in ``libsubcort_b200.so`` (C-ABI: ``include/subcort_b200.h`
 There is no CPU fallback: importing works anywhere, but the first call that needs the
 network or the gather raises if the CUDA library or a B200 is missing.
 """
-__all__ = ["base", "nets", "load_options", "nifti", "synthetic"]
+__all__ = ["base", "nets", "load_options", "nifti", "synthetic", "parallel"]

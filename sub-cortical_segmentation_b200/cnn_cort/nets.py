@@ -22,6 +22,7 @@ from collections import OrderedDict
 import numpy as np
 
 from . import _native
+from . import parallel
 
 BRANCHES = ('axial', 'coronal', 'saggital')   # reference spelling, nets.py:202
 _CONV = ((1, 20), (20, 20), (20, 40), (40, 40), (40, 60))
@@ -245,12 +246,10 @@ class Net(object):
             losses, sizes = [], []
             for s in range(0, len(tr), bs):
                 gidx = tr[s:s + bs]
-                lidx = gidx[rank::world] if world > 1 else gidx
+                lidx = parallel.shard_batch(gidx, rank, world)
                 b = to_dev(lidx)
                 ctx.train_forward_backward(*b, n_global=len(gidx), seed=int(rng.randint(1 << 62)) + rank, loss_out=loss_buf)
-                if world > 1:
-                    dist.all_reduce(grads)
-                    dist.all_reduce(loss_buf)
+                parallel.allreduce_gradients(grads, loss_buf)
                 ctx.adam_step(lr=self.update_learning_rate, stat_scale=1.0 / world)
                 losses.append(loss_buf.clone())
                 sizes.append(len(gidx))
