@@ -189,7 +189,7 @@ def main():
         ctx.load_weights(nets.pack_params(pickle.load(f, encoding="latin1")))
     if args.gemm >= 0:
         ctx.set_option("gemm", args.gemm)
-    backend = "tcgen05-tf32" if ctx.counter("gemm") == 1 else "simt-fp32"
+    backend = "tcgen05-bf16x3" if ctx.counter("gemm") == 1 else "simt-fp32"
 
     d_vol = torch.from_numpy(norm).cuda()
     d_atlas = torch.from_numpy(atlas).cuda()
@@ -289,7 +289,7 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
            "ms_per_step": ms_max / args.steps, "seconds_per_volume": ms_max / args.steps * 1e-3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if backend.startswith("tcgen05") else "f32",
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if backend.startswith("tcgen05") else "f32",
            "data": "synthetic",
            "config": {"workload": "miccai2012_v1 inference on B200, one synthetic %d^3 T1 + synthetic atlas priors per GPU, full brain "
                                   "(speedup_segmentation=False, all %d voxels)" % (size, n_cand),

@@ -156,7 +156,7 @@ int64_t sc_get_counter(sc_ctx* ctx, const char* key) {
 }
 
 static const char* kProfNames[PC_COUNT] = {"gather", "nonzero", "scatter", "patch_branch", "conv1", "conv2", "conv3",
-                                           "conv4", "conv5", "gemm_d1", "gemm_fc1", "gemm_fc2", "atlas", "out_softmax",
+                                           "conv4", "conv5", "gemm_d1", "gemm_fc1", "gemm_fc2", "atlas", "out_softmax", "pool",
                                            "train_fwd", "train_bwd", "adam"};
 int sc_profile_classes(void) { return PC_COUNT; }
 const char* sc_profile_name(int cls) { return cls >= 0 && cls < PC_COUNT ? kProfNames[cls] : ""; }

@@ -95,8 +95,9 @@ constexpr int kD1K = 9 * kC5Ld;  // 576: K of d1 as a 3x3 dilation-4 conv over c
 struct GemmW {      // one dense layer prepared for both GEMM back-ends
   float* w_kn;      // [Kpad][Npad] row-major fp32 (SIMT path), zero padded
   float* w_nk;      // [Npad][Kpad] K-major split bf16 hi|lo blocks (tcgen05 path), zero padded
-  float* bias;      // [Npad]
+  float* bias;      // [Npad]  (BN shift for the conv layers)
   float* alpha;     // [Npad] (PReLU; 1 where identity)
+  float* scale;     // [Npad] multiplies the accumulator before the bias (BN scale), or nullptr = 1
   int K, N, Kpad, Npad;
 };
 
@@ -106,6 +107,7 @@ struct BranchW {
   float* scale[5];      // BN folded: gamma*inv_std
   float* shift[5];      // beta - mean*scale
   float* alpha[5];
+  GemmW conv_tc[5];     // l=1..4: conv2..conv5 as implicit GEMMs over NHWC-64 maps (K = tap*64+ci, N padded to 64)
   GemmW d1;             // patchwise: K=540 (c*9+h*3+w order)
   GemmW d1_dense;       // dense: K=576 (tap*64+ci), same N
 };
@@ -118,7 +120,7 @@ struct Workspace {
 // per-kernel-class timing with CUDA events on the launching stream (sc_set_option "profile")
 enum ProfClass {
   PC_GATHER = 0, PC_NONZERO, PC_SCATTER, PC_PATCH_BRANCH, PC_CONV1, PC_CONV2, PC_CONV3, PC_CONV4, PC_CONV5,
-  PC_GEMM_D1, PC_GEMM_FC1, PC_GEMM_FC2, PC_ATLAS, PC_OUT, PC_TRAIN_FWD, PC_TRAIN_BWD, PC_ADAM, PC_COUNT
+  PC_GEMM_D1, PC_GEMM_FC1, PC_GEMM_FC2, PC_ATLAS, PC_OUT, PC_POOL, PC_TRAIN_FWD, PC_TRAIN_BWD, PC_ADAM, PC_COUNT
 };
 struct ProfEvent { int cls; cudaEvent_t a, b; };
 

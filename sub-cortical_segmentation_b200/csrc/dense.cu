@@ -225,6 +225,111 @@ static int launch_dense_conv(sc_ctx* ctx, const ConvArgs& a, int prof_cls, cudaS
   return SC_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// tensor-core pipeline pieces: conv1 straight into the NHWC-64 split-bf16 layout, and the stride-1
+// max-pools as their own (HBM-bound) pass -- a TMA-fed MMA cannot fold the pool into its load.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_conv1_nhwc_kernel(const float* __restrict__ vol, ViewGeo g, int sbeg, int ns,
+                                                               const float* __restrict__ w, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, const float* __restrict__ alpha,
+                                                               float* __restrict__ out, int outR, int outC) {
+  __shared__ float sw[9 * 20], ssc[20], ssh[20], sal[20];
+  for (int i = threadIdx.x; i < 180; i += 256) sw[i] = w[i];
+  if (threadIdx.x < 20) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; sal[threadIdx.x] = alpha[threadIdx.x]; }
+  __syncthreads();
+  const int64_t total = (int64_t)ns * outR * outC;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int j = (int)(e % outC);
+    const int i = (int)((e / outC) % outR);
+    const int s = (int)(e / ((int64_t)outC * outR));
+    const float* base = vol + (int64_t)(g.s0 + sbeg + s) * g.ss;
+    float x[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int rr = g.r0 + i + ky - 16;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int cc = g.c0 + j + kx - 16;
+        x[ky * 3 + kx] = (rr >= 0 && rr < g.R && cc >= 0 && cc < g.C) ? __ldg(base + (int64_t)rr * g.rs + (int64_t)cc * g.cs) : 0.f;
+      }
+    }
+    float* o = out + e * kC5Ld;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int co = q * 4 + k;
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a = fmaf(x[t], sw[t * 20 + co], a);
+        v[k] = prelu(fmaf(a, ssc[co], ssh[co]), sal[co]);
+      }
+      store_split4(o, q * 4, v[0], v[1], v[2], v[3]);
+    }
+#pragma unroll
+    for (int q = 5; q < 16; ++q) store_split4(o, q * 4, 0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// out[s][r][c][:] = max over {0,pd}x{0,pd} of in[s][r+dr][c+dc][:]  on NHWC-64 split-bf16 maps (exact: the
+// winning pixel's hi|lo pair is copied).  One thread per (pixel, 4 channels).
+__global__ void __launch_bounds__(256) pool_nhwc_kernel(const float* __restrict__ in, int inR, int inC, float* __restrict__ out,
+                                                        int outR, int outC, int ns, int pd) {
+  const int64_t total = (int64_t)ns * outR * outC * 16;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int q = (int)(e & 15);
+    const int64_t px = e >> 4;
+    const int c = (int)(px % outC);
+    const int r = (int)((px / outC) % outR);
+    const int s = (int)(px / ((int64_t)outC * outR));
+    uint2 bh = make_uint2(0, 0), bl = make_uint2(0, 0);
+    float best[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int rr = r + (k >> 1) * pd, cc = c + (k & 1) * pd;
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(in + (((int64_t)s * inR + rr) * inC + cc) * kC5Ld) + q * 4;
+      const uint2 h = *reinterpret_cast<const uint2*>(p);
+      const uint2 l = *reinterpret_cast<const uint2*>(p + 64);
+      const uint32_t hw[2] = {h.x, h.y}, lw[2] = {l.x, l.y};
+      uint32_t oh[2] = {bh.x, bh.y}, ol[2] = {bl.x, bl.y};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t hb = (hw[t >> 1] >> ((t & 1) * 16)) & 0xffffu, lb = (lw[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
+        const float v = __uint_as_float(hb << 16) + __uint_as_float(lb << 16);
+        if (k == 0 || v > best[t]) {
+          best[t] = v;
+          const uint32_t m = 0xffffu << ((t & 1) * 16);
+          oh[t >> 1] = (oh[t >> 1] & ~m) | (hb << ((t & 1) * 16));
+          ol[t >> 1] = (ol[t >> 1] & ~m) | (lb << ((t & 1) * 16));
+        }
+      }
+      bh = make_uint2(oh[0], oh[1]); bl = make_uint2(ol[0], ol[1]);
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out + px * kC5Ld) + q * 4;
+    *reinterpret_cast<uint2*>(o) = bh;
+    *reinterpret_cast<uint2*>(o + 64) = bl;
+  }
+}
+
+static int launch_conv_tc(sc_ctx* ctx, const GemmW& w, const float* in, int inR, int inC, float* out, int outR, int outC, int ns,
+                          int dil, int prof_cls, cudaStream_t st) {
+  GemmProblem p;
+  p.A = in; p.lda = kC5Ld; p.a_ys = (int64_t)inC * kC5Ld; p.a_zs = (int64_t)inR * inC * kC5Ld;
+  p.ntaps = 9; p.kc = kC5Ld;
+  for (int t = 0; t < 9; ++t) {
+    p.tap_dx[t] = (t % 3) * dil; p.tap_dy[t] = (t / 3) * dil;
+    p.tap_off[t] = ((int64_t)p.tap_dy[t] * inC + p.tap_dx[t]) * kC5Ld;
+  }
+  p.a_base = in; p.a_dims[0] = kC5Ld; p.a_dims[1] = inC; p.a_dims[2] = inR; p.a_dims[3] = ns;
+  p.a_strides[0] = kC5Ld; p.a_strides[1] = p.a_ys; p.a_strides[2] = p.a_zs;
+  p.a_y0 = p.a_z0 = 0;
+  p.C = out; p.ldc = kC5Ld; p.c_ys = (int64_t)outC * kC5Ld; p.c_zs = (int64_t)outR * outC * kC5Ld;
+  p.M = outC; p.Y = outR; p.Z = ns;
+  p.n_store = 64; p.c_col0 = 0; p.out_split = 1; p.prof_cls = prof_cls;
+  return launch_gemm_tc(ctx, p, w, st);
+}
+
 // plain (dilation 1, no folded pool, planar) 3x3 valid conv over [n][CIN][R][ld] maps: the training
 // forward convs and -- with the roles of the channel axes swapped and raw taps -- their dgrads.
 int launch_conv3x3(sc_ctx* ctx, int cin, int cout, const ConvArgs& a, int prof_cls, cudaStream_t st) {
@@ -312,8 +417,13 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   size_t per_slice_max = 0;
   for (int v = 0; v < 3; ++v) {
     const size_t br = vg[v].br, bc = vg[v].bc;
-    size_t f = 20 * (br + 29) * round8(bc + 29) + 20 * (br + 27) * round8(bc + 27) + 40 * (br + 22) * round8(bc + 22) +
-               40 * (br + 18) * round8(bc + 18);
+    size_t f;
+    if (tc)   // NHWC-64 maps: conv1, conv2, pool1, conv3, conv4, pool2
+      f = kC5Ld * ((br + 29) * (bc + 29) + (br + 27) * (bc + 27) + (br + 26) * (bc + 26) + (br + 22) * (bc + 22) +
+                   (br + 18) * (bc + 18) + (br + 16) * (bc + 16)) + 6 * 64;
+    else
+      f = 20 * (br + 29) * round8(bc + 29) + 20 * (br + 27) * round8(bc + 27) + 40 * (br + 22) * round8(bc + 22) +
+          40 * (br + 18) * round8(bc + 18);
     per_slice_max = f > per_slice_max ? f : per_slice_max;
   }
   const size_t scratch_budget = (size_t)1536 << 20;
@@ -348,7 +458,45 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     const int r3 = g.br + 22, l3 = round8(g.bc + 22);
     const int r4 = g.br + 18, l4 = round8(g.bc + 18);
     const int r5 = g.br + 8, c5 = g.bc + 8;
-    for (int sb = 0; sb < g.ns; sb += group) {
+    for (int sb = 0; sb < g.ns && tc; sb += group) {
+      // ---- tensor-core pipeline: every map NHWC-64 split-bf16, every conv an implicit GEMM (bf16x3) ----
+      const int ns = g.ns - sb < group ? g.ns - sb : group;
+      const int R1 = g.br + 29, C1 = g.bc + 29, R2 = g.br + 27, C2 = g.bc + 27, Rp1 = g.br + 26, Cp1 = g.bc + 26;
+      const int R3 = g.br + 22, C3 = g.bc + 22, R4 = g.br + 18, C4 = g.bc + 18, Rp2 = g.br + 16, Cp2 = g.bc + 16;
+      auto carve = [&](float*& cur, int R, int C) { float* p = cur; cur += align256((size_t)ns * R * C * kC5Ld * 4) / 4; return p; };
+      float* cur = reinterpret_cast<float*>(scratch);
+      float* m1 = carve(cur, R1, C1); float* m2 = carve(cur, R2, C2); float* mp1 = carve(cur, Rp1, Cp1);
+      float* m3 = carve(cur, R3, C3); float* m4 = carve(cur, R4, C4); float* mp2 = carve(cur, Rp2, Cp2);
+      {
+        const int64_t work = (int64_t)ns * R1 * C1;
+        const int64_t blocks = (work + 255) / 256;
+        const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
+        ProfScope prof(ctx, PC_CONV1, st);
+        dense_conv1_nhwc_kernel<<<grid, 256, 0, st>>>(vol, g, sb, ns, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], m1, R1, C1);
+        ctx->launches++;
+        SC_CUDA(cudaGetLastError());
+      }
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], m1, R1, C1, m2, R2, C2, ns, 1, PC_CONV2, st));
+      {
+        const int64_t work = (int64_t)ns * Rp1 * Cp1 * 16;
+        const unsigned grid = (unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64);
+        ProfScope prof(ctx, PC_POOL, st);
+        pool_nhwc_kernel<<<grid, 256, 0, st>>>(m2, R2, C2, mp1, Rp1, Cp1, ns, 1);
+        ctx->launches++;
+      }
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], mp1, Rp1, Cp1, m3, R3, C3, ns, 2, PC_CONV3, st));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, R3, C3, m4, R4, C4, ns, 2, PC_CONV4, st));
+      {
+        const int64_t work = (int64_t)ns * Rp2 * Cp2 * 16;
+        const unsigned grid = (unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64);
+        ProfScope prof(ctx, PC_POOL, st);
+        pool_nhwc_kernel<<<grid, 256, 0, st>>>(m4, R4, C4, mp2, Rp2, Cp2, ns, 2);
+        ctx->launches++;
+      }
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, Rp2, Cp2, a5[v] + (size_t)sb * r5 * c5 * kC5Ld, r5, c5, ns, 4, PC_CONV5, st));
+      SC_CUDA(cudaGetLastError());
+    }
+    for (int sb = 0; sb < g.ns && !tc; sb += group) {
       const int ns = g.ns - sb < group ? g.ns - sb : group;
       float* c1 = reinterpret_cast<float*>(scratch);
       float* c2 = c1 + align256((size_t)ns * 20 * r1 * l1 * 4) / 4;

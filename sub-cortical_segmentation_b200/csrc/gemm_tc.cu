@@ -55,6 +55,7 @@ struct TcArgs {
   long long ldc, c_ys, c_zs;
   const float* bias;
   const float* alpha;
+  const float* scale;
   int out_split;
 };
 
@@ -120,6 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
   float* s_alpha = s_bias + 192;
+  float* s_scale = s_alpha + 192;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long bid = blockIdx.x;
@@ -141,6 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   for (int i = threadIdx.x; i < a.bn; i += TC_THREADS) {
     s_bias[i] = n0 + i < a.npad ? __ldg(a.bias + n0 + i) : 0.f;
     s_alpha[i] = n0 + i < a.npad ? __ldg(a.alpha + n0 + i) : 1.f;
+    s_scale[i] = (a.scale && n0 + i < a.npad) ? __ldg(a.scale + n0 + i) : 1.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -214,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int c = c0 + g * 4 + k;
-              v[k] = prelu(__uint_as_float(r[g * 4 + k]) + s_bias[c], s_alpha[c]);
+              v[k] = prelu(fmaf(__uint_as_float(r[g * 4 + k]), s_scale[c], s_bias[c]), s_alpha[c]);
             }
             store_row4(crow, a.c_col0 + n, a.out_split, v[0], v[1], v[2], v[3]);
           }
@@ -270,7 +273,7 @@ void tc_destroy(sc_ctx* ctx) {
 static int pick_bn(int n_store) {
   // widest tile <= 192 (two CTAs x 256 TMEM columns per SM) that wastes the fewest columns
   int best = 16, best_cost = 1 << 30;
-  for (int bn = 192; bn >= 64; bn -= 16) {
+  for (int bn = 192; bn >= 32; bn -= 16) {
     const int tiles = (n_store + bn - 1) / bn;
     const int cost = tiles * bn * 4 + tiles * 128;  // padded columns + A re-reads
     if (cost < best_cost) { best_cost = cost; best = bn; }
@@ -295,13 +298,13 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.a_y0 = p.a_y0; a.a_z0 = p.a_z0;
   for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; }
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
-  a.bias = w.bias; a.alpha = w.alpha; a.out_split = p.out_split;
+  a.bias = w.bias; a.alpha = w.alpha; a.scale = w.scale; a.out_split = p.out_split;
   SC_CHECK(p.c_col0 % 4 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 4");
   const int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
   a.stages = (108 * 1024) / stage_bytes;
   if (a.stages > 4) a.stages = 4;
   SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
-  const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 2 * 192 * 4;
+  const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 3 * 192 * 4;
 
   CUtensorMap mapA, mapB;
   {

@@ -36,7 +36,7 @@ struct Arena {
   }
 };
 
-struct GemmOff { size_t kn, nk, bias, alpha; };
+struct GemmOff { size_t kn, nk, bias, alpha, scale; };
 
 static GemmOff make_gemm(Arena& A, GemmW& g, int K, int N, int Kpad, int Npad) {
   g.K = K; g.N = N; g.Kpad = Kpad; g.Npad = Npad;
@@ -45,6 +45,8 @@ static GemmOff make_gemm(Arena& A, GemmW& g, int K, int N, int Kpad, int Npad) {
   o.nk = A.alloc((size_t)Npad * Kpad);
   o.bias = A.alloc(Npad);
   o.alpha = A.alloc(Npad);
+  o.scale = A.alloc(Npad);
+  for (int n = 0; n < Npad; ++n) { A.host[o.scale + n] = 1.f; A.host[o.alpha + n] = 1.f; }
   return o;
 }
 static void set_w(Arena& A, const GemmOff& o, const GemmW& g, int k, int n, float v) {
@@ -56,7 +58,7 @@ static void set_w(Arena& A, const GemmOff& o, const GemmW& g, int k, int n, floa
   row[(k >> 6) * 128 + 64 + (k & 63)] = bf16_rn(v - bf16_to_float(hi));
 }
 static void bind(GemmW& g, const GemmOff& o, float* base) {
-  g.w_kn = base + o.kn; g.w_nk = base + o.nk; g.bias = base + o.bias; g.alpha = base + o.alpha;
+  g.w_kn = base + o.kn; g.w_nk = base + o.nk; g.bias = base + o.bias; g.alpha = base + o.alpha; g.scale = base + o.scale;
 }
 
 int derive_weights(sc_ctx* ctx, cudaStream_t st) {
@@ -66,7 +68,7 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
   SC_CUDA(cudaStreamSynchronize(st));
 
   Arena A;
-  struct BOff { size_t c1, conv[5], scale[5], shift[5], alpha[5]; GemmOff d1, d1d; } bo[3];
+  struct BOff { size_t c1, conv[5], scale[5], shift[5], alpha[5]; GemmOff d1, d1d, ctc[5]; } bo[3];
   GemmOff fc1o, fc2o;
   size_t outw, outb;
   for (int b = 0; b < 3; ++b) {
@@ -86,12 +88,21 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
       bo[b].scale[l] = A.alloc(64);
       bo[b].shift[l] = A.alloc(64);
       bo[b].alpha[l] = A.alloc(64);
+      if (l > 0) bo[b].ctc[l] = make_gemm(A, ctx->br[b].conv_tc[l], 9 * kC5Ld, co_n, 9 * kC5Ld, 64);
       for (int c = 0; c < co_n; ++c) {
         const float beta = h[B.bn[l][0] + c], gamma = h[B.bn[l][1] + c], mean = h[B.bn[l][2] + c], inv = h[B.bn[l][3] + c];
         const float s = gamma * inv;
         A.host[bo[b].scale[l] + c] = s;
         A.host[bo[b].shift[l] + c] = beta - mean * s;
         A.host[bo[b].alpha[l] + c] = h[B.alpha[l] + c];
+        if (l > 0) {
+          A.host[bo[b].ctc[l].scale + c] = s;
+          A.host[bo[b].ctc[l].bias + c] = beta - mean * s;
+          A.host[bo[b].ctc[l].alpha + c] = h[B.alpha[l] + c];
+          for (int ci = 0; ci < ci_n; ++ci)
+            for (int t = 0; t < 9; ++t)   // flipped taps (true convolution), k = tap*64 + ci
+              set_w(A, bo[b].ctc[l], ctx->br[b].conv_tc[l], t * kC5Ld + ci, c, h[B.convW[l] + ((size_t)c * ci_n + ci) * 9 + (8 - t)]);
+        }
       }
     }
     bo[b].d1 = make_gemm(A, ctx->br[b].d1, 540, 180, kFeatLd, 192);
@@ -146,6 +157,7 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
       ctx->br[b].shift[l] = base + bo[b].shift[l];
       ctx->br[b].alpha[l] = base + bo[b].alpha[l];
     }
+    for (int l = 1; l < 5; ++l) bind(ctx->br[b].conv_tc[l], bo[b].ctc[l], base);
     bind(ctx->br[b].d1, bo[b].d1, base);
     bind(ctx->br[b].d1_dense, bo[b].d1d, base);
   }
