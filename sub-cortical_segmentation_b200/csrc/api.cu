@@ -133,6 +133,16 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     ctx->gemm_backend = (int)value;
     return SC_OK;
   }
+  if (!strcmp(key, "tc_variant")) {
+    SC_CHECK(value == 1 || value == 2, SC_ERR_ARG, "sc_set_option: tc_variant must be 1 or 2");
+    ctx->tc_variant = (int)value;
+    return SC_OK;
+  }
+  if (!strcmp(key, "tc_kx_reuse")) {
+    SC_CHECK(value >= 0 && value <= 2, SC_ERR_ARG, "sc_set_option: tc_kx_reuse must be 0, 1 or 2");
+    ctx->tc_kx_reuse = (int)value;
+    return SC_OK;
+  }
   if (!strcmp(key, "profile")) {
     ctx->profile = value != 0;
     return SC_OK;

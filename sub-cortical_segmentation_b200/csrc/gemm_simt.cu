@@ -109,81 +109,79 @@ int launch_gemm(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t 
   return SC_OK;
 }
 
-// out_layer (270 -> 15) + softmax + argmax: one warp per voxel, weights in shared memory.
-__global__ void __launch_bounds__(256) out_softmax_kernel(const float* __restrict__ h2, int64_t n,
+// out_layer (270 -> 15) + softmax + argmax: one thread per voxel (each thread streams its own 1 088 B row
+// through L1 with float4 loads; the 16 KB weight matrix is read from shared memory as warp-wide broadcasts).
+__global__ void __launch_bounds__(128) out_softmax_kernel(const float* __restrict__ h2, int64_t n,
                                                           const float* __restrict__ W, const float* __restrict__ b,
                                                           float* __restrict__ proba, int32_t* __restrict__ label,
                                                           uint8_t* __restrict__ label8, const uint8_t* __restrict__ mask,
                                                           const OutGeo geo, const int use_geo) {
   __shared__ __align__(16) float sW[270 * 16];
-  for (int i = threadIdx.x; i < 270 * 16; i += 256) sW[i] = W[i];
+  for (int i = threadIdx.x; i < 270 * 16; i += 128) sW[i] = W[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t warps = (int64_t)gridDim.x * 8;
-  for (int64_t v = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); v < n; v += warps) {
-    const float* row = h2 + v * kH2Ld;
-    float z[15];
+  const int64_t v = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (v >= n) return;
+  int64_t o = v;
+  if (use_geo) {
+    const int64_t plane = (int64_t)geo.by * geo.bz;
+    const int ix = (int)(v / plane);
+    const int rem = (int)(v - (int64_t)ix * plane);
+    const int iy = rem / geo.bz, iz = rem - iy * geo.bz;
+    o = ((int64_t)(geo.x0 + ix) * geo.Y + (geo.y0 + iy)) * geo.Z + (geo.z0 + iz);
+    if (mask && mask[o] == 0) return;
+  }
+  const float4* row = reinterpret_cast<const float4*>(h2 + v * kH2Ld);
+  float z[15];
 #pragma unroll
-    for (int c = 0; c < 15; ++c) z[c] = 0.f;
-    for (int k = lane; k < 270; k += 32) {
-      const float x = __ldg(row + k);
-      const float4* w4 = reinterpret_cast<const float4*>(sW + k * 16);
-      const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-      z[0] = fmaf(x, w0.x, z[0]); z[1] = fmaf(x, w0.y, z[1]); z[2] = fmaf(x, w0.z, z[2]); z[3] = fmaf(x, w0.w, z[3]);
-      z[4] = fmaf(x, w1.x, z[4]); z[5] = fmaf(x, w1.y, z[5]); z[6] = fmaf(x, w1.z, z[6]); z[7] = fmaf(x, w1.w, z[7]);
-      z[8] = fmaf(x, w2.x, z[8]); z[9] = fmaf(x, w2.y, z[9]); z[10] = fmaf(x, w2.z, z[10]); z[11] = fmaf(x, w2.w, z[11]);
-      z[12] = fmaf(x, w3.x, z[12]); z[13] = fmaf(x, w3.y, z[13]); z[14] = fmaf(x, w3.z, z[14]);
-    }
+  for (int c = 0; c < 15; ++c) z[c] = __ldg(b + c);
+#pragma unroll 2
+  for (int k4 = 0; k4 < 68; ++k4) {
+    const float4 xv = __ldg(row + k4);
+    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-    for (int c = 0; c < 15; ++c) {
-      float s = z[c];
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      z[c] = s + __ldg(b + c);
-    }
-    float mx = z[0];
-#pragma unroll
-    for (int c = 1; c < 15; ++c) mx = fmaxf(mx, z[c]);
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < 15; ++c) { z[c] = expf(z[c] - mx); sum += z[c]; }
-    const float inv = 1.f / sum;
-    int best = 0;
-    float bp = z[0] * inv;
-#pragma unroll
-    for (int c = 0; c < 15; ++c) {
-      z[c] *= inv;
-      if (z[c] > bp) { bp = z[c]; best = c; }
-    }
-    int64_t o = v;
-    if (use_geo) {
-      const int64_t plane = (int64_t)geo.by * geo.bz;
-      const int ix = (int)(v / plane);
-      const int rem = (int)(v - (int64_t)ix * plane);
-      const int iy = rem / geo.bz, iz = rem - iy * geo.bz;
-      o = ((int64_t)(geo.x0 + ix) * geo.Y + (geo.y0 + iy)) * geo.Z + (geo.z0 + iz);
-      if (mask && mask[o] == 0) continue;
-    }
-    if (proba && lane < 15) {
-      float pv = z[0];
-#pragma unroll
-      for (int c = 1; c < 15; ++c) if (lane == c) pv = z[c];
-      proba[o * 15 + lane] = pv;
-    }
-    if (lane == 0) {
-      if (label) label[o] = best;
-      if (label8) label8[o] = (uint8_t)best;
+    for (int j = 0; j < 4; ++j) {
+      const int k = k4 * 4 + j;
+      if (k < 270) {
+        const float4* w4 = reinterpret_cast<const float4*>(sW + k * 16);
+        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+        z[0] = fmaf(x[j], w0.x, z[0]); z[1] = fmaf(x[j], w0.y, z[1]); z[2] = fmaf(x[j], w0.z, z[2]); z[3] = fmaf(x[j], w0.w, z[3]);
+        z[4] = fmaf(x[j], w1.x, z[4]); z[5] = fmaf(x[j], w1.y, z[5]); z[6] = fmaf(x[j], w1.z, z[6]); z[7] = fmaf(x[j], w1.w, z[7]);
+        z[8] = fmaf(x[j], w2.x, z[8]); z[9] = fmaf(x[j], w2.y, z[9]); z[10] = fmaf(x[j], w2.z, z[10]); z[11] = fmaf(x[j], w2.w, z[11]);
+        z[12] = fmaf(x[j], w3.x, z[12]); z[13] = fmaf(x[j], w3.y, z[13]); z[14] = fmaf(x[j], w3.z, z[14]);
+      }
     }
   }
+  float mx = z[0];
+#pragma unroll
+  for (int c = 1; c < 15; ++c) mx = fmaxf(mx, z[c]);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 15; ++c) { z[c] = expf(z[c] - mx); sum += z[c]; }
+  const float inv = 1.f / sum;
+  int best = 0;
+  float bp = z[0] * inv;
+#pragma unroll
+  for (int c = 0; c < 15; ++c) {
+    z[c] *= inv;
+    if (z[c] > bp) { bp = z[c]; best = c; }
+  }
+  if (proba) {
+#pragma unroll
+    for (int c = 0; c < 15; ++c) proba[o * 15 + c] = z[c];
+  }
+  if (label) label[o] = best;
+  if (label8) label8[o] = (uint8_t)best;
 }
 
 int launch_out_softmax(sc_ctx* ctx, const float* h2, int64_t n, float* proba, int32_t* label, uint8_t* label8,
                        const uint8_t* mask, const OutGeo* geo, cudaStream_t st) {
   if (n == 0) return SC_OK;
-  const int64_t blocks = (n + 7) / 8;
-  const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 16 ? blocks : (int64_t)ctx->sm_count * 16);
+  const int64_t blocks = (n + 127) / 128;
+  SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "out_softmax: too many rows");
+  const unsigned grid = (unsigned)blocks;
   OutGeo g = geo ? *geo : OutGeo{0, 0, 0, 1, 1, 1, 1};
   ProfScope prof(ctx, PC_OUT, st);
-  out_softmax_kernel<<<grid, 256, 0, st>>>(h2, n, ctx->out_w, ctx->out_b, proba, label, label8, mask, g, geo ? 1 : 0);
+  out_softmax_kernel<<<grid, 128, 0, st>>>(h2, n, ctx->out_w, ctx->out_b, proba, label, label8, mask, g, geo ? 1 : 0);
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
   return SC_OK;

@@ -57,6 +57,14 @@ struct TcArgs {
   const float* alpha;
   const float* scale;
   int out_split;
+  // persistent variant
+  long long num_tiles;
+  int w_resident;     // all weight k-blocks stay in shared memory for the CTA's lifetime (conv layers)
+  int kx_reuse;       // 0: one A load per tap; 1/2: one (128+2d)-pixel A load per filter row, the three column taps
+                      // are descriptor start offsets (2: with the descriptor's base_offset field set)
+  int dil;            // tap_dx step (pixels) in kx_reuse mode
+  int a_half;         // bytes reserved for one A half-stage (hi or lo), multiple of 1024
+  int a_tx;           // bytes one A half-load actually delivers (box rows * 128)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -233,6 +241,200 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).
+//   * shared-memory ring of A (+W) stages fed by TMA, decoupled from the MMA warp by full/empty mbarriers
+//   * two TMEM accumulators (columns 0.. and 256..): the epilogue of tile i overlaps the main loop of tile i+1
+//   * conv layers keep all 9 x (hi|lo) weight blocks resident in shared memory (144 KB), loaded once
+//   * optional kx-reuse: one (128+2d)-pixel A box per filter row serves the three column taps
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_half = a.bn * 128;
+  const int w_block = 2 * b_half;                               // hi | lo of one 64-wide k block of W
+  const int w_res_bytes = a.w_resident ? a.nkb * w_block : 0;
+  const int stage_bytes = 2 * a.a_half + (a.w_resident ? 0 : w_block);
+  uint8_t* sW = smem;
+  uint8_t* sStage = smem + w_res_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + a.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + a.stages;
+  uint64_t* tfull = bars + 2 * a.stages;     // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;              // [2] accumulator drained
+  uint64_t* wfull = tempty + 2;              // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_alpha = s_bias + 192;
+  float* s_scale = s_alpha + 192;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int steps_per_tile = a.kx_reuse ? 3 : a.nkb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (a.nt == 1) {   // a single column tile: epilogue constants are tile-invariant
+    for (int i = threadIdx.x; i < a.bn; i += TC_THREADS) {
+      s_bias[i] = i < a.npad ? __ldg(a.bias + i) : 0.f;
+      s_alpha[i] = i < a.npad ? __ldg(a.alpha + i) : 1.f;
+      s_scale[i] = (a.scale && i < a.npad) ? __ldg(a.scale + i) : 1.f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+      if (a.w_resident) {
+        mbar_expect_tx(wfull, (uint32_t)w_res_bytes);
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          tma_load_2d(&mapB, wfull, sW + kb * w_block, kb * 2 * TC_BK, 0);
+          tma_load_2d(&mapB, wfull, sW + kb * w_block + b_half, kb * 2 * TC_BK + TC_BK, 0);
+        }
+      }
+      uint32_t it = 0;   // global stage-use counter
+      for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        long long r = t;
+        const int n_tile = (int)(r % a.nt); r /= a.nt;
+        const int m_tile = (int)(r % a.mt); r /= a.mt;
+        const int y = (int)(r % a.Y);
+        const int z = (int)(r / a.Y);
+        const int m0 = m_tile * TC_BM, n0 = n_tile * a.bn;
+        for (int st = 0; st < steps_per_tile; ++st, ++it) {
+          const int s = it % a.stages;
+          const uint32_t use = it / a.stages;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          mbar_expect_tx(&full[s], (uint32_t)(2 * a.a_tx + (a.w_resident ? 0 : w_block)));
+          uint8_t* sp = sStage + s * stage_bytes;
+          const int kb = a.kx_reuse ? st * 3 : st;                 // first weight block of this step
+          const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
+          const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
+          tma_load_4d(&mapA, &full[s], sp, ka, px, ln, pl);
+          tma_load_4d(&mapA, &full[s], sp + a.a_half, ka + TC_BK, px, ln, pl);
+          if (!a.w_resident) {
+            tma_load_2d(&mapB, &full[s], sp + 2 * a.a_half, kb * 2 * TC_BK, n0);
+            tma_load_2d(&mapB, &full[s], sp + 2 * a.a_half + b_half, kb * 2 * TC_BK + TC_BK, n0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      if (a.w_resident) mbar_wait(wfull, 0);
+      uint32_t it = 0, ti = 0;
+      for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++ti) {
+        const uint32_t b = ti & 1, buse = ti >> 1;
+        mbar_wait(&tempty[b], (buse & 1) ^ 1);                    // accumulator b drained by the epilogue
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + b * 256;
+        for (int st = 0; st < steps_per_tile; ++st, ++it) {
+          const int s = it % a.stages;
+          mbar_wait(&full[s], (it / a.stages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sp = smem_u32(sStage + s * stage_bytes);
+          const int nsub = a.kx_reuse ? 3 : 1;
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int kb = a.kx_reuse ? st * 3 + sub : st;
+            const uint32_t shift = a.kx_reuse ? (uint32_t)(sub * a.dil) : 0u;      // operand starts `shift` pixels into the box
+            const uint64_t bo = a.kx_reuse == 2 ? ((uint64_t)(shift & 7u) << 49) : 0ull;
+            const uint64_t ah = umma_desc(sp + shift * 128) | bo, al = umma_desc(sp + a.a_half + shift * 128) | bo;
+            const uint32_t wp = a.w_resident ? smem_u32(sW + kb * w_block) : sp + 2 * a.a_half;
+            const uint64_t wh = umma_desc(wp), wl = umma_desc(wp + b_half);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t o = (uint64_t)(j * 2);
+              umma_bf16(acc, al + o, wh + o, idesc, (st | sub | j) != 0);
+              umma_bf16(acc, ah + o, wl + o, idesc, 1);
+              umma_bf16(acc, ah + o, wh + o, idesc, 1);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[b]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    uint32_t ti = 0;
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++ti) {
+      long long r = t;
+      const int n_tile = (int)(r % a.nt); r /= a.nt;
+      const int m_tile = (int)(r % a.mt); r /= a.mt;
+      const int y = (int)(r % a.Y);
+      const int z = (int)(r / a.Y);
+      const int m0 = m_tile * TC_BM, n0 = n_tile * a.bn;
+      const uint32_t b = ti & 1, buse = ti >> 1;
+      mbar_wait(&tfull[b], buse & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + q * 32 + lane;
+      float* crow = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys + (long long)m * a.ldc;
+      const bool row_ok = m < a.M;
+      for (int c0 = 0; c0 < a.bn; c0 += 16) {
+        uint32_t rr[16];
+        const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+              "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + c0 + g * 4;
+            if (n < a.n_store) {
+              float v[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = c0 + g * 4 + k;
+                float sc_, bi, al;
+                if (a.nt == 1) { sc_ = s_scale[c]; bi = s_bias[c]; al = s_alpha[c]; }
+                else {
+                  const int nn = n0 + c;
+                  const bool ok = nn < a.npad;
+                  sc_ = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f; bi = ok ? __ldg(a.bias + nn) : 0.f; al = ok ? __ldg(a.alpha + nn) : 1.f;
+                }
+                v[k] = prelu(fmaf(__uint_as_float(rr[g * 4 + k]), sc_, bi), al);
+              }
+              store_row4(crow, a.c_col0 + n, a.out_split, v[0], v[1], v[2], v[3]);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // plain fp32 [rows][576] -> split bf16 hi|lo blocks (test entry sc_dense_layer only)
 __global__ void split_rows_kernel(const float* __restrict__ in, int64_t rows, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,18 +502,38 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
   a.bias = w.bias; a.alpha = w.alpha; a.scale = w.scale; a.out_split = p.out_split;
   SC_CHECK(p.c_col0 % 4 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 4");
-  const int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
-  a.stages = (108 * 1024) / stage_bytes;
-  if (a.stages > 4) a.stages = 4;
-  SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
-  const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 3 * 192 * 4;
+  const bool persistent = ctx->tc_variant != 1;
+  const long long blocks = (long long)a.mt * a.nt * p.Y * p.Z;
+  SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
+  a.num_tiles = blocks;
+  a.w_resident = 0; a.kx_reuse = 0; a.dil = 0; a.a_half = TC_A_HALF; a.a_tx = TC_A_HALF;
+  int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
+  size_t smem = 0;
+  if (!persistent) {
+    a.stages = (108 * 1024) / stage_bytes;
+    if (a.stages > 4) a.stages = 4;
+    SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
+    smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 3 * 192 * 4;
+  } else {
+    const int budget = 226 * 1024 - 1024 - 4096;   // alignment slack + barriers / epilogue constants
+    const int w_all = a.nkb * 2 * a.bn * 128;
+    a.w_resident = (a.nt == 1 && p.ntaps == 9 && w_all + 2 * 2 * 17408 <= budget) ? 1 : 0;
+    if (a.w_resident && ctx->tc_kx_reuse && a.kpt == 1 && p.tap_dx[1] > 0 && p.tap_dx[2] == 2 * p.tap_dx[1] && p.tap_dx[1] <= 4) {
+      a.kx_reuse = ctx->tc_kx_reuse; a.dil = p.tap_dx[1]; a.a_half = 17408; a.a_tx = (TC_BM + 2 * a.dil) * 128;
+    }
+    stage_bytes = 2 * a.a_half + (a.w_resident ? 0 : 2 * a.bn * 128);
+    a.stages = (budget - (a.w_resident ? w_all : 0)) / stage_bytes;
+    if (a.stages > 6) a.stages = 6;
+    SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: tile too wide for two stages (bn=%d)", a.bn);
+    smem = 1024 + (size_t)(a.w_resident ? w_all : 0) + (size_t)a.stages * stage_bytes + (2 * a.stages + 5) * 8 + 16 + 3 * 192 * 4;
+  }
 
   CUtensorMap mapA, mapB;
   {
     // a row of kc logical columns is 2*kc bf16 (hi | lo per 64-wide block)
     cuuint64_t dims[4] = {(cuuint64_t)p.a_dims[0] * 2, (cuuint64_t)p.a_dims[1], (cuuint64_t)p.a_dims[2], (cuuint64_t)p.a_dims[3]};
     cuuint64_t strides[3] = {(cuuint64_t)p.a_strides[0] * 4, (cuuint64_t)p.a_strides[1] * 4, (cuuint64_t)p.a_strides[2] * 4};
-    cuuint32_t box[4] = {TC_BK, TC_BM, 1, 1};
+    cuuint32_t box[4] = {TC_BK, (cuuint32_t)(a.kx_reuse ? TC_BM + 2 * a.dil : TC_BM), 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = s->encode(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<float*>(p.a_base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -332,13 +554,18 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   static bool configured = false;
   if (!configured) {
     SC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    SC_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
-  SC_CHECK(smem <= 112 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
-  const long long blocks = (long long)a.mt * a.nt * p.Y * p.Z;
-  SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
   ProfScope prof(ctx, p.prof_cls, st);
-  gemm_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, st>>>(mapA, mapB, a);
+  if (!persistent) {
+    SC_CHECK(smem <= 112 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
+    gemm_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, st>>>(mapA, mapB, a);
+  } else {
+    SC_CHECK(smem <= 226 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
+    const unsigned grid = (unsigned)(blocks < ctx->sm_count ? blocks : ctx->sm_count);
+    gemm_tc_persistent_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, a);
+  }
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
