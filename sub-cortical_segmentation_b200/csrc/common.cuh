@@ -152,7 +152,7 @@ struct sc_ctx {
   int64_t* h_count = nullptr;    // pinned
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
   int tc_variant = 2;            // 1: one tile per CTA (two CTAs / SM), 2: persistent, double-buffered TMEM
-  int tc_kx_reuse = 0;           // 0 off, 1 / 2: conv A boxes shared by the three column taps (2: base_offset set)
+  int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
   bool profile = false;
   std::vector<sc::ProfEvent> prof_live;
   std::vector<sc::ProfEvent> prof_free;

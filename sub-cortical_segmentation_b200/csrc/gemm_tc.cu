@@ -65,6 +65,7 @@ struct TcArgs {
   int dil;            // tap_dx step (pixels) in kx_reuse mode
   int a_half;         // bytes reserved for one A half-stage (hi or lo), multiple of 1024
   int a_tx;           // bytes one A half-load actually delivers (box rows * 128)
+  int zero_to;        // columns [bn, zero_to) of the single column tile are written as zeros (channel padding)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -270,9 +271,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   uint64_t* tempty = tfull + 2;              // [2] accumulator drained
   uint64_t* wfull = tempty + 2;              // resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
-  float* s_alpha = s_bias + 192;
-  float* s_scale = s_alpha + 192;
+  float* s_const = reinterpret_cast<float*>(tmem_slot + 2);   // [2 buffers][bias 192 | alpha 192 | scale 192]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int steps_per_tile = a.kx_reuse ? 3 : a.nkb;
@@ -286,13 +285,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (a.nt == 1) {   // a single column tile: epilogue constants are tile-invariant
-    for (int i = threadIdx.x; i < a.bn; i += TC_THREADS) {
-      s_bias[i] = i < a.npad ? __ldg(a.bias + i) : 0.f;
-      s_alpha[i] = i < a.npad ? __ldg(a.alpha + i) : 1.f;
-      s_scale[i] = (a.scale && i < a.npad) ? __ldg(a.scale + i) : 1.f;
-    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -385,6 +377,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       const int z = (int)(r / a.Y);
       const int m0 = m_tile * TC_BM, n0 = n_tile * a.bn;
       const uint32_t b = ti & 1, buse = ti >> 1;
+      // this tile's epilogue constants -> shared memory (buffer b; its previous readers finished two tiles ago)
+      float* cb = s_const + b * 576;
+      if (ti < 2 || a.nt > 1) {
+        for (int i = threadIdx.x - 64; i < a.bn; i += 128) {
+          const int nn = n0 + i;
+          const bool ok = nn < a.npad;
+          cb[i] = ok ? __ldg(a.bias + nn) : 0.f;
+          cb[192 + i] = ok ? __ldg(a.alpha + nn) : 1.f;
+          cb[384 + i] = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(&tfull[b], buse & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int m = m0 + q * 32 + lane;
@@ -408,14 +412,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int c = c0 + g * 4 + k;
-                float sc_, bi, al;
-                if (a.nt == 1) { sc_ = s_scale[c]; bi = s_bias[c]; al = s_alpha[c]; }
-                else {
-                  const int nn = n0 + c;
-                  const bool ok = nn < a.npad;
-                  sc_ = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f; bi = ok ? __ldg(a.bias + nn) : 0.f; al = ok ? __ldg(a.alpha + nn) : 1.f;
-                }
-                v[k] = prelu(fmaf(__uint_as_float(rr[g * 4 + k]), sc_, bi), al);
+                v[k] = prelu(fmaf(__uint_as_float(rr[g * 4 + k]), cb[384 + c], cb[c]), cb[192 + c]);
               }
               store_row4(crow, a.c_col0 + n, a.out_split, v[0], v[1], v[2], v[3]);
             }
@@ -425,6 +422,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
+      if (row_ok)
+        for (int n = a.bn; n < a.zero_to; n += 4) store_row4(crow, a.c_col0 + n, a.out_split, 0.f, 0.f, 0.f, 0.f);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -494,9 +493,17 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.c_col0 = p.c_col0;
   a.nkb = p.ntaps * a.kpt;
   a.bn = pick_bn(p.n_store);
+  a.zero_to = 0;
+  if (ctx->tc_variant != 1 && p.ntaps == 9 && w.N < p.n_store && p.n_store <= 64) {
+    // conv layers: compute only the real output channels (rounded to 16), zero-fill the channel padding;
+    // the narrower resident weight block leaves room for more A stages
+    a.bn = (w.N + 15) & ~15;
+    a.zero_to = p.n_store;
+  }
   a.nt = (p.n_store + a.bn - 1) / a.bn;
+  if (a.zero_to) a.nt = 1;
   a.mt = (p.M + TC_BM - 1) / TC_BM;
-  a.Y = p.Y; a.M = p.M; a.n_store = p.n_store; a.npad = w.Npad;
+  a.Y = p.Y; a.M = p.M; a.n_store = a.zero_to ? a.bn : p.n_store; a.npad = w.Npad;
   a.a_y0 = p.a_y0; a.a_z0 = p.a_z0;
   for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; }
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
@@ -515,7 +522,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
     smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 3 * 192 * 4;
   } else {
-    const int budget = 226 * 1024 - 1024 - 4096;   // alignment slack + barriers / epilogue constants
+    const int budget = 226 * 1024 - 1024 - 6144;   // alignment slack + barriers / epilogue constants
     const int w_all = a.nkb * 2 * a.bn * 128;
     a.w_resident = (a.nt == 1 && p.ntaps == 9 && w_all + 2 * 2 * 17408 <= budget) ? 1 : 0;
     if (a.w_resident && ctx->tc_kx_reuse && a.kpt == 1 && p.tap_dx[1] > 0 && p.tap_dx[2] == 2 * p.tap_dx[1] && p.tap_dx[1] <= 4) {
@@ -525,7 +532,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.stages = (budget - (a.w_resident ? w_all : 0)) / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: tile too wide for two stages (bn=%d)", a.bn);
-    smem = 1024 + (size_t)(a.w_resident ? w_all : 0) + (size_t)a.stages * stage_bytes + (2 * a.stages + 5) * 8 + 16 + 3 * 192 * 4;
+    smem = 1024 + (size_t)(a.w_resident ? w_all : 0) + (size_t)a.stages * stage_bytes + (2 * a.stages + 5) * 8 + 16 + 6 * 192 * 4;
   }
 
   CUtensorMap mapA, mapB;
