@@ -113,7 +113,7 @@ SC_API int sc_forward_from_volume(sc_ctx* ctx, const float* vol_dev, const int32
 
 /* one dense layer of the head on its own (parity tests of the GEMM back-ends): which = 0..2 the
  * d1 layer of the axial / coronal / saggital branch (in [n][576] flattened conv5 maps, 540 used -> out [n][192],
- * columns 0..179 valid), 3 = FC1 (in [n][576] -> out [n][576], columns 0..539 written), 4 = fc_2
+ * columns 0..179 valid), 3 = FC1 (in [n][576] = the feature buffer, 192 columns per view of which 180 are used -> out [n][576], columns 0..539 valid), 4 = fc_2
  * (in [n][576] = FC1 output | atlas | zero pad -> out [n][272]).  backend: 0 SIMT fp32, 1 tcgen05 split-bf16 (three MMAs).
  * replaces: DenseLayer + PReLU, cnn_cort/nets.py:179-180, 217-218, 227-228. */
 SC_API int sc_dense_layer(sc_ctx* ctx, int which, const float* in_dev, int64_t n, float* out_dev, int backend, void* stream);

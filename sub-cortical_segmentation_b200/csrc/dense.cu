@@ -357,10 +357,9 @@ int launch_conv1_patches(sc_ctx* ctx, const float* patches, int n, const float* 
   return SC_OK;
 }
 
-// atlas prior (with the background fix of base.py:392-394) -> columns 540..575 of the h1 rows;
-// also clears the K padding (columns 540..575) of the feature rows.
+// atlas prior (with the background fix of base.py:392-394) -> columns 540..575 of the h1 rows
 __global__ void dense_atlas_kernel(const float* __restrict__ atlas, OutGeo g, int ix0, int64_t rows, float* __restrict__ h1,
-                                   float* __restrict__ feats, int split) {
+                                   int split) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= rows) return;
   const int64_t plane = (int64_t)g.by * g.bz;
@@ -378,12 +377,10 @@ __global__ void dense_atlas_kernel(const float* __restrict__ atlas, OutGeo g, in
   if (s == 0.f) a[14] = 1.f;
   a[15] = 0.f;
   float* hr = h1 + m * kH1Ld;
-  float* fr = feats + m * kFeatLd;
 #pragma unroll
   for (int q = 0; q < 9; ++q) {
     if (q < 4) store_row4(hr, 540 + 4 * q, split, a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
     else store_row4(hr, 540 + 4 * q, split, 0.f, 0.f, 0.f, 0.f);
-    store_row4(fr, 540 + 4 * q, split, 0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -547,8 +544,8 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       p.a_base = a5[v]; p.a_dims[0] = kC5Ld; p.a_dims[1] = c5; p.a_dims[2] = r5; p.a_dims[3] = g.ns;
       p.a_strides[0] = kC5Ld; p.a_strides[1] = c5 * kC5Ld; p.a_strides[2] = r5 * c5 * kC5Ld;
       p.a_y0 = v == 2 ? 0 : ix0; p.a_z0 = v == 2 ? ix0 : 0;
-      p.ldc = 0; p.out_split = tc ? 1 : 0; p.c_col0 = v * 180; p.prof_cls = PC_GEMM_D1;
-      p.n_store = 180;
+      p.ldc = 0; p.out_split = tc ? 1 : 0; p.c_col0 = v * 192; p.prof_cls = PC_GEMM_D1;
+      p.n_store = 192;   // 180 features + 12 zero columns (zero weights / bias) per view
       if (v == 0) {        // m = y, lines = x (slab), planes = z
         p.A = a5[0] + (int64_t)ix0 * p.a_ys; p.M = by; p.Y = nx; p.Z = bz;
         p.ldc = (int64_t)bz * kFeatLd; p.c_ys = plane * kFeatLd; p.c_zs = kFeatLd;
@@ -562,16 +559,18 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       p.C = feats;
       SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->br[v].d1_dense, st) : launch_gemm(ctx, p, ctx->br[v].d1_dense, st));
     }
-    { ProfScope prof(ctx, PC_ATLAS, st);
-      dense_atlas_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(atlas, og, ix0, rows, h1, feats, tc ? 1 : 0); }
-    ctx->launches++;
-    SC_CUDA(cudaGetLastError());
     GemmProblem p;
     SC_CHECK(rows < (1ll << 31), SC_ERR_ARG, "sc_segment_volume: chunk too large");
     gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)rows);
     p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
+    {  // after FC1: the tensor-core epilogue writes whole 16-column chunks (columns 540..543 as zeros)
+      ProfScope prof(ctx, PC_ATLAS, st);
+      dense_atlas_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(atlas, og, ix0, rows, h1, tc ? 1 : 0);
+    }
+    ctx->launches++;
+    SC_CUDA(cudaGetLastError());
     gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)rows);
     p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.out_split = 0;
     p.prof_cls = PC_GEMM_FC2;

@@ -271,7 +271,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   uint64_t* tempty = tfull + 2;              // [2] accumulator drained
   uint64_t* wfull = tempty + 2;              // resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
-  float* s_const = reinterpret_cast<float*>(tmem_slot + 2);   // [2 buffers][bias 192 | alpha 192 | scale 192]
+  float* s_const = reinterpret_cast<float*>(tmem_slot + 2);   // [2 buffers][bias bn | alpha bn | scale bn]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + 2 * 3 * a.bn);   // [4 epilogue warps][32 rows][80 B] store-transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int steps_per_tile = a.kx_reuse ? 3 : a.nkb;
@@ -378,22 +379,26 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       const int m0 = m_tile * TC_BM, n0 = n_tile * a.bn;
       const uint32_t b = ti & 1, buse = ti >> 1;
       // this tile's epilogue constants -> shared memory (buffer b; its previous readers finished two tiles ago)
-      float* cb = s_const + b * 576;
+      float* cb = s_const + b * 3 * a.bn;
       if (ti < 2 || a.nt > 1) {
         for (int i = threadIdx.x - 64; i < a.bn; i += 128) {
           const int nn = n0 + i;
           const bool ok = nn < a.npad;
           cb[i] = ok ? __ldg(a.bias + nn) : 0.f;
-          cb[192 + i] = ok ? __ldg(a.alpha + nn) : 1.f;
-          cb[384 + i] = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f;
+          cb[a.bn + i] = ok ? __ldg(a.alpha + nn) : 1.f;
+          cb[2 * a.bn + i] = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(&tfull[b], buse & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int m = m0 + q * 32 + lane;
-      float* crow = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys + (long long)m * a.ldc;
-      const bool row_ok = m < a.M;
+      // Each thread owns one accumulator row, but a row-per-thread store touches 32 sectors per instruction.
+      // A 2.5 KB per-warp shared tile transposes every 16-column chunk so that adjacent lanes write adjacent
+      // 16 B pieces: every global store instruction fills whole 32 B sectors.
+      float* ctile = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys;
+      const int mw = m0 + q * 32;                       // first row of this warp
+      uint8_t* stg = s_stage + q * 2560;
+      uint8_t* mine = stg + lane * 80;
       for (int c0 = 0; c0 < a.bn; c0 += 16) {
         uint32_t rr[16];
         const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -403,27 +408,66 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
               "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row_ok) {
+        if (n0 + c0 >= a.n_store) continue;             // warp-uniform
+        float v[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + c0 + g * 4;
-            if (n < a.n_store) {
-              float v[4];
+        for (int k = 0; k < 16; ++k) v[k] = prelu(fmaf(__uint_as_float(rr[k]), cb[2 * a.bn + c0 + k], cb[c0 + k]), cb[a.bn + c0 + k]);
+        const int ncol = a.c_col0 + n0 + c0;            // multiple of 16
+        if (a.out_split) {
+          uint32_t hi[8], lo[8];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int c = c0 + g * 4 + k;
-                v[k] = prelu(fmaf(__uint_as_float(rr[g * 4 + k]), cb[384 + c], cb[c]), cb[192 + c]);
-              }
-              store_row4(crow, a.c_col0 + n, a.out_split, v[0], v[1], v[2], v[3]);
+          for (int k = 0; k < 8; ++k) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
+            hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          *reinterpret_cast<uint4*>(mine) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(mine + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(mine + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(mine + 48) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          __syncwarp();
+          const int boff = (ncol >> 6) * 128 + (ncol & 63);   // bf16 offset of the hi piece inside the row
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int half = i >> 1, row = (i & 1) * 16 + (lane >> 1), part = lane & 1;
+            const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 80 + half * 32 + part * 16);
+            if (mw + row < a.M) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ctile + (long long)(mw + row) * a.ldc) + boff + half * 64 + part * 8;
+              *reinterpret_cast<uint4*>(dst) = d;
             }
           }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(mine + 16 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2), part = lane & 3;
+            const float4 d = *reinterpret_cast<const float4*>(stg + row * 80 + part * 16);
+            if (mw + row < a.M) *reinterpret_cast<float4*>(ctile + (long long)(mw + row) * a.ldc + ncol + part * 4) = d;
+          }
         }
+        __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
-      if (row_ok)
-        for (int n = a.bn; n < a.zero_to; n += 4) store_row4(crow, a.c_col0 + n, a.out_split, 0.f, 0.f, 0.f, 0.f);
+      // channel padding of the conv maps: zeros, same coalesced mapping (split layout only)
+      for (int c0 = a.bn; c0 < a.zero_to; c0 += 16) {
+        const int ncol = a.c_col0 + c0;
+        const int boff = (ncol >> 6) * 128 + (ncol & 63);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int half = i >> 1, row = (i & 1) * 16 + (lane >> 1), part = lane & 1;
+          if (mw + row < a.M) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ctile + (long long)(mw + row) * a.ldc) + boff + half * 64 + part * 8;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -504,6 +548,10 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   if (a.zero_to) a.nt = 1;
   a.mt = (p.M + TC_BM - 1) / TC_BM;
   a.Y = p.Y; a.M = p.M; a.n_store = a.zero_to ? a.bn : p.n_store; a.npad = w.Npad;
+  if (ctx->tc_variant != 1) {
+    a.n_store = (a.n_store + 15) & ~15;   // whole 16-column chunks: the caller lets pad columns be overwritten with zeros
+    SC_CHECK(p.c_col0 % 16 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 16 for the persistent kernel");
+  }
   a.a_y0 = p.a_y0; a.a_z0 = p.a_z0;
   for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; }
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
@@ -522,7 +570,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
     smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 3 * 192 * 4;
   } else {
-    const int budget = 226 * 1024 - 1024 - 6144;   // alignment slack + barriers / epilogue constants
+    const int budget = 227 * 1024 - 1024 - 128 - 16 - 2 * 3 * a.bn * 4 - 10240;   // alignment slack, barriers, epilogue constants, store tiles
     const int w_all = a.nkb * 2 * a.bn * 128;
     a.w_resident = (a.nt == 1 && p.ntaps == 9 && w_all + 2 * 2 * 17408 <= budget) ? 1 : 0;
     if (a.w_resident && ctx->tc_kx_reuse && a.kpt == 1 && p.tap_dx[1] > 0 && p.tap_dx[2] == 2 * p.tap_dx[1] && p.tap_dx[1] <= 4) {
@@ -532,7 +580,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.stages = (budget - (a.w_resident ? w_all : 0)) / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: tile too wide for two stages (bn=%d)", a.bn);
-    smem = 1024 + (size_t)(a.w_resident ? w_all : 0) + (size_t)a.stages * stage_bytes + (2 * a.stages + 5) * 8 + 16 + 6 * 192 * 4;
+    smem = 1024 + (size_t)(a.w_resident ? w_all : 0) + (size_t)a.stages * stage_bytes + (2 * a.stages + 5) * 8 + 16 + 2 * 3 * a.bn * 4 + 10240;
   }
 
   CUtensorMap mapA, mapB;
@@ -561,7 +609,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   static bool configured = false;
   if (!configured) {
     SC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    SC_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    SC_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   ProfScope prof(ctx, p.prof_cls, st);
@@ -569,7 +617,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     SC_CHECK(smem <= 112 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
     gemm_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, st>>>(mapA, mapB, a);
   } else {
-    SC_CHECK(smem <= 226 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
+    SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
     const unsigned grid = (unsigned)(blocks < ctx->sm_count ? blocks : ctx->sm_count);
     gemm_tc_persistent_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, a);
   }

@@ -232,8 +232,7 @@ int launch_branch_patches(sc_ctx* ctx, int b, const float* patches, int64_t n, f
 
 // [n][15] atlas rows -> columns 540..575 of h1 (no background fix here: the caller's in4 already has it);
 // also clears the K padding (columns 540..575) of the feature rows.
-__global__ void atlas_rows_kernel(const float* __restrict__ in4, int64_t n, float* __restrict__ h1, float* __restrict__ feats,
-                                  int split) {
+__global__ void atlas_rows_kernel(const float* __restrict__ in4, int64_t n, float* __restrict__ h1, int split) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 9) return;
   const int64_t m = i / 9;
@@ -243,7 +242,6 @@ __global__ void atlas_rows_kernel(const float* __restrict__ in4, int64_t n, floa
   for (int k = 0; k < 4; ++k)
     if (q * 4 + k < 15) a[k] = __ldg(in4 + m * 15 + q * 4 + k);
   store_row4(h1 + m * kH1Ld, 540 + 4 * q, split, a[0], a[1], a[2], a[3]);
-  store_row4(feats + m * kFeatLd, 540 + 4 * q, split, 0.f, 0.f, 0.f, 0.f);
 }
 
 int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, int64_t n,
@@ -265,19 +263,19 @@ int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float
       SC_TRY(launch_branch_patches(ctx, b, ins[b] + s * 1024, m, c5b, st));
       GemmProblem p;
       gemm_problem_rows(p, c5b, kFeatLd, kFeatLd, (int)m);
-      p.C = feats; p.ldc = kFeatLd; p.c_col0 = b * 180;
-      p.n_store = 180; p.out_split = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
+      p.C = feats; p.ldc = kFeatLd; p.c_col0 = b * 192;
+      p.n_store = 192; p.out_split = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
       SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->br[b].d1, st) : launch_gemm(ctx, p, ctx->br[b].d1, st));
     }
-    { ProfScope prof(ctx, PC_ATLAS, st);
-    atlas_rows_kernel<<<(unsigned)((m * 9 + 255) / 256), 256, 0, st>>>(in4 + s * 15, m, h1, feats, tc ? 1 : 0); }
-    ctx->launches++;
-    SC_CUDA(cudaGetLastError());
     GemmProblem p;
     gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)m);
     p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
+    { ProfScope prof(ctx, PC_ATLAS, st);   // after FC1 (whose epilogue may zero columns 540..543)
+      atlas_rows_kernel<<<(unsigned)((m * 9 + 255) / 256), 256, 0, st>>>(in4 + s * 15, m, h1, tc ? 1 : 0); }
+    ctx->launches++;
+    SC_CUDA(cudaGetLastError());
     gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)m);
     p.C = h2; p.ldc = kH2Ld; p.n_store = kH2Ld; p.out_split = 0;
     p.prof_cls = PC_GEMM_FC2;

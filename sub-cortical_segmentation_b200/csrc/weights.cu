@@ -121,8 +121,8 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
     }
   }
   fc1o = make_gemm(A, ctx->fc1, 540, 540, kFeatLd, 576);
-  for (int k = 0; k < 540; ++k)
-    for (int n = 0; n < 540; ++n) set_w(A, fc1o, ctx->fc1, k, n, h[P.fc1W + (size_t)k * 540 + n]);
+  for (int k = 0; k < 540; ++k)   // feature buffer: 192 columns per view (180 used) -> k' = view*192 + j
+    for (int n = 0; n < 540; ++n) set_w(A, fc1o, ctx->fc1, (k / 180) * 192 + (k % 180), n, h[P.fc1W + (size_t)k * 540 + n]);
   for (int n = 0; n < 576; ++n) {
     A.host[fc1o.bias + n] = n < 540 ? h[P.fc1b + n] : 0.f;
     A.host[fc1o.alpha + n] = n < 540 ? h[P.a1 + n] : 1.f;

@@ -48,6 +48,11 @@ def test_dense_layer_backends(ctx, P, which, n):
     x = np.zeros((n, width_in), np.float32)
     x[:, :k] = rng.randn(n, k).astype(np.float32)
     ref = _ref(P, which, x)
+    if which == 3:   # FC1 reads the feature buffer: 192 columns per view, 180 used
+        f = x[:, :540].copy()
+        x[:] = 0
+        for v in range(3):
+            x[:, v * 192:v * 192 + 180] = f[:, v * 180:(v + 1) * 180]
     ncol = ref.shape[1]
     scale = np.abs(ref).max()
     got0 = ctx.dense_layer(which, dev(x), 0).cpu().numpy()[:, :ncol]
