@@ -112,6 +112,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// predicated issue: every lane of the MMA warp runs the (warp-uniform) descriptor arithmetic so that it stays in
+// the uniform datapath; only the elected lane executes the tcgen05.mma itself
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -331,42 +353,43 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      if (a.w_resident) mbar_wait(wfull, 0);
-      uint32_t it = 0, ti = 0;
-      for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++ti) {
-        const uint32_t b = ti & 1, buse = ti >> 1;
-        mbar_wait(&tempty[b], (buse & 1) ^ 1);                    // accumulator b drained by the epilogue
+    // whole warp converged; one elected lane issues (see umma_bf16_elect)
+    const uint32_t leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (a.w_resident) mbar_wait(wfull, 0);
+    const uint32_t sW_u = smem_u32(sW), sStage_u = smem_u32(sStage);
+    const int nsub = a.kx_reuse ? 3 : 1;
+    uint32_t it = 0, ti = 0;
+    for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++ti) {
+      const uint32_t b = ti & 1, buse = ti >> 1;
+      mbar_wait(&tempty[b], (buse & 1) ^ 1);                    // accumulator b drained by the epilogue
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + b * 256;
+      for (int st = 0; st < steps_per_tile; ++st, ++it) {
+        const int s = it % a.stages;
+        mbar_wait(&full[s], (it / a.stages) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem_base + b * 256;
-        for (int st = 0; st < steps_per_tile; ++st, ++it) {
-          const int s = it % a.stages;
-          mbar_wait(&full[s], (it / a.stages) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sp = smem_u32(sStage + s * stage_bytes);
-          const int nsub = a.kx_reuse ? 3 : 1;
-          for (int sub = 0; sub < nsub; ++sub) {
-            const int kb = a.kx_reuse ? st * 3 + sub : st;
-            const uint32_t shift = a.kx_reuse ? (uint32_t)(sub * a.dil) : 0u;      // operand starts `shift` pixels into the box
-            const uint64_t bo = a.kx_reuse == 2 ? ((uint64_t)(shift & 7u) << 49) : 0ull;
-            const uint64_t ah = umma_desc(sp + shift * 128) | bo, al = umma_desc(sp + a.a_half + shift * 128) | bo;
-            const uint32_t wp = a.w_resident ? smem_u32(sW + kb * w_block) : sp + 2 * a.a_half;
-            const uint64_t wh = umma_desc(wp), wl = umma_desc(wp + b_half);
+        const uint32_t sp = sStage_u + s * stage_bytes;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int kb = a.kx_reuse ? st * 3 + sub : st;
+          const uint32_t shift = a.kx_reuse ? (uint32_t)(sub * a.dil) * 128u : 0u;   // operand starts `sub*dil` pixels into the box
+          const uint64_t ah = umma_desc(sp + shift), al = umma_desc(sp + a.a_half + shift);
+          const uint32_t wp = a.w_resident ? sW_u + kb * w_block : sp + 2 * a.a_half;
+          const uint64_t wh = umma_desc(wp), wl = umma_desc(wp + b_half);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t o = (uint64_t)(j * 2);
-              umma_bf16(acc, al + o, wh + o, idesc, (st | sub | j) != 0);
-              umma_bf16(acc, ah + o, wl + o, idesc, 1);
-              umma_bf16(acc, ah + o, wh + o, idesc, 1);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t o = (uint64_t)(j * 2);
+            umma_bf16_elect(acc, al + o, wh + o, idesc, (st | sub | j) != 0, leader);
+            umma_bf16_elect(acc, ah + o, wl + o, idesc, 1, leader);
+            umma_bf16_elect(acc, ah + o, wh + o, idesc, 1, leader);
           }
-          umma_commit(&empty[s]);
         }
-        umma_commit(&tfull[b]);
+        if (leader) umma_commit(&empty[s]);
+        __syncwarp();
       }
+      if (leader) umma_commit(&tfull[b]);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     uint32_t ti = 0;
