@@ -208,6 +208,7 @@ struct GemmProblem {
   int tap_dx[9], tap_dy[9];  // tap shifts in pixels / lines
   int a_y0, a_z0;       // line / plane offset of this launch inside the buffer
   int prof_cls;         // ProfClass of this launch
+  int k_used;           // conv layers: real input channels per tap (the rest of the 64-wide block is zero); 0 = all
   int n_store;          // columns written (<= w.Npad)
   int c_col0;           // first output column inside the C row (C points at the row start)
   int out_split;        // write C rows in the split bf16 hi|lo block layout (they feed a tcgen05 GEMM)
@@ -215,7 +216,7 @@ struct GemmProblem {
 int launch_gemm(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
 // plain [M][lda] row-major A, one tap: fills both the pointer form and the tensor-map form
 inline void gemm_problem_rows(GemmProblem& p, const float* A, int64_t lda, int kc, int M) {
-  p.c_col0 = 0; p.out_split = 0;
+  p.c_col0 = 0; p.out_split = 0; p.k_used = 0;
   p.A = A; p.lda = lda; p.a_ys = p.a_zs = 0; p.ntaps = 1; p.tap_off[0] = 0; p.kc = kc;
   p.M = M; p.Y = p.Z = 1; p.c_ys = p.c_zs = 0;
   p.a_base = A; p.a_dims[0] = kc; p.a_dims[1] = M; p.a_dims[2] = p.a_dims[3] = 1;

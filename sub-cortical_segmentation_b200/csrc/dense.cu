@@ -233,42 +233,53 @@ __global__ void __launch_bounds__(256) dense_conv1_nhwc_kernel(const float* __re
                                                                const float* __restrict__ w, const float* __restrict__ scale,
                                                                const float* __restrict__ shift, const float* __restrict__ alpha,
                                                                float* __restrict__ out, int outR, int outC) {
+  // 256 consecutive pixels per CTA: one thread computes one pixel's 20 channels into a shared [256][272 B] tile
+  // (pitch padded against bank conflicts), then the CTA streams the tile out with 16 B per thread, fully coalesced.
   __shared__ float sw[9 * 20], ssc[20], ssh[20], sal[20];
+  extern __shared__ __align__(16) uint8_t tile[];   // 256 * 272 B
   for (int i = threadIdx.x; i < 180; i += 256) sw[i] = w[i];
   if (threadIdx.x < 20) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; sal[threadIdx.x] = alpha[threadIdx.x]; }
+  for (int i = threadIdx.x; i < 256 * 17; i += 256) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);  // channel padding stays zero
   __syncthreads();
   const int64_t total = (int64_t)ns * outR * outC;
-  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
-    const int j = (int)(e % outC);
-    const int i = (int)((e / outC) % outR);
-    const int s = (int)(e / ((int64_t)outC * outR));
-    const float* base = vol + (int64_t)(g.s0 + sbeg + s) * g.ss;
-    float x[9];
+  for (int64_t base = (int64_t)blockIdx.x * 256; base < total; base += (int64_t)gridDim.x * 256) {
+    const int64_t e = base + threadIdx.x;
+    if (e < total) {
+      const int j = (int)(e % outC);
+      const int i = (int)((e / outC) % outR);
+      const int s = (int)(e / ((int64_t)outC * outR));
+      const float* vb = vol + (int64_t)(g.s0 + sbeg + s) * g.ss;
+      float x[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int rr = g.r0 + i + ky - 16;
+      for (int ky = 0; ky < 3; ++ky) {
+        const int rr = g.r0 + i + ky - 16;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int cc = g.c0 + j + kx - 16;
-        x[ky * 3 + kx] = (rr >= 0 && rr < g.R && cc >= 0 && cc < g.C) ? __ldg(base + (int64_t)rr * g.rs + (int64_t)cc * g.cs) : 0.f;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int cc = g.c0 + j + kx - 16;
+          x[ky * 3 + kx] = (rr >= 0 && rr < g.R && cc >= 0 && cc < g.C) ? __ldg(vb + (int64_t)rr * g.rs + (int64_t)cc * g.cs) : 0.f;
+        }
+      }
+      float* o = reinterpret_cast<float*>(tile + threadIdx.x * 272);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int co = q * 4 + k;
+          float a = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) a = fmaf(x[t], sw[t * 20 + co], a);
+          v[k] = prelu(fmaf(a, ssc[co], ssh[co]), sal[co]);
+        }
+        store_split4(o, q * 4, v[0], v[1], v[2], v[3]);
       }
     }
-    float* o = out + e * kC5Ld;
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      float v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int co = q * 4 + k;
-        float a = 0.f;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) a = fmaf(x[t], sw[t * 20 + co], a);
-        v[k] = prelu(fmaf(a, ssc[co], ssh[co]), sal[co]);
-      }
-      store_split4(o, q * 4, v[0], v[1], v[2], v[3]);
-    }
-#pragma unroll
-    for (int q = 5; q < 16; ++q) store_split4(o, q * 4, 0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int64_t npx = total - base < 256 ? total - base : 256;
+    uint4* dst = reinterpret_cast<uint4*>(out + base * kC5Ld);
+    for (int i = threadIdx.x; i < (int)npx * 16; i += 256)
+      dst[i] = *reinterpret_cast<const uint4*>(tile + (i >> 4) * 272 + (i & 15) * 16);
+    __syncthreads();
   }
 }
 
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(256) pool_nhwc_kernel(const float* __restrict_
 }
 
 static int launch_conv_tc(sc_ctx* ctx, const GemmW& w, const float* in, int inR, int inC, float* out, int outR, int outC, int ns,
-                          int dil, int prof_cls, cudaStream_t st) {
+                          int dil, int k_used, int prof_cls, cudaStream_t st) {
   GemmProblem p;
   p.A = in; p.lda = kC5Ld; p.a_ys = (int64_t)inC * kC5Ld; p.a_zs = (int64_t)inR * inC * kC5Ld;
   p.ntaps = 9; p.kc = kC5Ld;
@@ -327,6 +338,7 @@ static int launch_conv_tc(sc_ctx* ctx, const GemmW& w, const float* in, int inR,
   p.C = out; p.ldc = kC5Ld; p.c_ys = (int64_t)outC * kC5Ld; p.c_zs = (int64_t)outR * outC * kC5Ld;
   p.M = outC; p.Y = outR; p.Z = ns;
   p.n_store = 64; p.c_col0 = 0; p.out_split = 1; p.prof_cls = prof_cls;
+  p.k_used = k_used;
   return launch_gemm_tc(ctx, p, w, st);
 }
 
@@ -469,11 +481,13 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
         const int64_t blocks = (work + 255) / 256;
         const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
         ProfScope prof(ctx, PC_CONV1, st);
-        dense_conv1_nhwc_kernel<<<grid, 256, 0, st>>>(vol, g, sb, ns, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], m1, R1, C1);
+        static bool c1cfg = false;
+        if (!c1cfg) { SC_CUDA(cudaFuncSetAttribute(dense_conv1_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 272)); c1cfg = true; }
+        dense_conv1_nhwc_kernel<<<grid, 256, 256 * 272, st>>>(vol, g, sb, ns, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], m1, R1, C1);
         ctx->launches++;
         SC_CUDA(cudaGetLastError());
       }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], m1, R1, C1, m2, R2, C2, ns, 1, PC_CONV2, st));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], m1, R1, C1, m2, R2, C2, ns, 1, 20, PC_CONV2, st));
       {
         const int64_t work = (int64_t)ns * Rp1 * Cp1 * 16;
         const unsigned grid = (unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64);
@@ -481,8 +495,8 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
         pool_nhwc_kernel<<<grid, 256, 0, st>>>(m2, R2, C2, mp1, Rp1, Cp1, ns, 1);
         ctx->launches++;
       }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], mp1, Rp1, Cp1, m3, R3, C3, ns, 2, PC_CONV3, st));
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, R3, C3, m4, R4, C4, ns, 2, PC_CONV4, st));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], mp1, Rp1, Cp1, m3, R3, C3, ns, 2, 20, PC_CONV3, st));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, R3, C3, m4, R4, C4, ns, 2, 40, PC_CONV4, st));
       {
         const int64_t work = (int64_t)ns * Rp2 * Cp2 * 16;
         const unsigned grid = (unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64);
@@ -490,7 +504,7 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
         pool_nhwc_kernel<<<grid, 256, 0, st>>>(m4, R4, C4, mp2, Rp2, Cp2, ns, 2);
         ctx->launches++;
       }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, Rp2, Cp2, a5[v] + (size_t)sb * r5 * c5 * kC5Ld, r5, c5, ns, 4, PC_CONV5, st));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, Rp2, Cp2, a5[v] + (size_t)sb * r5 * c5 * kC5Ld, r5, c5, ns, 4, 40, PC_CONV5, st));
       SC_CUDA(cudaGetLastError());
     }
     for (int sb = 0; sb < g.ns && !tc; sb += group) {
@@ -544,7 +558,7 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       p.a_base = a5[v]; p.a_dims[0] = kC5Ld; p.a_dims[1] = c5; p.a_dims[2] = r5; p.a_dims[3] = g.ns;
       p.a_strides[0] = kC5Ld; p.a_strides[1] = c5 * kC5Ld; p.a_strides[2] = r5 * c5 * kC5Ld;
       p.a_y0 = v == 2 ? 0 : ix0; p.a_z0 = v == 2 ? ix0 : 0;
-      p.ldc = 0; p.out_split = tc ? 1 : 0; p.c_col0 = v * 192; p.prof_cls = PC_GEMM_D1;
+      p.ldc = 0; p.out_split = tc ? 1 : 0; p.c_col0 = v * 192; p.prof_cls = PC_GEMM_D1; p.k_used = 0;
       p.n_store = 192;   // 180 features + 12 zero columns (zero weights / bias) per view
       if (v == 0) {        // m = y, lines = x (slab), planes = z
         p.A = a5[0] + (int64_t)ix0 * p.a_ys; p.M = by; p.Y = nx; p.Z = bz;

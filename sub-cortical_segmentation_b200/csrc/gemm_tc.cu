@@ -66,6 +66,7 @@ struct TcArgs {
   int a_half;         // bytes reserved for one A half-stage (hi or lo), multiple of 1024
   int a_tx;           // bytes one A half-load actually delivers (box rows * 128)
   int zero_to;        // columns [bn, zero_to) of the single column tile are written as zeros (channel padding)
+  int ksteps;         // 16-wide k steps actually issued per 64-wide block (conv layers: ceil(Cin/16); the rest is zero padding)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -376,8 +377,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           const uint64_t ah = umma_desc(sp + shift), al = umma_desc(sp + a.a_half + shift);
           const uint32_t wp = a.w_resident ? sW_u + kb * w_block : sp + 2 * a.a_half;
           const uint64_t wh = umma_desc(wp), wl = umma_desc(wp + b_half);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < a.ksteps; ++j) {
             const uint64_t o = (uint64_t)(j * 2);
             umma_bf16_elect(acc, al + o, wh + o, idesc, (st | sub | j) != 0, leader);
             umma_bf16_elect(acc, ah + o, wl + o, idesc, 1, leader);
@@ -585,6 +585,8 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
   a.num_tiles = blocks;
   a.w_resident = 0; a.kx_reuse = 0; a.dil = 0; a.a_half = TC_A_HALF; a.a_tx = TC_A_HALF;
+  a.ksteps = 4;
+  if (p.ntaps == 9 && a.kpt == 1 && p.k_used > 0) a.ksteps = (p.k_used + 15) / 16;
   int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
   size_t smem = 0;
   if (!persistent) {
