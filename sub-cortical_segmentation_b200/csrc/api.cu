@@ -138,6 +138,11 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     ctx->tc_variant = (int)value;
     return SC_OK;
   }
+  if (!strcmp(key, "tc_nacc")) {
+    SC_CHECK(value == 1 || value == 2 || value == 4, SC_ERR_ARG, "sc_set_option: tc_nacc must be 1, 2 or 4");
+    ctx->tc_nacc = (int)value;
+    return SC_OK;
+  }
   if (!strcmp(key, "tc_kx_reuse")) {
     SC_CHECK(value >= 0 && value <= 2, SC_ERR_ARG, "sc_set_option: tc_kx_reuse must be 0, 1 or 2");
     ctx->tc_kx_reuse = (int)value;

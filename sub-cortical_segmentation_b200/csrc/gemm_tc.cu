@@ -67,6 +67,7 @@ struct TcArgs {
   int a_tx;           // bytes one A half-load actually delivers (box rows * 128)
   int zero_to;        // columns [bn, zero_to) of the single column tile are written as zeros (channel padding)
   int ksteps;         // 16-wide k steps actually issued per 64-wide block (conv layers: ceil(Cin/16); the rest is zero padding)
+  int nacc;           // independent accumulator chains per tile (narrow tiles: back-to-back MMAs into one TMEM tile serialise)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -366,6 +367,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       mbar_wait(&tempty[b], (buse & 1) ^ 1);                    // accumulator b drained by the epilogue
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + b * 256;
+      uint32_t cnt = 0;                                         // MMA groups issued for this tile
       for (int st = 0; st < steps_per_tile; ++st, ++it) {
         const int s = it % a.stages;
         mbar_wait(&full[s], (it / a.stages) & 1);
@@ -377,11 +379,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           const uint64_t ah = umma_desc(sp + shift), al = umma_desc(sp + a.a_half + shift);
           const uint32_t wp = a.w_resident ? sW_u + kb * w_block : sp + 2 * a.a_half;
           const uint64_t wh = umma_desc(wp), wl = umma_desc(wp + b_half);
-          for (int j = 0; j < a.ksteps; ++j) {
+          for (int j = 0; j < a.ksteps; ++j, ++cnt) {
             const uint64_t o = (uint64_t)(j * 2);
-            umma_bf16_elect(acc, al + o, wh + o, idesc, (st | sub | j) != 0, leader);
-            umma_bf16_elect(acc, ah + o, wl + o, idesc, 1, leader);
-            umma_bf16_elect(acc, ah + o, wh + o, idesc, 1, leader);
+            // round-robin over nacc accumulator chains (64 columns apart); the epilogue adds them up
+            const uint32_t ac = acc + (cnt % (uint32_t)a.nacc) * 64u;
+            umma_bf16_elect(ac, al + o, wh + o, idesc, cnt >= (uint32_t)a.nacc, leader);
+            umma_bf16_elect(ac, ah + o, wl + o, idesc, 1, leader);
+            umma_bf16_elect(ac, ah + o, wh + o, idesc, 1, leader);
           }
         }
         if (leader) umma_commit(&empty[s]);
@@ -431,6 +435,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
               "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int x = 1; x < a.nacc; ++x) {              // add the other accumulator chains
+          uint32_t r2[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]), "=r"(r2[8]),
+                "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
+              : "r"(taddr + (uint32_t)x * 64u));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(__uint_as_float(rr[k]) + __uint_as_float(r2[k]));
+        }
         if (n0 + c0 >= a.n_store) continue;             // warp-uniform
         float v[16];
 #pragma unroll
@@ -587,6 +602,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.w_resident = 0; a.kx_reuse = 0; a.dil = 0; a.a_half = TC_A_HALF; a.a_tx = TC_A_HALF;
   a.ksteps = 4;
   if (p.ntaps == 9 && a.kpt == 1 && p.k_used > 0) a.ksteps = (p.k_used + 15) / 16;
+  a.nacc = (a.bn <= 64 && ctx->tc_nacc > 1) ? ctx->tc_nacc : 1;
   int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
   size_t smem = 0;
   if (!persistent) {
