@@ -1,5 +1,6 @@
 // extern "C" surface of libsubcort_b200.so (declared in include/subcort_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -138,6 +139,11 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     ctx->tc_variant = (int)value;
     return SC_OK;
   }
+  if (!strcmp(key, "tc_timing")) {   // value = ProfClass index to instrument, -1 = off
+    ctx->tc_timing_cls = (int)value;
+    if (value >= 0 && !ctx->tc_timing_buf) SC_CUDA(cudaMalloc(&ctx->tc_timing_buf, sizeof(unsigned long long) * 8 * 1024));
+    return SC_OK;
+  }
   if (!strcmp(key, "tc_nacc")) {
     SC_CHECK(value == 1 || value == 2 || value == 4, SC_ERR_ARG, "sc_set_option: tc_nacc must be 1, 2 or 4");
     ctx->tc_nacc = (int)value;
@@ -163,6 +169,14 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
 
 int64_t sc_get_counter(sc_ctx* ctx, const char* key) {
   if (!ctx || !key) return -1;
+  if (!strncmp(key, "tc_timing:", 10) && ctx->tc_timing_buf) {   // "tc_timing:<index>" -> one debug counter
+    const int i = atoi(key + 10);
+    unsigned long long v = 0;
+    if (i < 0 || i >= 8 * 1024) return -1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(&v, ctx->tc_timing_buf + i, sizeof(v), cudaMemcpyDeviceToHost);
+    return (int64_t)v;
+  }
   if (!strcmp(key, "launches")) return ctx->launches;
   if (!strcmp(key, "gemm")) return ctx->gemm_backend;
   if (!strcmp(key, "adam_t")) return ctx->adam_t;

@@ -153,6 +153,8 @@ struct sc_ctx {
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
   int tc_variant = 2;            // 1: one tile per CTA (two CTAs / SM), 2: persistent, double-buffered TMEM
   int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
+  int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
+  unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
   int tc_nacc = 1;               // accumulator chains per narrow (<= 64 column) tile: 1, 2 or 4
   bool profile = false;
   std::vector<sc::ProfEvent> prof_live;

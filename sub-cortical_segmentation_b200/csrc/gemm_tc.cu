@@ -68,6 +68,7 @@ struct TcArgs {
   int zero_to;        // columns [bn, zero_to) of the single column tile are written as zeros (channel padding)
   int ksteps;         // 16-wide k steps actually issued per 64-wide block (conv layers: ceil(Cin/16); the rest is zero padding)
   int nacc;           // independent accumulator chains per tile (narrow tiles: back-to-back MMAs into one TMEM tile serialise)
+  unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -328,6 +329,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         }
       }
       uint32_t it = 0;   // global stage-use counter
+      long long dbg_acc[1] = {0};
+      const long long tstart = a.dbg ? clock64() : 0;
       for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
         long long r = t;
         const int n_tile = (int)(r % a.nt); r /= a.nt;
@@ -338,7 +341,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         for (int st = 0; st < steps_per_tile; ++st, ++it) {
           const int s = it % a.stages;
           const uint32_t use = it / a.stages;
-          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          if (use > 0) {
+            const long long c0 = a.dbg ? clock64() : 0;
+            mbar_wait(&empty[s], (use - 1) & 1);
+            if (a.dbg) dbg_acc[0] += clock64() - c0;
+          }
           mbar_expect_tx(&full[s], (uint32_t)(2 * a.a_tx + (a.w_resident ? 0 : w_block)));
           uint8_t* sp = sStage + s * stage_bytes;
           const int kb = a.kx_reuse ? st * 3 : st;                 // first weight block of this step
@@ -352,6 +359,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           }
         }
       }
+      if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = (unsigned long long)dbg_acc[0]; a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - tstart); }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -362,15 +370,21 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     const uint32_t sW_u = smem_u32(sW), sStage_u = smem_u32(sStage);
     const int nsub = a.kx_reuse ? 3 : 1;
     uint32_t it = 0, ti = 0;
+    long long w_full = 0, w_tempty = 0;
+    const long long tstart = a.dbg ? clock64() : 0;
     for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++ti) {
       const uint32_t b = ti & 1, buse = ti >> 1;
+      long long c0 = a.dbg ? clock64() : 0;
       mbar_wait(&tempty[b], (buse & 1) ^ 1);                    // accumulator b drained by the epilogue
+      if (a.dbg) w_tempty += clock64() - c0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + b * 256;
       uint32_t cnt = 0;                                         // MMA groups issued for this tile
       for (int st = 0; st < steps_per_tile; ++st, ++it) {
         const int s = it % a.stages;
+        c0 = a.dbg ? clock64() : 0;
         mbar_wait(&full[s], (it / a.stages) & 1);
+        if (a.dbg) w_full += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sp = sStage_u + s * stage_bytes;
         for (int sub = 0; sub < nsub; ++sub) {
@@ -394,9 +408,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       if (leader) umma_commit(&tfull[b]);
       __syncwarp();
     }
+    if (a.dbg && leader) {
+      a.dbg[blockIdx.x * 8 + 2] = (unsigned long long)w_full; a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
+      a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - tstart);
+    }
   } else {
     const int q = warp & 3;
     uint32_t ti = 0;
+    long long w_tfull = 0;
+    const long long tstart = a.dbg ? clock64() : 0;
     for (long long t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++ti) {
       long long r = t;
       const int n_tile = (int)(r % a.nt); r /= a.nt;
@@ -417,7 +437,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      const long long c0w = a.dbg ? clock64() : 0;
       mbar_wait(&tfull[b], buse & 1);
+      if (a.dbg) w_tfull += clock64() - c0w;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // Each thread owns one accumulator row, but a row-per-thread store touches 32 sectors per instruction.
       // A 2.5 KB per-warp shared tile transposes every 16-column chunk so that adjacent lanes write adjacent
@@ -506,6 +528,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           }
         }
       }
+    }
+    if (a.dbg && threadIdx.x == 64) {
+      a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - tstart);
+      a.dbg[blockIdx.x * 8 + 7] = ti;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -603,6 +629,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.ksteps = 4;
   if (p.ntaps == 9 && a.kpt == 1 && p.k_used > 0) a.ksteps = (p.k_used + 15) / 16;
   a.nacc = (a.bn <= 64 && ctx->tc_nacc > 1) ? ctx->tc_nacc : 1;
+  a.dbg = (ctx->tc_timing_cls == p.prof_cls) ? ctx->tc_timing_buf : nullptr;
   int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
   size_t smem = 0;
   if (!persistent) {
