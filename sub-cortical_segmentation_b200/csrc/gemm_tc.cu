@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // carve: [stages x (A hi | A lo | W hi | W lo)][barriers][tmem ptr][bias][alpha]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024 B aligned, still a shared-space pointer
   const int b_half = a.bn * 128;
   const int stage_bytes = 2 * TC_A_HALF + 2 * b_half;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
@@ -282,7 +282,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024 B aligned, still a shared-space pointer
   const int b_half = a.bn * 128;
   const int w_block = 2 * b_half;                               // hi | lo of one 64-wide k block of W
   const int w_res_bytes = a.w_resident ? a.nkb * w_block : 0;
@@ -369,6 +369,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     if (a.w_resident) mbar_wait(wfull, 0);
     const uint32_t sW_u = smem_u32(sW), sStage_u = smem_u32(sStage);
     const int nsub = a.kx_reuse ? 3 : 1;
+    const uint64_t shift_step = a.kx_reuse ? (uint64_t)(a.dil * 8) : 0ull;   // dil pixels * 128 B, in 16 B descriptor units
     uint32_t it = 0, ti = 0;
     long long w_full = 0, w_tempty = 0;
     const long long tstart = a.dbg ? clock64() : 0;
@@ -379,7 +380,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       if (a.dbg) w_tempty += clock64() - c0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + b * 256;
-      uint32_t cnt = 0;                                         // MMA groups issued for this tile
       for (int st = 0; st < steps_per_tile; ++st, ++it) {
         const int s = it % a.stages;
         c0 = a.dbg ? clock64() : 0;
@@ -387,19 +387,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         if (a.dbg) w_full += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sp = sStage_u + s * stage_bytes;
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int kb = a.kx_reuse ? st * 3 + sub : st;
-          const uint32_t shift = a.kx_reuse ? (uint32_t)(sub * a.dil) * 128u : 0u;   // operand starts `sub*dil` pixels into the box
-          const uint64_t ah = umma_desc(sp + shift), al = umma_desc(sp + a.a_half + shift);
-          const uint32_t wp = a.w_resident ? sW_u + kb * w_block : sp + 2 * a.a_half;
+        const uint64_t ah0 = umma_desc(sp), al0 = umma_desc(sp + a.a_half);
+        uint32_t wp = a.w_resident ? sW_u + (a.kx_reuse ? st * 3 : st) * w_block : sp + 2 * a.a_half;
+        uint64_t shift = 0;                                     // kx-reuse: operand starts sub*dil pixels (x 128 B >> 4) into the box
+        for (int sub = 0; sub < nsub; ++sub, wp += w_block, shift += shift_step) {
+          const uint64_t ah = ah0 + shift, al = al0 + shift;
           const uint64_t wh = umma_desc(wp), wl = umma_desc(wp + b_half);
-          for (int j = 0; j < a.ksteps; ++j, ++cnt) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
             const uint64_t o = (uint64_t)(j * 2);
-            // round-robin over nacc accumulator chains (64 columns apart); the epilogue adds them up
-            const uint32_t ac = acc + (cnt % (uint32_t)a.nacc) * 64u;
-            umma_bf16_elect(ac, al + o, wh + o, idesc, cnt >= (uint32_t)a.nacc, leader);
-            umma_bf16_elect(ac, ah + o, wl + o, idesc, 1, leader);
-            umma_bf16_elect(ac, ah + o, wh + o, idesc, 1, leader);
+            const uint32_t on = (leader && j < a.ksteps) ? 1u : 0u;
+            umma_bf16_elect(acc, al + o, wh + o, idesc, (st | sub | j) != 0, on);
+            umma_bf16_elect(acc, ah + o, wl + o, idesc, 1, on);
+            umma_bf16_elect(acc, ah + o, wh + o, idesc, 1, on);
           }
         }
         if (leader) umma_commit(&empty[s]);
@@ -457,21 +457,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
               "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        for (int x = 1; x < a.nacc; ++x) {              // add the other accumulator chains
-          uint32_t r2[16];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]), "=r"(r2[8]),
-                "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
-              : "r"(taddr + (uint32_t)x * 64u));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(__uint_as_float(rr[k]) + __uint_as_float(r2[k]));
-        }
         if (n0 + c0 >= a.n_store) continue;             // warp-uniform
         float v[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = prelu(fmaf(__uint_as_float(rr[k]), cb[2 * a.bn + c0 + k], cb[c0 + k]), cb[a.bn + c0 + k]);
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const float4 bi = *reinterpret_cast<const float4*>(cb + c0 + 4 * k4);
+          const float4 al = *reinterpret_cast<const float4*>(cb + a.bn + c0 + 4 * k4);
+          const float4 sc_ = *reinterpret_cast<const float4*>(cb + 2 * a.bn + c0 + 4 * k4);
+          v[4 * k4 + 0] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 0]), sc_.x, bi.x), al.x);
+          v[4 * k4 + 1] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 1]), sc_.y, bi.y), al.y);
+          v[4 * k4 + 2] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 2]), sc_.z, bi.z), al.z);
+          v[4 * k4 + 3] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 3]), sc_.w, bi.w), al.w);
+        }
         const int ncol = a.c_col0 + n0 + c0;            // multiple of 16
         if (a.out_split) {
           uint32_t hi[8], lo[8];
@@ -628,7 +625,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.w_resident = 0; a.kx_reuse = 0; a.dil = 0; a.a_half = TC_A_HALF; a.a_tx = TC_A_HALF;
   a.ksteps = 4;
   if (p.ntaps == 9 && a.kpt == 1 && p.k_used > 0) a.ksteps = (p.k_used + 15) / 16;
-  a.nacc = (a.bn <= 64 && ctx->tc_nacc > 1) ? ctx->tc_nacc : 1;
+  a.nacc = 1;
   a.dbg = (ctx->tc_timing_cls == p.prof_cls) ? ctx->tc_timing_buf : nullptr;
   int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
   size_t smem = 0;
