@@ -68,6 +68,7 @@ struct TcArgs {
   int zero_to;        // columns [bn, zero_to) of the single column tile are written as zeros (channel padding)
   int ksteps;         // 16-wide k steps actually issued per 64-wide block (conv layers: ceil(Cin/16); the rest is zero padding)
   int nacc;           // independent accumulator chains per tile (narrow tiles: back-to-back MMAs into one TMEM tile serialise)
+  int epi_warps;      // epilogue warps of the persistent kernel (4, 8 or 16)
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
 };
 
@@ -279,7 +280,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(576, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024 B aligned, still a shared-space pointer
@@ -297,14 +298,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   uint64_t* wfull = tempty + 2;              // resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
   float* s_const = reinterpret_cast<float*>(tmem_slot + 2);   // [2 buffers][bias bn | alpha bn | scale bn]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + 2 * 3 * a.bn);   // [4 epilogue warps][32 rows][80 B] store-transpose tiles
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + 2 * 3 * a.bn);   // [epilogue warps][32 rows][80 B] store-transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int steps_per_tile = a.kx_reuse ? 3 : a.nkb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], (blockDim.x >> 5) - 2); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -413,7 +414,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - tstart);
     }
   } else {
+    // 4*G epilogue warps: warp w reads TMEM lanes of quarter w%4 (hardware rule) and every G-th 16-column chunk.
+    // Several warps per scheduler hide the dependent-issue latency a single epilogue warp would expose.
     const int q = warp & 3;
+    const int nepi = (blockDim.x >> 5) - 2, G = nepi >> 2, grp = (warp - 2) >> 2;
+    const int epi_threads = nepi * 32;
     uint32_t ti = 0;
     long long w_tfull = 0;
     const long long tstart = a.dbg ? clock64() : 0;
@@ -428,14 +433,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       // this tile's epilogue constants -> shared memory (buffer b; its previous readers finished two tiles ago)
       float* cb = s_const + b * 3 * a.bn;
       if (ti < 2 || a.nt > 1) {
-        for (int i = threadIdx.x - 64; i < a.bn; i += 128) {
+        for (int i = threadIdx.x - 64; i < a.bn; i += epi_threads) {
           const int nn = n0 + i;
           const bool ok = nn < a.npad;
           cb[i] = ok ? __ldg(a.bias + nn) : 0.f;
           cb[a.bn + i] = ok ? __ldg(a.alpha + nn) : 1.f;
           cb[2 * a.bn + i] = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
       }
       const long long c0w = a.dbg ? clock64() : 0;
       mbar_wait(&tfull[b], buse & 1);
@@ -446,9 +451,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       // 16 B pieces: every global store instruction fills whole 32 B sectors.
       float* ctile = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys;
       const int mw = m0 + q * 32;                       // first row of this warp
-      uint8_t* stg = s_stage + q * 2560;
+      uint8_t* stg = s_stage + (warp - 2) * 2560;
       uint8_t* mine = stg + lane * 80;
-      for (int c0 = 0; c0 < a.bn; c0 += 16) {
+      for (int c0 = grp * 16; c0 < a.bn; c0 += 16 * G) {
         uint32_t rr[16];
         const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         asm volatile(
@@ -513,7 +518,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
       // channel padding of the conv maps: zeros, same coalesced mapping (split layout only)
-      for (int c0 = a.bn; c0 < a.zero_to; c0 += 16) {
+      for (int c0 = a.bn + grp * 16; c0 < a.zero_to; c0 += 16 * G) {
         const int ncol = a.c_col0 + c0;
         const int boff = (ncol >> 6) * 128 + (ncol & 63);
 #pragma unroll
@@ -625,7 +630,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.w_resident = 0; a.kx_reuse = 0; a.dil = 0; a.a_half = TC_A_HALF; a.a_tx = TC_A_HALF;
   a.ksteps = 4;
   if (p.ntaps == 9 && a.kpt == 1 && p.k_used > 0) a.ksteps = (p.k_used + 15) / 16;
-  a.nacc = 1;
+  a.nacc = 1; a.epi_warps = 4;
   a.dbg = (ctx->tc_timing_cls == p.prof_cls) ? ctx->tc_timing_buf : nullptr;
   int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
   size_t smem = 0;
@@ -635,7 +640,12 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
     smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 3 * 192 * 4;
   } else {
-    const int budget = 227 * 1024 - 1024 - 128 - 16 - 2 * 3 * a.bn * 4 - 10240;   // alignment slack, barriers, epilogue constants, store tiles
+    // epilogue warps: 16 for wide tiles, 8 for conv tiles, 4 when the resident weights leave no room (conv5)
+    int epi_warps = a.bn > 64 ? 16 : 8;
+    if (p.ntaps == 9 && a.nt == 1 && a.nkb * 2 * a.bn * 128 + 2 * 2 * 17408 + 2 * 3 * a.bn * 4 + 1168 + epi_warps * 2560 > 227 * 1024 - 1024)
+      epi_warps = 4;
+    a.epi_warps = epi_warps;
+    const int budget = 227 * 1024 - 1024 - 128 - 16 - 2 * 3 * a.bn * 4 - epi_warps * 2560;   // alignment slack, barriers, epilogue constants, store tiles
     const int w_all = a.nkb * 2 * a.bn * 128;
     a.w_resident = (a.nt == 1 && p.ntaps == 9 && w_all + 2 * 2 * 17408 <= budget) ? 1 : 0;
     if (a.w_resident && ctx->tc_kx_reuse && a.kpt == 1 && p.tap_dx[1] > 0 && p.tap_dx[2] == 2 * p.tap_dx[1] && p.tap_dx[1] <= 4) {
@@ -645,7 +655,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.stages = (budget - (a.w_resident ? w_all : 0)) / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: tile too wide for two stages (bn=%d)", a.bn);
-    smem = 1024 + (size_t)(a.w_resident ? w_all : 0) + (size_t)a.stages * stage_bytes + (2 * a.stages + 5) * 8 + 16 + 2 * 3 * a.bn * 4 + 10240;
+    smem = 1024 + (size_t)(a.w_resident ? w_all : 0) + (size_t)a.stages * stage_bytes + (2 * a.stages + 5) * 8 + 16 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
   }
 
   CUtensorMap mapA, mapB;
@@ -684,7 +694,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   } else {
     SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
     const unsigned grid = (unsigned)(blocks < ctx->sm_count ? blocks : ctx->sm_count);
-    gemm_tc_persistent_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, a);
+    gemm_tc_persistent_kernel<<<grid, 64 + 32 * a.epi_warps, smem, st>>>(mapA, mapB, a);
   }
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
