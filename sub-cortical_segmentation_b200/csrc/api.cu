@@ -144,6 +144,10 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     if (value >= 0 && !ctx->tc_timing_buf) SC_CUDA(cudaMalloc(&ctx->tc_timing_buf, sizeof(unsigned long long) * 8 * 1024));
     return SC_OK;
   }
+  if (!strcmp(key, "tc_fuse_w")) {
+    ctx->tc_fuse_w = value != 0;
+    return SC_OK;
+  }
   if (!strcmp(key, "tc_nacc")) {
     SC_CHECK(value == 1 || value == 2 || value == 4, SC_ERR_ARG, "sc_set_option: tc_nacc must be 1, 2 or 4");
     ctx->tc_nacc = (int)value;

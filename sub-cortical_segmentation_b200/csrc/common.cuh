@@ -155,6 +155,7 @@ struct sc_ctx {
   int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
+  int tc_fuse_w = 1;             // conv tiles: fold xh*wh and xh*wl into one double-width MMA
   int tc_nacc = 1;               // accumulator chains per narrow (<= 64 column) tile: 1, 2 or 4
   bool profile = false;
   std::vector<sc::ProfEvent> prof_live;

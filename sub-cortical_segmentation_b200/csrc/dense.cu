@@ -284,26 +284,24 @@ __global__ void __launch_bounds__(256) dense_conv1_nhwc_kernel(const float* __re
 }
 
 // out[s][r][c][:] = max over {0,pd}x{0,pd} of in[s][r+dr][c+dc][:]  on NHWC-64 split-bf16 maps (exact: the
-// winning pixel's hi|lo pair is copied).  One thread per (pixel, 4 channels).
+// winning pixel's hi|lo pair is copied).  grid.y = output row (s*outR + r); 16 threads per pixel, 8 B of hi and 8 B of lo each.
 __global__ void __launch_bounds__(256) pool_nhwc_kernel(const float* __restrict__ in, int inR, int inC, float* __restrict__ out,
-                                                        int outR, int outC, int ns, int pd) {
-  const int64_t total = (int64_t)ns * outR * outC * 16;
-  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
-    const int q = (int)(e & 15);
-    const int64_t px = e >> 4;
-    const int c = (int)(px % outC);
-    const int r = (int)((px / outC) % outR);
-    const int s = (int)(px / ((int64_t)outC * outR));
-    uint2 bh = make_uint2(0, 0), bl = make_uint2(0, 0);
+                                                        int outR, int outC, int pd) {
+  const int row = blockIdx.y;                  // s * outR + r
+  const int s = row / outR, r = row - s * outR;
+  const float* irow = in + ((int64_t)s * inR + r) * inC * kC5Ld;
+  float* orow = out + (int64_t)row * outC * kC5Ld;
+  const int64_t rstride = (int64_t)pd * inC * kC5Ld;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < outC * 16; e += gridDim.x * 256) {
+    const int q = e & 15, c = e >> 4;
+    uint32_t oh[2] = {0, 0}, ol[2] = {0, 0};
     float best[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int rr = r + (k >> 1) * pd, cc = c + (k & 1) * pd;
-      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(in + (((int64_t)s * inR + rr) * inC + cc) * kC5Ld) + q * 4;
-      const uint2 h = *reinterpret_cast<const uint2*>(p);
-      const uint2 l = *reinterpret_cast<const uint2*>(p + 64);
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(irow + (k >> 1) * rstride + (int64_t)(c + (k & 1) * pd) * kC5Ld) + q * 4;
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
+      const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + 64));
       const uint32_t hw[2] = {h.x, h.y}, lw[2] = {l.x, l.y};
-      uint32_t oh[2] = {bh.x, bh.y}, ol[2] = {bl.x, bl.y};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const uint32_t hb = (hw[t >> 1] >> ((t & 1) * 16)) & 0xffffu, lb = (lw[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
@@ -315,11 +313,10 @@ __global__ void __launch_bounds__(256) pool_nhwc_kernel(const float* __restrict_
           ol[t >> 1] = (ol[t >> 1] & ~m) | (lb << ((t & 1) * 16));
         }
       }
-      bh = make_uint2(oh[0], oh[1]); bl = make_uint2(ol[0], ol[1]);
     }
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out + px * kC5Ld) + q * 4;
-    *reinterpret_cast<uint2*>(o) = bh;
-    *reinterpret_cast<uint2*>(o + 64) = bl;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(orow + (int64_t)c * kC5Ld) + q * 4;
+    *reinterpret_cast<uint2*>(o) = make_uint2(oh[0], oh[1]);
+    *reinterpret_cast<uint2*>(o + 64) = make_uint2(ol[0], ol[1]);
   }
 }
 
@@ -489,19 +486,15 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       }
       SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], m1, R1, C1, m2, R2, C2, ns, 1, 20, PC_CONV2, st));
       {
-        const int64_t work = (int64_t)ns * Rp1 * Cp1 * 16;
-        const unsigned grid = (unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64);
         ProfScope prof(ctx, PC_POOL, st);
-        pool_nhwc_kernel<<<grid, 256, 0, st>>>(m2, R2, C2, mp1, Rp1, Cp1, ns, 1);
+        pool_nhwc_kernel<<<dim3((Cp1 * 16 + 255) / 256, ns * Rp1), 256, 0, st>>>(m2, R2, C2, mp1, Rp1, Cp1, 1);
         ctx->launches++;
       }
       SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], mp1, Rp1, Cp1, m3, R3, C3, ns, 2, 20, PC_CONV3, st));
       SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, R3, C3, m4, R4, C4, ns, 2, 40, PC_CONV4, st));
       {
-        const int64_t work = (int64_t)ns * Rp2 * Cp2 * 16;
-        const unsigned grid = (unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64);
         ProfScope prof(ctx, PC_POOL, st);
-        pool_nhwc_kernel<<<grid, 256, 0, st>>>(m4, R4, C4, mp2, Rp2, Cp2, ns, 2);
+        pool_nhwc_kernel<<<dim3((Cp2 * 16 + 255) / 256, ns * Rp2), 256, 0, st>>>(m4, R4, C4, mp2, Rp2, Cp2, 2);
         ctx->launches++;
       }
       SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, Rp2, Cp2, a5[v] + (size_t)sb * r5 * c5 * kC5Ld, r5, c5, ns, 4, 40, PC_CONV5, st));

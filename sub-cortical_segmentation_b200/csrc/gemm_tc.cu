@@ -69,6 +69,8 @@ struct TcArgs {
   int ksteps;         // 16-wide k steps actually issued per 64-wide block (conv layers: ceil(Cin/16); the rest is zero padding)
   int nacc;           // independent accumulator chains per tile (narrow tiles: back-to-back MMAs into one TMEM tile serialise)
   int epi_warps;      // epilogue warps of the persistent kernel (4, 8 or 16)
+  int fuse_w;         // narrow tiles: xh * [wh | wl] as ONE MMA of 2*bn columns (the epilogue adds the halves) + xl * wh:
+                      // two instead of three MMAs and A shared-memory reads per product
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
 };
 
@@ -367,6 +369,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     // whole warp converged; one elected lane issues (see umma_bf16_elect)
     const uint32_t leader = elect_one();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 2) << 17) | ((uint32_t)(TC_BM >> 4) << 24);  // N = 2*bn
     if (a.w_resident) mbar_wait(wfull, 0);
     const uint32_t sW_u = smem_u32(sW), sStage_u = smem_u32(sStage);
     const int nsub = a.kx_reuse ? 3 : 1;
@@ -398,9 +401,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           for (int j = 0; j < 4; ++j) {
             const uint64_t o = (uint64_t)(j * 2);
             const uint32_t on = (leader && j < a.ksteps) ? 1u : 0u;
-            umma_bf16_elect(acc, al + o, wh + o, idesc, (st | sub | j) != 0, on);
-            umma_bf16_elect(acc, ah + o, wl + o, idesc, 1, on);
-            umma_bf16_elect(acc, ah + o, wh + o, idesc, 1, on);
+            if (a.fuse_w) {   // [wh | wl] are adjacent row blocks of the weight stage: one descriptor, N = 2*bn
+              umma_bf16_elect(acc, ah + o, wh + o, idesc2, (st | sub | j) != 0, on);
+              umma_bf16_elect(acc, al + o, wh + o, idesc, 1, on);
+            } else {
+              umma_bf16_elect(acc, al + o, wh + o, idesc, (st | sub | j) != 0, on);
+              umma_bf16_elect(acc, ah + o, wl + o, idesc, 1, on);
+              umma_bf16_elect(acc, ah + o, wh + o, idesc, 1, on);
+            }
           }
         }
         if (leader) umma_commit(&empty[s]);
@@ -462,6 +470,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
               "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (a.fuse_w) {                                 // second half of the fused accumulator: xh * wl
+          uint32_t r2[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]), "=r"(r2[8]),
+                "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
+              : "r"(taddr + (uint32_t)a.bn));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(__uint_as_float(rr[k]) + __uint_as_float(r2[k]));
+        }
         if (n0 + c0 >= a.n_store) continue;             // warp-uniform
         float v[16];
 #pragma unroll
@@ -631,6 +650,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.ksteps = 4;
   if (p.ntaps == 9 && a.kpt == 1 && p.k_used > 0) a.ksteps = (p.k_used + 15) / 16;
   a.nacc = 1; a.epi_warps = 4;
+  a.fuse_w = (ctx->tc_variant != 1 && p.ntaps == 9 && a.nt == 1 && 2 * a.bn <= 256 && ctx->tc_fuse_w) ? 1 : 0;
   a.dbg = (ctx->tc_timing_cls == p.prof_cls) ? ctx->tc_timing_buf : nullptr;
   int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
   size_t smem = 0;
