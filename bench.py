@@ -257,6 +257,43 @@ def main():
     e2e_value = world * n_cand * e2e_steps / (float(t.item()) * 1e-3)
     agree = float((torch.from_numpy(h_lab.numpy()).cuda() == d_lab).float().mean())
 
+    # ---- secondary measurements on rank 0: K1 gather bandwidth and the patchwise (predict_proba) path ----
+    extra = {}
+    if rank == 0:
+        nb = 100000                                   # one reference test batch (test_batch_size, configuration.cfg:19)
+        xyz = ctx.nonzero_coords(d_mask)[5000000:5000000 + nb].contiguous()
+        bufs = [torch.empty((nb, 1, 32, 32), device="cuda") for _ in range(3)] + [torch.empty((nb, 15), device="cuda")]
+        import ctypes
+        def gather():
+            _native._check(ctx.lib.sc_gather_patches(ctx.h, d_vol.data_ptr(), _native._dims(d_vol.shape), d_atlas.data_ptr(), 1,
+                                                     xyz.data_ptr(), nb, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(),
+                                                     bufs[3].data_ptr(), torch.cuda.current_stream().cuda_stream))
+        for _ in range(3):
+            gather()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            gather()
+        e1.record()
+        torch.cuda.synchronize()
+        g_ms = e0.elapsed_time(e1) / 20
+        gbs = nb * 12424 / (g_ms * 1e-3) / 1e9       # 12 424 algorithmic bytes per voxel
+        extra["gather"] = {"kernel": "gather_patches_kernel", "voxels_per_call": nb, "ms_per_call": g_ms, "voxels_per_s": nb / (g_ms * 1e-3),
+                           "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                           "note": "3 x [n,1,32,32] fp32 patches + [n,15] atlas vectors written per call; outputs (1.2 GB) exceed L2"}
+        ctx.forward_from_volume(d_vol, d_atlas, xyz)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            ctx.forward_from_volume(d_vol, d_atlas, xyz)
+        e1.record()
+        torch.cuda.synchronize()
+        p_ms = e0.elapsed_time(e1) / 3
+        extra["patchwise"] = {"call": "sc_forward_from_volume (gather + predict_proba on patches, one 100 000-voxel test batch)",
+                              "ms_per_batch": p_ms, "voxels_per_s": nb / (p_ms * 1e-3),
+                              "algorithmic_tflops": nb * FLOP_PATCHWISE / (p_ms * 1e-3) / 1e12}
+        del bufs
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -300,6 +337,7 @@ def main():
                    "d2h_bytes_per_step": int(nvox), "steps": e2e_steps, "label_agreement_with_device_path": agree,
                    "call": "sc_segment_volume_host (pinned host volume + atlas + mask in, uint8 label volume out)"},
            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernels": table}
+    out.update(extra)
     if cpu_base:
         out["cpu_baseline"] = cpu_base
     print(json.dumps(out))
