@@ -161,8 +161,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--gemm", type=int, default=-1, help="-1 library default, 0 SIMT fp32, 1 tcgen05 TF32")
-    ap.add_argument("--ref-sample", type=int, default=2048)
-    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--ref-sample", type=int, default=16384)
+    ap.add_argument("--cpu-sample", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
