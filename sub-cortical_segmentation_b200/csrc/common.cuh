@@ -148,6 +148,7 @@ struct sc_ctx {
   float* out_b = nullptr;        // [16]
   sc::Workspace ws;              // inference scratch (grow-only)
   sc::Workspace ws_train;        // training scratch
+  float* train_consts = nullptr; // 64 ones | 64 zeros (identity BN epilogue of the conv1 kernel)
   int64_t* d_count = nullptr;    // device scalar for stream compaction
   int64_t* h_count = nullptr;    // pinned
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)

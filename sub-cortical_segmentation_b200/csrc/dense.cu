@@ -294,29 +294,22 @@ __global__ void __launch_bounds__(256) pool_nhwc_kernel(const float* __restrict_
   const int64_t rstride = (int64_t)pd * inC * kC5Ld;
   for (int e = blockIdx.x * 256 + threadIdx.x; e < outC * 16; e += gridDim.x * 256) {
     const int q = e & 15, c = e >> 4;
-    uint32_t oh[2] = {0, 0}, ol[2] = {0, 0};
+    // hi + lo is exact in fp32, so the maximum is taken on the reconstructed values and split again
+    // (the re-split reproduces the same represented value)
     float best[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(irow + (k >> 1) * rstride + (int64_t)(c + (k & 1) * pd) * kC5Ld) + q * 4;
       const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
       const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + 64));
-      const uint32_t hw[2] = {h.x, h.y}, lw[2] = {l.x, l.y};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const uint32_t hb = (hw[t >> 1] >> ((t & 1) * 16)) & 0xffffu, lb = (lw[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
-        const float v = __uint_as_float(hb << 16) + __uint_as_float(lb << 16);
-        if (k == 0 || v > best[t]) {
-          best[t] = v;
-          const uint32_t m = 0xffffu << ((t & 1) * 16);
-          oh[t >> 1] = (oh[t >> 1] & ~m) | (hb << ((t & 1) * 16));
-          ol[t >> 1] = (ol[t >> 1] & ~m) | (lb << ((t & 1) * 16));
-        }
-      }
+      const float v0 = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+      const float v1 = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+      const float v2 = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+      const float v3 = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+      if (k == 0) { best[0] = v0; best[1] = v1; best[2] = v2; best[3] = v3; }
+      else { best[0] = fmaxf(best[0], v0); best[1] = fmaxf(best[1], v1); best[2] = fmaxf(best[2], v2); best[3] = fmaxf(best[3], v3); }
     }
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(orow + (int64_t)c * kC5Ld) + q * 4;
-    *reinterpret_cast<uint2*>(o) = make_uint2(oh[0], oh[1]);
-    *reinterpret_cast<uint2*>(o + 64) = make_uint2(ol[0], ol[1]);
+    store_split4(orow + (int64_t)c * kC5Ld, q * 4, best[0], best[1], best[2], best[3]);
   }
 }
 

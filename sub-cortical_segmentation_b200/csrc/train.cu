@@ -368,6 +368,111 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict
   }
 }
 
+
+// ---- 3x3 valid convolution over small planar maps (training forward and dgrad) ----------------------------------
+// Same register tiling as the dense-path conv kernel (320 threads = 64 pixel groups of 8 columns x 5 channel groups,
+// input channels staged through shared memory in chunks of 10), but the 64 pixel groups are spread over
+// NS samples x TH rows x SEG column segments so that the 3x3 .. 30x30 training maps do not waste a 16x32 tile.
+template <int CIN, int COUT, int NS, int TH, int SEG>
+struct TConvCfg {
+  static constexpr int CHUNK = 10, CO_T = COUT / 5;
+  static constexpr int IH = TH + 2, IW = SEG * 8 + 4, IWP = IW;   // IW == 4 (mod 8): conflict-free LDS.128
+  static constexpr int IN_FLOATS = CHUNK * NS * IH * IWP, W_FLOATS = CHUNK * 9 * COUT;
+  static constexpr size_t SMEM = (size_t)(IN_FLOATS + W_FLOATS) * sizeof(float);
+  static_assert(NS * TH * SEG == 64, "64 pixel groups per CTA");
+};
+
+template <int CIN, int COUT, int NS, int TH, int SEG>
+__global__ void __launch_bounds__(320) train_conv_kernel(const float* __restrict__ in, int inR, int inLd, float* __restrict__ out,
+                                                         int outR, int outLd, const float* __restrict__ w, int n) {
+  using Cfg = TConvCfg<CIN, COUT, NS, TH, SEG>;
+  extern __shared__ __align__(16) float smem[];
+  float* s_in = smem;
+  float* s_w = smem + Cfg::IN_FLOATS;
+  const int tid = threadIdx.x;
+  const int cg = tid >> 6, pg = tid & 63;
+  const int seg = pg % SEG, prow = (pg / SEG) % TH, smp = pg / (SEG * TH);
+  const int tr0 = blockIdx.y * TH, tc0 = blockIdx.x * SEG * 8, s0 = blockIdx.z * NS;
+  float acc[8][Cfg::CO_T];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int c = 0; c < Cfg::CO_T; ++c) acc[p][c] = 0.f;
+  for (int ci0 = 0; ci0 < CIN; ci0 += Cfg::CHUNK) {
+    __syncthreads();
+    for (int e = tid; e < Cfg::CHUNK * NS * Cfg::IH * Cfg::IW; e += 320) {
+      const int col = e % Cfg::IW;
+      const int row = (e / Cfg::IW) % Cfg::IH;
+      const int sm = (e / (Cfg::IW * Cfg::IH)) % NS;
+      const int ci = e / (Cfg::IW * Cfg::IH * NS);
+      const int gr = tr0 + row, gc = tc0 + col, gs = s0 + sm;
+      float v = 0.f;
+      if (gs < n && gr < inR && gc < inLd) v = __ldg(in + (((int64_t)gs * CIN + ci0 + ci) * inR + gr) * inLd + gc);
+      s_in[((ci * NS + sm) * Cfg::IH + row) * Cfg::IWP + col] = v;
+    }
+    for (int e = tid; e < Cfg::W_FLOATS / 4; e += 320)
+      reinterpret_cast<float4*>(s_w)[e] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)ci0 * 9 * COUT) + e);
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < Cfg::CHUNK; ++ci) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        float x[12];
+        const float4* src = reinterpret_cast<const float4*>(s_in + ((ci * NS + smp) * Cfg::IH + prow + ky) * Cfg::IWP + seg * 8);
+#pragma unroll
+        for (int v = 0; v < 3; ++v) { const float4 t = src[v]; x[v * 4] = t.x; x[v * 4 + 1] = t.y; x[v * 4 + 2] = t.z; x[v * 4 + 3] = t.w; }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          float wv[Cfg::CO_T];
+          const float4* wsrc = reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * COUT + cg * Cfg::CO_T);
+#pragma unroll
+          for (int v = 0; v < Cfg::CO_T / 4; ++v) { const float4 t = wsrc[v]; wv[v * 4] = t.x; wv[v * 4 + 1] = t.y; wv[v * 4 + 2] = t.z; wv[v * 4 + 3] = t.w; }
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+#pragma unroll
+            for (int c = 0; c < Cfg::CO_T; ++c) acc[p][c] = fmaf(x[kx + p], wv[c], acc[p][c]);
+        }
+      }
+    }
+  }
+  const int orow = tr0 + prow, ocol = tc0 + seg * 8, os = s0 + smp;
+  if (os >= n || orow >= outR || ocol >= outLd) return;
+#pragma unroll
+  for (int c = 0; c < Cfg::CO_T; ++c) {
+    float* o = out + (((int64_t)os * COUT + cg * Cfg::CO_T + c) * outR + orow) * outLd + ocol;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
+  }
+}
+
+template <int CIN, int COUT, int NS, int TH, int SEG>
+static int launch_tconv(sc_ctx* ctx, const float* in, int inR, int inLd, float* out, int outR, int outLd, const float* w, int n,
+                        int cls, cudaStream_t st) {
+  using Cfg = TConvCfg<CIN, COUT, NS, TH, SEG>;
+  auto kern = train_conv_kernel<CIN, COUT, NS, TH, SEG>;
+  static bool configured = false;
+  if (!configured) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); configured = true; }
+  dim3 grid((outLd + SEG * 8 - 1) / (SEG * 8), (outR + TH - 1) / TH, (n + NS - 1) / NS);
+  ProfScope prof(ctx, cls, st);
+  kern<<<grid, 320, Cfg::SMEM, st>>>(in, inR, inLd, out, outR, outLd, w, n);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// dispatch by (cin, cout, output size): forward conv2..conv5 and the four dgrads
+static int train_conv(sc_ctx* ctx, int cin, int cout, const float* in, int inR, int inLd, float* out, int outR, int outLd,
+                      const float* w, int n, int cls, cudaStream_t st) {
+  if (cin == 20 && cout == 20) return launch_tconv<20, 20, 1, 16, 4>(ctx, in, inR, inLd, out, outR, outLd, w, n, cls, st);
+  if (cin == 20 && cout == 40) return launch_tconv<20, 40, 2, 16, 2>(ctx, in, inR, inLd, out, outR, outLd, w, n, cls, st);
+  if (cin == 40 && cout == 40) return launch_tconv<40, 40, 2, 16, 2>(ctx, in, inR, inLd, out, outR, outLd, w, n, cls, st);
+  if (cin == 40 && cout == 60) return launch_tconv<40, 60, 16, 4, 1>(ctx, in, inR, inLd, out, outR, outLd, w, n, cls, st);
+  if (cin == 60 && cout == 40) return launch_tconv<60, 40, 8, 8, 1>(ctx, in, inR, inLd, out, outR, outLd, w, n, cls, st);
+  if (cin == 40 && cout == 20) return launch_tconv<40, 20, 2, 16, 2>(ctx, in, inR, inLd, out, outR, outLd, w, n, cls, st);
+  set_error("train_conv: unsupported channel pair %d -> %d", cin, cout);
+  return SC_ERR_ARG;
+}
+
 // ---- optimiser -------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             const uint8_t* __restrict__ trainable, int n, float a_t, float b1, float b2, float eps, float gscale,
@@ -474,12 +579,13 @@ int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, cons
 
   SC_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * SC_PARAM_FLOATS, st));
   SC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  SC_CUDA(cudaMemsetAsync(zeros, 0, 64 * 4, st));
-  {
-    float h1[64];
-    for (int i = 0; i < 64; ++i) h1[i] = 1.f;
-    SC_CUDA(cudaMemcpyAsync(ones, h1, sizeof(h1), cudaMemcpyHostToDevice, st));
+  if (!ctx->train_consts) {
+    SC_CUDA(cudaMalloc(&ctx->train_consts, 128 * sizeof(float)));
+    float h1[128];
+    for (int i = 0; i < 128; ++i) h1[i] = i < 64 ? 1.f : 0.f;
+    SC_CUDA(cudaMemcpy(ctx->train_consts, h1, sizeof(h1), cudaMemcpyHostToDevice));
   }
+  ones = ctx->train_consts; zeros = ctx->train_consts + 64;
   if (masks_in) SC_CUDA(cudaMemcpyAsync(masks, masks_in, (size_t)n * 2700, cudaMemcpyDeviceToDevice, st));
   else { make_masks_kernel<<<ew_grid((int64_t)n * 2700), 256, 0, st>>>(masks, (int64_t)n * 2700, seed); ctx->launches++; }
 
@@ -493,11 +599,7 @@ int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, cons
       if (l == 0) {
         SC_TRY(launch_conv1_patches(ctx, ins[b], n, bb[b].wf[0], ones, zeros, ones, bb[b].X[0], st));
       } else {
-        ConvArgs a;
-        a.in = bb[b].A[l - 1]; a.inR = kInH[l]; a.inLd = kInLd[l];
-        a.out = bb[b].X[l]; a.outR = kH[l]; a.outC = kH[l]; a.outLd = kLd[l];
-        a.w = bb[b].wf[l]; a.scale = ones; a.shift = zeros; a.alpha = ones; a.ns = n; a.round_out = 0;
-        SC_TRY(launch_conv3x3(ctx, ci, co, a, PC_TRAIN_FWD, st));
+        SC_TRY(train_conv(ctx, ci, co, bb[b].A[l - 1], kInH[l], kInLd[l], bb[b].X[l], kH[l], kLd[l], bb[b].wf[l], n, PC_TRAIN_FWD, st));
       }
       SC_CUDA(cudaMemsetAsync(sums, 0, 64 * 3 * sizeof(double), st));
       bn_stats_kernel<<<dim3(co, 32), 256, 0, st>>>(bb[b].X[l], n, co, kH[l], kH[l], kLd[l], sums);
@@ -571,11 +673,7 @@ int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, cons
       ctx->launches += 4;
       if (l > 0) {
         // dgrad: d(input) = valid conv of the zero-padded dx with the raw taps, channel roles swapped
-        ConvArgs a;
-        a.in = dXpad; a.inR = H + 4; a.inLd = pld2;
-        a.out = dA; a.outR = kInH[l]; a.outC = kInH[l]; a.outLd = kInLd[l];
-        a.w = bb[b].wd[l]; a.scale = ones; a.shift = zeros; a.alpha = ones; a.ns = n; a.round_out = 0;
-        SC_TRY(launch_conv3x3(ctx, co, ci, a, PC_TRAIN_BWD, st));
+        SC_TRY(train_conv(ctx, co, ci, dXpad, H + 4, pld2, dA, kInH[l], kInLd[l], bb[b].wd[l], n, PC_TRAIN_BWD, st));
       }
     }
   }
