@@ -369,6 +369,92 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict
 }
 
 
+
+// wgrad, register-tiled: one thread owns 4 output channels x 1 input channel x 9 taps (36 accumulators) and walks the
+// pixels of its CTA's samples four at a time (sliding 6-wide input window per filter row: 22 shared loads per 144 FMA).
+// CTA = (COUT/4) x 20 threads, one tile of 20 input channels, `spc` samples; one atomicAdd per accumulator at the end.
+template <int COUT>
+__global__ void __launch_bounds__((COUT / 4) * 20) conv_wgrad_tiled_kernel(const float* __restrict__ in, int Cin, int inH, int inLd,
+                                                                          const float* __restrict__ dx, int H, int ld, int n, int spc,
+                                                                          float* __restrict__ gW) {
+  extern __shared__ __align__(16) float sm[];
+  const int plane = (inH + 1) * inLd + 9;               // odd stride: the 20 channel planes fall into different banks
+  const int planep = plane | 1;
+  float* in_s = sm;                                      // [20][planep]
+  float* dx_s = sm + ((20 * planep + 3) & ~3);           // [H*H][COUT]
+  const int nthr = (COUT / 4) * 20;
+  const int tid = threadIdx.x, cog = tid / 20, ci = tid - cog * 20;
+  const int ci0 = blockIdx.x * 20;
+  const int s_begin = blockIdx.y * spc, s_end = min(n, s_begin + spc);
+  float acc[4][9];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
+  for (int s = s_begin; s < s_end; ++s) {
+    __syncthreads();
+    for (int e = tid; e < 20 * planep; e += nthr) {
+      const int c = e / planep, off = e - c * planep;
+      const int r = off / inLd, col = off - r * inLd;
+      float v = 0.f;
+      if (r < inH && col < inH) v = __ldg(in + (((int64_t)s * Cin + ci0 + c) * inH + r) * inLd + col);
+      in_s[e] = v;
+    }
+    for (int e = tid; e < COUT * H * H; e += nthr) {
+      const int x = e % H, y = (e / H) % H, co = e / (H * H);
+      dx_s[(y * H + x) * COUT + co] = __ldg(dx + (((int64_t)s * COUT + co) * H + y) * ld + x);
+    }
+    __syncthreads();
+    const float* ip = in_s + ci * planep;
+    for (int y = 0; y < H; ++y) {
+      for (int x0 = 0; x0 < H; x0 += 4) {
+        float d[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (x0 + j < H) v = *reinterpret_cast<const float4*>(dx_s + (y * H + x0 + j) * COUT + cog * 4);
+          d[j][0] = v.x; d[j][1] = v.y; d[j][2] = v.z; d[j][3] = v.w;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          float row[6];
+          const float* rp = ip + (y + 2 - ky) * inLd + x0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) row[k] = rp[k];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[c][ky * 3 + kx] = fmaf(d[j][c], row[j + 2 - kx], acc[c][ky * 3 + kx]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(&gW[((int64_t)(cog * 4 + c) * Cin + ci0 + ci) * 9 + t], acc[c][t]);
+}
+
+template <int COUT>
+static int launch_wgrad_tiled(sc_ctx* ctx, const float* in, int Cin, int inH, int inLd, const float* dx, int H, int ld, int n,
+                              float* gW, cudaStream_t st) {
+  const int planep = ((inH + 1) * inLd + 9) | 1;
+  const size_t smem = ((size_t)((20 * planep + 3) & ~3) + (size_t)COUT * H * H) * sizeof(float);
+  auto kern = conv_wgrad_tiled_kernel<COUT>;
+  static size_t configured = 0;
+  if (smem > configured) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+  int spc = 2048 / (H * H);                 // ~2 000 pixels of reduction per CTA
+  if (spc < 1) spc = 1;
+  dim3 grid(Cin / 20, (n + spc - 1) / spc);
+  ProfScope prof(ctx, PC_TRAIN_BWD, st);
+  kern<<<grid, (COUT / 4) * 20, smem, st>>>(in, Cin, inH, inLd, dx, H, ld, n, spc, gW);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
 // ---- 3x3 valid convolution over small planar maps (training forward and dgrad) ----------------------------------
 // Same register tiling as the dense-path conv kernel (320 threads = 64 pixel groups of 8 columns x 5 channel groups,
 // input channels staged through shared memory in chunks of 10), but the 64 pixel groups are spread over
@@ -668,9 +754,18 @@ int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, cons
                                                                         l > 0 ? dXpad : nullptr, pld2);
       // wgrad against this layer's input (the previous activation, or the patches for conv1)
       const float* lin = l == 0 ? ins[b] : bb[b].A[l - 1];
-      int zc = n < 32 ? n : 32;
-      conv_wgrad_kernel<<<dim3(co, ci, zc), 128, 0, st>>>(lin, ci, kInH[l], kInLd[l], dX, co, H, H, ld, n, G + Ob.convW[l]);
-      ctx->launches += 4;
+      if (l == 0) {
+        int zc = n < 32 ? n : 32;
+        conv_wgrad_kernel<<<dim3(co, ci, zc), 128, 0, st>>>(lin, ci, kInH[l], kInLd[l], dX, co, H, H, ld, n, G + Ob.convW[l]);
+        ctx->launches++;
+      } else if (co == 20) {
+        SC_TRY(launch_wgrad_tiled<20>(ctx, lin, ci, kInH[l], kInLd[l], dX, H, ld, n, G + Ob.convW[l], st));
+      } else if (co == 40) {
+        SC_TRY(launch_wgrad_tiled<40>(ctx, lin, ci, kInH[l], kInLd[l], dX, H, ld, n, G + Ob.convW[l], st));
+      } else {
+        SC_TRY(launch_wgrad_tiled<60>(ctx, lin, ci, kInH[l], kInLd[l], dX, H, ld, n, G + Ob.convW[l], st));
+      }
+      ctx->launches += 3;
       if (l > 0) {
         // dgrad: d(input) = valid conv of the zero-padded dx with the raw taps, channel roles swapped
         SC_TRY(train_conv(ctx, co, ci, dXpad, H + 4, pld2, dA, kInH[l], kInLd[l], bb[b].wd[l], n, PC_TRAIN_BWD, st));
