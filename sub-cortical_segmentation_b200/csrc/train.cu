@@ -445,7 +445,10 @@ static int launch_wgrad_tiled(sc_ctx* ctx, const float* in, int Cin, int inH, in
   auto kern = conv_wgrad_tiled_kernel<COUT>;
   static size_t configured = 0;
   if (smem > configured) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
-  int spc = 2048 / (H * H);                 // ~2 000 pixels of reduction per CTA
+  // samples per CTA: ~2 000 pixels of reduction each, but never fewer than ~2 CTAs per SM
+  int spc = 2048 / (H * H);
+  const int fill = (n * (Cin / 20) + 2 * ctx->sm_count - 1) / (2 * ctx->sm_count);
+  if (spc > fill) spc = fill;
   if (spc < 1) spc = 1;
   dim3 grid(Cin / 20, (n + spc - 1) / spc);
   ProfScope prof(ctx, PC_TRAIN_BWD, st);
