@@ -82,6 +82,11 @@ SC_API int sc_get_params(sc_ctx* ctx, float* blob_host, int64_t n_floats);
 SC_API int sc_nonzero_coords(sc_ctx* ctx, const void* vol_dev, int elem_bytes, const int32_t dims[3],
                       int32_t* xyz_dev, int64_t capacity, int64_t* n_out_host, void* stream);
 
+/* replaces: scipy.ndimage.binary_dilation(mask, iterations=10) of the crop path (base.py:369): default
+ * 6-connected structuring element, zero border.  mask/out uint8 [X][Y][Z] (0 / non-zero in, 0 / 1 out), out != mask. */
+SC_API int sc_dilate_mask(sc_ctx* ctx, const uint8_t* mask_dev, const int32_t dims[3], int iterations,
+                   uint8_t* out_dev, void* stream);
+
 /* ---- orthogonal patch gather ---------------------------------------------------------
  * replaces: get_patches x3 views (base.py:272-308) + the atlas vector with background fix
  * (base.py:387-394) of one load_patch_batch batch.  Outputs are [n][1][32][32] float32 per

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "sc_load_weights": (ctypes.c_int, [_vp, _vp, _c_i64]),
     "sc_get_params": (ctypes.c_int, [_vp, _vp, _c_i64]),
     "sc_nonzero_coords": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _c_i64, _p(_c_i64), _vp]),
+    "sc_dilate_mask": (ctypes.c_int, [_vp, _vp, _p(_c_i32), ctypes.c_int, _vp, _vp]),
     "sc_gather_patches": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, ctypes.c_int, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp]),
     "sc_gather_center_labels": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _c_i64, _vp, _vp]),
     "sc_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp]),
@@ -158,6 +159,13 @@ class Context(object):
         if n.value:
             _check(self.lib.sc_nonzero_coords(self.h, _ptr(vol), eb, _dims(vol.shape), _ptr(xyz), n.value, None, _stream()))
         return xyz
+
+    def dilate_mask(self, mask, iterations):
+        """uint8 CUDA mask [X,Y,Z] -> scipy.ndimage.binary_dilation(mask, iterations=iterations) as uint8 0/1"""
+        import torch
+        out = torch.empty_like(mask)
+        _check(self.lib.sc_dilate_mask(self.h, _ptr(mask), _dims(mask.shape), int(iterations), _ptr(out), _stream()))
+        return out
 
     def gather_patches(self, vol, xyz, atlas=None, bg_fix=True, views=(True, True, True)):
         import torch

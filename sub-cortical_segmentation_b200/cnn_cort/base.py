@@ -139,8 +139,10 @@ def candidate_mask(image, dir_name, options):
     if crop is None:
         crop = str(options.get('crop', 'True')).strip().lower() in ('true', '1', 'yes', 'on')
     if crop:
-        mask_atlas = nib.load(os.path.join(dir_name, 'tmp', 'MNI_subcortical_mask.nii.gz'))
-        return ndimage.binary_dilation(mask_atlas.get_data(), iterations=10).astype(bool)
+        mask_atlas = nib.load(os.path.join(dir_name, 'tmp', 'MNI_subcortical_mask.nii.gz')).get_data()
+        ctx = get_context(options.get('device'))
+        m = _dev(np.ascontiguousarray(mask_atlas != 0).view(np.uint8), ctx.device)
+        return ctx.dilate_mask(m, 10).cpu().numpy().astype(bool)   # == ndimage.binary_dilation(mask, iterations=10)
     return image.astype(bool)
 
 

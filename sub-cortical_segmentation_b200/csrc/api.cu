@@ -242,6 +242,13 @@ int sc_nonzero_coords(sc_ctx* ctx, const void* vol_dev, int elem_bytes, const in
   return launch_nonzero(ctx, vol_dev, elem_bytes, dims, xyz_dev, capacity, n_out_host, (cudaStream_t)stream);
 }
 
+int sc_dilate_mask(sc_ctx* ctx, const uint8_t* mask_dev, const int32_t dims[3], int iterations, uint8_t* out_dev, void* stream) {
+  SC_CHECK(ctx && mask_dev && out_dev && mask_dev != out_dev, SC_ERR_ARG, "sc_dilate_mask: bad argument");
+  SC_TRY(check_dims(dims, "sc_dilate_mask"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return launch_dilate(ctx, mask_dev, dims, iterations, out_dev, (cudaStream_t)stream);
+}
+
 int sc_gather_patches(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3], const float* atlas_dev, int bg_fix,
                       const int32_t* xyz_dev, int64_t n, float* axial_dev, float* coronal_dev, float* saggital_dev,
                       float* atlas_out_dev, void* stream) {

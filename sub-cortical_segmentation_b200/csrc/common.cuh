@@ -190,6 +190,7 @@ int launch_center_labels(sc_ctx* ctx, const uint8_t* lab, const int32_t* dims, c
                          uint8_t* y, cudaStream_t st);
 int launch_nonzero(sc_ctx* ctx, const void* vol, int elem_bytes, const int32_t* dims, int32_t* xyz,
                    int64_t capacity, int64_t* n_out_host, cudaStream_t st);
+int launch_dilate(sc_ctx* ctx, const uint8_t* mask, const int32_t* dims, int iterations, uint8_t* out, cudaStream_t st);
 int launch_scatter(sc_ctx* ctx, const int32_t* xyz, int64_t n, const int32_t* label, const float* proba,
                    const int32_t* dims, uint8_t* label_vol, float* proba_vol, cudaStream_t st);
 

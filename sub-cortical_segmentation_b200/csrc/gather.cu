@@ -270,6 +270,45 @@ int launch_nonzero(sc_ctx* ctx, const void* vol, int elem_bytes, const int32_t* 
   return SC_OK;
 }
 
+// one iteration of scipy.ndimage.binary_dilation with the default (6-connected cross) structuring element and
+// border_value 0: out = in | any face neighbour.  Ten iterations = the reference's crop mask (base.py:369).
+__global__ void dilate6_kernel(const uint8_t* __restrict__ in, int X, int Y, int Z, uint8_t* __restrict__ out) {
+  const int64_t total = (int64_t)X * Y * Z;
+  const int64_t YZ = (int64_t)Y * Z;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(v / YZ);
+    const int r = (int)(v - (int64_t)x * YZ);
+    const int y = r / Z, z = r - y * Z;
+    uint8_t m = in[v];
+    if (!m) {
+      m = (x > 0 && in[v - YZ]) || (x + 1 < X && in[v + YZ]) || (y > 0 && in[v - Z]) || (y + 1 < Y && in[v + Z]) ||
+          (z > 0 && in[v - 1]) || (z + 1 < Z && in[v + 1]);
+    }
+    out[v] = m ? 1 : 0;
+  }
+}
+
+int launch_dilate(sc_ctx* ctx, const uint8_t* mask, const int32_t* dims, int iterations, uint8_t* out, cudaStream_t st) {
+  const int64_t total = (int64_t)dims[0] * dims[1] * dims[2];
+  SC_CHECK(iterations >= 0, SC_ERR_ARG, "sc_dilate_mask: negative iteration count");
+  if (iterations == 0) {
+    SC_CUDA(cudaMemcpyAsync(out, mask, total, cudaMemcpyDeviceToDevice, st));
+    return SC_OK;
+  }
+  SC_TRY(ensure_ws(ctx->ws, (size_t)total + 256));
+  uint8_t* tmp = reinterpret_cast<uint8_t*>(ctx->ws.ptr);
+  const unsigned grid = (unsigned)((total + 255) / 256 < (int64_t)ctx->sm_count * 32 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 32);
+  const uint8_t* src = mask;
+  for (int i = 0; i < iterations; ++i) {   // ping-pong so that the last iteration lands in `out`
+    uint8_t* dst = ((iterations - 1 - i) & 1) ? tmp : out;
+    dilate6_kernel<<<grid, 256, 0, st>>>(src, dims[0], dims[1], dims[2], dst);
+    ctx->launches++;
+    src = dst;
+  }
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
 __global__ void scatter_kernel(const int32_t* __restrict__ xyz, int64_t n, const int32_t* __restrict__ label,
                                const float* __restrict__ proba, int Y, int Z, uint8_t* __restrict__ label_vol,
                                float* __restrict__ proba_vol) {

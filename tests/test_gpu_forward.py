@@ -174,3 +174,25 @@ def test_test_scan_end_to_end(ctx, tmp_path, weights_path):
     options['post_process'] = 'True'; options['out_probabilities'] = 'False'; options['inference'] = 'dense'
     base.test_scan(net, t1_names[0], options)
     assert os.path.exists(os.path.join(d, 'out_subcortical_seg_prec.nii.gz'))
+
+
+def test_full_size_volume_properties(ctx):
+    """BASELINE size (256^3, every voxel): size-independent properties -- the dense path equals the patchwise path on a
+    random sample of voxels, the candidate mask gates the writes, labels are the arg-max of the probabilities."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shape = (256, 256, 256)
+    vol = torch.randn(shape, device="cuda", generator=g)
+    atlas = torch.rand(shape + (15,), device="cuda", generator=g) ** 8
+    atlas = atlas / atlas.sum(-1, keepdim=True)
+    mask = (torch.rand(shape, device="cuda", generator=g) < 0.9).to(torch.uint8)
+    lab = torch.full(shape, 77, dtype=torch.uint8, device="cuda")
+    ctx.segment_volume(vol, atlas, cand_mask=mask, label_vol=lab)
+    assert bool((lab[mask == 0] == 77).all()) and int(lab[mask != 0].max()) <= 14
+    idx = torch.randint(0, vol.numel(), (3000,), device="cuda", generator=g)
+    idx = idx[mask.view(-1)[idx] != 0]
+    xyz = torch.stack([idx // 65536, (idx // 256) % 256, idx % 256], 1).to(torch.int32)
+    p_patch, l_patch = ctx.forward_from_volume(vol, atlas, xyz)
+    agree = float((l_patch.long() == lab.view(-1)[idx].long()).float().mean())
+    assert agree >= 0.999, agree
+    del vol, atlas, mask, lab
+    torch.cuda.empty_cache()

@@ -144,3 +144,31 @@ def test_base_helpers_match_reference_semantics(ctx, G):
     assert np.array_equal(p, G["A_coronal"].astype(np.float32))
     sub = base.get_mask_voxels(G["C_mask"], size=7)
     assert len(sub) == 7 and set(sub) <= set(vox)
+
+
+@pytest.mark.parametrize("shape,it", [((40, 40, 40), 10), ((17, 23, 9), 3), ((8, 8, 8), 1), ((30, 12, 50), 0)])
+def test_dilate_mask_equals_scipy(ctx, shape, it):
+    from scipy import ndimage
+    rng = np.random.RandomState(sum(shape) + it)
+    m = rng.rand(*shape) < 0.01
+    m[0, 0, 0] = True                       # border behaviour (border_value = 0)
+    m[-1, -1, -1] = True
+    got = ctx.dilate_mask(dev(m.view(np.uint8)), it).cpu().numpy().astype(bool)
+    ref = ndimage.binary_dilation(m, iterations=it) if it else m
+    assert np.array_equal(got, ref)
+
+
+def test_error_codes_not_exceptions(ctx):
+    """bad arguments come back as negative status codes with a message (no exception crosses the C boundary)"""
+    import ctypes
+    from cnn_cort import _native
+    lib = ctx.lib
+    dims = (ctypes.c_int32 * 3)(4, 4, 4)
+    assert lib.sc_gather_patches(ctx.h, None, dims, None, 0, None, 5, None, None, None, None, None) == -2
+    assert b"sc_gather_patches" in lib.sc_last_error()
+    assert lib.sc_set_option(ctx.h, b"no_such_key", 1) == -2
+    assert lib.sc_forward(ctx.h, None, None, None, None, 4, None, None, None) in (-2, -3)   # no weights / null input
+    bad = (ctypes.c_int32 * 3)(0, 4, 4)
+    assert lib.sc_nonzero_coords(ctx.h, ctypes.c_void_p(1), 1, bad, None, 0, None, None) == -2
+    with pytest.raises(_native.NativeError):
+        ctx.load_weights(np.zeros(10, np.float32))
