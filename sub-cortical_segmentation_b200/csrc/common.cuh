@@ -260,6 +260,9 @@ struct ConvArgs {
 int launch_conv3x3(sc_ctx* ctx, int cin, int cout, const ConvArgs& a, int prof_cls, cudaStream_t st);
 int launch_conv1_patches(sc_ctx* ctx, const float* patches, int n, const float* w, const float* scale, const float* shift,
                          const float* alpha, float* out, cudaStream_t st);
+size_t branch_patches_tc_bytes(int64_t n);
+int branch_patches_tc(sc_ctx* ctx, int branch, const float* patches, int64_t n, float* scratch, float* feats /*[n][576] split*/,
+                      cudaStream_t st);
 int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, const int32_t* box,
                    const uint8_t* cand, uint8_t* label_vol, float* proba_vol, cudaStream_t st);
 

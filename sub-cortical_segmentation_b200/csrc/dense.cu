@@ -313,13 +313,17 @@ __global__ void __launch_bounds__(256) pool_nhwc_kernel(const float* __restrict_
   }
 }
 
+// flat_pitch > 0: the map is a flattened pixel sequence (patchwise path: rows of `flat_pitch` pixels, patches back to
+// back); a filter row is then a shift of flat_pitch pixels along the same axis and wrap-around outputs are garbage
+// that later layers never read.
 static int launch_conv_tc(sc_ctx* ctx, const GemmW& w, const float* in, int inR, int inC, float* out, int outR, int outC, int ns,
-                          int dil, int k_used, int prof_cls, cudaStream_t st) {
+                          int dil, int k_used, int prof_cls, cudaStream_t st, int flat_pitch = 0) {
   GemmProblem p;
   p.A = in; p.lda = kC5Ld; p.a_ys = (int64_t)inC * kC5Ld; p.a_zs = (int64_t)inR * inC * kC5Ld;
   p.ntaps = 9; p.kc = kC5Ld;
   for (int t = 0; t < 9; ++t) {
-    p.tap_dx[t] = (t % 3) * dil; p.tap_dy[t] = (t / 3) * dil;
+    if (flat_pitch) { p.tap_dx[t] = (t / 3) * flat_pitch + (t % 3) * dil; p.tap_dy[t] = 0; }
+    else { p.tap_dx[t] = (t % 3) * dil; p.tap_dy[t] = (t / 3) * dil; }
     p.tap_off[t] = ((int64_t)p.tap_dy[t] * inC + p.tap_dx[t]) * kC5Ld;
   }
   p.a_base = in; p.a_dims[0] = kC5Ld; p.a_dims[1] = inC; p.a_dims[2] = inR; p.a_dims[3] = ns;
@@ -330,6 +334,101 @@ static int launch_conv_tc(sc_ctx* ctx, const GemmW& w, const float* in, int inR,
   p.n_store = 64; p.c_col0 = 0; p.out_split = 1; p.prof_cls = prof_cls;
   p.k_used = k_used;
   return launch_gemm_tc(ctx, p, w, st);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Patchwise branch on the tensor cores (predict_proba on patch dicts): every map of a chunk of patches is one flattened
+// NHWC-64 split-bf16 pixel sequence (pitch 32 / 16 / 8 per pooling level, patches back to back), so conv2..conv5 are the
+// same implicit GEMMs as in the dense path (filter row = shift by the pitch) and d1 reads the 3x3 conv5 map as 9 taps.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool2x2s2_patch_kernel(const float* __restrict__ in, int inPitch, int inPos, float* __restrict__ out,
+                                                              int outH, int outW, int outPitch, int outPos, int64_t n) {
+  const int64_t total = n * outPos * 16;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int q = (int)(e & 15);
+    const int64_t pos = e >> 4;
+    const int64_t patch = pos / outPos;
+    const int j = (int)(pos - patch * outPos);
+    const int y = j / outPitch, x = j - y * outPitch;
+    float best[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y < outH && x < outW) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(
+            in + (patch * inPos + (int64_t)(2 * y + (k >> 1)) * inPitch + 2 * x + (k & 1)) * kC5Ld) + q * 4;
+        const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + 64));
+        const float v0 = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+        const float v1 = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+        const float v2 = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+        const float v3 = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+        if (k == 0) { best[0] = v0; best[1] = v1; best[2] = v2; best[3] = v3; }
+        else { best[0] = fmaxf(best[0], v0); best[1] = fmaxf(best[1], v1); best[2] = fmaxf(best[2], v2); best[3] = fmaxf(best[3], v3); }
+      }
+    }
+    store_split4(out + pos * kC5Ld, q * 4, best[0], best[1], best[2], best[3]);
+  }
+}
+
+size_t branch_patches_tc_bytes(int64_t n) {
+  return (size_t)n * (2 * 960 + 3 * 224 + 2 * 40) * kC5Ld * sizeof(float) + 4096;
+}
+
+int branch_patches_tc(sc_ctx* ctx, int b, const float* patches, int64_t n, float* scratch, float* feats, cudaStream_t st) {
+  const BranchW& W = ctx->br[b];
+  float* c1 = scratch;
+  float* c2 = c1 + (size_t)n * 960 * kC5Ld;
+  float* p1 = c2 + (size_t)n * 960 * kC5Ld;
+  float* c3 = p1 + (size_t)n * 224 * kC5Ld;
+  float* c4 = c3 + (size_t)n * 224 * kC5Ld;
+  float* p2 = c4 + (size_t)n * 224 * kC5Ld;
+  float* c5 = p2 + (size_t)n * 40 * kC5Ld;
+  {
+    ViewGeo g = {1024, 32, 1, 0, (int)n, 16, 16, 30, 30, 32, 32};   // origin 16 cancels the dense path's zero-pad offset
+    const int64_t blocks = (n * 960 + 255) / 256;
+    const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
+    static bool c1cfg = false;
+    if (!c1cfg) { SC_CUDA(cudaFuncSetAttribute(dense_conv1_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 272)); c1cfg = true; }
+    ProfScope prof(ctx, PC_CONV1, st);
+    dense_conv1_nhwc_kernel<<<grid, 256, 256 * 272, st>>>(patches, g, 0, (int)n, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], c1, 30, 32);
+    ctx->launches++;
+  }
+  SC_CHECK(n * 960 < (1ll << 31), SC_ERR_ARG, "patchwise chunk too large");
+  SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], c1, 1, (int)(n * 960), c2, 1, (int)(n * 960), 1, 1, 20, PC_CONV2, st, 32));
+  {
+    const int64_t work = n * 224 * 16;
+    ProfScope prof(ctx, PC_POOL, st);
+    pool2x2s2_patch_kernel<<<(unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64), 256, 0, st>>>(
+        c2, 32, 960, p1, 14, 14, 16, 224, n);
+    ctx->launches++;
+  }
+  SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], p1, 1, (int)(n * 224), c3, 1, (int)(n * 224), 1, 1, 20, PC_CONV3, st, 16));
+  SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], c3, 1, (int)(n * 224), c4, 1, (int)(n * 224), 1, 1, 40, PC_CONV4, st, 16));
+  {
+    const int64_t work = n * 40 * 16;
+    ProfScope prof(ctx, PC_POOL, st);
+    pool2x2s2_patch_kernel<<<(unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64), 256, 0, st>>>(
+        c4, 16, 224, p2, 5, 5, 8, 40, n);
+    ctx->launches++;
+  }
+  SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], p2, 1, (int)(n * 40), c5, 1, (int)(n * 40), 1, 1, 40, PC_CONV5, st, 8));
+  // d1: rows = patches, the 3x3 positions of the conv5 map (pitch 8) are the 9 taps; K = tap*64 + c
+  GemmProblem p;
+  p.A = c5; p.lda = 40 * kC5Ld; p.a_ys = 0; p.a_zs = 0;
+  p.ntaps = 9; p.kc = kC5Ld; p.k_used = 0;
+  for (int t = 0; t < 9; ++t) {
+    p.tap_dx[t] = 0; p.tap_dy[t] = (t / 3) * 8 + (t % 3);
+    p.tap_off[t] = (int64_t)p.tap_dy[t] * kC5Ld;
+  }
+  p.a_base = c5; p.a_dims[0] = kC5Ld; p.a_dims[1] = n; p.a_dims[2] = 40; p.a_dims[3] = 1;
+  p.a_strides[0] = 40 * kC5Ld; p.a_strides[1] = kC5Ld; p.a_strides[2] = (int64_t)n * 40 * kC5Ld;
+  p.a_y0 = p.a_z0 = 0;
+  p.C = feats; p.ldc = kFeatLd; p.c_ys = p.c_zs = 0; p.M = (int)n; p.Y = p.Z = 1;
+  p.n_store = 192; p.c_col0 = b * 192; p.out_split = 1; p.prof_cls = PC_GEMM_D1;
+  SC_TRY(launch_gemm_tc(ctx, p, W.d1_dense, st));
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
 }
 
 // plain (dilation 1, no folded pool, planar) 3x3 valid conv over [n][CIN][R][ld] maps: the training

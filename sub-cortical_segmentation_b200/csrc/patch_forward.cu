@@ -247,25 +247,35 @@ __global__ void atlas_rows_kernel(const float* __restrict__ in4, int64_t n, floa
 int forward_patches(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, int64_t n,
                     float* proba, int32_t* label, cudaStream_t st) {
   const bool tc = ctx->gemm_backend == 1;
-  const int64_t chunk = 32768;
+  const int64_t chunk = 32768, sub = 4096;      // head rows per pass / patches per tensor-core conv pass
   const size_t row_floats = 3 * kFeatLd + kFeatLd + kH1Ld + kH2Ld;
   const int64_t cmax = n < chunk ? n : chunk;
-  SC_TRY(ensure_ws(ctx->ws, (size_t)cmax * row_floats * sizeof(float) + 1024));
+  const size_t head_bytes = (size_t)cmax * row_floats * sizeof(float) + 1024;
+  const size_t conv_bytes = tc ? branch_patches_tc_bytes(cmax < sub ? cmax : sub) : 0;
+  SC_TRY(ensure_ws(ctx->ws, head_bytes + conv_bytes));
   float* c5 = reinterpret_cast<float*>(ctx->ws.ptr);
   float* feats = c5 + (size_t)cmax * 3 * kFeatLd;
   float* h1 = feats + (size_t)cmax * kFeatLd;
   float* h2 = h1 + (size_t)cmax * kH1Ld;
+  float* conv_scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->ws.ptr) + ((head_bytes + 255) & ~(size_t)255));
   const float* ins[3] = {in1, in2, in3};
   for (int64_t s = 0; s < n; s += chunk) {
     const int64_t m = n - s < chunk ? n - s : chunk;
     for (int b = 0; b < 3; ++b) {
+      if (tc) {   // conv1..conv5 + d1 on the tensor cores, 4096 patches at a time
+        for (int64_t t = 0; t < m; t += sub) {
+          const int64_t mm = m - t < sub ? m - t : sub;
+          SC_TRY(branch_patches_tc(ctx, b, ins[b] + (s + t) * 1024, mm, conv_scratch, feats + t * kFeatLd, st));
+        }
+        continue;
+      }
       float* c5b = c5 + (size_t)b * cmax * kFeatLd;
       SC_TRY(launch_branch_patches(ctx, b, ins[b] + s * 1024, m, c5b, st));
       GemmProblem p;
       gemm_problem_rows(p, c5b, kFeatLd, kFeatLd, (int)m);
       p.C = feats; p.ldc = kFeatLd; p.c_col0 = b * 192;
-      p.n_store = 192; p.out_split = tc ? 1 : 0; p.prof_cls = PC_GEMM_D1;
-      SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->br[b].d1, st) : launch_gemm(ctx, p, ctx->br[b].d1, st));
+      p.n_store = 192; p.out_split = 0; p.prof_cls = PC_GEMM_D1;
+      SC_TRY(launch_gemm(ctx, p, ctx->br[b].d1, st));
     }
     GemmProblem p;
     gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)m);
