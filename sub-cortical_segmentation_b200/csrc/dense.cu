@@ -283,23 +283,20 @@ __global__ void __launch_bounds__(256) dense_conv1_nhwc_kernel(const float* __re
   }
 }
 
-// out[s][r][c][:] = max over {0,pd}x{0,pd} of in[s][r+dr][c+dc][:]  on NHWC-64 split-bf16 maps (exact: the
-// winning pixel's hi|lo pair is copied).  grid.y = output row (s*outR + r); 16 threads per pixel, 8 B of hi and 8 B of lo each.
-__global__ void __launch_bounds__(256) pool_nhwc_kernel(const float* __restrict__ in, int inR, int inC, float* __restrict__ out,
-                                                        int outR, int outC, int pd) {
-  const int row = blockIdx.y;                  // s * outR + r
-  const int s = row / outR, r = row - s * outR;
-  const float* irow = in + ((int64_t)s * inR + r) * inC * kC5Ld;
-  float* orow = out + (int64_t)row * outC * kC5Ld;
-  const int64_t rstride = (int64_t)pd * inC * kC5Ld;
-  for (int e = blockIdx.x * 256 + threadIdx.x; e < outC * 16; e += gridDim.x * 256) {
-    const int q = e & 15, c = e >> 4;
-    // hi + lo is exact in fp32, so the maximum is taken on the reconstructed values and split again
-    // (the re-split reproduces the same represented value)
+// stride-1 max-pool (window {0,pd}^2) on a flattened NHWC-64 split-bf16 map (positions = slices x rows x pitch, back to
+// back): out[p] = max(in[p], in[p+pd], in[p+pd*pitch], in[p+pd*pitch+pd]); hi + lo is exact in fp32, so the maximum is
+// taken on the reconstructed values and split again (the re-split reproduces the same represented value).  Positions whose window leaves the buffer are skipped (they are never read).
+__global__ void __launch_bounds__(256) pool_flat_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t npos, int pitch, int pd) {
+  const int64_t total = npos * 16;
+  const int64_t reach = (int64_t)pd * pitch + pd;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int q = (int)(e & 15);
+    const int64_t pos = e >> 4;
+    if (pos + reach >= npos) continue;
     float best[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(irow + (k >> 1) * rstride + (int64_t)(c + (k & 1) * pd) * kC5Ld) + q * 4;
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(in + (pos + (k >> 1) * (int64_t)pd * pitch + (k & 1) * pd) * kC5Ld) + q * 4;
       const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
       const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + 64));
       const float v0 = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
@@ -309,20 +306,17 @@ __global__ void __launch_bounds__(256) pool_nhwc_kernel(const float* __restrict_
       if (k == 0) { best[0] = v0; best[1] = v1; best[2] = v2; best[3] = v3; }
       else { best[0] = fmaxf(best[0], v0); best[1] = fmaxf(best[1], v1); best[2] = fmaxf(best[2], v2); best[3] = fmaxf(best[3], v3); }
     }
-    store_split4(orow + (int64_t)c * kC5Ld, q * 4, best[0], best[1], best[2], best[3]);
+    store_split4(out + pos * kC5Ld, q * 4, best[0], best[1], best[2], best[3]);
   }
 }
 
-// flat_pitch > 0: the map is a flattened pixel sequence (patchwise path: rows of `flat_pitch` pixels, patches back to
-// back); a filter row is then a shift of flat_pitch pixels along the same axis and wrap-around outputs are garbage
-// that later layers never read.
 static int launch_conv_tc(sc_ctx* ctx, const GemmW& w, const float* in, int inR, int inC, float* out, int outR, int outC, int ns,
                           int dil, int k_used, int prof_cls, cudaStream_t st, int flat_pitch = 0) {
   GemmProblem p;
   p.A = in; p.lda = kC5Ld; p.a_ys = (int64_t)inC * kC5Ld; p.a_zs = (int64_t)inR * inC * kC5Ld;
   p.ntaps = 9; p.kc = kC5Ld;
   for (int t = 0; t < 9; ++t) {
-    if (flat_pitch) { p.tap_dx[t] = (t / 3) * flat_pitch + (t % 3) * dil; p.tap_dy[t] = 0; }
+    if (flat_pitch) { p.tap_dx[t] = (t / 3) * dil * flat_pitch + (t % 3) * dil; p.tap_dy[t] = 0; }
     else { p.tap_dx[t] = (t % 3) * dil; p.tap_dy[t] = (t / 3) * dil; }
     p.tap_off[t] = ((int64_t)p.tap_dy[t] * inC + p.tap_dx[t]) * kC5Ld;
   }
@@ -510,15 +504,16 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   size_t a5_off[3], a5_bytes = 0;
   for (int v = 0; v < 3; ++v) {
     a5_off[v] = a5_bytes;
-    a5_bytes += align256((size_t)vg[v].ns * (vg[v].br + 8) * (vg[v].bc + 8) * kC5Ld * sizeof(float));
+    // tensor-core mode: every map of a view is a flattened pixel sequence with the conv1 geometry (rows br+29, pitch bc+29)
+    a5_bytes += tc ? align256((size_t)vg[v].ns * (vg[v].br + 29) * (vg[v].bc + 29) * kC5Ld * sizeof(float))
+                   : align256((size_t)vg[v].ns * (vg[v].br + 8) * (vg[v].bc + 8) * kC5Ld * sizeof(float));
   }
   size_t per_slice_max = 0;
   for (int v = 0; v < 3; ++v) {
     const size_t br = vg[v].br, bc = vg[v].bc;
     size_t f;
-    if (tc)   // NHWC-64 maps: conv1, conv2, pool1, conv3, conv4, pool2
-      f = kC5Ld * ((br + 29) * (bc + 29) + (br + 27) * (bc + 27) + (br + 26) * (bc + 26) + (br + 22) * (bc + 22) +
-                   (br + 18) * (bc + 18) + (br + 16) * (bc + 16)) + 6 * 64;
+    if (tc)   // NHWC-64 maps: conv1, conv2, pool1, conv3, conv4, pool2 -- all with the conv1 geometry
+      f = kC5Ld * 6 * (br + 29) * (bc + 29) + 6 * 64;
     else
       f = 20 * (br + 29) * round8(bc + 29) + 20 * (br + 27) * round8(bc + 27) + 40 * (br + 22) * round8(bc + 22) +
           40 * (br + 18) * round8(bc + 18);
@@ -559,15 +554,19 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     for (int sb = 0; sb < g.ns && tc; sb += group) {
       // ---- tensor-core pipeline: every map NHWC-64 split-bf16, every conv an implicit GEMM (bf16x3) ----
       const int ns = g.ns - sb < group ? g.ns - sb : group;
-      const int R1 = g.br + 29, C1 = g.bc + 29, R2 = g.br + 27, C2 = g.bc + 27, Rp1 = g.br + 26, Cp1 = g.bc + 26;
-      const int R3 = g.br + 22, C3 = g.bc + 22, R4 = g.br + 18, C4 = g.bc + 18, Rp2 = g.br + 16, Cp2 = g.bc + 16;
-      auto carve = [&](float*& cur, int R, int C) { float* p = cur; cur += align256((size_t)ns * R * C * kC5Ld * 4) / 4; return p; };
+      // Flattened maps: all six intermediate maps share the conv1 geometry (R1 rows, pitch C1) and lie back to back per
+      // slice, so a 128-pixel MMA tile runs across row (and slice) boundaries -- no per-row tile quantisation -- and a
+      // filter row is a shift of dil*C1 pixels.  Positions outside a layer's valid region hold garbage that valid
+      // outputs never read (rows of the implicit GEMM are independent).
+      const int R1 = g.br + 29, C1 = g.bc + 29;
+      const int64_t npos = (int64_t)ns * R1 * C1;
+      SC_CHECK(npos < (1ll << 31), SC_ERR_ARG, "sc_segment_volume: slice group too large");
+      auto carve = [&](float*& cur) { float* p = cur; cur += align256((size_t)npos * kC5Ld * 4) / 4; return p; };
       float* cur = reinterpret_cast<float*>(scratch);
-      float* m1 = carve(cur, R1, C1); float* m2 = carve(cur, R2, C2); float* mp1 = carve(cur, Rp1, Cp1);
-      float* m3 = carve(cur, R3, C3); float* m4 = carve(cur, R4, C4); float* mp2 = carve(cur, Rp2, Cp2);
+      float* m1 = carve(cur); float* m2 = carve(cur); float* mp1 = carve(cur);
+      float* m3 = carve(cur); float* m4 = carve(cur); float* mp2 = carve(cur);
       {
-        const int64_t work = (int64_t)ns * R1 * C1;
-        const int64_t blocks = (work + 255) / 256;
+        const int64_t blocks = (npos + 255) / 256;
         const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
         ProfScope prof(ctx, PC_CONV1, st);
         static bool c1cfg = false;
@@ -576,20 +575,22 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
         ctx->launches++;
         SC_CUDA(cudaGetLastError());
       }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], m1, R1, C1, m2, R2, C2, ns, 1, 20, PC_CONV2, st));
+      const int P = (int)npos;
+      const unsigned pgrid = (unsigned)((npos * 16 + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (npos * 16 + 255) / 256 : (int64_t)ctx->sm_count * 64);
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], m1, 1, P, m2, 1, P, 1, 1, 20, PC_CONV2, st, C1));
       {
         ProfScope prof(ctx, PC_POOL, st);
-        pool_nhwc_kernel<<<dim3((Cp1 * 16 + 255) / 256, ns * Rp1), 256, 0, st>>>(m2, R2, C2, mp1, Rp1, Cp1, 1);
+        pool_flat_kernel<<<pgrid, 256, 0, st>>>(m2, mp1, npos, C1, 1);
         ctx->launches++;
       }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], mp1, Rp1, Cp1, m3, R3, C3, ns, 2, 20, PC_CONV3, st));
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, R3, C3, m4, R4, C4, ns, 2, 40, PC_CONV4, st));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], mp1, 1, P, m3, 1, P, 1, 2, 20, PC_CONV3, st, C1));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, 1, P, m4, 1, P, 1, 2, 40, PC_CONV4, st, C1));
       {
         ProfScope prof(ctx, PC_POOL, st);
-        pool_nhwc_kernel<<<dim3((Cp2 * 16 + 255) / 256, ns * Rp2), 256, 0, st>>>(m4, R4, C4, mp2, Rp2, Cp2, 2);
+        pool_flat_kernel<<<pgrid, 256, 0, st>>>(m4, mp2, npos, C1, 2);
         ctx->launches++;
       }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, Rp2, Cp2, a5[v] + (size_t)sb * r5 * c5 * kC5Ld, r5, c5, ns, 4, 40, PC_CONV5, st));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, 1, P, a5[v] + (size_t)sb * R1 * C1 * kC5Ld, 1, P, 1, 4, 40, PC_CONV5, st, C1));
       SC_CUDA(cudaGetLastError());
     }
     for (int sb = 0; sb < g.ns && !tc; sb += group) {
@@ -632,7 +633,7 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     const int64_t rows = (int64_t)nx * plane;
     for (int v = 0; v < 3; ++v) {
       const ViewGeo& g = vg[v];
-      const int64_t c5 = g.bc + 8, r5 = g.br + 8;
+      const int64_t c5 = tc ? g.bc + 29 : g.bc + 8, r5 = tc ? g.br + 29 : g.br + 8;   // tensor-core mode: conv1 geometry (see phase 1)
       GemmProblem p;
       p.lda = kC5Ld; p.a_ys = c5 * kC5Ld; p.a_zs = r5 * c5 * kC5Ld;
       p.ntaps = 9; p.kc = kC5Ld;
