@@ -296,6 +296,7 @@ def main():
 
     if rank != 0:
         if world > 1:
+            dist.barrier()            # rank 0 is still measuring its secondary sections / CPU baseline
             dist.destroy_process_group()
         return
 
@@ -346,8 +347,9 @@ def main():
     out.update(extra)
     if cpu_base:
         out["cpu_baseline"] = cpu_base
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

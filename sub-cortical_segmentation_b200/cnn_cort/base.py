@@ -3,9 +3,9 @@
 Kept names: load_data, load_test_names, generate_training_set, load_patch_vectors,
 get_atlas_vectors, load_patches, get_patches, get_mask_voxels, load_patch_batch, test_scan,
 post_process_segmentation.  Candidate indexing, patch / atlas gathering, the network and the
-result scatter run in ``libsubcort_b200.so``; NIfTI I/O, intensity normalisation, the
-scipy dilation of the crop mask and the connected-component post-processing stay on the
-host exactly where the reference has them (outside the timed path).
+result scatter and the 10x dilation of the crop mask run in ``libsubcort_b200.so``; NIfTI
+I/O, intensity normalisation and the connected-component post-processing stay on the host
+exactly where the reference has them (outside the timed path).
 
 Deliberate deviations from reference quirks: Q1 prediction is not gated
 by ``debug``; Q2 ``speedup_segmentation`` is parsed as a boolean; Q10 one forward pass

@@ -247,8 +247,12 @@ class Net(object):
             for s in range(0, len(tr), bs):
                 gidx = tr[s:s + bs]
                 lidx = parallel.shard_batch(gidx, rank, world)
-                b = to_dev(lidx)
-                ctx.train_forward_backward(*b, n_global=len(gidx), seed=int(rng.randint(1 << 62)) + rank, loss_out=loss_buf)
+                if len(lidx):
+                    b = to_dev(lidx)
+                    ctx.train_forward_backward(*b, n_global=len(gidx), seed=int(rng.randint(1 << 62)) + rank, loss_out=loss_buf)
+                else:                      # a last partial batch smaller than the world size: contribute zeros
+                    grads.zero_()
+                    loss_buf.zero_()
                 parallel.allreduce_gradients(grads, loss_buf)
                 ctx.adam_step(lr=self.update_learning_rate, stat_scale=1.0 / world)
                 losses.append(loss_buf.clone())
