@@ -314,8 +314,12 @@ def main():
     # executed tensor work of the bf16x3 split: 3 MMAs per algorithmic product, plus K / N padding of the tile
     pad = {"gemm_d1": 3 * (576 / 540.0) * (192 / 180.0), "gemm_fc1": 3 * (576 / 540.0) * (576 / 540.0),
            "gemm_fc2": 3 * (576 / 555.0) * (288 / 270.0)}.get(dom)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")     # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath) and size == 256 and backend.startswith("tcgen05"):
+        traffic = json.load(open(tpath))["bytes_per_launch"].get(dom)
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops"], "traffic": None,
+                "frac": achieved / peaks["tflops"], "traffic": traffic,
                 "executed_over_algorithmic": pad,
                 "tensor_pipe_frac_executed": (achieved * pad / peaks["tflops"]) if (pad and backend.startswith("tcgen05")) else None,
                 "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json); the kernel issues 3 bf16 MMAs per algorithmic product "
