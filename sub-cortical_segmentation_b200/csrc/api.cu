@@ -135,7 +135,7 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     return SC_OK;
   }
   if (!strcmp(key, "tc_variant")) {
-    SC_CHECK(value == 1 || value == 2, SC_ERR_ARG, "sc_set_option: tc_variant must be 1 or 2");
+    SC_CHECK(value >= 1 && value <= 3, SC_ERR_ARG, "sc_set_option: tc_variant must be 1, 2 or 3");
     ctx->tc_variant = (int)value;
     return SC_OK;
   }

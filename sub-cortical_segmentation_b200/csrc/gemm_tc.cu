@@ -563,6 +563,262 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the wide streaming-weight tiles (d1, FC1, fc_2): a cluster of two CTAs on
+// an SM pair computes a 256-row tile.  Each CTA loads its own 128 rows of A but only HALF of the weight block
+// (bn/2 rows), so the weight bytes every SM has to ingest per MMA halve and a third pipeline stage fits.
+//   * both producers signal the LEADER's full barrier (cta_group::2 TMA, peer bit cleared in the barrier address)
+//   * the leader's MMA warp issues tcgen05.mma.cta_group::2 (M = 256) and multicasts its commits to both CTAs
+//   * every CTA's epilogue warps drain their own TMEM half and arrive on the leader's tempty barrier (remote arrive)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
+                                                    uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on the same barrier offset in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {   // arrive on `bar` of CTA `cta` of the cluster
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int hb = a.bn >> 1;                               // weight rows held by this CTA
+  const int b_half = hb * 128;                            // bytes of its hi (or lo) weight half-block
+  const int stage_bytes = 2 * TC_A_HALF + 2 * b_half;
+  uint8_t* sStage = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + a.stages * stage_bytes);
+  uint64_t* full = bars;                                  // used in the leader only (both producers signal it)
+  uint64_t* empty = bars + a.stages;                      // per CTA, arrived by the leader's multicast commit
+  uint64_t* tfull = bars + 2 * a.stages;                  // [2] per CTA
+  uint64_t* tempty = tfull + 2;                           // [2] leader only: both CTAs' epilogue warps arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_const = reinterpret_cast<float*>(tmem_slot + 2);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + 2 * 3 * a.bn);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nepi = (blockDim.x >> 5) - 2;
+  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * nepi); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+      uint32_t it = 0;
+      for (long long t = pair; t < a.num_tiles; t += npairs) {
+        long long r = t;
+        const int n_tile = (int)(r % a.nt); r /= a.nt;
+        const int m_tile = (int)(r % a.mt); r /= a.mt;
+        const int y = (int)(r % a.Y);
+        const int z = (int)(r / a.Y);
+        const int m0 = m_tile * 256 + (int)rank * TC_BM, n0 = n_tile * a.bn + (int)rank * hb;
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t use = it / a.stages;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          const uint32_t lbar = smem_u32(&full[s]) & 0xFEFFFFFFu;      // the leader's barrier (peer bit cleared)
+          if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));   // both CTAs' bytes land on it
+          uint8_t* sp = sStage + s * stage_bytes;
+          const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
+          const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
+          tma_load_4d_2sm(&mapA, lbar, sp, ka, px, ln, pl);
+          tma_load_4d_2sm(&mapA, lbar, sp + TC_A_HALF, ka + TC_BK, px, ln, pl);
+          tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
+          tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t leader = elect_one();
+      // instruction descriptor: D=F32, A=B=BF16, K-major, N = bn, M = 256 (two CTAs x 128 rows)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t sStage_u = smem_u32(sStage);
+      uint32_t it = 0, ti = 0;
+      for (long long t = pair; t < a.num_tiles; t += npairs, ++ti) {
+        const uint32_t b = ti & 1, buse = ti >> 1;
+        mbar_wait(&tempty[b], (buse & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + b * 256;
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % a.stages;
+          mbar_wait(&full[s], (it / a.stages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sp = sStage_u + s * stage_bytes;
+          const uint64_t ah = umma_desc(sp), al = umma_desc(sp + TC_A_HALF);
+          const uint64_t wh = umma_desc(sp + 2 * TC_A_HALF), wl = umma_desc(sp + 2 * TC_A_HALF + b_half);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t o = (uint64_t)(j * 2);
+            umma_bf16_2sm_elect(acc, al + o, wh + o, idesc, (kb | j) != 0, leader);
+            umma_bf16_2sm_elect(acc, ah + o, wl + o, idesc, 1, leader);
+            umma_bf16_2sm_elect(acc, ah + o, wh + o, idesc, 1, leader);
+          }
+          if (leader) umma_commit_2sm(&empty[s]);
+          __syncwarp();
+        }
+        if (leader) umma_commit_2sm(&tfull[b]);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int G = nepi >> 2, grp = (warp - 2) >> 2;
+    const int epi_threads = nepi * 32;
+    uint32_t ti = 0;
+    for (long long t = pair; t < a.num_tiles; t += npairs, ++ti) {
+      long long r = t;
+      const int n_tile = (int)(r % a.nt); r /= a.nt;
+      const int m_tile = (int)(r % a.mt); r /= a.mt;
+      const int y = (int)(r % a.Y);
+      const int z = (int)(r / a.Y);
+      const int m0 = m_tile * 256 + (int)rank * TC_BM, n0 = n_tile * a.bn;
+      const uint32_t b = ti & 1, buse = ti >> 1;
+      float* cb = s_const + b * 3 * a.bn;
+      if (ti < 2 || a.nt > 1) {
+        for (int i = threadIdx.x - 64; i < a.bn; i += epi_threads) {
+          const int nn = n0 + i;
+          const bool ok = nn < a.npad;
+          cb[i] = ok ? __ldg(a.bias + nn) : 0.f;
+          cb[a.bn + i] = ok ? __ldg(a.alpha + nn) : 1.f;
+          cb[2 * a.bn + i] = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
+      }
+      mbar_wait(&tfull[b], buse & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* ctile = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys;
+      const int mw = m0 + q * 32;
+      uint8_t* stg = s_stage + (warp - 2) * 2560;
+      uint8_t* mine = stg + lane * 80;
+      for (int c0 = grp * 16; c0 < a.bn; c0 += 16 * G) {
+        uint32_t rr[16];
+        const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+              "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n0 + c0 >= a.n_store) continue;
+        float v[16];
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const float4 bi = *reinterpret_cast<const float4*>(cb + c0 + 4 * k4);
+          const float4 al = *reinterpret_cast<const float4*>(cb + a.bn + c0 + 4 * k4);
+          const float4 sc_ = *reinterpret_cast<const float4*>(cb + 2 * a.bn + c0 + 4 * k4);
+          v[4 * k4 + 0] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 0]), sc_.x, bi.x), al.x);
+          v[4 * k4 + 1] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 1]), sc_.y, bi.y), al.y);
+          v[4 * k4 + 2] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 2]), sc_.z, bi.z), al.z);
+          v[4 * k4 + 3] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 3]), sc_.w, bi.w), al.w);
+        }
+        const int ncol = a.c_col0 + n0 + c0;
+        if (a.out_split) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
+            hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          *reinterpret_cast<uint4*>(mine) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(mine + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(mine + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(mine + 48) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          __syncwarp();
+          const int boff = (ncol >> 6) * 128 + (ncol & 63);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int half = i >> 1, row = (i & 1) * 16 + (lane >> 1), part = lane & 1;
+            const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 80 + half * 32 + part * 16);
+            if (mw + row < a.M) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ctile + (long long)(mw + row) * a.ldc) + boff + half * 64 + part * 8;
+              *reinterpret_cast<uint4*>(dst) = d;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(mine + 16 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2), part = lane & 3;
+            const float4 d = *reinterpret_cast<const float4*>(stg + row * 80 + part * 16);
+            if (mw + row < a.M) *reinterpret_cast<float4*>(ctile + (long long)(mw + row) * a.ldc + ncol + part * 4) = d;
+          }
+        }
+        __syncwarp();
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tempty[b], 0);     // the leader's MMA warp owns the accumulator hand-off
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                     // neither CTA may free TMEM while the pair still uses it
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // plain fp32 [rows][576] -> split bf16 hi|lo blocks (test entry sc_dense_layer only)
 __global__ void split_rows_kernel(const float* __restrict__ in, int64_t rows, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -643,6 +899,8 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.bias = w.bias; a.alpha = w.alpha; a.scale = w.scale; a.out_split = p.out_split;
   SC_CHECK(p.c_col0 % 4 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 4");
   const bool persistent = ctx->tc_variant != 1;
+  // CTA pairs (cta_group::2) for the wide streaming-weight layers
+  const bool pair = ctx->tc_variant == 3 && a.bn >= 128 && a.bn % 16 == 0 && !(p.ntaps == 9 && a.nkb * 2 * a.bn * 128 <= 150 * 1024);
   const long long blocks = (long long)a.mt * a.nt * p.Y * p.Z;
   SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
   a.num_tiles = blocks;
@@ -654,7 +912,17 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.dbg = (ctx->tc_timing_cls == p.prof_cls) ? ctx->tc_timing_buf : nullptr;
   int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
   size_t smem = 0;
-  if (!persistent) {
+  if (pair) {
+    a.mt = (p.M + 255) / 256;
+    a.num_tiles = (long long)a.mt * a.nt * p.Y * p.Z;
+    a.epi_warps = 16;
+    stage_bytes = 2 * TC_A_HALF + 2 * (a.bn / 2) * 128;
+    const int budget = 227 * 1024 - 1024 - 128 - 16 - 2 * 3 * a.bn * 4 - a.epi_warps * 2560;
+    a.stages = budget / stage_bytes;
+    if (a.stages > 6) a.stages = 6;
+    SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: pair tile too wide");
+    smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 4) * 8 + 16 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
+  } else if (!persistent) {
     a.stages = (108 * 1024) / stage_bytes;
     if (a.stages > 4) a.stages = 4;
     SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
@@ -694,7 +962,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   {
     cuuint64_t dims[2] = {(cuuint64_t)w.Kpad * 2, (cuuint64_t)w.Npad};
     cuuint64_t strides[1] = {(cuuint64_t)w.Kpad * 4};
-    cuuint32_t box[2] = {TC_BK, (cuuint32_t)a.bn};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)(pair ? a.bn / 2 : a.bn)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = s->encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w_nk, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -705,10 +973,15 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   if (!configured) {
     SC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     SC_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SC_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   ProfScope prof(ctx, p.prof_cls, st);
-  if (!persistent) {
+  if (pair) {
+    SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
+    long long pairs = a.num_tiles < ctx->sm_count / 2 ? a.num_tiles : ctx->sm_count / 2;
+    gemm_tc_pair_kernel<<<(unsigned)(2 * pairs), 64 + 32 * a.epi_warps, smem, st>>>(mapA, mapB, a);   // __cluster_dims__(2,1,1)
+  } else if (!persistent) {
     SC_CHECK(smem <= 112 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
     gemm_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, st>>>(mapA, mapB, a);
   } else {
