@@ -629,7 +629,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint64_t* tfull = bars + 2 * a.stages;                  // [2] per CTA
   uint64_t* tempty = tfull + 2;                           // [2] leader only: both CTAs' epilogue warps arrive
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_const = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_const = reinterpret_cast<float*>(tmem_slot + 4);          // keeps the float4 loads of the constants 16 B aligned
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + 2 * 3 * a.bn);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -921,7 +921,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.stages = budget / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: pair tile too wide");
-    smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 4) * 8 + 16 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
+    smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 4) * 8 + 32 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
   } else if (!persistent) {
     a.stages = (108 * 1024) / stage_bytes;
     if (a.stages > 4) a.stages = 4;
