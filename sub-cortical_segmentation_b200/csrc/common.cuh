@@ -152,7 +152,7 @@ struct sc_ctx {
   int64_t* d_count = nullptr;    // device scalar for stream compaction
   int64_t* h_count = nullptr;    // pinned
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
-  int tc_variant = 2;            // 1: one tile per CTA (two CTAs / SM), 2: persistent, double-buffered TMEM
+  int tc_variant = 3;            // 1: one tile per CTA (two CTAs / SM), 2: persistent, double-buffered TMEM, 3: 2 + CTA pairs (cta_group::2) for the wide layers
   int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
