@@ -119,3 +119,35 @@ def test_fit_loop_history_checkpoint_and_early_stopping(tmp_path):
     p = net2.predict_proba({'in1': x[0], 'in2': x[1], 'in3': x[2], 'in4': at})
     assert p.shape == (n, 15) and np.allclose(p.sum(1), 1, atol=1e-4)
     assert net2.predict({'in1': x[0], 'in2': x[1], 'in3': x[2], 'in4': at}).dtype == np.int64
+
+
+def test_load_data_and_generate_training_set(tmp_path):
+    """a-8: load_data -> generate_training_set on synthetic subjects (boundary-restricted sampling) vs the oracle."""
+    from cnn_cort import base, nifti, synthetic
+    from oracle import gather as og
+    root = str(tmp_path)
+    for i, name in enumerate(("s01", "s02")):
+        synthetic.write_subject(root, name, shape=(44, 40, 36), seed=20 + i, with_labels=True)
+    options = {'train_folder': root, 't1_name': 'T1.nii.gz', 'roi_name': 'gt_15_classes.nii.gz', 'patch_size': [32, 32],
+               'debug': 'False', 'device': 0}
+    x_axial, x_cor, x_sag, y_axial, x_atlas, names = base.load_data(options)
+    assert len(x_axial) == len(x_cor) == len(x_sag) == len(y_axial) == len(x_atlas) == len(names) == 2
+    for s, name in enumerate(("s01", "s02")):
+        t1 = nifti.load(os.path.join(root, name, "T1.nii.gz")).get_data()
+        lab = nifti.load(os.path.join(root, name, "gt_15_classes.nii.gz")).get_data()
+        atlas = nifti.load(os.path.join(root, name, "tmp", "MNI_sub_probabilities.nii.gz")).get_data()
+        norm = og.normalise(t1, np.float32)
+        pos = og.get_mask_voxels(np.logical_and(lab > 0, lab < 15))
+        n_pos = len(pos)
+        assert x_axial[s].shape == (2 * n_pos, 32, 32) and x_axial[s].dtype == np.float32
+        # positives: all of them, in np.nonzero order, bit-exact patches and labels
+        for got, mode in zip((x_axial[s], x_cor[s], x_sag[s]), og.VIEWS):
+            assert np.array_equal(got[:n_pos], og.get_patches(norm, pos, (32, 32), mode))
+        assert np.array_equal(y_axial[s][:n_pos, 16, 16], lab[pos[:, 0], pos[:, 1], pos[:, 2]])
+        assert np.array_equal(x_atlas[s][:n_pos], og.atlas_vectors_train(atlas, pos))
+        # negatives: n_pos distinct label-15 voxels (random subset)
+        assert (y_axial[s][n_pos:, 16, 16] == 15).all()
+    xa, xc, xs, xat, y = base.generate_training_set(x_axial, x_cor, x_sag, x_atlas, y_axial, options)
+    n = sum(len(a) for a in x_axial)
+    assert xa.shape == (n, 1, 32, 32) and xat.shape == (n, 15) and y.shape == (n,) and y.dtype == np.uint8
+    assert y.max() <= 14 and (y == 0).sum() == n // 2           # label 15 -> class 0, balanced
