@@ -101,12 +101,22 @@ struct GemmW {      // one dense layer prepared for both GEMM back-ends
   int K, N, Kpad, Npad;
 };
 
+struct SweepW {     // one conv layer prepared for the strip-sweep tcgen05 kernel (conv_sweep.cu)
+  float* panels;    // [npanels][2*bn][64] bf16: rows 0..bn-1 = W hi, bn..2bn-1 = W lo; column block (gk & 3) of panel gk >> 2
+                    // holds k-step gk = tap * ksteps + ci / 16 (flipped taps, zero padded)
+  float* scale;     // BN folded scale / shift and PReLU slope, padded to 64 with zeros
+  float* shift;
+  float* alpha;
+  int bn, ksteps, npanels;
+};
+
 struct BranchW {
   float* c1_w;          // [9][20]  flipped taps, tap = ky*3+kx
   float* conv_w[5];     // l=1..4 used: [Cin][9][Cout] flipped (conv2..conv5)
   float* scale[5];      // BN folded: gamma*inv_std
   float* shift[5];      // beta - mean*scale
   float* alpha[5];
+  SweepW conv_sw[5];    // l=1..4: conv2..conv5 for the strip-sweep kernel
   GemmW conv_tc[5];     // l=1..4: conv2..conv5 as implicit GEMMs over NHWC-64 maps (K = tap*64+ci, N padded to 64)
   GemmW d1;             // patchwise: K=540 (c*9+h*3+w order)
   GemmW d1_dense;       // dense: K=576 (tap*64+ci), same N
@@ -218,11 +228,12 @@ struct GemmProblem {
   int n_store;          // columns written (<= w.Npad)
   int c_col0;           // first output column inside the C row (C points at the row start)
   int out_split;        // write C rows in the split bf16 hi|lo block layout (they feed a tcgen05 GEMM)
+  int a_swap = 0;       // tensor-map dimension order is (k, pixel, plane, line) instead of (k, pixel, line, plane)
 };
 int launch_gemm(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
 // plain [M][lda] row-major A, one tap: fills both the pointer form and the tensor-map form
 inline void gemm_problem_rows(GemmProblem& p, const float* A, int64_t lda, int kc, int M) {
-  p.c_col0 = 0; p.out_split = 0; p.k_used = 0;
+  p.c_col0 = 0; p.out_split = 0; p.k_used = 0; p.a_swap = 0;
   p.A = A; p.lda = lda; p.a_ys = p.a_zs = 0; p.ntaps = 1; p.tap_off[0] = 0; p.kc = kc;
   p.M = M; p.Y = p.Z = 1; p.c_ys = p.c_zs = 0;
   p.a_base = A; p.a_dims[0] = kc; p.a_dims[1] = M; p.a_dims[2] = p.a_dims[3] = 1;
@@ -242,6 +253,11 @@ int tc_init(sc_ctx* ctx);
 void tc_destroy(sc_ctx* ctx);
 int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
 int launch_split_rows(sc_ctx* ctx, const float* in, int64_t rows, float* out, cudaStream_t st);  // [rows][576] plain -> split
+
+// conv_sweep.cu : strip-sweep 3x3 dilated conv (+ fused stride-1 max-pool) over wide-row maps.
+// in_fmt / out_fmt: 1 = 128 B pixels (32 bf16 hi | 32 lo), 0 = 256 B pixels (64 hi | 64 lo)
+int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt, int out_chunks,
+                      int Pw, int R, int dil, int pool, int prof_cls, cudaStream_t st);
 
 // patch_forward.cu
 int launch_branch_patches(sc_ctx* ctx, int branch, const float* patches, int64_t n, float* c5_out /*[n][540]*/,
@@ -288,6 +304,20 @@ __device__ __forceinline__ void store_split4(float* row, int n, float v0, float 
   lp.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
   *reinterpret_cast<uint2*>(r) = hp;
   *reinterpret_cast<uint2*>(r + 64) = lp;
+}
+// the same for the 128 B pixel format: 32 bf16 hi | 32 bf16 lo (n < 32)
+__device__ __forceinline__ void store_split4_b32(void* px, int n, float v0, float v1, float v2, float v3) {
+  __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(px) + n;
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1), h2 = __float2bfloat16_rn(v2), h3 = __float2bfloat16_rn(v3);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+  const __nv_bfloat16 l2 = __float2bfloat16_rn(v2 - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v3 - __bfloat162float(h3));
+  uint2 hp, lp;
+  hp.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hp.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  lp.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  lp.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  *reinterpret_cast<uint2*>(r) = hp;
+  *reinterpret_cast<uint2*>(r + 32) = lp;
 }
 __device__ __forceinline__ void store_row1(float* row, int n, int split, float v) {
   if (!split) { row[n] = v; return; }

@@ -283,6 +283,61 @@ __global__ void __launch_bounds__(256) dense_conv1_nhwc_kernel(const float* __re
   }
 }
 
+// conv1 for the strip-sweep pipeline: wide-row layout (position = (row * ns + slice) * outC + col, conv_sweep.cu) and
+// 128 B pixels (32 bf16 hi | 32 bf16 lo, channels 20..31 zero).  One thread per pixel into a shared tile, then the CTA
+// streams the tile out fully coalesced.
+__global__ void __launch_bounds__(256) dense_conv1_wide_kernel(const float* __restrict__ vol, ViewGeo g, int ns,
+                                                               const float* __restrict__ w, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, const float* __restrict__ alpha,
+                                                               float* __restrict__ out, int outR, int outC) {
+  __shared__ float sw[9 * 20], ssc[20], ssh[20], sal[20];
+  extern __shared__ __align__(16) uint8_t tile[];   // 256 * 144 B
+  for (int i = threadIdx.x; i < 180; i += 256) sw[i] = w[i];
+  if (threadIdx.x < 20) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; sal[threadIdx.x] = alpha[threadIdx.x]; }
+  for (int i = threadIdx.x; i < 256 * 9; i += 256) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);  // channel padding stays zero
+  __syncthreads();
+  const int64_t total = (int64_t)ns * outR * outC;
+  for (int64_t base = (int64_t)blockIdx.x * 256; base < total; base += (int64_t)gridDim.x * 256) {
+    const int64_t e = base + threadIdx.x;
+    if (e < total) {
+      const int j = (int)(e % outC);
+      const int s = (int)((e / outC) % ns);
+      const int i = (int)(e / ((int64_t)outC * ns));
+      const float* vb = vol + (int64_t)(g.s0 + s) * g.ss;
+      float x[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int rr = g.r0 + i + ky - 16;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int cc = g.c0 + j + kx - 16;
+          x[ky * 3 + kx] = (rr >= 0 && rr < g.R && cc >= 0 && cc < g.C) ? __ldg(vb + (int64_t)rr * g.rs + (int64_t)cc * g.cs) : 0.f;
+        }
+      }
+      uint8_t* o = tile + threadIdx.x * 144;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int co = q * 4 + k;
+          float a = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) a = fmaf(x[t], sw[t * 20 + co], a);
+          v[k] = prelu(fmaf(a, ssc[co], ssh[co]), sal[co]);
+        }
+        store_split4_b32(o, q * 4, v[0], v[1], v[2], v[3]);
+      }
+    }
+    __syncthreads();
+    const int64_t npx = total - base < 256 ? total - base : 256;
+    uint4* dst = reinterpret_cast<uint4*>(out + base * 32);
+    for (int i = threadIdx.x; i < (int)npx * 8; i += 256)
+      dst[i] = *reinterpret_cast<const uint4*>(tile + (i >> 3) * 144 + (i & 7) * 16);
+    __syncthreads();
+  }
+}
+
 // stride-1 max-pool (window {0,pd}^2) on a flattened NHWC-64 split-bf16 map (positions = slices x rows x pitch, back to
 // back): out[p] = max(in[p], in[p+pd], in[p+pd*pitch], in[p+pd*pitch+pd]); hi + lo is exact in fp32, so the maximum is
 // taken on the reconstructed values and split again (the re-split reproduces the same represented value).  Positions whose window leaves the buffer are skipped (they are never read).
@@ -508,22 +563,24 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     a5_bytes += tc ? align256((size_t)vg[v].ns * (vg[v].br + 29) * (vg[v].bc + 29) * kC5Ld * sizeof(float))
                    : align256((size_t)vg[v].ns * (vg[v].br + 8) * (vg[v].bc + 8) * kC5Ld * sizeof(float));
   }
-  size_t per_slice_max = 0;
+  size_t per_slice_max = 0, view_max = 0;
   for (int v = 0; v < 3; ++v) {
     const size_t br = vg[v].br, bc = vg[v].bc;
     size_t f;
-    if (tc)   // NHWC-64 maps: conv1, conv2, pool1, conv3, conv4, pool2 -- all with the conv1 geometry
-      f = kC5Ld * 6 * (br + 29) * (bc + 29) + 6 * 64;
-    else
-      f = 20 * (br + 29) * round8(bc + 29) + 20 * (br + 27) * round8(bc + 27) + 40 * (br + 22) * round8(bc + 22) +
-          40 * (br + 18) * round8(bc + 18);
+    if (tc) {  // strip-sweep pipeline: whole-view wide-row maps conv1 and pool1 (128 B pixels), conv3, conv4, pool2 (256 B pixels)
+      f = (size_t)vg[v].ns * (br + 29) * (bc + 29) * (2 * 32 + 3 * 64) + 5 * 64;
+      view_max = f > view_max ? f : view_max;
+      continue;
+    }
+    f = 20 * (br + 29) * round8(bc + 29) + 20 * (br + 27) * round8(bc + 27) + 40 * (br + 22) * round8(bc + 22) +
+        40 * (br + 18) * round8(bc + 18);
     per_slice_max = f > per_slice_max ? f : per_slice_max;
   }
   const size_t scratch_budget = (size_t)1536 << 20;
-  int group = (int)(scratch_budget / (per_slice_max * sizeof(float) + 1024));
+  int group = tc ? 1 : (int)(scratch_budget / (per_slice_max * sizeof(float) + 1024));
   if (group < 1) group = 1;
   if (group > 64) group = 64;
-  const size_t scratch_bytes = align256((per_slice_max * sizeof(float) + 1024) * group);
+  const size_t scratch_bytes = tc ? align256(view_max * sizeof(float) + 4096) : align256((per_slice_max * sizeof(float) + 1024) * group);
   const int64_t plane = (int64_t)by * bz;
   int slab = (int)(ctx->chunk_voxels / plane);
   if (slab < 1) slab = 1;
@@ -551,46 +608,41 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     const int r3 = g.br + 22, l3 = round8(g.bc + 22);
     const int r4 = g.br + 18, l4 = round8(g.bc + 18);
     const int r5 = g.br + 8, c5 = g.bc + 8;
-    for (int sb = 0; sb < g.ns && tc; sb += group) {
-      // ---- tensor-core pipeline: every map NHWC-64 split-bf16, every conv an implicit GEMM (bf16x3) ----
-      const int ns = g.ns - sb < group ? g.ns - sb : group;
-      // Flattened maps: all six intermediate maps share the conv1 geometry (R1 rows, pitch C1) and lie back to back per
-      // slice, so a 128-pixel MMA tile runs across row (and slice) boundaries -- no per-row tile quantisation -- and a
-      // filter row is a shift of dil*C1 pixels.  Positions outside a layer's valid region hold garbage that valid
-      // outputs never read (rows of the implicit GEMM are independent).
+    if (tc) {
+      // ---- tensor-core pipeline (conv_sweep.cu): whole-view wide-row maps, position = (row * ns + slice) * C1 + col, all
+      // with the conv1 geometry (R1 rows, C1 columns per slice).  Positions outside a layer's valid region hold garbage
+      // that valid outputs never read.  conv2 + pool1 and conv3 run as strip sweeps (every input row loaded once, pool
+      // fused into the epilogue); conv4 / pool2 / conv5 still run on the flattened sequence (filter row = shift by Pw).
       const int R1 = g.br + 29, C1 = g.bc + 29;
-      const int64_t npos = (int64_t)ns * R1 * C1;
-      SC_CHECK(npos < (1ll << 31), SC_ERR_ARG, "sc_segment_volume: slice group too large");
-      auto carve = [&](float*& cur) { float* p = cur; cur += align256((size_t)npos * kC5Ld * 4) / 4; return p; };
+      const int64_t Pw64 = (int64_t)g.ns * C1;
+      const int64_t npos = Pw64 * R1;
+      SC_CHECK(npos < (1ll << 31), SC_ERR_ARG, "sc_segment_volume: view too large");
+      const int Pw = (int)Pw64;
+      auto carve = [&](float*& cur, int px_floats) { float* p = cur; cur += align256((size_t)npos * px_floats * 4) / 4; return p; };
       float* cur = reinterpret_cast<float*>(scratch);
-      float* m1 = carve(cur); float* m2 = carve(cur); float* mp1 = carve(cur);
-      float* m3 = carve(cur); float* m4 = carve(cur); float* mp2 = carve(cur);
+      float* m1 = carve(cur, 32); float* mp1 = carve(cur, 32);
+      float* m3 = carve(cur, 64); float* m4 = carve(cur, 64); float* mp2 = carve(cur, 64);
       {
         const int64_t blocks = (npos + 255) / 256;
         const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
         ProfScope prof(ctx, PC_CONV1, st);
         static bool c1cfg = false;
-        if (!c1cfg) { SC_CUDA(cudaFuncSetAttribute(dense_conv1_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 272)); c1cfg = true; }
-        dense_conv1_nhwc_kernel<<<grid, 256, 256 * 272, st>>>(vol, g, sb, ns, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], m1, R1, C1);
+        if (!c1cfg) { SC_CUDA(cudaFuncSetAttribute(dense_conv1_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 144)); c1cfg = true; }
+        dense_conv1_wide_kernel<<<grid, 256, 256 * 144, st>>>(vol, g, g.ns, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], m1, R1, C1);
         ctx->launches++;
         SC_CUDA(cudaGetLastError());
       }
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, 2, Pw, R1, 1, 1, PC_CONV2, st));     // conv2 + pool1
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, 4, Pw, R1, 2, 0, PC_CONV3, st));     // conv3
       const int P = (int)npos;
       const unsigned pgrid = (unsigned)((npos * 16 + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (npos * 16 + 255) / 256 : (int64_t)ctx->sm_count * 64);
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], m1, 1, P, m2, 1, P, 1, 1, 20, PC_CONV2, st, C1));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, 1, P, m4, 1, P, 1, 2, 40, PC_CONV4, st, Pw));
       {
         ProfScope prof(ctx, PC_POOL, st);
-        pool_flat_kernel<<<pgrid, 256, 0, st>>>(m2, mp1, npos, C1, 1);
+        pool_flat_kernel<<<pgrid, 256, 0, st>>>(m4, mp2, npos, Pw, 2);
         ctx->launches++;
       }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], mp1, 1, P, m3, 1, P, 1, 2, 20, PC_CONV3, st, C1));
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, 1, P, m4, 1, P, 1, 2, 40, PC_CONV4, st, C1));
-      {
-        ProfScope prof(ctx, PC_POOL, st);
-        pool_flat_kernel<<<pgrid, 256, 0, st>>>(m4, mp2, npos, C1, 2);
-        ctx->launches++;
-      }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, 1, P, a5[v] + (size_t)sb * R1 * C1 * kC5Ld, 1, P, 1, 4, 40, PC_CONV5, st, C1));
+      SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, 1, P, a5[v], 1, P, 1, 4, 40, PC_CONV5, st, Pw));
       SC_CUDA(cudaGetLastError());
     }
     for (int sb = 0; sb < g.ns && !tc; sb += group) {
@@ -643,6 +695,12 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       }
       p.a_base = a5[v]; p.a_dims[0] = kC5Ld; p.a_dims[1] = c5; p.a_dims[2] = r5; p.a_dims[3] = g.ns;
       p.a_strides[0] = kC5Ld; p.a_strides[1] = c5 * kC5Ld; p.a_strides[2] = r5 * c5 * kC5Ld;
+      p.a_swap = 0;
+      if (tc) {   // wide-row map: (k, col, slice, row) with strides (pixel, C1 pixels, ns * C1 pixels)
+        p.a_dims[2] = g.ns; p.a_dims[3] = r5;
+        p.a_strides[1] = c5 * kC5Ld; p.a_strides[2] = (int64_t)g.ns * c5 * kC5Ld;
+        p.a_swap = 1;
+      }
       p.a_y0 = v == 2 ? 0 : ix0; p.a_z0 = v == 2 ? ix0 : 0;
       p.ldc = 0; p.out_split = tc ? 1 : 0; p.c_col0 = v * 192; p.prof_cls = PC_GEMM_D1; p.k_used = 0;
       p.n_store = 192;   // 180 features + 12 zero columns (zero weights / bias) per view

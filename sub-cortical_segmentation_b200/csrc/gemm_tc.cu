@@ -20,19 +20,9 @@
 //   warps 2-5 epilogue: tcgen05.ld 32x32b.x16 -> bias + PReLU -> plain fp32 or split bf16 rows
 // Two CTAs are co-resident per SM (<= 256 TMEM columns and <= 112 KB shared memory each) so that
 // one tile's loads / epilogue overlap the other's MMAs.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sc {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-struct TcState {
-  EncodeTiledFn encode;
-};
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                    // logical k per block (64 bf16 = one 128 B swizzle row)
@@ -50,6 +40,7 @@ struct TcArgs {
   int M;              // rows per line
   int n_store, npad, c_col0;
   int a_y0, a_z0;     // coordinate offsets of line / plane in the A tensor map
+  int a_swap;         // tensor-map dimension order (k, pixel, plane, line): swap the last two coordinates
   int tap_dx[9], tap_dy[9];
   float* C;
   long long ldc, c_ys, c_zs;
@@ -73,76 +64,6 @@ struct TcArgs {
                       // two instead of three MMAs and A shared-memory reads per product
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-// predicated issue: every lane of the MMA warp runs the (warp-uniform) descriptor arithmetic so that it stays in
-// the uniform datapath; only the elected lane executes the tcgen05.mma itself
-__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
-                                                uint32_t elected) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
-}
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}" : "=r"(pred));
-  return pred;
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
@@ -198,8 +119,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint8_t* st = smem + s * stage_bytes;
         const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;   // bf16 element offset of the block's hi half
         const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
-        tma_load_4d(&mapA, &full[s], st, ka, px, ln, pl);
-        tma_load_4d(&mapA, &full[s], st + TC_A_HALF, ka + TC_BK, px, ln, pl);
+        tma_load_4d(&mapA, &full[s], st, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
+        tma_load_4d(&mapA, &full[s], st + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
         tma_load_2d(&mapB, &full[s], st + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
         tma_load_2d(&mapB, &full[s], st + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
       }
@@ -278,9 +199,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 //   * conv layers keep all 9 x (hi|lo) weight blocks resident in shared memory (144 KB), loaded once
 //   * optional kx-reuse: one (128+2d)-pixel A box per filter row serves the three column taps
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(576, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
@@ -354,8 +272,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           const int kb = a.kx_reuse ? st * 3 : st;                 // first weight block of this step
           const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
           const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
-          tma_load_4d(&mapA, &full[s], sp, ka, px, ln, pl);
-          tma_load_4d(&mapA, &full[s], sp + a.a_half, ka + TC_BK, px, ln, pl);
+          tma_load_4d(&mapA, &full[s], sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
+          tma_load_4d(&mapA, &full[s], sp + a.a_half, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
           if (!a.w_resident) {
             tma_load_2d(&mapB, &full[s], sp + 2 * a.a_half, kb * 2 * TC_BK, n0);
             tma_load_2d(&mapB, &full[s], sp + 2 * a.a_half + b_half, kb * 2 * TC_BK + TC_BK, n0);
@@ -673,8 +591,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           uint8_t* sp = sStage + s * stage_bytes;
           const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
           const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
-          tma_load_4d_2sm(&mapA, lbar, sp, ka, px, ln, pl);
-          tma_load_4d_2sm(&mapA, lbar, sp + TC_A_HALF, ka + TC_BK, px, ln, pl);
+          tma_load_4d_2sm(&mapA, lbar, sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
+          tma_load_4d_2sm(&mapA, lbar, sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
           tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
           tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
         }
@@ -893,7 +811,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.n_store = (a.n_store + 15) & ~15;   // whole 16-column chunks: the caller lets pad columns be overwritten with zeros
     SC_CHECK(p.c_col0 % 16 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 16 for the persistent kernel");
   }
-  a.a_y0 = p.a_y0; a.a_z0 = p.a_z0;
+  a.a_y0 = p.a_y0; a.a_z0 = p.a_z0; a.a_swap = p.a_swap;
   for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; }
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
   a.bias = w.bias; a.alpha = w.alpha; a.scale = w.scale; a.out_split = p.out_split;

@@ -68,7 +68,7 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
   SC_CUDA(cudaStreamSynchronize(st));
 
   Arena A;
-  struct BOff { size_t c1, conv[5], scale[5], shift[5], alpha[5]; GemmOff d1, d1d, ctc[5]; } bo[3];
+  struct BOff { size_t c1, conv[5], scale[5], shift[5], alpha[5], sw[5]; GemmOff d1, d1d, ctc[5]; } bo[3];
   GemmOff fc1o, fc2o;
   size_t outw, outb;
   for (int b = 0; b < 3; ++b) {
@@ -89,6 +89,21 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
       bo[b].shift[l] = A.alloc(64);
       bo[b].alpha[l] = A.alloc(64);
       if (l > 0) bo[b].ctc[l] = make_gemm(A, ctx->br[b].conv_tc[l], 9 * kC5Ld, co_n, 9 * kC5Ld, 64);
+      if (l > 0) {   // strip-sweep kernel: k-step-packed weight panels, W hi rows then W lo rows
+        SweepW& S = ctx->br[b].conv_sw[l];
+        S.ksteps = (ci_n + 15) / 16; S.bn = (co_n + 15) & ~15; S.npanels = (9 * S.ksteps + 3) / 4;
+        bo[b].sw[l] = A.alloc((size_t)S.npanels * 2 * S.bn * 32);
+        uint16_t* pw = reinterpret_cast<uint16_t*>(&A.host[bo[b].sw[l]]);
+        for (int co = 0; co < co_n; ++co)
+          for (int ci = 0; ci < ci_n; ++ci)
+            for (int t = 0; t < 9; ++t) {
+              const float v = h[B.convW[l] + ((size_t)co * ci_n + ci) * 9 + (8 - t)];
+              const int gk = t * S.ksteps + ci / 16, kk = (gk & 3) * 16 + (ci & 15);
+              const uint16_t hi = bf16_rn(v);
+              pw[((size_t)(gk >> 2) * 2 * S.bn + co) * 64 + kk] = hi;
+              pw[((size_t)(gk >> 2) * 2 * S.bn + S.bn + co) * 64 + kk] = bf16_rn(v - bf16_to_float(hi));
+            }
+      }
       for (int c = 0; c < co_n; ++c) {
         const float beta = h[B.bn[l][0] + c], gamma = h[B.bn[l][1] + c], mean = h[B.bn[l][2] + c], inv = h[B.bn[l][3] + c];
         const float s = gamma * inv;
@@ -158,6 +173,10 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
       ctx->br[b].alpha[l] = base + bo[b].alpha[l];
     }
     for (int l = 1; l < 5; ++l) bind(ctx->br[b].conv_tc[l], bo[b].ctc[l], base);
+    for (int l = 1; l < 5; ++l) {
+      SweepW& S = ctx->br[b].conv_sw[l];
+      S.panels = base + bo[b].sw[l]; S.scale = ctx->br[b].scale[l]; S.shift = ctx->br[b].shift[l]; S.alpha = ctx->br[b].alpha[l];
+    }
     bind(ctx->br[b].d1, bo[b].d1, base);
     bind(ctx->br[b].d1_dense, bo[b].d1d, base);
   }
