@@ -17,7 +17,7 @@ atlas = atlas / atlas.sum(-1, keepdim=True)
 lab = torch.zeros(shape, dtype=torch.uint8, device="cuda")
 ctx.segment_volume(vol, atlas, label_vol=lab)
 names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_tempty", "mma_total", "epi_wait_tfull", "epi_total", "tiles"]
-for cls, nm in [(5, "conv2"), (7, "conv4"), (8, "conv5"), (9, "gemm_d1"), (10, "gemm_fc1"), (11, "gemm_fc2")]:
+for cls, nm in [(5, "conv2"), (6, "conv3"), (7, "conv4"), (8, "conv5")]:
     ctx.set_option("tc_timing", cls)
     ctx.segment_volume(vol, atlas, label_vol=lab)
     torch.cuda.synchronize()

@@ -166,6 +166,7 @@ struct sc_ctx {
   int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
+  int tc_sweep45 = 1;            // bit 0: conv4 + pool2 as a strip sweep, bit 1: conv5 as a strip sweep
   int tc_fuse_w = 1;             // conv tiles: fold xh*wh and xh*wl into one double-width MMA
   int tc_nacc = 1;               // accumulator chains per narrow (<= 64 column) tile: 1, 2 or 4
   bool profile = false;
@@ -256,7 +257,7 @@ int launch_split_rows(sc_ctx* ctx, const float* in, int64_t rows, float* out, cu
 
 // conv_sweep.cu : strip-sweep 3x3 dilated conv (+ fused stride-1 max-pool) over wide-row maps.
 // in_fmt / out_fmt: 1 = 128 B pixels (32 bf16 hi | 32 lo), 0 = 256 B pixels (64 hi | 64 lo)
-int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt, int out_chunks,
+int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
                       int Pw, int R, int dil, int pool, int prof_cls, cudaStream_t st);
 
 // patch_forward.cu

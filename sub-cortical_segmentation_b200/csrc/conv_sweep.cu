@@ -11,9 +11,10 @@
 //   warp 1    MMA issue, converged, compile-time unrolled: per output row 9 taps x KSTEPS x
 //             { xh * [wh | wl] (N = 2*bn),  xl * wh (N = bn) }  -- the bf16x3 split product as two MMAs;
 //             column taps are descriptor start offsets inside the row box, weights stay resident (k-step-packed panels)
-//   warps 2-9 epilogue: TMEM -> BN scale/shift -> PReLU -> [fused 2x2 stride-1 max-pool: horizontal neighbour by
-//             shuffle / a small exchange buffer, vertical neighbour = the previous row kept in registers]
-//             -> split bf16 hi|lo -> warp-transposed coalesced stores
+//   warps 2-17 epilogue (4 lane quarters x 4 column groups): TMEM -> BN scale/shift -> PReLU -> [fused 2x2 stride-1
+//             max-pool: horizontal neighbour by shuffle / a small exchange buffer, vertical neighbour = the previous
+//             row kept in registers] -> split bf16 hi|lo -> SWIZZLE_128B output tile in shared memory -> one TMA
+//             tensor store per row box (no per-thread global addressing; partial boxes are clipped by the TMA unit)
 // Two TMEM accumulators: the epilogue of row i overlaps the MMAs of row i+1.
 //
 // Pixel formats: F32CH: 128 B = 32 bf16 hi | 32 bf16 lo (20-channel maps); F64CH: 256 B = 64 hi | 64 lo.
@@ -33,10 +34,10 @@ struct SweepArgs {
   int in_boxes;           // 1: F32CH input (hi|lo in one 128 B row), 2: F64CH input (hi box, lo box)
   int lo_off;             // byte offset of the lo operand inside a ring slot (64 or SW_SLOT_HALF)
   int out_fmt;            // 1: F32CH, 0: F64CH
-  int out_chunks;         // 16-channel chunks written per pixel (chunks beyond bn are zeros)
+  int out_bufs;           // output tiles in shared memory (2: double-buffered, 1 when shared memory is short)
   int npanels;            // weight panels (4 k-steps each)
-  unsigned char* out;
   const float* scale; const float* shift; const float* alpha;
+  unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
 };
 
 __device__ __forceinline__ void sweep_mma(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t elected) {
@@ -62,11 +63,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+template <int CW>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[CW]) {
+  if constexpr (CW == 16) tmem_ld16(taddr, r); else tmem_ld8(taddr, r);
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), two values per call (packed conversions)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // KSTEPS: 16-channel k-steps per tap; DIL: dilation; POOL: fuse the stride-1 max-pool with window {0, DIL}^2;
-// NCH: 16-column chunks per epilogue warp; LO64: lo operand 64 B into the row (F32CH) instead of in its own box
-template <int KSTEPS, int DIL, int POOL, int NCH, bool LO64>
-__global__ void __launch_bounds__(320, 1)
-conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const SweepArgs a) {
+// CW: accumulator columns per epilogue warp (8 or 16; 4 column groups); LO64: lo operand 64 B into the row (F32CH)
+// instead of in its own box; OUT32: output pixels are F32CH
+template <int KSTEPS, int DIL, int POOL, int CW, bool LO64, bool OUT32>
+__global__ void __launch_bounds__(576, 1)
+conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
+                  const SweepArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int BOXPX = 128 + 2 * DIL;
@@ -78,7 +103,9 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int w_bytes = a.npanels * panel_bytes;
   uint8_t* sW = smem;
   uint8_t* sRing = smem + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + a.stages * SLOT);
+  constexpr int OB_BYTES = OUT32 ? 16384 : 32768;                      // one output row tile: 128 pixels, hi box [+ lo box]
+  uint8_t* sOut = sRing + a.stages * SLOT;                             // 1024-aligned (SLOT, w_bytes are multiples of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + a.out_bufs * OB_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + a.stages;
   uint64_t* tfull = bars + 2 * a.stages;
@@ -86,14 +113,13 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   uint64_t* wfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
   float* s_const = reinterpret_cast<float*>(tmem_slot + 2);            // [scale 64 | shift 64 | alpha 64]
-  float* s_xch = s_const + 192;                                        // [2 row parities][2 groups][NCH][4 quarters][2][16]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_xch + 2 * 2 * 2 * 4 * 2 * 16);   // [8 warps][32 rows][80 B]
+  float* s_xch = s_const + 192;                                        // [2 row parities][4 groups][4 quarters][2][16]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 16); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -107,6 +133,9 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     s_const[64 + i] = ok ? __ldg(a.shift + i) : 0.f;
     s_const[128 + i] = ok ? __ldg(a.alpha + i) : 0.f;
   }
+  for (int i = threadIdx.x; i < a.out_bufs * OB_BYTES / 16; i += blockDim.x)   // channel padding of the output tiles stays zero
+    reinterpret_cast<uint4*>(sOut)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -128,9 +157,12 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapW)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapO)) : "memory");
       mbar_expect_tx(wfull, (uint32_t)w_bytes);
       for (int p = 0; p < a.npanels; ++p) tma_load_2d(&mapW, wfull, sW + p * panel_bytes, 0, p * 2 * a.bn);
       uint32_t g = 0;
+      long long w_empty = 0;
+      const long long tstart = a.dbg ? clock64() : 0;
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         int w0, q, n0, Lc;
         decode(item, w0, q, n0, Lc);
@@ -138,7 +170,11 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int nload = Lc + POOL + 2;
         for (int m = 0; m < nload; ++m, ++g) {
           const uint32_t s = g % a.stages, use = g / a.stages;
-          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          if (use > 0) {
+            const long long c0 = a.dbg ? clock64() : 0;
+            mbar_wait(&empty[s], (use - 1) & 1);
+            if (a.dbg) w_empty += clock64() - c0;
+          }
           mbar_expect_tx(&full[s], (uint32_t)(NBOX * BOX_BYTES));
           uint8_t* sp = sRing + s * SLOT;
           const int r = q + DIL * (n0 + m);          // rows beyond the map are zero-filled by the TMA unit
@@ -146,6 +182,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (NBOX == 2) tma_load_3d(&mapA, &full[s], sp + SW_SLOT_HALF, 64, w0, r);
         }
       }
+      if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = (unsigned long long)w_empty; a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - tstart); }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -157,6 +194,8 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t ring_lo = desc_lo(smem_u32(sRing));
     const uint32_t panel16 = (uint32_t)(panel_bytes >> 4);
     uint32_t g0 = 0, t = 0;
+    long long w_full = 0, w_tempty = 0;
+    const long long tstart = a.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
@@ -164,7 +203,9 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int nrow = Lc + POOL;
       for (int m = 0; m < nrow; ++m, ++t) {
         const uint32_t b = t & 1;
+        long long c0 = a.dbg ? clock64() : 0;
         mbar_wait(&tempty[b], ((t >> 1) & 1) ^ 1);
+        if (a.dbg) { const long long c1 = clock64(); w_tempty += c1 - c0; c0 = c1; }
         uint32_t sl[3];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -173,6 +214,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (m == 0 || ky == 2) mbar_wait(&full[s], (g / a.stages) & 1);
           sl[ky] = ring_lo + s * (SLOT >> 4);
         }
+        if (a.dbg) w_full += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + b * 256;
 #pragma unroll
@@ -202,47 +244,56 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
       g0 += nrow + 2;
     }
+    if (a.dbg && leader) {
+      a.dbg[blockIdx.x * 8 + 2] = (unsigned long long)w_full; a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
+      a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - tstart);
+    }
   } else {
     const int q4 = warp & 3;                 // TMEM lane quarter this warp may read
-    const int ew = warp - 2;                 // 0..7
-    const int grp = ew >> 2;                 // column-chunk group
-    uint8_t* stg = s_stage + ew * 2560;
-    uint8_t* mine = stg + lane * 80;
-    const int px_bytes = a.out_fmt ? 128 : 256;
-    const int lo_byte = a.out_fmt ? 64 : 128;
-    uint32_t t = 0;
+    const int ew = warp - 2;                 // 0..15
+    const int grp = ew >> 2;                 // column group
+    const int c0 = grp * CW;                 // first accumulator column of this warp
+    const bool real = c0 < a.bn;             // groups beyond the computed columns only take part in the barriers
+    const int px = q4 * 32 + lane;           // pixel inside the strip = row of the output tile
+    const bool issuer = threadIdx.x == 64;
+    // byte offsets of this thread's hi / lo pieces inside a tile (SWIZZLE_128B: 16 B chunk index ^= row & 7)
+    const uint32_t row_off = (uint32_t)px * 128u;
+    const uint32_t sw = (uint32_t)(px & 7);
+    const uint32_t hi_chunk = (uint32_t)(c0 >> 3);
+    const uint32_t lo_base = OUT32 ? 0u : 16384u, lo_chunk = OUT32 ? 4u + hi_chunk : hi_chunk;
+    uint32_t t = 0, e = 0;                   // conv rows consumed, rows emitted
+    long long w_tfull = 0;
+    const long long tstart = a.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
       if (Lc <= 0) continue;
       const int nrow = Lc + POOL;
-      float hprev[NCH][16];
+      float hprev[CW];
 #pragma unroll
-      for (int j = 0; j < NCH; ++j)
-#pragma unroll
-        for (int k = 0; k < 16; ++k) hprev[j][k] = 0.f;
+      for (int k = 0; k < CW; ++k) hprev[k] = 0.f;
       for (int m = 0; m < nrow; ++m, ++t) {
         const uint32_t b = t & 1;
+        const long long c0w = a.dbg ? clock64() : 0;
         mbar_wait(&tfull[b], (t >> 1) & 1);
+        if (a.dbg) w_tfull += clock64() - c0w;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float v[NCH][16];
+        float v[CW];
+        if (real) {
+          uint32_t r1[CW], r2[CW];
+          const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
+          tmem_ld<CW>(taddr, r1);
+          tmem_ld<CW>(taddr + (uint32_t)a.bn, r2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          const int c0 = (grp + 2 * j) * 16;
-          if (c0 < a.bn) {
-            uint32_t r1[16], r2[16];
-            const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
-            tmem_ld16(taddr, r1);
-            tmem_ld16(taddr + (uint32_t)a.bn, r2);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const float acc = __uint_as_float(r1[k]) + __uint_as_float(r2[k]);
-              v[j][k] = prelu(fmaf(acc, s_const[c0 + k], s_const[64 + c0 + k]), s_const[128 + c0 + k]);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[j][k] = 0.f;
+          for (int k4 = 0; k4 < CW / 4; ++k4) {
+            const float4 sc_ = *reinterpret_cast<const float4*>(s_const + c0 + 4 * k4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_const + 64 + c0 + 4 * k4);
+            const float4 al = *reinterpret_cast<const float4*>(s_const + 128 + c0 + 4 * k4);
+            v[4 * k4 + 0] = prelu(fmaf(__uint_as_float(r1[4 * k4 + 0]) + __uint_as_float(r2[4 * k4 + 0]), sc_.x, sh.x), al.x);
+            v[4 * k4 + 1] = prelu(fmaf(__uint_as_float(r1[4 * k4 + 1]) + __uint_as_float(r2[4 * k4 + 1]), sc_.y, sh.y), al.y);
+            v[4 * k4 + 2] = prelu(fmaf(__uint_as_float(r1[4 * k4 + 2]) + __uint_as_float(r2[4 * k4 + 2]), sc_.z, sh.z), al.z);
+            v[4 * k4 + 3] = prelu(fmaf(__uint_as_float(r1[4 * k4 + 3]) + __uint_as_float(r2[4 * k4 + 3]), sc_.w, sh.w), al.w);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -250,64 +301,66 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (lane == 0) mbar_arrive(&tempty[b]);
 
         int r_out = q + DIL * (n0 + m);
-        bool emit = true;
         if (POOL) {
           // horizontal neighbour (DIL pixels to the right): same warp by shuffle, next quarter through shared memory
-          float* xw = s_xch + ((((t & 1) * 2 + grp) * 2) * 4 + q4) * 2 * 16;      // [row parity][grp][j][q4][pd][16], j = 0
-          if (lane < DIL) {
+          if (real) {
+            float* xw = s_xch + (((t & 1) * 4 + grp) * 4 + q4) * 32;      // [row parity][group][quarter][pd][16]
+            if (lane < DIL) {
 #pragma unroll
-            for (int j = 0; j < NCH; ++j)
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                *reinterpret_cast<float4*>(xw + j * 4 * 2 * 16 + lane * 16 + 4 * k4) = make_float4(v[j][4 * k4], v[j][4 * k4 + 1], v[j][4 * k4 + 2], v[j][4 * k4 + 3]);
-          }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-          const float* xr = s_xch + ((((t & 1) * 2 + grp) * 2) * 4 + ((q4 + 1) & 3)) * 2 * 16 + (lane >= 32 - DIL ? (lane - (32 - DIL)) * 16 : 0);
-#pragma unroll
-          for (int j = 0; j < NCH; ++j)
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              float nb = __shfl_down_sync(0xffffffffu, v[j][k], DIL);
-              if (lane >= 32 - DIL) nb = xr[j * 4 * 2 * 16 + k];
-              const float h = fmaxf(v[j][k], nb);
-              v[j][k] = fmaxf(h, hprev[j][k]);     // vertical neighbour: previous class row
-              hprev[j][k] = h;
+              for (int k4 = 0; k4 < CW / 4; ++k4)
+                *reinterpret_cast<float4*>(xw + lane * 16 + 4 * k4) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
             }
-          emit = m > 0;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            const bool edge = lane >= 32 - DIL;
+            const float* xr = s_xch + (((t & 1) * 4 + grp) * 4 + ((q4 + 1) & 3)) * 32 + (edge ? (lane - (32 - DIL)) * 16 : 0);
+#pragma unroll
+            for (int k4 = 0; k4 < CW / 4; ++k4) {
+              const float4 x4 = *reinterpret_cast<const float4*>(xr + 4 * k4);
+              const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float nb = __shfl_down_sync(0xffffffffu, v[4 * k4 + k], DIL);
+                if (edge) nb = xs[k];
+                const float h = fmaxf(v[4 * k4 + k], nb);
+                v[4 * k4 + k] = fmaxf(h, hprev[4 * k4 + k]);     // vertical neighbour: previous class row
+                hprev[4 * k4 + k] = h;
+              }
+            }
+          }
+          if (m == 0) continue;                    // block-uniform: the first conv row of an item only primes the pool
           r_out -= DIL;
         }
-        if (!emit || r_out >= a.R) continue;       // warp-uniform
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          const int c0 = (grp + 2 * j) * 16;
-          if (c0 >= a.out_chunks * 16) continue;   // warp-uniform
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[j][2 * k]), h1 = __float2bfloat16_rn(v[j][2 * k + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[j][2 * k] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[j][2 * k + 1] - __bfloat162float(h1));
-            hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
-          *reinterpret_cast<uint4*>(mine) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(mine + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          *reinterpret_cast<uint4*>(mine + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(mine + 48) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          __syncwarp();
-          unsigned char* orow = a.out + (long long)r_out * a.Pw * px_bytes + c0 * 2;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int half = i >> 1, row = (i & 1) * 16 + (lane >> 1), part = lane & 1;
-            const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 80 + half * 32 + part * 16);
-            const int pl = q4 * 32 + row;          // pixel inside the strip
-            const int w = w0 + pl;
-            if (pl < a.strip_w && w < a.Pw)
-              *reinterpret_cast<uint4*>(orow + (long long)w * px_bytes + half * lo_byte + part * 16) = d;
-          }
-          __syncwarp();
+        // ---- emit row r_out: pieces -> swizzled output tile -> TMA store
+        uint8_t* ob = sOut + (e % (uint32_t)a.out_bufs) * OB_BYTES;
+        if (a.out_bufs == 1) {                      // single tile: wait until the previous store has read it
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 5, 512;" ::: "memory");
         }
+        if (real) {
+          uint32_t hi[CW / 2], lo[CW / 2];
+#pragma unroll
+          for (int k = 0; k < CW / 2; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+#pragma unroll
+          for (int c = 0; c < CW / 8; ++c) {
+            *reinterpret_cast<uint4*>(ob + row_off + (((hi_chunk + c) ^ sw) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            *reinterpret_cast<uint4*>(ob + lo_base + row_off + (((lo_chunk + c) ^ sw) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        if (a.out_bufs == 2 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the other tile is free again
+        asm volatile("bar.sync 6, 512;" ::: "memory");
+        if (issuer) {
+          tma_store_3d(&mapO, ob, 0, w0, r_out);
+          if (!OUT32) tma_store_3d(&mapO, ob + 16384, 64, w0, r_out);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++e;
       }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (a.dbg && threadIdx.x == 64) {
+      a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - tstart);
+      a.dbg[blockIdx.x * 8 + 7] = t;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -321,22 +374,23 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-template <int KSTEPS, int DIL, int POOL, int NCH, bool LO64>
-static int launch_sweep_t(sc_ctx* ctx, const CUtensorMap& mapA, const CUtensorMap& mapW, const SweepArgs& a, size_t smem, cudaStream_t st) {
-  auto kern = conv_sweep_kernel<KSTEPS, DIL, POOL, NCH, LO64>;
+template <int KSTEPS, int DIL, int POOL, int CW, bool LO64, bool OUT32>
+static int launch_sweep_t(sc_ctx* ctx, const CUtensorMap& mapA, const CUtensorMap& mapW, const CUtensorMap& mapO, const SweepArgs& a,
+                          size_t smem, cudaStream_t st) {
+  auto kern = conv_sweep_kernel<KSTEPS, DIL, POOL, CW, LO64, OUT32>;
   static bool configured = false;
   if (!configured) {
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int grid = a.n_items < ctx->sm_count ? a.n_items : ctx->sm_count;
-  kern<<<grid, 320, smem, st>>>(mapA, mapW, a);
+  kern<<<grid, 576, smem, st>>>(mapA, mapW, mapO, a);
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
 }
 
-int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt, int out_chunks,
+int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
                       int Pw, int R, int dil, int pool, int prof_cls, cudaStream_t st) {
   TcState* s = reinterpret_cast<TcState*>(ctx->tc_state);
   SC_CHECK(s != nullptr, SC_ERR_UNSUPPORTED, "tcgen05 back-end not initialised");
@@ -356,20 +410,26 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   a.n_items = a.nstrips * dil * nseg;
   a.in_boxes = in_fmt ? 1 : 2;
   a.lo_off = in_fmt ? 64 : SW_SLOT_HALF;
-  a.out_fmt = out_fmt; a.out_chunks = out_chunks;
+  a.out_fmt = out_fmt;
   a.npanels = w.npanels;
-  a.out = reinterpret_cast<unsigned char*>(out);
   a.scale = w.scale; a.shift = w.shift; a.alpha = w.alpha;
-  SC_CHECK(out_chunks * 16 <= (out_fmt ? 32 : 64) && w.bn <= 64 && w.bn % 16 == 0, SC_ERR_ARG, "conv_sweep: bad channel geometry");
+  a.dbg = (ctx->tc_timing_cls == prof_cls) ? ctx->tc_timing_buf : nullptr;
+  SC_CHECK(w.bn <= (out_fmt ? 32 : 64) && w.bn % 16 == 0, SC_ERR_ARG, "conv_sweep: bad channel geometry");
   const int slot = a.in_boxes * SW_SLOT_HALF;
   const int w_bytes = w.npanels * 2 * w.bn * 128;
-  const int fixed = 1024 + w_bytes + 256 /*barriers, tmem slot*/ + 192 * 4 + 2 * 2 * 2 * 4 * 2 * 16 * 4 + 8 * 2560;
-  a.stages = (227 * 1024 - fixed) / slot;
+  const int ob_bytes = out_fmt ? 16384 : 32768;
+  const int fixed = 1024 + w_bytes + 256 /*barriers, tmem slot*/ + 192 * 4 + 2 * 4 * 4 * 2 * 16 * 4;
+  a.out_bufs = 2;
+  a.stages = (227 * 1024 - fixed - 2 * ob_bytes) / slot;
+  if (a.stages < 4) {                                                   // short of shared memory: single output tile
+    a.out_bufs = 1;
+    a.stages = (227 * 1024 - fixed - ob_bytes) / slot;
+  }
   if (a.stages > 8) a.stages = 8;
   SC_CHECK(a.stages >= 3, SC_ERR_ARG, "conv_sweep: ring does not fit (layer %d)", layer);
-  const size_t smem = (size_t)fixed + (size_t)a.stages * slot;
+  const size_t smem = (size_t)fixed + (size_t)a.stages * slot + (size_t)a.out_bufs * ob_bytes;
 
-  CUtensorMap mapA, mapW;
+  CUtensorMap mapA, mapW, mapO;
   {
     const int pxe = in_fmt ? 64 : 128;                                    // bf16 elements per pixel
     cuuint64_t dims[3] = {(cuuint64_t)pxe, (cuuint64_t)Pw, (cuuint64_t)R};
@@ -391,17 +451,30 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "conv_sweep: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
   }
+  {
+    // output: one box of strip_w pixels x 128 B per store (hi and lo boxes for the 256 B pixels); the columns a strip
+    // does not own (pool reach) are simply not part of the box
+    const int pxe = out_fmt ? 64 : 128;
+    cuuint64_t dims[3] = {(cuuint64_t)pxe, (cuuint64_t)Pw, (cuuint64_t)R};
+    cuuint64_t strides[2] = {(cuuint64_t)pxe * 2, (cuuint64_t)Pw * pxe * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)a.strip_w, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = s->encode(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "conv_sweep: cuTensorMapEncodeTiled(O) failed with %d", (int)r);
+  }
   ProfScope prof(ctx, prof_cls, st);
-  const int nch = (out_chunks + 1) / 2;
-  if (w.ksteps == 2 && dil == 1 && pool && nch == 1 && in_fmt) return launch_sweep_t<2, 1, 1, 1, true>(ctx, mapA, mapW, a, smem, st);   // conv2 + pool1
-  if (w.ksteps == 2 && dil == 2 && !pool && nch == 2 && in_fmt) return launch_sweep_t<2, 2, 0, 2, true>(ctx, mapA, mapW, a, smem, st);  // conv3
-  if (w.ksteps == 3 && dil == 2 && pool && nch == 2 && !in_fmt) return launch_sweep_t<3, 2, 1, 2, false>(ctx, mapA, mapW, a, smem, st); // conv4 + pool2
-  if (w.ksteps == 3 && dil == 4 && !pool && nch == 2 && !in_fmt) return launch_sweep_t<3, 4, 0, 2, false>(ctx, mapA, mapW, a, smem, st); // conv5
+  const bool i32 = in_fmt != 0, o32 = out_fmt != 0;
+  if (w.ksteps == 2 && dil == 1 && pool && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 1, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // conv2 + pool1
+  if (w.ksteps == 2 && dil == 2 && !pool && i32 && !o32) return launch_sweep_t<2, 2, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);              // conv3
+  if (w.ksteps == 3 && dil == 2 && pool && !i32 && !o32) return launch_sweep_t<3, 2, 1, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);             // conv4 + pool2
+  if (w.ksteps == 3 && dil == 4 && !pool && !i32 && !o32) return launch_sweep_t<3, 4, 0, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);            // conv5
   // patchwise maps (dilation 1 everywhere, stride-2 pools stay separate passes)
-  if (w.ksteps == 2 && dil == 1 && !pool && nch == 1 && in_fmt) return launch_sweep_t<2, 1, 0, 1, true>(ctx, mapA, mapW, a, smem, st);
-  if (w.ksteps == 2 && dil == 1 && !pool && nch == 2 && in_fmt) return launch_sweep_t<2, 1, 0, 2, true>(ctx, mapA, mapW, a, smem, st);
-  if (w.ksteps == 3 && dil == 1 && !pool && nch == 2 && !in_fmt) return launch_sweep_t<3, 1, 0, 2, false>(ctx, mapA, mapW, a, smem, st);
-  set_error("conv_sweep: no kernel instance for ksteps=%d dil=%d pool=%d chunks=%d in_fmt=%d", w.ksteps, dil, pool, out_chunks, in_fmt);
+  if (w.ksteps == 2 && dil == 1 && !pool && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 0, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);
+  if (w.ksteps == 2 && dil == 1 && !pool && i32 && !o32) return launch_sweep_t<2, 1, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);
+  if (w.ksteps == 3 && dil == 1 && !pool && !i32 && !o32) return launch_sweep_t<3, 1, 0, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);
+  set_error("conv_sweep: no kernel instance for ksteps=%d dil=%d pool=%d in_fmt=%d out_fmt=%d", w.ksteps, dil, pool, in_fmt, out_fmt);
   return SC_ERR_ARG;
 }
 

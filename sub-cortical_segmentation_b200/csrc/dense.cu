@@ -632,12 +632,14 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
         ctx->launches++;
         SC_CUDA(cudaGetLastError());
       }
-      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, 2, Pw, R1, 1, 1, PC_CONV2, st));     // conv2 + pool1
-      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, 4, Pw, R1, 2, 0, PC_CONV3, st));     // conv3
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, Pw, R1, 1, 1, PC_CONV2, st));     // conv2 + pool1
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, Pw, R1, 2, 0, PC_CONV3, st));     // conv3
       const int P = (int)npos;
       const unsigned pgrid = (unsigned)((npos * 16 + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (npos * 16 + 255) / 256 : (int64_t)ctx->sm_count * 64);
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, 1, P, m4, 1, P, 1, 2, 40, PC_CONV4, st, Pw));
-      {
+      if (ctx->tc_sweep45 & 1) {
+        SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, m3, 0, mp2, 0, Pw, R1, 2, 1, PC_CONV4, st));   // conv4 + pool2
+      } else {
+        SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, 1, P, m4, 1, P, 1, 2, 40, PC_CONV4, st, Pw));
         ProfScope prof(ctx, PC_POOL, st);
         pool_flat_kernel<<<pgrid, 256, 0, st>>>(m4, mp2, npos, Pw, 2);
         ctx->launches++;
