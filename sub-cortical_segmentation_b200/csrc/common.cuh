@@ -89,6 +89,7 @@ constexpr int kH1 = 555;         // FC1 out (540) + atlas (15)
 constexpr int kH1Ld = 576;       // row stride (K of fc_2)
 constexpr int kH2 = 270;
 constexpr int kH2Ld = 272;
+constexpr int kH2LdTc = 320;     // tcgen05 dense path: h2 rows in the split layout, 5 k-blocks of 64 (the out_layer GEMM reads them)
 constexpr int kC5Ld = 64;        // conv5 output channels padded 60 -> 64 (NHWC)
 constexpr int kD1K = 9 * kC5Ld;  // 576: K of d1 as a 3x3 dilation-4 conv over conv5 output
 
@@ -154,6 +155,7 @@ struct sc_ctx {
   size_t derived_floats = 0;
   sc::BranchW br[3];
   sc::GemmW fc1, fc2;
+  sc::GemmW outl;                // out_layer 270 -> 15 as a K = 320, N = 16 GEMM (tcgen05 softmax epilogue)
   float* out_w = nullptr;        // [270][16]
   float* out_b = nullptr;        // [16]
   sc::Workspace ws;              // inference scratch (grow-only)
@@ -229,6 +231,7 @@ struct GemmProblem {
   int n_store;          // columns written (<= w.Npad)
   int c_col0;           // first output column inside the C row (C points at the row start)
   int out_split;        // write C rows in the split bf16 hi|lo block layout (they feed a tcgen05 GEMM)
+  const struct SoftmaxOut* sm = nullptr;   // tcgen05 back-end: softmax / argmax epilogue instead of the row store (out_layer)
   int a_swap = 0;       // tensor-map dimension order is (k, pixel, plane, line) instead of (k, pixel, line, plane)
 };
 int launch_gemm(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
@@ -246,6 +249,8 @@ inline void gemm_problem_rows(GemmProblem& p, const float* A, int64_t lda, int k
 // geo != nullptr: row m is voxel (ix,iy,iz) of a box slab; results go to the volume-shaped
 // outputs (label8 / proba) at that voxel, skipped where mask[voxel] == 0.
 struct OutGeo { int x0, y0, z0, by, bz, Y, Z; };
+// out_layer + softmax fused into the tcgen05 GEMM epilogue (N = 16): where the results of row m go
+struct SoftmaxOut { float* proba; int32_t* label32; uint8_t* label8; const uint8_t* mask; OutGeo geo; int use_geo; };
 int launch_out_softmax(sc_ctx* ctx, const float* h2, int64_t n, float* proba, int32_t* label32, uint8_t* label8,
                        const uint8_t* mask, const OutGeo* geo, cudaStream_t st);
 

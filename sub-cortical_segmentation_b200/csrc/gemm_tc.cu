@@ -63,6 +63,8 @@ struct TcArgs {
   int fuse_w;         // narrow tiles: xh * [wh | wl] as ONE MMA of 2*bn columns (the epilogue adds the halves) + xl * wh:
                       // two instead of three MMAs and A shared-memory reads per product
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
+  int sm_on;          // persistent kernel, bn = 16: softmax / argmax epilogue (out_layer), results scattered through `sm`
+  SoftmaxOut sm;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -379,6 +381,60 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       const int mw = m0 + q * 32;                       // first row of this warp
       uint8_t* stg = s_stage + (warp - 2) * 2560;
       uint8_t* mine = stg + lane * 80;
+      if (a.sm_on) {
+        // out_layer (cnn_cort/nets.py:229-231): 15 logits per row -> softmax; argmax on the float32 probabilities,
+        // first maximum wins (np.argmax).  One thread owns one row.
+        if (grp == 0) {
+          uint32_t rr[16];
+          const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+                "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const long long m = (long long)mw + lane;
+          bool ok = m < a.M;
+          long long o = m;
+          if (ok && a.sm.use_geo) {
+            const long long plane = (long long)a.sm.geo.by * a.sm.geo.bz;
+            const int ix = (int)(m / plane);
+            const int rem = (int)(m - (long long)ix * plane);
+            const int iy = rem / a.sm.geo.bz, iz = rem - iy * a.sm.geo.bz;
+            o = ((long long)(a.sm.geo.x0 + ix) * a.sm.geo.Y + (a.sm.geo.y0 + iy)) * a.sm.geo.Z + (a.sm.geo.z0 + iz);
+            if (a.sm.mask && a.sm.mask[o] == 0) ok = false;
+          }
+          if (ok) {
+            float zz[15];
+#pragma unroll
+            for (int c = 0; c < 15; ++c) zz[c] = __uint_as_float(rr[c]) + cb[c];
+            float mx = zz[0];
+#pragma unroll
+            for (int c = 1; c < 15; ++c) mx = fmaxf(mx, zz[c]);
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 15; ++c) { zz[c] = expf(zz[c] - mx); sum += zz[c]; }
+            const float inv = 1.f / sum;
+            int best = 0;
+            float bp = zz[0] * inv;
+#pragma unroll
+            for (int c = 0; c < 15; ++c) {
+              zz[c] *= inv;
+              if (zz[c] > bp) { bp = zz[c]; best = c; }
+            }
+            if (a.sm.proba) {
+#pragma unroll
+              for (int c = 0; c < 15; ++c) a.sm.proba[o * 15 + c] = zz[c];
+            }
+            if (a.sm.label32) a.sm.label32[o] = best;
+            if (a.sm.label8) a.sm.label8[o] = (uint8_t)best;
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[b]);
+        continue;
+      }
       for (int c0 = grp * 16; c0 < a.bn; c0 += 16 * G) {
         uint32_t rr[16];
         const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -796,6 +852,11 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.c_col0 = p.c_col0;
   a.nkb = p.ntaps * a.kpt;
   a.bn = pick_bn(p.n_store);
+  a.sm_on = 0;
+  if (p.sm) {
+    SC_CHECK(ctx->tc_variant != 1 && p.n_store == 16 && p.ntaps == 1, SC_ERR_ARG, "gemm_tc: the softmax epilogue needs the persistent kernel and a 16-column layer");
+    a.bn = 16; a.sm_on = 1; a.sm = *p.sm;
+  }
   a.zero_to = 0;
   if (ctx->tc_variant != 1 && p.ntaps == 9 && w.N < p.n_store && p.n_store <= 64) {
     // conv layers: compute only the real output channels (rounded to 16), zero-fill the channel padding;
