@@ -144,6 +144,10 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     if (value >= 0 && !ctx->tc_timing_buf) SC_CUDA(cudaMalloc(&ctx->tc_timing_buf, sizeof(unsigned long long) * 8 * 1024));
     return SC_OK;
   }
+  if (!strcmp(key, "tc_atlas_fused")) {
+    ctx->tc_atlas_fused = value != 0;
+    return SC_OK;
+  }
   if (!strcmp(key, "tc_sweep45")) {   // bit 0: conv4 + pool2, bit 1: conv5 run as strip sweeps (conv_sweep.cu)
     SC_CHECK(value >= 0 && value <= 3, SC_ERR_ARG, "sc_set_option: tc_sweep45 must be 0..3");
     ctx->tc_sweep45 = (int)value;

@@ -168,6 +168,7 @@ struct sc_ctx {
   int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
+  int tc_atlas_fused = 1;        // FC1's CTA-pair epilogue writes the atlas columns of h1 (no separate atlas pass)
   int tc_sweep45 = 1;            // bit 0: conv4 + pool2 as a strip sweep, bit 1: conv5 as a strip sweep
   int tc_fuse_w = 1;             // conv tiles: fold xh*wh and xh*wl into one double-width MMA
   int tc_nacc = 1;               // accumulator chains per narrow (<= 64 column) tile: 1, 2 or 4
@@ -210,6 +211,9 @@ int launch_scatter(sc_ctx* ctx, const int32_t* xyz, int64_t n, const int32_t* la
 // weights.cu
 int derive_weights(sc_ctx* ctx, cudaStream_t st);
 
+// row m of a box slab <-> voxel (x0 + m / (by*bz), y0 + (m / bz) % by, z0 + m % bz) of a [X][Y][Z] volume
+struct OutGeo { int x0, y0, z0, by, bz, Y, Z; };
+
 // gemm_simt.cu : C = prelu(A*W + b), implicit-GEMM with taps
 struct GemmProblem {
   const float* A;       // A(m, y, z, tap, k) = A[z*a_zs + y*a_ys + m*lda + tap_off[tap] + k]
@@ -231,6 +235,8 @@ struct GemmProblem {
   int n_store;          // columns written (<= w.Npad)
   int c_col0;           // first output column inside the C row (C points at the row start)
   int out_split;        // write C rows in the split bf16 hi|lo block layout (they feed a tcgen05 GEMM)
+  const float* atlas = nullptr;            // tcgen05 pair kernel (FC1): write the atlas prior of every row (with the background
+  OutGeo ageo;                             // fix of base.py:392-394) into columns 540..554 and zeros up to 575
   const struct SoftmaxOut* sm = nullptr;   // tcgen05 back-end: softmax / argmax epilogue instead of the row store (out_layer)
   int a_swap = 0;       // tensor-map dimension order is (k, pixel, plane, line) instead of (k, pixel, line, plane)
 };
@@ -248,7 +254,6 @@ inline void gemm_problem_rows(GemmProblem& p, const float* A, int64_t lda, int k
 // rows of h2 -> softmax / argmax.  geo == nullptr: row m writes proba[m], label32[m].
 // geo != nullptr: row m is voxel (ix,iy,iz) of a box slab; results go to the volume-shaped
 // outputs (label8 / proba) at that voxel, skipped where mask[voxel] == 0.
-struct OutGeo { int x0, y0, z0, by, bz, Y, Z; };
 // out_layer + softmax fused into the tcgen05 GEMM epilogue (N = 16): where the results of row m go
 struct SoftmaxOut { float* proba; int32_t* label32; uint8_t* label8; const uint8_t* mask; OutGeo geo; int use_geo; };
 int launch_out_softmax(sc_ctx* ctx, const float* h2, int64_t n, float* proba, int32_t* label32, uint8_t* label8,

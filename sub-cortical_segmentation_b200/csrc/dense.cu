@@ -727,12 +727,15 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)rows);
     p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
+    const bool atlas_fused = tc && ctx->tc_variant == 3 && ctx->tc_atlas_fused;   // the CTA-pair kernel writes the atlas columns in its epilogue
+    if (atlas_fused) { p.atlas = atlas; p.ageo = og; p.ageo.x0 = b[0] + ix0; }
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
-    {  // after FC1: the tensor-core epilogue writes whole 16-column chunks (columns 540..543 as zeros)
+    p.atlas = nullptr;
+    if (!atlas_fused) {  // after FC1: the tensor-core epilogue writes whole 16-column chunks (columns 540..543 as zeros)
       ProfScope prof(ctx, PC_ATLAS, st);
       dense_atlas_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(atlas, og, ix0, rows, h1, tc ? 1 : 0);
+      ctx->launches++;
     }
-    ctx->launches++;
     SC_CUDA(cudaGetLastError());
     gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)rows);
     p.C = h2; p.ldc = h2ld; p.n_store = kH2Ld; p.out_split = tc ? 1 : 0;

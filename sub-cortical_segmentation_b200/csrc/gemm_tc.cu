@@ -63,6 +63,8 @@ struct TcArgs {
   int fuse_w;         // narrow tiles: xh * [wh | wl] as ONE MMA of 2*bn columns (the epilogue adds the halves) + xl * wh:
                       // two instead of three MMAs and A shared-memory reads per product
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
+  const float* atlas; // pair kernel: atlas prior volume [X][Y][Z][15] -> output columns 540..575 (see GemmProblem::atlas)
+  OutGeo ageo;
   int sm_on;          // persistent kernel, bn = 16: softmax / argmax epilogue (out_layer), results scattered through `sm`
   SoftmaxOut sm;
 };
@@ -740,6 +742,34 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           v[4 * k4 + 3] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 3]), sc_.w, bi.w), al.w);
         }
         const int ncol = a.c_col0 + n0 + c0;
+        if (a.atlas && (ncol == 528 || ncol == 544)) {
+          // atlas prior of this thread's row (cnn_cort/base.py:387-394): atlas[x,y,z,:], all-zero rows become one-hot
+          // background; the float32 sum follows numpy's pairwise order.  Columns 540..554 of the h1 row.
+          const long long mrow = (long long)mw + lane;
+          float at[15];
+          if (mrow < a.M) {
+            const long long plane = (long long)a.ageo.by * a.ageo.bz;
+            const int ix = (int)(mrow / plane);
+            const int rem = (int)(mrow - (long long)ix * plane);
+            const int iy = rem / a.ageo.bz, iz = rem - iy * a.ageo.bz;
+            const long long vx = ((long long)(a.ageo.x0 + ix) * a.ageo.Y + (a.ageo.y0 + iy)) * a.ageo.Z + (a.ageo.z0 + iz);
+#pragma unroll
+            for (int c = 0; c < 15; ++c) at[c] = __ldg(a.atlas + vx * 15 + c);
+            float sum = __fadd_rn(__fadd_rn(__fadd_rn(at[0], at[1]), __fadd_rn(at[2], at[3])),
+                                  __fadd_rn(__fadd_rn(at[4], at[5]), __fadd_rn(at[6], at[7])));
+#pragma unroll
+            for (int k = 8; k < 15; ++k) sum = __fadd_rn(sum, at[k]);
+            if (sum == 0.f) at[14] = 1.f;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 15; ++c) at[c] = 0.f;
+          }
+          if (ncol == 528) { v[12] = at[0]; v[13] = at[1]; v[14] = at[2]; v[15] = at[3]; }
+          else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = k < 11 ? at[4 + k] : 0.f;
+          }
+        }
         if (a.out_split) {
           uint32_t hi[8], lo[8];
 #pragma unroll
@@ -853,6 +883,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.nkb = p.ntaps * a.kpt;
   a.bn = pick_bn(p.n_store);
   a.sm_on = 0;
+  a.atlas = p.atlas; a.ageo = p.ageo;
   if (p.sm) {
     SC_CHECK(ctx->tc_variant != 1 && p.n_store == 16 && p.ntaps == 1, SC_ERR_ARG, "gemm_tc: the softmax epilogue needs the persistent kernel and a 16-column layer");
     a.bn = 16; a.sm_on = 1; a.sm = *p.sm;
@@ -870,6 +901,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.Y = p.Y; a.M = p.M; a.n_store = a.zero_to ? a.bn : p.n_store; a.npad = w.Npad;
   if (ctx->tc_variant != 1) {
     a.n_store = (a.n_store + 15) & ~15;   // whole 16-column chunks: the caller lets pad columns be overwritten with zeros
+    if (p.atlas) a.n_store = 576;
     SC_CHECK(p.c_col0 % 16 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 16 for the persistent kernel");
   }
   a.a_y0 = p.a_y0; a.a_z0 = p.a_z0; a.a_swap = p.a_swap;
@@ -880,6 +912,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   const bool persistent = ctx->tc_variant != 1;
   // CTA pairs (cta_group::2) for the wide streaming-weight layers
   const bool pair = ctx->tc_variant == 3 && a.bn >= 128 && a.bn % 16 == 0 && !(p.ntaps == 9 && a.nkb * 2 * a.bn * 128 <= 150 * 1024);
+  SC_CHECK(!p.atlas || (pair && p.c_col0 == 0 && p.n_store == 540 && w.Npad == 576), SC_ERR_ARG, "gemm_tc: the atlas epilogue is for FC1 in the CTA-pair kernel");
   const long long blocks = (long long)a.mt * a.nt * p.Y * p.Z;
   SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
   a.num_tiles = blocks;
