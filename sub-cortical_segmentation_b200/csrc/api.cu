@@ -149,7 +149,7 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     return SC_OK;
   }
   if (!strcmp(key, "tc_sweep45")) {   // bit 0: conv4 + pool2, bit 1: conv5 run as strip sweeps (conv_sweep.cu)
-    SC_CHECK(value >= 0 && value <= 3, SC_ERR_ARG, "sc_set_option: tc_sweep45 must be 0..3");
+    SC_CHECK(value >= 0 && value <= 7, SC_ERR_ARG, "sc_set_option: tc_sweep45 must be 0..7");
     ctx->tc_sweep45 = (int)value;
     return SC_OK;
   }

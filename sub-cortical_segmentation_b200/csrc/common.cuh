@@ -105,6 +105,7 @@ struct GemmW {      // one dense layer prepared for both GEMM back-ends
 struct SweepW {     // one conv layer prepared for the strip-sweep tcgen05 kernel (conv_sweep.cu)
   float* panels;    // [npanels][2*bn][64] bf16: rows 0..bn-1 = W hi, bn..2bn-1 = W lo; column block (gk & 3) of panel gk >> 2
                     // holds k-step gk = tap * ksteps + ci / 16 (flipped taps, zero padded)
+  float* panels_pair;  // the same for the CTA-pair kernel: per panel the rows of rank 0 then rank 1, each W hi[bn/2] | W lo[bn/2]
   float* scale;     // BN folded scale / shift and PReLU slope, padded to 64 with zeros
   float* shift;
   float* alpha;
@@ -169,7 +170,7 @@ struct sc_ctx {
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
   int tc_atlas_fused = 1;        // FC1's CTA-pair epilogue writes the atlas columns of h1 (no separate atlas pass)
-  int tc_sweep45 = 1;            // bit 0: conv4 + pool2 as a strip sweep, bit 1: conv5 as a strip sweep
+  int tc_sweep45 = 7;            // bit 0: conv4 + pool2 as a strip sweep, bit 1: conv5 as a strip sweep, bit 2: CTA pairs for both
   int tc_fuse_w = 1;             // conv tiles: fold xh*wh and xh*wl into one double-width MMA
   int tc_nacc = 1;               // accumulator chains per narrow (<= 64 column) tile: 1, 2 or 4
   bool profile = false;

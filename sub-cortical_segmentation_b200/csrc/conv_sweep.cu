@@ -372,6 +372,294 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the 40-channel-input layers (conv4 + pool2, conv5), whose resident weights do
+// not leave room for a ring in one CTA.  A cluster of two CTAs sweeps two adjacent strips in lock-step:
+//   * every CTA loads its own strip's rows, but only HALF of the output channels' weights (N split across the pair)
+//   * both producers signal the LEADER's full barrier; the leader's MMA warp issues tcgen05.mma.cta_group::2 (M = 256)
+//     -- the plain three-MMA split product xl*wh + xh*wl + xh*wh into ONE accumulator (the [wh | wl] column fusion would
+//     need asymmetric weight halves) -- and multicasts its commits to both CTAs
+//   * every CTA's epilogue drains its own 128 TMEM lanes and arrives remotely on the leader's accumulator-empty barrier
+// Input and output pixels are 256 B (64 hi | 64 lo); 4 column groups of 16.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sweep_mma_2sm(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(acc), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(elected), "r"(0x40004040u) : "memory");
+}
+
+template <int KSTEPS, int DIL, int POOL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
+conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
+                       const SweepArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int BOXPX = 128 + 2 * DIL;
+  constexpr int BOX_BYTES = BOXPX * 128;
+  constexpr int SLOT = 2 * SW_SLOT_HALF;
+  constexpr int CW = 16;
+  const int panel_bytes = a.bn * 128;                                   // this CTA's half: bn/2 rows of W hi, bn/2 rows of W lo
+  const int w_bytes = a.npanels * panel_bytes;
+  uint8_t* sW = smem;
+  uint8_t* sRing = smem + ((w_bytes + 1023) & ~1023);
+  constexpr int OB_BYTES = 32768;
+  uint8_t* sOut = sRing + a.stages * SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + a.out_bufs * OB_BYTES);
+  uint64_t* full = bars;                        // leader only: both producers signal it
+  uint64_t* empty = bars + a.stages;            // per CTA, arrived by the leader's multicast commit
+  uint64_t* tfull = bars + 2 * a.stages;        // per CTA
+  uint64_t* tempty = tfull + 2;                 // leader only: both CTAs' epilogue warps arrive
+  uint64_t* wfull = tempty + 2;                 // leader only: both CTAs' weight halves
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* s_const = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_xch = s_const + 192;                 // pooled layers only
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 32); }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    const bool ok = i < a.bn;
+    s_const[i] = ok ? __ldg(a.scale + i) : 0.f;
+    s_const[64 + i] = ok ? __ldg(a.shift + i) : 0.f;
+    s_const[128 + i] = ok ? __ldg(a.alpha + i) : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.out_bufs * OB_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sOut)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair item -> (strip pair, class q, segment); this CTA's strip is 2 * strip_pair + rank
+  const int nsp = (a.nstrips + 1) >> 1;
+  auto decode = [&](int item, int& w0, int& q, int& n0, int& Lc) {
+    const int sp = item % nsp;
+    const int rest = item / nsp;
+    q = rest % DIL;
+    const int seg = rest / DIL;
+    w0 = (2 * sp + (int)rank) * a.strip_w;       // may lie beyond the map: loads are zero-filled, stores clipped
+    const int Nq = (a.R - q + DIL - 1) / DIL;
+    n0 = seg * a.L;
+    Lc = Nq - n0 < a.L ? Nq - n0 : a.L;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapW)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapO)) : "memory");
+      {
+        const uint32_t lbar = smem_u32(wfull) & 0xFEFFFFFFu;            // the leader's barrier (peer bit cleared)
+        if (rank == 0) mbar_expect_tx(wfull, (uint32_t)(2 * w_bytes));
+        for (int p = 0; p < a.npanels; ++p) tma_load_2d_2sm(&mapW, lbar, sW + p * panel_bytes, 0, (p * 2 + (int)rank) * a.bn);
+      }
+      uint32_t g = 0;
+      for (int item = pair; item < a.n_items; item += npairs) {
+        int w0, q, n0, Lc;
+        decode(item, w0, q, n0, Lc);
+        if (Lc <= 0) continue;
+        const int nload = Lc + POOL + 2;
+        for (int m = 0; m < nload; ++m, ++g) {
+          const uint32_t s = g % a.stages, use = g / a.stages;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          const uint32_t lbar = smem_u32(&full[s]) & 0xFEFFFFFFu;
+          if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * 2 * BOX_BYTES));   // both CTAs' boxes land on it
+          uint8_t* sp = sRing + s * SLOT;
+          const int r = q + DIL * (n0 + m);
+          tma_load_3d_2sm(&mapA, lbar, sp, 0, w0, r);
+          tma_load_3d_2sm(&mapA, lbar, sp + SW_SLOT_HALF, 64, w0, r);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t leader = elect_one();
+      // D = F32, A = B = BF16, K-major, N = bn (bn/2 weight rows from each CTA), M = 256
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      mbar_wait(wfull, 0);
+      const uint32_t w_lo = desc_lo(smem_u32(sW));
+      const uint32_t ring_lo = desc_lo(smem_u32(sRing));
+      const uint32_t panel16 = (uint32_t)(panel_bytes >> 4);
+      const uint32_t wl_off = (uint32_t)((a.bn >> 1) * 128) >> 4;       // W lo rows follow the bn/2 W hi rows
+      uint32_t g0 = 0, t = 0;
+      for (int item = pair; item < a.n_items; item += npairs) {
+        int w0, q, n0, Lc;
+        decode(item, w0, q, n0, Lc);
+        if (Lc <= 0) continue;
+        const int nrow = Lc + POOL;
+        for (int m = 0; m < nrow; ++m, ++t) {
+          const uint32_t b = t & 1;
+          mbar_wait(&tempty[b], ((t >> 1) & 1) ^ 1);
+          uint32_t sl[3];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint32_t g = g0 + m + ky;
+            const uint32_t s = g % a.stages;
+            if (m == 0 || ky == 2) mbar_wait(&full[s], (g / a.stages) & 1);
+            sl[ky] = ring_lo + s * (SLOT >> 4);
+          }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t acc = tmem_base + b * 256;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+              for (int ks = 0; ks < KSTEPS; ++ks) {
+                const int gk = (ky * 3 + kx) * KSTEPS + ks;
+                const uint32_t a_hi = sl[ky] + (uint32_t)(kx * DIL * 8 + ks * 2);
+                const uint32_t a_lo = a_hi + (uint32_t)(SW_SLOT_HALF >> 4);
+                const uint32_t wh = w_lo + (uint32_t)(gk >> 2) * panel16 + (uint32_t)((gk & 3) * 2);
+                sweep_mma_2sm(acc, a_lo, wh, idesc, gk != 0, leader);
+                sweep_mma_2sm(acc, a_hi, wh + wl_off, idesc, 1, leader);
+                sweep_mma_2sm(acc, a_hi, wh, idesc, 1, leader);
+              }
+            }
+          }
+          if (leader) {
+            umma_commit_2sm(&empty[(g0 + m) % a.stages]);
+            if (m == nrow - 1) {
+              umma_commit_2sm(&empty[(g0 + m + 1) % a.stages]);
+              umma_commit_2sm(&empty[(g0 + m + 2) % a.stages]);
+            }
+            umma_commit_2sm(&tfull[b]);
+          }
+          __syncwarp();
+        }
+        g0 += nrow + 2;
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
+    const int c0 = grp * CW;
+    const bool real = c0 < a.bn;
+    const int px = q4 * 32 + lane;
+    const bool issuer = threadIdx.x == 64;
+    const uint32_t row_off = (uint32_t)px * 128u;
+    const uint32_t sw = (uint32_t)(px & 7);
+    const uint32_t hi_chunk = (uint32_t)(c0 >> 3);
+    uint32_t t = 0, e = 0;
+    for (int item = pair; item < a.n_items; item += npairs) {
+      int w0, q, n0, Lc;
+      decode(item, w0, q, n0, Lc);
+      if (Lc <= 0) continue;
+      const int nrow = Lc + POOL;
+      float hprev[CW];
+#pragma unroll
+      for (int k = 0; k < CW; ++k) hprev[k] = 0.f;
+      for (int m = 0; m < nrow; ++m, ++t) {
+        const uint32_t b = t & 1;
+        mbar_wait(&tfull[b], (t >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float v[CW];
+        if (real) {
+          uint32_t r1[CW];
+          tmem_ld16(tmem_base + b * 256 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, r1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k4 = 0; k4 < CW / 4; ++k4) {
+            const float4 sc_ = *reinterpret_cast<const float4*>(s_const + c0 + 4 * k4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_const + 64 + c0 + 4 * k4);
+            const float4 al = *reinterpret_cast<const float4*>(s_const + 128 + c0 + 4 * k4);
+            v[4 * k4 + 0] = prelu(fmaf(__uint_as_float(r1[4 * k4 + 0]), sc_.x, sh.x), al.x);
+            v[4 * k4 + 1] = prelu(fmaf(__uint_as_float(r1[4 * k4 + 1]), sc_.y, sh.y), al.y);
+            v[4 * k4 + 2] = prelu(fmaf(__uint_as_float(r1[4 * k4 + 2]), sc_.z, sh.z), al.z);
+            v[4 * k4 + 3] = prelu(fmaf(__uint_as_float(r1[4 * k4 + 3]), sc_.w, sh.w), al.w);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(&tempty[b], 0);     // the leader's MMA warp owns the accumulator hand-off
+
+        int r_out = q + DIL * (n0 + m);
+        if (POOL) {
+          if (real) {
+            float* xw = s_xch + (((t & 1) * 4 + grp) * 4 + q4) * 32;
+            if (lane < DIL) {
+#pragma unroll
+              for (int k4 = 0; k4 < CW / 4; ++k4)
+                *reinterpret_cast<float4*>(xw + lane * 16 + 4 * k4) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            const bool edge = lane >= 32 - DIL;
+            const float* xr = s_xch + (((t & 1) * 4 + grp) * 4 + ((q4 + 1) & 3)) * 32 + (edge ? (lane - (32 - DIL)) * 16 : 0);
+#pragma unroll
+            for (int k4 = 0; k4 < CW / 4; ++k4) {
+              const float4 x4 = *reinterpret_cast<const float4*>(xr + 4 * k4);
+              const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float nb = __shfl_down_sync(0xffffffffu, v[4 * k4 + k], DIL);
+                if (edge) nb = xs[k];
+                const float h = fmaxf(v[4 * k4 + k], nb);
+                v[4 * k4 + k] = fmaxf(h, hprev[4 * k4 + k]);
+                hprev[4 * k4 + k] = h;
+              }
+            }
+          }
+          if (m == 0) continue;
+          r_out -= DIL;
+        }
+        uint8_t* ob = sOut + (e % (uint32_t)a.out_bufs) * OB_BYTES;
+        if (a.out_bufs == 1) {
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 5, 512;" ::: "memory");
+        }
+        if (real) {
+          uint32_t hi[CW / 2], lo[CW / 2];
+#pragma unroll
+          for (int k = 0; k < CW / 2; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+#pragma unroll
+          for (int c = 0; c < CW / 8; ++c) {
+            *reinterpret_cast<uint4*>(ob + row_off + (((hi_chunk + c) ^ sw) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            *reinterpret_cast<uint4*>(ob + 16384 + row_off + (((hi_chunk + c) ^ sw) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        if (a.out_bufs == 2 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 6, 512;" ::: "memory");
+        if (issuer) {
+          tma_store_3d(&mapO, ob, 0, w0, r_out);
+          tma_store_3d(&mapO, ob + 16384, 64, w0, r_out);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++e;
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                     // neither CTA may free TMEM while the pair still uses it
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 template <int KSTEPS, int DIL, int POOL, int CW, bool LO64, bool OUT32>
@@ -426,7 +714,8 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     a.stages = (227 * 1024 - fixed - ob_bytes) / slot;
   }
   if (a.stages > 8) a.stages = 8;
-  SC_CHECK(a.stages >= 3, SC_ERR_ARG, "conv_sweep: ring does not fit (layer %d)", layer);
+  const bool use_pair = w.ksteps == 3 && !in_fmt && !out_fmt && (ctx->tc_sweep45 & 4);
+  SC_CHECK(use_pair || a.stages >= 3, SC_ERR_ARG, "conv_sweep: ring does not fit (layer %d)", layer);
   const size_t smem = (size_t)fixed + (size_t)a.stages * slot + (size_t)a.out_bufs * ob_bytes;
 
   CUtensorMap mapA, mapW, mapO;
@@ -464,8 +753,56 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "conv_sweep: cuTensorMapEncodeTiled(O) failed with %d", (int)r);
   }
-  ProfScope prof(ctx, prof_cls, st);
   const bool i32 = in_fmt != 0, o32 = out_fmt != 0;
+  if (use_pair) {
+    // ---- CTA pairs: half of the weights per CTA, ring of >= 4 rows ----
+    const int nsp = (a.nstrips + 1) / 2;
+    const int pairs_max = ctx->sm_count / 2;
+    nseg = (4 * pairs_max + nsp * dil - 1) / (nsp * dil);
+    L = (nq + nseg - 1) / nseg;
+    if (L < 12) L = 12;
+    if (L > 96) L = 96;
+    nseg = (nq + L - 1) / L;
+    a.L = L; a.nseg = nseg;
+    a.n_items = nsp * dil * nseg;
+    const int wp_bytes = w.npanels * w.bn * 128;
+    const int fixed_p = 1024 + ((wp_bytes + 1023) & ~1023) + 256 + 192 * 4 + (pool ? 2 * 4 * 4 * 2 * 16 * 4 : 0);
+    a.out_bufs = 2;
+    a.stages = (227 * 1024 - fixed_p - 2 * ob_bytes) / slot;
+    if (a.stages < 4) { a.out_bufs = 1; a.stages = (227 * 1024 - fixed_p - ob_bytes) / slot; }
+    if (a.stages > 8) a.stages = 8;
+    SC_CHECK(a.stages >= 3, SC_ERR_ARG, "conv_sweep: pair ring does not fit (layer %d)", layer);
+    const size_t smem_p = (size_t)fixed_p + (size_t)a.stages * slot + (size_t)a.out_bufs * ob_bytes;
+    CUtensorMap mapWp;
+    cuuint64_t dims[2] = {64, (cuuint64_t)w.npanels * 2 * w.bn};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)w.bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = s->encode(&mapWp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.panels_pair, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "conv_sweep: cuTensorMapEncodeTiled(W pair) failed with %d", (int)r);
+    const int npairs = a.n_items < pairs_max ? a.n_items : pairs_max;
+    ProfScope prof(ctx, prof_cls, st);
+    if (dil == 2 && pool) {
+      auto kern = conv_sweep_pair_kernel<3, 2, 1>;
+      static bool cfg = false;
+      if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+      kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
+    } else if (dil == 4 && !pool) {
+      auto kern = conv_sweep_pair_kernel<3, 4, 0>;
+      static bool cfg = false;
+      if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+      kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
+    } else {
+      set_error("conv_sweep: no pair kernel instance for dil=%d pool=%d", dil, pool);
+      return SC_ERR_ARG;
+    }
+    ctx->launches++;
+    SC_CUDA(cudaGetLastError());
+    return SC_OK;
+  }
+  ProfScope prof(ctx, prof_cls, st);
   if (w.ksteps == 2 && dil == 1 && pool && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 1, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // conv2 + pool1
   if (w.ksteps == 2 && dil == 2 && !pool && i32 && !o32) return launch_sweep_t<2, 2, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);              // conv3
   if (w.ksteps == 3 && dil == 2 && pool && !i32 && !o32) return launch_sweep_t<3, 2, 1, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);             // conv4 + pool2

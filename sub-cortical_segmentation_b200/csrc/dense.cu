@@ -645,7 +645,8 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
         pool_flat_kernel<<<pgrid, 256, 0, st>>>(m4, mp2, npos, Pw, 2);
         ctx->launches++;
       }
-      SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, 1, P, a5[v], 1, P, 1, 4, 40, PC_CONV5, st, Pw));
+      if ((ctx->tc_sweep45 & 6) == 6) SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, mp2, 0, a5[v], 0, Pw, R1, 4, 0, PC_CONV5, st));   // conv5 (CTA pairs)
+      else SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, 1, P, a5[v], 1, P, 1, 4, 40, PC_CONV5, st, Pw));
       SC_CUDA(cudaGetLastError());
     }
     for (int sb = 0; sb < g.ns && !tc; sb += group) {

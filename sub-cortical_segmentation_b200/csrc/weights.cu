@@ -68,7 +68,7 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
   SC_CUDA(cudaStreamSynchronize(st));
 
   Arena A;
-  struct BOff { size_t c1, conv[5], scale[5], shift[5], alpha[5], sw[5]; GemmOff d1, d1d, ctc[5]; } bo[3];
+  struct BOff { size_t c1, conv[5], scale[5], shift[5], alpha[5], sw[5], swp[5]; GemmOff d1, d1d, ctc[5]; } bo[3];
   GemmOff fc1o, fc2o, outo;
   size_t outw, outb;
   for (int b = 0; b < 3; ++b) {
@@ -93,7 +93,10 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
         SweepW& S = ctx->br[b].conv_sw[l];
         S.ksteps = (ci_n + 15) / 16; S.bn = (co_n + 15) & ~15; S.npanels = (9 * S.ksteps + 3) / 4;
         bo[b].sw[l] = A.alloc((size_t)S.npanels * 2 * S.bn * 32);
+        bo[b].swp[l] = A.alloc((size_t)S.npanels * 2 * S.bn * 32);
         uint16_t* pw = reinterpret_cast<uint16_t*>(&A.host[bo[b].sw[l]]);
+        uint16_t* pp = reinterpret_cast<uint16_t*>(&A.host[bo[b].swp[l]]);
+        const int hb = S.bn / 2;
         for (int co = 0; co < co_n; ++co)
           for (int ci = 0; ci < ci_n; ++ci)
             for (int t = 0; t < 9; ++t) {
@@ -102,6 +105,10 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
               const uint16_t hi = bf16_rn(v);
               pw[((size_t)(gk >> 2) * 2 * S.bn + co) * 64 + kk] = hi;
               pw[((size_t)(gk >> 2) * 2 * S.bn + S.bn + co) * 64 + kk] = bf16_rn(v - bf16_to_float(hi));
+              // pair layout: rank = co / (bn/2) owns this output channel
+              const size_t prow = ((size_t)(gk >> 2) * 2 + co / hb) * S.bn + co % hb;
+              pp[prow * 64 + kk] = hi;
+              pp[(prow + hb) * 64 + kk] = bf16_rn(v - bf16_to_float(hi));
             }
       }
       for (int c = 0; c < co_n; ++c) {
@@ -179,7 +186,7 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
     for (int l = 1; l < 5; ++l) bind(ctx->br[b].conv_tc[l], bo[b].ctc[l], base);
     for (int l = 1; l < 5; ++l) {
       SweepW& S = ctx->br[b].conv_sw[l];
-      S.panels = base + bo[b].sw[l]; S.scale = ctx->br[b].scale[l]; S.shift = ctx->br[b].shift[l]; S.alpha = ctx->br[b].alpha[l];
+      S.panels = base + bo[b].sw[l]; S.panels_pair = base + bo[b].swp[l]; S.scale = ctx->br[b].scale[l]; S.shift = ctx->br[b].shift[l]; S.alpha = ctx->br[b].alpha[l];
     }
     bind(ctx->br[b].d1, bo[b].d1, base);
     bind(ctx->br[b].d1_dense, bo[b].d1d, base);
