@@ -12,18 +12,21 @@ namespace sc {
 
 constexpr int kGroup = 32;  // candidates per CTA
 
-// One CTA (256 threads) gathers the three 32x32 views of kGroup candidates.
-//  coronal  [dx][dz] at y and saggital [dy][dz] at x: a patch row is contiguous along z, so one
-//           warp copies one row (lane = column): 128 B coalesced read (unaligned start) -> 128 B store.
-//  axial    [dx][dy] at z: no contiguous in-plane axis.  Lanes run over the CANDIDATES instead
-//           (consecutive candidates of np.nonzero order are consecutive in z => one 128 B line),
-//           a 32x33 shared tile transposes so that the store is again one full patch row per warp.
+// One CTA (256 threads) gathers the three 32x32 views of kGroup candidates.  The kernel is bound by the patch
+// WRITES (12 KB per candidate); everything is arranged so that a 128 B patch row costs a handful of instructions.
+//  coronal  [dx][dz] at y and saggital [dy][dz] at x: a patch row is contiguous along z.  One warp copies one whole
+//           patch (lane = column, loop over the 32 rows with running pointers): 128 B coalesced read (unaligned
+//           start) -> 128 B streaming store per row.
+//  axial    [dx][dy] at z: no contiguous in-plane axis.  Lanes run over the CANDIDATES instead (consecutive candidates
+//           of np.nonzero order are consecutive in z => one 128 B line per load); every warp owns a private 32x33
+//           shared tile that transposes one patch row index at a time, so the stores are again full patch rows and no
+//           block-wide barrier is needed.
 __global__ void __launch_bounds__(256) gather_patches_kernel(
     const float* __restrict__ vol, int X, int Y, int Z, const float* __restrict__ atlas, int bg_fix,
     const int32_t* __restrict__ xyz, int64_t n, float* __restrict__ ax, float* __restrict__ co,
     float* __restrict__ sa, float* __restrict__ atlas_out) {
   __shared__ int sx[kGroup], sy[kGroup], sz[kGroup];
-  __shared__ float tile[32][33];
+  __shared__ float tile[8][32][33];
   __shared__ float satl[kGroup][16];
   const int64_t base = (int64_t)blockIdx.x * kGroup;
   const int cnt = (int)min((int64_t)kGroup, n - base);
@@ -37,48 +40,54 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(
   __syncthreads();
   const int64_t YZ = (int64_t)Y * Z;
 
-  // ---- coronal and saggital: row copies ------------------------------------------------
-  for (int job = warp; job < cnt * 32; job += 8) {
-    const int c = job >> 5, i = job & 31;
+  // ---- coronal and saggital: one warp per (candidate, view) ------------------------------
+  for (int job = warp; job < cnt * 2; job += 8) {
+    const int c = job >> 1, view = job & 1;
+    float* dst = view ? sa : co;
+    if (!dst) continue;
     const int x = sx[c], y = sy[c], z = sz[c];
     const int zz = z - 16 + lane;
     const bool zin = (zz >= 0) && (zz < Z);
-    const int64_t o = (base + c) * 1024 + i * 32 + lane;
-    if (co) {
-      const int xx = x - 16 + i;
+    // view 0 (coronal): rows run over x at fixed y; view 1 (saggital): rows run over y at fixed x
+    const int r0 = (view ? y : x) - 16, rmax = view ? Y : X;
+    const int64_t rstride = view ? (int64_t)Z : YZ;
+    const float* src = vol + (view ? (int64_t)x * YZ : (int64_t)y * Z) + (int64_t)r0 * rstride + zz;
+    float* out = dst + (base + c) * 1024 + lane;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int rr = r0 + i;
       float v = 0.f;
-      if (zin && xx >= 0 && xx < X) v = __ldg(vol + (int64_t)xx * YZ + (int64_t)y * Z + zz);
-      __stcs(co + o, v);
-    }
-    if (sa) {
-      const int yy = y - 16 + i;
-      float v = 0.f;
-      if (zin && yy >= 0 && yy < Y) v = __ldg(vol + (int64_t)x * YZ + (int64_t)yy * Z + zz);
-      __stcs(sa + o, v);
+      if (zin && rr >= 0 && rr < rmax) v = __ldg(src);
+      __stcs(out, v);
+      src += rstride;
+      out += 32;
     }
   }
 
-  // ---- axial: lanes over candidates, transposed through shared memory --------------------
+  // ---- axial: lanes over candidates, transposed through a warp-private shared tile -------
   if (ax) {
     const int x = sx[lane], y = sy[lane], z = sz[lane];
-    for (int i = 0; i < 32; ++i) {
+    float (*tw)[33] = tile[warp];
+    for (int i = warp; i < 32; i += 8) {
       const int xx = x - 16 + i;
       const bool xin = (xx >= 0) && (xx < X) && (lane < cnt);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = warp * 4 + jj;
+      const float* src = vol + (int64_t)xx * YZ + (int64_t)(y - 16) * Z + z;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
         const int yy = y - 16 + j;
         float v = 0.f;
-        if (xin && yy >= 0 && yy < Y) v = __ldg(vol + (int64_t)xx * YZ + (int64_t)yy * Z + z);
-        tile[j][lane] = v;
+        if (xin && yy >= 0 && yy < Y) v = __ldg(src);
+        tw[j][lane] = v;
+        src += Z;
       }
-      __syncthreads();
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = warp * 4 + cc;
-        if (c < cnt) __stcs(ax + (base + c) * 1024 + i * 32 + lane, tile[lane][c]);
+      __syncwarp();
+      float* out = ax + base * 1024 + i * 32 + lane;
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) {
+        if (c < cnt) __stcs(out, tw[lane][c]);
+        out += 1024;
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
 
