@@ -230,6 +230,7 @@ struct GemmProblem {
   int64_t a_dims[4];    // extents: k, pixels per line, lines, planes
   int64_t a_strides[3]; // element strides of pixel, line, plane
   int tap_dx[9], tap_dy[9];  // tap shifts in pixels / lines
+  int tap_dz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // ... / planes (tcgen05 back-end only)
   int a_y0, a_z0;       // line / plane offset of this launch inside the buffer
   int prof_cls;         // ProfClass of this launch
   int k_used;           // conv layers: real input channels per tap (the rest of the 64-wide block is zero); 0 = all

@@ -85,7 +85,8 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// KSTEPS: 16-channel k-steps per tap; DIL: dilation; POOL: fuse the stride-1 max-pool with window {0, DIL}^2;
+// KSTEPS: 16-channel k-steps per tap; DIL: dilation; POOL: 1 = fuse the stride-1 max-pool with window {0, DIL}^2 (dense maps),
+// 2 = fuse the 2x2 stride-2 max-pool (patch maps: output pitch and rows halve, row segments start on even rows);
 // CW: accumulator columns per epilogue warp (8 or 16; 4 column groups); LO64: lo operand 64 B into the row (F32CH)
 // instead of in its own box; OUT32: output pixels are F32CH
 template <int KSTEPS, int DIL, int POOL, int CW, bool LO64, bool OUT32>
@@ -167,7 +168,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         int w0, q, n0, Lc;
         decode(item, w0, q, n0, Lc);
         if (Lc <= 0) continue;
-        const int nload = Lc + POOL + 2;
+        const int nload = Lc + (POOL == 1 ? 1 : 0) + 2;
         for (int m = 0; m < nload; ++m, ++g) {
           const uint32_t s = g % a.stages, use = g / a.stages;
           if (use > 0) {
@@ -200,7 +201,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
       if (Lc <= 0) continue;
-      const int nrow = Lc + POOL;
+      const int nrow = Lc + (POOL == 1 ? 1 : 0);
       for (int m = 0; m < nrow; ++m, ++t) {
         const uint32_t b = t & 1;
         long long c0 = a.dbg ? clock64() : 0;
@@ -257,8 +258,10 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int px = q4 * 32 + lane;           // pixel inside the strip = row of the output tile
     const bool issuer = threadIdx.x == 64;
     // byte offsets of this thread's hi / lo pieces inside a tile (SWIZZLE_128B: 16 B chunk index ^= row & 7)
-    const uint32_t row_off = (uint32_t)px * 128u;
-    const uint32_t sw = (uint32_t)(px & 7);
+    const int trow = POOL == 2 ? px >> 1 : px; // row of the output tile this thread writes (stride-2 pool: even lanes only)
+    const bool writer = POOL == 2 ? !(lane & 1) : true;
+    const uint32_t row_off = (uint32_t)trow * 128u;
+    const uint32_t sw = (uint32_t)(trow & 7);
     const uint32_t hi_chunk = (uint32_t)(c0 >> 3);
     const uint32_t lo_base = OUT32 ? 0u : 16384u, lo_chunk = OUT32 ? 4u + hi_chunk : hi_chunk;
     uint32_t t = 0, e = 0;                   // conv rows consumed, rows emitted
@@ -268,7 +271,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
       if (Lc <= 0) continue;
-      const int nrow = Lc + POOL;
+      const int nrow = Lc + (POOL == 1 ? 1 : 0);
       float hprev[CW];
 #pragma unroll
       for (int k = 0; k < CW; ++k) hprev[k] = 0.f;
@@ -301,7 +304,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (lane == 0) mbar_arrive(&tempty[b]);
 
         int r_out = q + DIL * (n0 + m);
-        if (POOL) {
+        if (POOL == 1) {
           // horizontal neighbour (DIL pixels to the right): same warp by shuffle, next quarter through shared memory
           if (real) {
             float* xw = s_xch + (((t & 1) * 4 + grp) * 4 + q4) * 32;      // [row parity][group][quarter][pd][16]
@@ -330,6 +333,20 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (m == 0) continue;                    // block-uniform: the first conv row of an item only primes the pool
           r_out -= DIL;
         }
+        if (POOL == 2) {
+          // 2x2 stride-2 max-pool: pixel pairs (2j, 2j+1) never straddle a lane quarter, row pairs (2k, 2k+1) lie inside
+          // an item (segments start on even rows); even lanes hold the pooled pixel j = px / 2 after an odd row
+          if (real) {
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+              const float h = fmaxf(v[k], __shfl_down_sync(0xffffffffu, v[k], 1));
+              v[k] = fmaxf(h, hprev[k]);
+              hprev[k] = (m & 1) ? 0.f : h;
+            }
+          }
+          if (!(m & 1)) continue;                  // block-uniform
+          r_out >>= 1;
+        }
         // ---- emit row r_out: pieces -> swizzled output tile -> TMA store
         uint8_t* ob = sOut + (e % (uint32_t)a.out_bufs) * OB_BYTES;
         if (a.out_bufs == 1) {                      // single tile: wait until the previous store has read it
@@ -342,6 +359,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           for (int k = 0; k < CW / 2; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
 #pragma unroll
           for (int c = 0; c < CW / 8; ++c) {
+            if (!writer) break;
             *reinterpret_cast<uint4*>(ob + row_off + (((hi_chunk + c) ^ sw) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
             *reinterpret_cast<uint4*>(ob + lo_base + row_off + (((lo_chunk + c) ^ sw) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
           }
@@ -350,8 +368,8 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (a.out_bufs == 2 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the other tile is free again
         asm volatile("bar.sync 6, 512;" ::: "memory");
         if (issuer) {
-          tma_store_3d(&mapO, ob, 0, w0, r_out);
-          if (!OUT32) tma_store_3d(&mapO, ob + 16384, 64, w0, r_out);
+          tma_store_3d(&mapO, ob, 0, POOL == 2 ? w0 >> 1 : w0, r_out);
+          if (!OUT32) tma_store_3d(&mapO, ob + 16384, 64, POOL == 2 ? w0 >> 1 : w0, r_out);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         ++e;
@@ -477,7 +495,7 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         int w0, q, n0, Lc;
         decode(item, w0, q, n0, Lc);
         if (Lc <= 0) continue;
-        const int nload = Lc + POOL + 2;
+        const int nload = Lc + (POOL == 1 ? 1 : 0) + 2;
         for (int m = 0; m < nload; ++m, ++g) {
           const uint32_t s = g % a.stages, use = g / a.stages;
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
@@ -506,7 +524,7 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         int w0, q, n0, Lc;
         decode(item, w0, q, n0, Lc);
         if (Lc <= 0) continue;
-        const int nrow = Lc + POOL;
+        const int nrow = Lc + (POOL == 1 ? 1 : 0);
         for (int m = 0; m < nrow; ++m, ++t) {
           const uint32_t b = t & 1;
           mbar_wait(&tempty[b], ((t >> 1) & 1) ^ 1);
@@ -557,15 +575,17 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     const bool real = c0 < a.bn;
     const int px = q4 * 32 + lane;
     const bool issuer = threadIdx.x == 64;
-    const uint32_t row_off = (uint32_t)px * 128u;
-    const uint32_t sw = (uint32_t)(px & 7);
+    const int trow = POOL == 2 ? px >> 1 : px;
+    const bool writer = POOL == 2 ? !(lane & 1) : true;
+    const uint32_t row_off = (uint32_t)trow * 128u;
+    const uint32_t sw = (uint32_t)(trow & 7);
     const uint32_t hi_chunk = (uint32_t)(c0 >> 3);
     uint32_t t = 0, e = 0;
     for (int item = pair; item < a.n_items; item += npairs) {
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
       if (Lc <= 0) continue;
-      const int nrow = Lc + POOL;
+      const int nrow = Lc + (POOL == 1 ? 1 : 0);
       float hprev[CW];
 #pragma unroll
       for (int k = 0; k < CW; ++k) hprev[k] = 0.f;
@@ -594,7 +614,7 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         if (lane == 0) mbar_arrive_cta(&tempty[b], 0);     // the leader's MMA warp owns the accumulator hand-off
 
         int r_out = q + DIL * (n0 + m);
-        if (POOL) {
+        if (POOL == 1) {
           if (real) {
             float* xw = s_xch + (((t & 1) * 4 + grp) * 4 + q4) * 32;
             if (lane < DIL) {
@@ -622,6 +642,20 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           if (m == 0) continue;
           r_out -= DIL;
         }
+        if (POOL == 2) {
+          // 2x2 stride-2 max-pool: pixel pairs (2j, 2j+1) never straddle a lane quarter, row pairs (2k, 2k+1) lie inside
+          // an item (segments start on even rows); even lanes hold the pooled pixel j = px / 2 after an odd row
+          if (real) {
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+              const float h = fmaxf(v[k], __shfl_down_sync(0xffffffffu, v[k], 1));
+              v[k] = fmaxf(h, hprev[k]);
+              hprev[k] = (m & 1) ? 0.f : h;
+            }
+          }
+          if (!(m & 1)) continue;                  // block-uniform
+          r_out >>= 1;
+        }
         uint8_t* ob = sOut + (e % (uint32_t)a.out_bufs) * OB_BYTES;
         if (a.out_bufs == 1) {
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -633,6 +667,7 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           for (int k = 0; k < CW / 2; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
 #pragma unroll
           for (int c = 0; c < CW / 8; ++c) {
+            if (!writer) break;
             *reinterpret_cast<uint4*>(ob + row_off + (((hi_chunk + c) ^ sw) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
             *reinterpret_cast<uint4*>(ob + 16384 + row_off + (((hi_chunk + c) ^ sw) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
           }
@@ -641,8 +676,8 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         if (a.out_bufs == 2 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("bar.sync 6, 512;" ::: "memory");
         if (issuer) {
-          tma_store_3d(&mapO, ob, 0, w0, r_out);
-          tma_store_3d(&mapO, ob + 16384, 64, w0, r_out);
+          tma_store_3d(&mapO, ob, 0, POOL == 2 ? w0 >> 1 : w0, r_out);
+          tma_store_3d(&mapO, ob + 16384, 64, POOL == 2 ? w0 >> 1 : w0, r_out);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         ++e;
@@ -685,7 +720,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   if (Pw <= 0 || R <= 0) return SC_OK;
   SweepArgs a;
   a.Pw = Pw; a.R = R; a.bn = w.bn;
-  a.strip_w = 128 - (pool ? dil : 0);
+  a.strip_w = 128 - (pool == 1 ? dil : 0);                            // pool: 0 none, 1 stride-1 window {0,d}^2, 2 = 2x2 stride 2
   a.nstrips = (Pw + a.strip_w - 1) / a.strip_w;
   const int nq = (R + dil - 1) / dil;                                   // class rows of the largest class
   // segments: enough items to balance the SMs, rows per item long enough to amortise the 2 (+1) halo rows
@@ -693,9 +728,11 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   int L = (nq + nseg - 1) / nseg;
   if (L < 12) L = 12;
   if (L > 96) L = 96;
+  if (pool == 2) L = (L + 1) & ~1;                                      // row pairs of the stride-2 pool stay inside an item
   nseg = (nq + L - 1) / L;
   a.L = L; a.nseg = nseg;
   a.n_items = a.nstrips * dil * nseg;
+  SC_CHECK(pool != 2 || dil == 1, SC_ERR_ARG, "conv_sweep: the stride-2 pool needs dilation 1");
   a.in_boxes = in_fmt ? 1 : 2;
   a.lo_off = in_fmt ? 64 : SW_SLOT_HALF;
   a.out_fmt = out_fmt;
@@ -744,9 +781,10 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     // output: one box of strip_w pixels x 128 B per store (hi and lo boxes for the 256 B pixels); the columns a strip
     // does not own (pool reach) are simply not part of the box
     const int pxe = out_fmt ? 64 : 128;
-    cuuint64_t dims[3] = {(cuuint64_t)pxe, (cuuint64_t)Pw, (cuuint64_t)R};
-    cuuint64_t strides[2] = {(cuuint64_t)pxe * 2, (cuuint64_t)Pw * pxe * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)a.strip_w, 1};
+    const int oPw = pool == 2 ? Pw / 2 : Pw, oR = pool == 2 ? R / 2 : R;   // stride-2 pool: pitch and rows halve
+    cuuint64_t dims[3] = {(cuuint64_t)pxe, (cuuint64_t)oPw, (cuuint64_t)oR};
+    cuuint64_t strides[2] = {(cuuint64_t)pxe * 2, (cuuint64_t)oPw * pxe * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)(pool == 2 ? 64 : a.strip_w), 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = s->encode(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -762,6 +800,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     L = (nq + nseg - 1) / nseg;
     if (L < 12) L = 12;
     if (L > 96) L = 96;
+    if (pool == 2) L = (L + 1) & ~1;
     nseg = (nq + L - 1) / L;
     a.L = L; a.nseg = nseg;
     a.n_items = nsp * dil * nseg;
@@ -772,6 +811,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     if (a.stages < 4) { a.out_bufs = 1; a.stages = (227 * 1024 - fixed_p - ob_bytes) / slot; }
     if (a.stages > 8) a.stages = 8;
     SC_CHECK(a.stages >= 3, SC_ERR_ARG, "conv_sweep: pair ring does not fit (layer %d)", layer);
+    SC_CHECK(pool != 2 || (Pw % 2 == 0), SC_ERR_ARG, "conv_sweep: odd pitch with the stride-2 pool");
     const size_t smem_p = (size_t)fixed_p + (size_t)a.stages * slot + (size_t)a.out_bufs * ob_bytes;
     CUtensorMap mapWp;
     cuuint64_t dims[2] = {64, (cuuint64_t)w.npanels * 2 * w.bn};
@@ -784,7 +824,17 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "conv_sweep: cuTensorMapEncodeTiled(W pair) failed with %d", (int)r);
     const int npairs = a.n_items < pairs_max ? a.n_items : pairs_max;
     ProfScope prof(ctx, prof_cls, st);
-    if (dil == 2 && pool) {
+    if (dil == 1 && pool == 2) {
+      auto kern = conv_sweep_pair_kernel<3, 1, 2>;
+      static bool cfg = false;
+      if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+      kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
+    } else if (dil == 1 && !pool) {
+      auto kern = conv_sweep_pair_kernel<3, 1, 0>;
+      static bool cfg = false;
+      if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+      kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
+    } else if (dil == 2 && pool == 1) {
       auto kern = conv_sweep_pair_kernel<3, 2, 1>;
       static bool cfg = false;
       if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
@@ -803,14 +853,13 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     return SC_OK;
   }
   ProfScope prof(ctx, prof_cls, st);
-  if (w.ksteps == 2 && dil == 1 && pool && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 1, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // conv2 + pool1
+  if (w.ksteps == 2 && dil == 1 && pool == 2 && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 2, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // patch maps: conv2 + 2x2/2 pool
+  if (w.ksteps == 2 && dil == 1 && pool == 1 && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 1, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // conv2 + pool1
   if (w.ksteps == 2 && dil == 2 && !pool && i32 && !o32) return launch_sweep_t<2, 2, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);              // conv3
-  if (w.ksteps == 3 && dil == 2 && pool && !i32 && !o32) return launch_sweep_t<3, 2, 1, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);             // conv4 + pool2
+  if (w.ksteps == 3 && dil == 2 && pool == 1 && !i32 && !o32) return launch_sweep_t<3, 2, 1, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);             // conv4 + pool2
   if (w.ksteps == 3 && dil == 4 && !pool && !i32 && !o32) return launch_sweep_t<3, 4, 0, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);            // conv5
   // patchwise maps (dilation 1 everywhere, stride-2 pools stay separate passes)
-  if (w.ksteps == 2 && dil == 1 && !pool && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 0, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);
   if (w.ksteps == 2 && dil == 1 && !pool && i32 && !o32) return launch_sweep_t<2, 1, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);
-  if (w.ksteps == 3 && dil == 1 && !pool && !i32 && !o32) return launch_sweep_t<3, 1, 0, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);
   set_error("conv_sweep: no kernel instance for ksteps=%d dil=%d pool=%d in_fmt=%d out_fmt=%d", w.ksteps, dil, pool, in_fmt, out_fmt);
   return SC_ERR_ARG;
 }

@@ -420,58 +420,49 @@ __global__ void __launch_bounds__(256) pool2x2s2_patch_kernel(const float* __res
   }
 }
 
+// Patch maps in the wide-row layout of conv_sweep.cu: the patches of a chunk lie side by side, position
+// (row r, patch p, col c) = r * (n * pitch) + p * pitch + c with pitch 32 / 16 / 8 per pooling level:
+//   conv1 [30][n][32] F32CH -> conv2 + 2x2/2 pool [15][n][16] F32CH -> conv3 [15][n][16] F64CH
+//   -> conv4 + 2x2/2 pool [7][n][8] F64CH -> conv5 [7][n][8] F64CH (3x3 valid) -> d1 reads its 9 taps through a 4-D tensor map
 size_t branch_patches_tc_bytes(int64_t n) {
-  return (size_t)n * (2 * 960 + 3 * 224 + 2 * 40) * kC5Ld * sizeof(float) + 4096;
+  return (size_t)n * ((960 + 240) * 32 + (240 + 56 + 56) * 64) * sizeof(float) + 5 * 256;
 }
 
 int branch_patches_tc(sc_ctx* ctx, int b, const float* patches, int64_t n, float* scratch, float* feats, cudaStream_t st) {
   const BranchW& W = ctx->br[b];
-  float* c1 = scratch;
-  float* c2 = c1 + (size_t)n * 960 * kC5Ld;
-  float* p1 = c2 + (size_t)n * 960 * kC5Ld;
-  float* c3 = p1 + (size_t)n * 224 * kC5Ld;
-  float* c4 = c3 + (size_t)n * 224 * kC5Ld;
-  float* p2 = c4 + (size_t)n * 224 * kC5Ld;
-  float* c5 = p2 + (size_t)n * 40 * kC5Ld;
+  auto carve = [&](float*& cur, size_t floats) { float* p = cur; cur += (floats + 63) & ~(size_t)63; return p; };
+  float* cur = scratch;
+  float* c1 = carve(cur, (size_t)n * 960 * 32);
+  float* p1 = carve(cur, (size_t)n * 240 * 32);
+  float* c3 = carve(cur, (size_t)n * 240 * 64);
+  float* p2 = carve(cur, (size_t)n * 56 * 64);
+  float* c5 = carve(cur, (size_t)n * 56 * 64);
+  SC_CHECK(n * 960 < (1ll << 31), SC_ERR_ARG, "patchwise chunk too large");
   {
     ViewGeo g = {1024, 32, 1, 0, (int)n, 16, 16, 30, 30, 32, 32};   // origin 16 cancels the dense path's zero-pad offset
     const int64_t blocks = (n * 960 + 255) / 256;
     const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
     static bool c1cfg = false;
-    if (!c1cfg) { SC_CUDA(cudaFuncSetAttribute(dense_conv1_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 272)); c1cfg = true; }
+    if (!c1cfg) { SC_CUDA(cudaFuncSetAttribute(dense_conv1_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 144)); c1cfg = true; }
     ProfScope prof(ctx, PC_CONV1, st);
-    dense_conv1_nhwc_kernel<<<grid, 256, 256 * 272, st>>>(patches, g, 0, (int)n, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], c1, 30, 32);
+    dense_conv1_wide_kernel<<<grid, 256, 256 * 144, st>>>(patches, g, (int)n, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], c1, 30, 32);
     ctx->launches++;
+    SC_CUDA(cudaGetLastError());
   }
-  SC_CHECK(n * 960 < (1ll << 31), SC_ERR_ARG, "patchwise chunk too large");
-  SC_TRY(launch_conv_tc(ctx, W.conv_tc[1], c1, 1, (int)(n * 960), c2, 1, (int)(n * 960), 1, 1, 20, PC_CONV2, st, 32));
-  {
-    const int64_t work = n * 224 * 16;
-    ProfScope prof(ctx, PC_POOL, st);
-    pool2x2s2_patch_kernel<<<(unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64), 256, 0, st>>>(
-        c2, 32, 960, p1, 14, 14, 16, 224, n);
-    ctx->launches++;
-  }
-  SC_TRY(launch_conv_tc(ctx, W.conv_tc[2], p1, 1, (int)(n * 224), c3, 1, (int)(n * 224), 1, 1, 20, PC_CONV3, st, 16));
-  SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], c3, 1, (int)(n * 224), c4, 1, (int)(n * 224), 1, 1, 40, PC_CONV4, st, 16));
-  {
-    const int64_t work = n * 40 * 16;
-    ProfScope prof(ctx, PC_POOL, st);
-    pool2x2s2_patch_kernel<<<(unsigned)((work + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (work + 255) / 256 : (int64_t)ctx->sm_count * 64), 256, 0, st>>>(
-        c4, 16, 224, p2, 5, 5, 8, 40, n);
-    ctx->launches++;
-  }
-  SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], p2, 1, (int)(n * 40), c5, 1, (int)(n * 40), 1, 1, 40, PC_CONV5, st, 8));
-  // d1: rows = patches, the 3x3 positions of the conv5 map (pitch 8) are the 9 taps; K = tap*64 + c
+  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, c1, 1, p1, 1, (int)(n * 32), 30, 1, 2, PC_CONV2, st));   // conv2 + pool1 -> [15][n][16]
+  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, p1, 1, c3, 0, (int)(n * 16), 15, 1, 0, PC_CONV3, st));   // conv3
+  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, c3, 0, p2, 0, (int)(n * 16), 15, 1, 2, PC_CONV4, st));   // conv4 + pool2 -> [7][n][8]
+  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, p2, 0, c5, 0, (int)(n * 8), 7, 1, 0, PC_CONV5, st));     // conv5
+  // d1: rows = patches; tap (ty, tx) of the 3x3 conv5 map is tensor-map coordinate (k, patch, tx, ty); K = tap*64 + c
   GemmProblem p;
-  p.A = c5; p.lda = 40 * kC5Ld; p.a_ys = 0; p.a_zs = 0;
+  p.A = c5; p.lda = 8 * kC5Ld; p.a_ys = 0; p.a_zs = 0;
   p.ntaps = 9; p.kc = kC5Ld; p.k_used = 0;
   for (int t = 0; t < 9; ++t) {
-    p.tap_dx[t] = 0; p.tap_dy[t] = (t / 3) * 8 + (t % 3);
-    p.tap_off[t] = (int64_t)p.tap_dy[t] * kC5Ld;
+    p.tap_dx[t] = 0; p.tap_dy[t] = t % 3; p.tap_dz[t] = t / 3;
+    p.tap_off[t] = ((int64_t)(t / 3) * n * 8 + (t % 3)) * kC5Ld;
   }
-  p.a_base = c5; p.a_dims[0] = kC5Ld; p.a_dims[1] = n; p.a_dims[2] = 40; p.a_dims[3] = 1;
-  p.a_strides[0] = 40 * kC5Ld; p.a_strides[1] = kC5Ld; p.a_strides[2] = (int64_t)n * 40 * kC5Ld;
+  p.a_base = c5; p.a_dims[0] = kC5Ld; p.a_dims[1] = n; p.a_dims[2] = 8; p.a_dims[3] = 7;
+  p.a_strides[0] = 8 * kC5Ld; p.a_strides[1] = kC5Ld; p.a_strides[2] = (int64_t)n * 8 * kC5Ld;
   p.a_y0 = p.a_z0 = 0;
   p.C = feats; p.ldc = kFeatLd; p.c_ys = p.c_zs = 0; p.M = (int)n; p.Y = p.Z = 1;
   p.n_store = 192; p.c_col0 = b * 192; p.out_split = 1; p.prof_cls = PC_GEMM_D1;

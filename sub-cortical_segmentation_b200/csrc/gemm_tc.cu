@@ -41,7 +41,7 @@ struct TcArgs {
   int n_store, npad, c_col0;
   int a_y0, a_z0;     // coordinate offsets of line / plane in the A tensor map
   int a_swap;         // tensor-map dimension order (k, pixel, plane, line): swap the last two coordinates
-  int tap_dx[9], tap_dy[9];
+  int tap_dx[9], tap_dy[9], tap_dz[9];
   float* C;
   long long ldc, c_ys, c_zs;
   const float* bias;
@@ -122,7 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
         uint8_t* st = smem + s * stage_bytes;
         const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;   // bf16 element offset of the block's hi half
-        const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
+        const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0 + a.tap_dz[tap];
         tma_load_4d(&mapA, &full[s], st, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
         tma_load_4d(&mapA, &full[s], st + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
         tma_load_2d(&mapB, &full[s], st + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
@@ -275,7 +275,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           uint8_t* sp = sStage + s * stage_bytes;
           const int kb = a.kx_reuse ? st * 3 : st;                 // first weight block of this step
           const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
-          const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
+          const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0 + a.tap_dz[tap];
           tma_load_4d(&mapA, &full[s], sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
           tma_load_4d(&mapA, &full[s], sp + a.a_half, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
           if (!a.w_resident) {
@@ -604,7 +604,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));   // both CTAs' bytes land on it
           uint8_t* sp = sStage + s * stage_bytes;
           const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
-          const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0;
+          const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0 + a.tap_dz[tap];
           tma_load_4d_2sm(&mapA, lbar, sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
           tma_load_4d_2sm(&mapA, lbar, sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
           tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
@@ -861,7 +861,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     SC_CHECK(p.c_col0 % 16 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 16 for the persistent kernel");
   }
   a.a_y0 = p.a_y0; a.a_z0 = p.a_z0; a.a_swap = p.a_swap;
-  for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; }
+  for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; a.tap_dz[t] = t < p.ntaps ? p.tap_dz[t] : 0; }
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
   a.bias = w.bias; a.alpha = w.alpha; a.scale = w.scale; a.out_split = p.out_split;
   SC_CHECK(p.c_col0 % 4 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 4");
