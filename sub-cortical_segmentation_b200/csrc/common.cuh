@@ -112,7 +112,10 @@ struct SweepW {     // one conv layer prepared for the strip-sweep tcgen05 kerne
   int bn, ksteps, npanels;
 };
 
+struct Conv1Consts { float w[9 * 20]; float scale[20], shift[20], alpha[20]; };   // conv1 taps + folded BN + PReLU, passed by value
+
 struct BranchW {
+  Conv1Consts c1_host;  // host copy of conv1's constants: kernel parameter (constant bank) of conv1_wide_kernel
   float* c1_w;          // [9][20]  flipped taps, tap = ky*3+kx
   float* conv_w[5];     // l=1..4 used: [Cin][9][Cout] flipped (conv2..conv5)
   float* scale[5];      // BN folded: gamma*inv_std
@@ -267,6 +270,18 @@ void tc_destroy(sc_ctx* ctx);
 int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream_t st);
 int launch_split_rows(sc_ctx* ctx, const float* in, int64_t rows, float* out, cudaStream_t st);  // [rows][576] plain -> split
 
+// one view of a box of the volume (or a stack of patches) as slices x rows x cols
+struct ViewGeo {
+  int64_t ss, rs, cs;   // element strides of slice / row / col in the [X][Y][Z] volume
+  int s0, ns;           // slice range of the box along the view's slice axis
+  int r0, c0;           // box origin inside the slice
+  int br, bc;           // box extent (rows, cols)
+  int R, C;             // full slice extent (zero outside)
+};
+
+// conv_sweep.cu : conv1 (1 -> 20 channels) straight from the volume / patches into a wide-row F32CH map
+int launch_conv1_wide(sc_ctx* ctx, const float* vol, const ViewGeo& g, int ns, const Conv1Consts& cw, float* out, int outR, int outC,
+                      cudaStream_t st);
 // conv_sweep.cu : strip-sweep 3x3 dilated conv (+ fused stride-1 max-pool) over wide-row maps.
 // in_fmt / out_fmt: 1 = 128 B pixels (32 bf16 hi | 32 lo), 0 = 256 B pixels (64 hi | 64 lo)
 int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,

@@ -695,6 +695,116 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// conv1 (1 -> 20 channels, cnn_cort/nets.py:171) straight from the volume (zero padding implicit) or from a stack of
+// patches into a wide-row F32CH map.  HBM-write bound (128 B per pixel): one thread computes one pixel's 20 channels and
+// writes them as three hi and three lo 16 B chunks into a SWIZZLE_128B shared tile of 256 pixels = a box of 32 x 8
+// (cols x slices, or slices x cols when the SLICE axis is the contiguous one of the volume, so that the nine input loads
+// of a warp stay coalesced); one TMA tensor store per tile, two tiles in flight.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+__global__ void __launch_bounds__(256) conv1_wide_kernel(const __grid_constant__ CUtensorMap mapO, const __grid_constant__ Conv1Consts cw,
+                                                         const float* __restrict__ vol, ViewGeo g, int ns, int outR, int outC, int slice_fast) {
+  // the 180 taps and 60 epilogue constants are kernel parameters: constant-bank operands of the FFMAs, no loads at all
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 2 x 32 KB
+  const int bc = slice_fast ? 8 : 32, bs = slice_fast ? 32 : 8;
+  const int nct = (outC + bc - 1) / bc, nst = (ns + bs - 1) / bs;
+  const long long n_tiles = (long long)outR * nst * nct;
+  const int f = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int cl = slice_fast ? sl : f, sloc = slice_fast ? f : sl;
+  const int trow = sloc * bc + cl;                                   // tile row of this thread's pixel (box order: col fastest)
+  const uint32_t row_off = (uint32_t)trow * 128u, swz = (uint32_t)(trow & 7);
+  uint32_t it = 0;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int ct = (int)(t % nct);
+    const int stl = (int)((t / nct) % nst);
+    const int i = (int)(t / ((long long)nct * nst));
+    const int j = ct * bc + cl, s = stl * bs + sloc;
+    uint8_t* ob = tiles + (it & 1) * 32768;
+    if (it >= 2) {                                                   // the store issued two tiles ago has read this buffer
+      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+    float v[20];
+    if (j < outC && s < ns) {
+      const float* vb = vol + (int64_t)(g.s0 + s) * g.ss;
+      float x[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int rr = g.r0 + i + ky - 16;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int cc = g.c0 + j + kx - 16;
+          x[ky * 3 + kx] = (rr >= 0 && rr < g.R && cc >= 0 && cc < g.C) ? __ldg(vb + (int64_t)rr * g.rs + (int64_t)cc * g.cs) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int co = 0; co < 20; ++co) {
+        float acc = 0.f;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) acc = fmaf(x[tp], cw.w[tp * 20 + co], acc);
+        v[co] = prelu(fmaf(acc, cw.scale[co], cw.shift[co]), cw.alpha[co]);
+      }
+    } else {
+#pragma unroll
+      for (int co = 0; co < 20; ++co) v[co] = 0.f;
+    }
+    uint32_t hi[12], lo[12];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+    hi[10] = hi[11] = lo[10] = lo[11] = 0u;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      *reinterpret_cast<uint4*>(ob + row_off + (((uint32_t)c ^ swz) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+      *reinterpret_cast<uint4*>(ob + row_off + (((uint32_t)(4 + c) ^ swz) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+    }
+    *reinterpret_cast<uint4*>(ob + row_off + ((3u ^ swz) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // channels 24..31 stay zero
+    *reinterpret_cast<uint4*>(ob + row_off + ((7u ^ swz) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tma_store_4d(&mapO, ob, 0, ct * bc, stl * bs, i);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+int launch_conv1_wide(sc_ctx* ctx, const float* vol, const ViewGeo& g, int ns, const Conv1Consts& cw, float* out, int outR, int outC,
+                      cudaStream_t st) {
+  TcState* s = reinterpret_cast<TcState*>(ctx->tc_state);
+  SC_CHECK(s != nullptr, SC_ERR_UNSUPPORTED, "tcgen05 back-end not initialised");
+  if (ns <= 0 || outR <= 0 || outC <= 0) return SC_OK;
+  const int slice_fast = (g.ss == 1 && g.cs != 1) ? 1 : 0;          // axial view of a volume: z (the slice axis) is contiguous
+  const int bc = slice_fast ? 8 : 32, bs = slice_fast ? 32 : 8;
+  CUtensorMap mapO;
+  cuuint64_t dims[4] = {64, (cuuint64_t)outC, (cuuint64_t)ns, (cuuint64_t)outR};
+  cuuint64_t strides[3] = {128, (cuuint64_t)outC * 128, (cuuint64_t)ns * outC * 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)bc, (cuuint32_t)bs, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = s->encode(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "conv1_wide: cuTensorMapEncodeTiled failed with %d", (int)r);
+  static bool configured = false;
+  if (!configured) {
+    SC_CUDA(cudaFuncSetAttribute(conv1_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768 + 1024));
+    configured = true;
+  }
+  const long long n_tiles = (long long)outR * ((ns + bs - 1) / bs) * ((outC + bc - 1) / bc);
+  const long long cap = (long long)ctx->sm_count * 3;               // 3 CTAs per SM (66 KB of shared memory each)
+  const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+  ProfScope prof(ctx, PC_CONV1, st);
+  conv1_wide_kernel<<<grid, 256, 2 * 32768 + 1024, st>>>(mapO, cw, vol, g, ns, outR, outC, slice_fast);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 template <int KSTEPS, int DIL, int POOL, int CW, bool LO64, bool OUT32>

@@ -18,13 +18,6 @@
 
 namespace sc {
 
-struct ViewGeo {
-  int64_t ss, rs, cs;   // element strides of slice / row / col in the [X][Y][Z] volume
-  int s0, ns;           // slice range of the box along the view's slice axis
-  int r0, c0;           // box origin inside the slice
-  int br, bc;           // box extent (rows, cols)
-  int R, C;             // full slice extent (zero outside)
-};
 
 __host__ __device__ inline int round8(int v) { return (v + 7) & ~7; }
 
@@ -283,61 +276,6 @@ __global__ void __launch_bounds__(256) dense_conv1_nhwc_kernel(const float* __re
   }
 }
 
-// conv1 for the strip-sweep pipeline: wide-row layout (position = (row * ns + slice) * outC + col, conv_sweep.cu) and
-// 128 B pixels (32 bf16 hi | 32 bf16 lo, channels 20..31 zero).  One thread per pixel into a shared tile, then the CTA
-// streams the tile out fully coalesced.
-__global__ void __launch_bounds__(256) dense_conv1_wide_kernel(const float* __restrict__ vol, ViewGeo g, int ns,
-                                                               const float* __restrict__ w, const float* __restrict__ scale,
-                                                               const float* __restrict__ shift, const float* __restrict__ alpha,
-                                                               float* __restrict__ out, int outR, int outC) {
-  __shared__ float sw[9 * 20], ssc[20], ssh[20], sal[20];
-  extern __shared__ __align__(16) uint8_t tile[];   // 256 * 144 B
-  for (int i = threadIdx.x; i < 180; i += 256) sw[i] = w[i];
-  if (threadIdx.x < 20) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; sal[threadIdx.x] = alpha[threadIdx.x]; }
-  for (int i = threadIdx.x; i < 256 * 9; i += 256) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);  // channel padding stays zero
-  __syncthreads();
-  const int64_t total = (int64_t)ns * outR * outC;
-  for (int64_t base = (int64_t)blockIdx.x * 256; base < total; base += (int64_t)gridDim.x * 256) {
-    const int64_t e = base + threadIdx.x;
-    if (e < total) {
-      const int j = (int)(e % outC);
-      const int s = (int)((e / outC) % ns);
-      const int i = (int)(e / ((int64_t)outC * ns));
-      const float* vb = vol + (int64_t)(g.s0 + s) * g.ss;
-      float x[9];
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int rr = g.r0 + i + ky - 16;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int cc = g.c0 + j + kx - 16;
-          x[ky * 3 + kx] = (rr >= 0 && rr < g.R && cc >= 0 && cc < g.C) ? __ldg(vb + (int64_t)rr * g.rs + (int64_t)cc * g.cs) : 0.f;
-        }
-      }
-      uint8_t* o = tile + threadIdx.x * 144;
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int co = q * 4 + k;
-          float a = 0.f;
-#pragma unroll
-          for (int t = 0; t < 9; ++t) a = fmaf(x[t], sw[t * 20 + co], a);
-          v[k] = prelu(fmaf(a, ssc[co], ssh[co]), sal[co]);
-        }
-        store_split4_b32(o, q * 4, v[0], v[1], v[2], v[3]);
-      }
-    }
-    __syncthreads();
-    const int64_t npx = total - base < 256 ? total - base : 256;
-    uint4* dst = reinterpret_cast<uint4*>(out + base * 32);
-    for (int i = threadIdx.x; i < (int)npx * 8; i += 256)
-      dst[i] = *reinterpret_cast<const uint4*>(tile + (i >> 3) * 144 + (i & 7) * 16);
-    __syncthreads();
-  }
-}
-
 // stride-1 max-pool (window {0,pd}^2) on a flattened NHWC-64 split-bf16 map (positions = slices x rows x pitch, back to
 // back): out[p] = max(in[p], in[p+pd], in[p+pd*pitch], in[p+pd*pitch+pd]); hi + lo is exact in fp32, so the maximum is
 // taken on the reconstructed values and split again (the re-split reproduces the same represented value).  Positions whose window leaves the buffer are skipped (they are never read).
@@ -440,14 +378,7 @@ int branch_patches_tc(sc_ctx* ctx, int b, const float* patches, int64_t n, float
   SC_CHECK(n * 960 < (1ll << 31), SC_ERR_ARG, "patchwise chunk too large");
   {
     ViewGeo g = {1024, 32, 1, 0, (int)n, 16, 16, 30, 30, 32, 32};   // origin 16 cancels the dense path's zero-pad offset
-    const int64_t blocks = (n * 960 + 255) / 256;
-    const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
-    static bool c1cfg = false;
-    if (!c1cfg) { SC_CUDA(cudaFuncSetAttribute(dense_conv1_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 144)); c1cfg = true; }
-    ProfScope prof(ctx, PC_CONV1, st);
-    dense_conv1_wide_kernel<<<grid, 256, 256 * 144, st>>>(patches, g, (int)n, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], c1, 30, 32);
-    ctx->launches++;
-    SC_CUDA(cudaGetLastError());
+    SC_TRY(launch_conv1_wide(ctx, patches, g, (int)n, W.c1_host, c1, 30, 32, st));
   }
   SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, c1, 1, p1, 1, (int)(n * 32), 30, 1, 2, PC_CONV2, st));   // conv2 + pool1 -> [15][n][16]
   SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, p1, 1, c3, 0, (int)(n * 16), 15, 1, 0, PC_CONV3, st));   // conv3
@@ -614,16 +545,7 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       float* cur = reinterpret_cast<float*>(scratch);
       float* m1 = carve(cur, 32); float* mp1 = carve(cur, 32);
       float* m3 = carve(cur, 64); float* m4 = carve(cur, 64); float* mp2 = carve(cur, 64);
-      {
-        const int64_t blocks = (npos + 255) / 256;
-        const unsigned grid = (unsigned)(blocks < (int64_t)ctx->sm_count * 32 ? blocks : (int64_t)ctx->sm_count * 32);
-        ProfScope prof(ctx, PC_CONV1, st);
-        static bool c1cfg = false;
-        if (!c1cfg) { SC_CUDA(cudaFuncSetAttribute(dense_conv1_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 144)); c1cfg = true; }
-        dense_conv1_wide_kernel<<<grid, 256, 256 * 144, st>>>(vol, g, g.ns, W.c1_w, W.scale[0], W.shift[0], W.alpha[0], m1, R1, C1);
-        ctx->launches++;
-        SC_CUDA(cudaGetLastError());
-      }
+      SC_TRY(launch_conv1_wide(ctx, vol, g, g.ns, W.c1_host, m1, R1, C1, st));
       SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, Pw, R1, 1, 1, PC_CONV2, st));     // conv2 + pool1
       SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, Pw, R1, 2, 0, PC_CONV3, st));     // conv3
       const int P = (int)npos;

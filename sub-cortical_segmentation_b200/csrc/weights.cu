@@ -75,7 +75,7 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
     const BranchOff& B = P.br[b];
     bo[b].c1 = A.alloc(9 * 20);
     for (int t = 0; t < 9; ++t)
-      for (int co = 0; co < 20; ++co) A.host[bo[b].c1 + t * 20 + co] = h[B.convW[0] + co * 9 + (8 - t)];
+      for (int co = 0; co < 20; ++co) A.host[bo[b].c1 + t * 20 + co] = ctx->br[b].c1_host.w[t * 20 + co] = h[B.convW[0] + co * 9 + (8 - t)];
     for (int l = 0; l < 5; ++l) {
       const int ci_n = kConvCin[l], co_n = kConvCout[l];
       if (l > 0) {
@@ -117,6 +117,7 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
         A.host[bo[b].scale[l] + c] = s;
         A.host[bo[b].shift[l] + c] = beta - mean * s;
         A.host[bo[b].alpha[l] + c] = h[B.alpha[l] + c];
+        if (l == 0) { ctx->br[b].c1_host.scale[c] = s; ctx->br[b].c1_host.shift[c] = beta - mean * s; ctx->br[b].c1_host.alpha[c] = h[B.alpha[l] + c]; }
         if (l > 0) {
           A.host[bo[b].ctc[l].scale + c] = s;
           A.host[bo[b].ctc[l].bias + c] = beta - mean * s;
