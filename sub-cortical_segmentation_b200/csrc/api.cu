@@ -122,6 +122,7 @@ int sc_destroy(sc_ctx* ctx) {
   cudaFree(ctx->d_count); cudaFreeHost(ctx->h_count); cudaFree(ctx->train_consts); cudaFree(ctx->tc_timing_buf);
   for (auto& ev : ctx->prof_live) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto& ev : ctx->prof_free) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_ev[0]); cudaEventDestroy(ctx->copy_ev[1]); }
   delete ctx;
   return SC_OK;
 }
@@ -366,12 +367,27 @@ int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dim
   uint8_t* d_mask = reinterpret_cast<uint8_t*>(base + vb + ab);
   uint8_t* d_lab = d_mask + mb;
   float* d_proba = proba_vol_host ? reinterpret_cast<float*>(base + vb + ab + 2 * mb) : nullptr;
+  // the atlas (15 floats per voxel, 94 % of the upload) is first needed after the conv phase: upload it on a side
+  // stream so that the copy engine works while the conv kernels run
+  if (!ctx->copy_stream) {
+    SC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) SC_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+  }
+  SC_CUDA(cudaEventRecord(ctx->copy_ev[0], st));                       // earlier work on `st` may still read the staging buffers
+  SC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+  SC_CUDA(cudaMemcpyAsync(d_atlas, atlas_host, nvox * 60, cudaMemcpyHostToDevice, ctx->copy_stream));
+  SC_CUDA(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
+  ctx->atlas_ready = ctx->copy_ev[1];
   SC_CUDA(cudaMemcpyAsync(d_vol, vol_host, nvox * 4, cudaMemcpyHostToDevice, st));
-  SC_CUDA(cudaMemcpyAsync(d_atlas, atlas_host, nvox * 60, cudaMemcpyHostToDevice, st));
   if (cand_mask_host) SC_CUDA(cudaMemcpyAsync(d_mask, cand_mask_host, nvox, cudaMemcpyHostToDevice, st));
   SC_CUDA(cudaMemsetAsync(d_lab, 0, nvox, st));
   if (d_proba) SC_CUDA(cudaMemsetAsync(d_proba, 0, nvox * 60, st));
-  SC_TRY(segment_volume(ctx, d_vol, dims, d_atlas, box, cand_mask_host ? d_mask : nullptr, d_lab, d_proba, st));
+  const int seg_status = segment_volume(ctx, d_vol, dims, d_atlas, box, cand_mask_host ? d_mask : nullptr, d_lab, d_proba, st);
+  if (ctx->atlas_ready) {                                              // not consumed (empty box or an error): join the side stream anyway
+    cudaStreamWaitEvent(st, ctx->atlas_ready, 0);
+    ctx->atlas_ready = nullptr;
+  }
+  SC_TRY(seg_status);
   if (label_vol_host) SC_CUDA(cudaMemcpyAsync(label_vol_host, d_lab, nvox, cudaMemcpyDeviceToHost, st));
   if (proba_vol_host) SC_CUDA(cudaMemcpyAsync(proba_vol_host, d_proba, nvox * 60, cudaMemcpyDeviceToHost, st));
   SC_CUDA(cudaStreamSynchronize(st));

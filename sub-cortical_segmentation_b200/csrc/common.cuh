@@ -176,6 +176,9 @@ struct sc_ctx {
   int tc_sweep45 = 7;            // bit 0: conv4 + pool2 as a strip sweep, bit 1: conv5 as a strip sweep, bit 2: CTA pairs for both
   int tc_fuse_w = 1;             // conv tiles: fold xh*wh and xh*wl into one double-width MMA
   int tc_nacc = 1;               // accumulator chains per narrow (<= 64 column) tile: 1, 2 or 4
+  cudaStream_t copy_stream = nullptr;   // sc_segment_volume_host: the 1 GB atlas upload overlaps the conv phase
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  cudaEvent_t atlas_ready = nullptr;    // when set, segment_volume waits for it before its first use of the atlas (phase 2)
   bool profile = false;
   std::vector<sc::ProfEvent> prof_live;
   std::vector<sc::ProfEvent> prof_free;

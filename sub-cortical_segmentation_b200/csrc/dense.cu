@@ -596,6 +596,10 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   }
 
   // ---- phase 2: d1 (x3) + FC head per slab of x-planes -------------------------------------
+  if (ctx->atlas_ready) {   // host entry point: the atlas upload ran on a side stream during phase 1
+    SC_CUDA(cudaStreamWaitEvent(st, ctx->atlas_ready, 0));
+    ctx->atlas_ready = nullptr;
+  }
   OutGeo og = {b[0], b[2], b[4], by, bz, Y, Z};
   // tensor-core mode: columns 272..319 of the split h2 rows are never written by fc_2 and must not hold NaN patterns
   if (tc) SC_CUDA(cudaMemsetAsync(h2, 0, h2_bytes, st));
