@@ -194,7 +194,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t w_lo = desc_lo(smem_u32(sW));
     const uint32_t ring_lo = desc_lo(smem_u32(sRing));
     const uint32_t panel16 = (uint32_t)(panel_bytes >> 4);
-    uint32_t g0 = 0, t = 0;
+    uint32_t gs = 0, gph = 0, t = 0;           // ring slot / phase parity of the item's current first row
     long long w_full = 0, w_tempty = 0;
     const long long tstart = a.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -207,13 +207,19 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         long long c0 = a.dbg ? clock64() : 0;
         mbar_wait(&tempty[b], ((t >> 1) & 1) ^ 1);
         if (a.dbg) { const long long c1 = clock64(); w_tempty += c1 - c0; c0 = c1; }
-        uint32_t sl[3];
+        // ring slots / phase parities of the three input rows, advanced incrementally (no divisions on this path)
+        uint32_t sl[3], ss[3], sp[3];
+        ss[0] = gs; sp[0] = gph;
+#pragma unroll
+        for (int ky = 1; ky < 3; ++ky) {
+          const bool wrap = ss[ky - 1] + 1 == (uint32_t)a.stages;
+          ss[ky] = wrap ? 0u : ss[ky - 1] + 1;
+          sp[ky] = sp[ky - 1] ^ (wrap ? 1u : 0u);
+        }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const uint32_t g = g0 + m + ky;
-          const uint32_t s = g % a.stages;
-          if (m == 0 || ky == 2) mbar_wait(&full[s], (g / a.stages) & 1);
-          sl[ky] = ring_lo + s * (SLOT >> 4);
+          if (m == 0 || ky == 2) mbar_wait(&full[ss[ky]], sp[ky]);
+          sl[ky] = ring_lo + ss[ky] * (SLOT >> 4);
         }
         if (a.dbg) w_full += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -234,16 +240,20 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           }
         }
         if (leader) {
-          umma_commit(&empty[(g0 + m) % a.stages]);
+          umma_commit(&empty[ss[0]]);
           if (m == nrow - 1) {
-            umma_commit(&empty[(g0 + m + 1) % a.stages]);
-            umma_commit(&empty[(g0 + m + 2) % a.stages]);
+            umma_commit(&empty[ss[1]]);
+            umma_commit(&empty[ss[2]]);
           }
           umma_commit(&tfull[b]);
         }
         __syncwarp();
+        gs = ss[1]; gph = sp[1];
+        if (m == nrow - 1) {                      // the two halo rows of the item are consumed as well
+          const bool wrap = ss[2] + 1 == (uint32_t)a.stages;
+          gs = wrap ? 0u : ss[2] + 1; gph = sp[2] ^ (wrap ? 1u : 0u);
+        }
       }
-      g0 += nrow + 2;
     }
     if (a.dbg && leader) {
       a.dbg[blockIdx.x * 8 + 2] = (unsigned long long)w_full; a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
@@ -519,7 +529,7 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       const uint32_t ring_lo = desc_lo(smem_u32(sRing));
       const uint32_t panel16 = (uint32_t)(panel_bytes >> 4);
       const uint32_t wl_off = (uint32_t)((a.bn >> 1) * 128) >> 4;       // W lo rows follow the bn/2 W hi rows
-      uint32_t g0 = 0, t = 0;
+      uint32_t gs = 0, gph = 0, t = 0;
       for (int item = pair; item < a.n_items; item += npairs) {
         int w0, q, n0, Lc;
         decode(item, w0, q, n0, Lc);
@@ -528,13 +538,18 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         for (int m = 0; m < nrow; ++m, ++t) {
           const uint32_t b = t & 1;
           mbar_wait(&tempty[b], ((t >> 1) & 1) ^ 1);
-          uint32_t sl[3];
+          uint32_t sl[3], ss[3], sp[3];
+          ss[0] = gs; sp[0] = gph;
+#pragma unroll
+          for (int ky = 1; ky < 3; ++ky) {
+            const bool wrap = ss[ky - 1] + 1 == (uint32_t)a.stages;
+            ss[ky] = wrap ? 0u : ss[ky - 1] + 1;
+            sp[ky] = sp[ky - 1] ^ (wrap ? 1u : 0u);
+          }
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const uint32_t g = g0 + m + ky;
-            const uint32_t s = g % a.stages;
-            if (m == 0 || ky == 2) mbar_wait(&full[s], (g / a.stages) & 1);
-            sl[ky] = ring_lo + s * (SLOT >> 4);
+            if (m == 0 || ky == 2) mbar_wait(&full[ss[ky]], sp[ky]);
+            sl[ky] = ring_lo + ss[ky] * (SLOT >> 4);
           }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t acc = tmem_base + b * 256;
@@ -555,16 +570,20 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             }
           }
           if (leader) {
-            umma_commit_2sm(&empty[(g0 + m) % a.stages]);
+            umma_commit_2sm(&empty[ss[0]]);
             if (m == nrow - 1) {
-              umma_commit_2sm(&empty[(g0 + m + 1) % a.stages]);
-              umma_commit_2sm(&empty[(g0 + m + 2) % a.stages]);
+              umma_commit_2sm(&empty[ss[1]]);
+              umma_commit_2sm(&empty[ss[2]]);
             }
             umma_commit_2sm(&tfull[b]);
           }
           __syncwarp();
+          gs = ss[1]; gph = sp[1];
+          if (m == nrow - 1) {
+            const bool wrap = ss[2] + 1 == (uint32_t)a.stages;
+            gs = wrap ? 0u : ss[2] + 1; gph = sp[2] ^ (wrap ? 1u : 0u);
+          }
         }
-        g0 += nrow + 2;
       }
     }
   } else {
