@@ -11,9 +11,9 @@
 // Coordinates: every layer buffer of a view shares the origin (r0, c0) of the requested
 // output box in padded-slice coordinates; layer L covers rows [r0, r1 + ext_L):
 //   ext: conv1 29, conv2 27, conv3 22, conv4 18, conv5 8, d1 0.
-// The 2x2 stride-1 pools are folded into the load stage of conv3 / conv5.
-// Layouts: conv1..conv4 planar [slice][C][rows][ld]; conv5 NHWC-64 [slice][rows][cols][64]
-// (the A operand of the d1 implicit GEMM, K = tap*64 + c).
+// This file: the orchestration (segment_volume, branch_patches_tc) and the fp32 SIMT back-end (planar maps
+// [slice][C][rows][ld], pools folded into the load stage of conv3 / conv5, conv5 output NHWC-64 = the A operand of the d1
+// implicit GEMM, K = tap*64 + c).  The default tensor-core back-end runs the conv layers in conv_sweep.cu (wide-row maps).
 #include "common.cuh"
 
 namespace sc {
@@ -219,63 +219,8 @@ static int launch_dense_conv(sc_ctx* ctx, const ConvArgs& a, int prof_cls, cudaS
 }
 
 // ---------------------------------------------------------------------------------------
-// tensor-core pipeline pieces: conv1 straight into the NHWC-64 split-bf16 layout, and the stride-1
-// max-pools as their own (HBM-bound) pass -- a TMA-fed MMA cannot fold the pool into its load.
+// pre-sweep tensor-core pipeline pieces (tc_sweep45 = 0, kept for A/B runs): the stride-1 max-pool as its own (HBM-bound) pass
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dense_conv1_nhwc_kernel(const float* __restrict__ vol, ViewGeo g, int sbeg, int ns,
-                                                               const float* __restrict__ w, const float* __restrict__ scale,
-                                                               const float* __restrict__ shift, const float* __restrict__ alpha,
-                                                               float* __restrict__ out, int outR, int outC) {
-  // 256 consecutive pixels per CTA: one thread computes one pixel's 20 channels into a shared [256][272 B] tile
-  // (pitch padded against bank conflicts), then the CTA streams the tile out with 16 B per thread, fully coalesced.
-  __shared__ float sw[9 * 20], ssc[20], ssh[20], sal[20];
-  extern __shared__ __align__(16) uint8_t tile[];   // 256 * 272 B
-  for (int i = threadIdx.x; i < 180; i += 256) sw[i] = w[i];
-  if (threadIdx.x < 20) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; sal[threadIdx.x] = alpha[threadIdx.x]; }
-  for (int i = threadIdx.x; i < 256 * 17; i += 256) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);  // channel padding stays zero
-  __syncthreads();
-  const int64_t total = (int64_t)ns * outR * outC;
-  for (int64_t base = (int64_t)blockIdx.x * 256; base < total; base += (int64_t)gridDim.x * 256) {
-    const int64_t e = base + threadIdx.x;
-    if (e < total) {
-      const int j = (int)(e % outC);
-      const int i = (int)((e / outC) % outR);
-      const int s = (int)(e / ((int64_t)outC * outR));
-      const float* vb = vol + (int64_t)(g.s0 + sbeg + s) * g.ss;
-      float x[9];
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int rr = g.r0 + i + ky - 16;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int cc = g.c0 + j + kx - 16;
-          x[ky * 3 + kx] = (rr >= 0 && rr < g.R && cc >= 0 && cc < g.C) ? __ldg(vb + (int64_t)rr * g.rs + (int64_t)cc * g.cs) : 0.f;
-        }
-      }
-      float* o = reinterpret_cast<float*>(tile + threadIdx.x * 272);
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int co = q * 4 + k;
-          float a = 0.f;
-#pragma unroll
-          for (int t = 0; t < 9; ++t) a = fmaf(x[t], sw[t * 20 + co], a);
-          v[k] = prelu(fmaf(a, ssc[co], ssh[co]), sal[co]);
-        }
-        store_split4(o, q * 4, v[0], v[1], v[2], v[3]);
-      }
-    }
-    __syncthreads();
-    const int64_t npx = total - base < 256 ? total - base : 256;
-    uint4* dst = reinterpret_cast<uint4*>(out + base * kC5Ld);
-    for (int i = threadIdx.x; i < (int)npx * 16; i += 256)
-      dst[i] = *reinterpret_cast<const uint4*>(tile + (i >> 4) * 272 + (i & 15) * 16);
-    __syncthreads();
-  }
-}
-
 // stride-1 max-pool (window {0,pd}^2) on a flattened NHWC-64 split-bf16 map (positions = slices x rows x pitch, back to
 // back): out[p] = max(in[p], in[p+pd], in[p+pd*pitch], in[p+pd*pitch+pd]); hi + lo is exact in fp32, so the maximum is
 // taken on the reconstructed values and split again (the re-split reproduces the same represented value).  Positions whose window leaves the buffer are skipped (they are never read).
@@ -325,39 +270,8 @@ static int launch_conv_tc(sc_ctx* ctx, const GemmW& w, const float* in, int inR,
 
 
 // ---------------------------------------------------------------------------------------
-// Patchwise branch on the tensor cores (predict_proba on patch dicts): every map of a chunk of patches is one flattened
-// NHWC-64 split-bf16 pixel sequence (pitch 32 / 16 / 8 per pooling level, patches back to back), so conv2..conv5 are the
-// same implicit GEMMs as in the dense path (filter row = shift by the pitch) and d1 reads the 3x3 conv5 map as 9 taps.
+// Patchwise branch on the tensor cores (predict_proba on patch dicts)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pool2x2s2_patch_kernel(const float* __restrict__ in, int inPitch, int inPos, float* __restrict__ out,
-                                                              int outH, int outW, int outPitch, int outPos, int64_t n) {
-  const int64_t total = n * outPos * 16;
-  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
-    const int q = (int)(e & 15);
-    const int64_t pos = e >> 4;
-    const int64_t patch = pos / outPos;
-    const int j = (int)(pos - patch * outPos);
-    const int y = j / outPitch, x = j - y * outPitch;
-    float best[4] = {0.f, 0.f, 0.f, 0.f};
-    if (y < outH && x < outW) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(
-            in + (patch * inPos + (int64_t)(2 * y + (k >> 1)) * inPitch + 2 * x + (k & 1)) * kC5Ld) + q * 4;
-        const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
-        const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + 64));
-        const float v0 = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
-        const float v1 = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
-        const float v2 = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
-        const float v3 = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
-        if (k == 0) { best[0] = v0; best[1] = v1; best[2] = v2; best[3] = v3; }
-        else { best[0] = fmaxf(best[0], v0); best[1] = fmaxf(best[1], v1); best[2] = fmaxf(best[2], v2); best[3] = fmaxf(best[3], v3); }
-      }
-    }
-    store_split4(out + pos * kC5Ld, q * 4, best[0], best[1], best[2], best[3]);
-  }
-}
-
 // Patch maps in the wide-row layout of conv_sweep.cu: the patches of a chunk lie side by side, position
 // (row r, patch p, col c) = r * (n * pitch) + p * pitch + c with pitch 32 / 16 / 8 per pooling level:
 //   conv1 [30][n][32] F32CH -> conv2 + 2x2/2 pool [15][n][16] F32CH -> conv3 [15][n][16] F64CH
