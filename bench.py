@@ -17,6 +17,8 @@ Prints ONE JSON line on rank 0.
 import argparse
 import json
 import os
+
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")   # keep NCCL's version banner out of stdout (one JSON line only)
 import subprocess
 import sys
 import threading

@@ -8,6 +8,8 @@ inference metric); same launch convention (torchrun for N > 1), one JSON line on
 import argparse
 import json
 import os
+
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")   # keep NCCL's version banner out of stdout (one JSON line only)
 import pickle
 import sys
 
