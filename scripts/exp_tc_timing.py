@@ -17,11 +17,11 @@ atlas = atlas / atlas.sum(-1, keepdim=True)
 lab = torch.zeros(shape, dtype=torch.uint8, device="cuda")
 ctx.segment_volume(vol, atlas, label_vol=lab)
 names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_tempty", "mma_total", "epi_wait_tfull", "epi_total", "tiles"]
-for cls, nm in [(5, "conv2"), (6, "conv3"), (7, "conv4"), (8, "conv5")]:
+for cls, nm in [(5, "conv2"), (6, "conv3"), (9, "gemm_d1"), (10, "gemm_fc1"), (11, "gemm_fc2")]:
     ctx.set_option("tc_timing", cls)
     ctx.segment_volume(vol, atlas, label_vol=lab)
     torch.cuda.synchronize()
-    v = np.array([[ctx.counter("tc_timing:%d" % (c * 8 + k)) for k in range(8)] for c in range(0, 148, 37)], dtype=np.float64)
+    v = np.array([[ctx.counter("tc_timing:%d" % (c * 8 + k)) for k in range(8)] for c in range(0, 74, 18)], dtype=np.float64)
     m = v.mean(0)
     print("%-9s tiles/CTA %5.0f | per tile: total %6.0f  mma waits full %6.0f tempty %6.0f | producer waits empty %6.0f | epilogue waits tfull %6.0f (busy %6.0f)" % (
         nm, m[7], m[4] / m[7], m[2] / m[7], m[3] / m[7], m[0] / m[7], m[5] / m[7], (m[6] - m[5]) / m[7]), flush=True)

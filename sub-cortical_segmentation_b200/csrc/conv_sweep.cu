@@ -76,15 +76,6 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), two values per call (packed conversions)
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 // KSTEPS: 16-channel k-steps per tap; DIL: dilation; POOL: 1 = fuse the stride-1 max-pool with window {0, DIL}^2 (dense maps),
 // 2 = fuse the 2x2 stride-2 max-pool (patch maps: output pitch and rows halve, row segments start on even rows);
 // CW: accumulator columns per epilogue warp (8 or 16; 4 column groups); LO64: lo operand 64 B into the row (F32CH)

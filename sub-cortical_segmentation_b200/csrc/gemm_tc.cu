@@ -473,13 +473,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         if (a.out_split) {
           uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
-            hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
+          for (int k = 0; k < 8; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
           *reinterpret_cast<uint4*>(mine) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(mine + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           *reinterpret_cast<uint4*>(mine + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -589,6 +583,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
       uint32_t it = 0;
+      long long w_empty = 0;
+      const long long tstart = a.dbg ? clock64() : 0;
       for (long long t = pair; t < a.num_tiles; t += npairs) {
         long long r = t;
         const int n_tile = (int)(r % a.nt); r /= a.nt;
@@ -599,7 +595,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
           const int s = it % a.stages;
           const uint32_t use = it / a.stages;
-          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          if (use > 0) {
+            const long long c0 = a.dbg ? clock64() : 0;
+            mbar_wait(&empty[s], (use - 1) & 1);
+            if (a.dbg) w_empty += clock64() - c0;
+          }
           const uint32_t lbar = smem_u32(&full[s]) & 0xFEFFFFFFu;      // the leader's barrier (peer bit cleared)
           if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));   // both CTAs' bytes land on it
           uint8_t* sp = sStage + s * stage_bytes;
@@ -611,6 +611,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
         }
       }
+      if (a.dbg && rank == 0) { a.dbg[pair * 8 + 0] = (unsigned long long)w_empty; a.dbg[pair * 8 + 1] = (unsigned long long)(clock64() - tstart); }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -620,14 +621,20 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t sStage_u = smem_u32(sStage);
       uint32_t it = 0, ti = 0;
+      long long w_full = 0, w_tempty = 0;
+      const long long tstart = a.dbg ? clock64() : 0;
       for (long long t = pair; t < a.num_tiles; t += npairs, ++ti) {
         const uint32_t b = ti & 1, buse = ti >> 1;
+        long long c0 = a.dbg ? clock64() : 0;
         mbar_wait(&tempty[b], (buse & 1) ^ 1);
+        if (a.dbg) w_tempty += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + b * 256;
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
           const int s = it % a.stages;
+          c0 = a.dbg ? clock64() : 0;
           mbar_wait(&full[s], (it / a.stages) & 1);
+          if (a.dbg) w_full += clock64() - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sp = sStage_u + s * stage_bytes;
           const uint64_t ah = umma_desc(sp), al = umma_desc(sp + TC_A_HALF);
@@ -645,12 +652,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (leader) umma_commit_2sm(&tfull[b]);
         __syncwarp();
       }
+      if (a.dbg && leader) {
+        a.dbg[pair * 8 + 2] = (unsigned long long)w_full; a.dbg[pair * 8 + 3] = (unsigned long long)w_tempty;
+        a.dbg[pair * 8 + 4] = (unsigned long long)(clock64() - tstart);
+      }
     }
   } else {
     const int q = warp & 3;
     const int G = nepi >> 2, grp = (warp - 2) >> 2;
     const int epi_threads = nepi * 32;
     uint32_t ti = 0;
+    long long w_tfull = 0;
+    const long long tstart = a.dbg ? clock64() : 0;
     for (long long t = pair; t < a.num_tiles; t += npairs, ++ti) {
       long long r = t;
       const int n_tile = (int)(r % a.nt); r /= a.nt;
@@ -670,7 +683,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
       }
+      const long long c0w = a.dbg ? clock64() : 0;
       mbar_wait(&tfull[b], buse & 1);
+      if (a.dbg) w_tfull += clock64() - c0w;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float* ctile = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys;
       const int mw = m0 + q * 32;
@@ -729,13 +744,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (a.out_split) {
           uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
-            hi[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
+          for (int k = 0; k < 8; ++k) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
           *reinterpret_cast<uint4*>(mine) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(mine + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           *reinterpret_cast<uint4*>(mine + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -768,6 +777,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(&tempty[b], 0);     // the leader's MMA warp owns the accumulator hand-off
+    }
+    if (a.dbg && rank == 0 && threadIdx.x == 64) {
+      a.dbg[pair * 8 + 5] = (unsigned long long)w_tfull; a.dbg[pair * 8 + 6] = (unsigned long long)(clock64() - tstart);
+      a.dbg[pair * 8 + 7] = ti;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -94,6 +94,15 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), two values per call (packed conversions)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ---- CTA pairs (cta_group::2, cluster of two) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
