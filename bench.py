@@ -263,6 +263,7 @@ def main():
     extra = {}
     if rank == 0:
         nb = 100000                                   # one reference test batch (test_batch_size, configuration.cfg:19)
+        time.sleep(2.0)                               # the secondary kernels are timed alone: let the power-capped clocks of the volume passes recover
         xyz = ctx.nonzero_coords(d_mask)[5000000:5000000 + nb].contiguous()
         bufs = [torch.empty((nb, 1, 32, 32), device="cuda") for _ in range(3)] + [torch.empty((nb, 15), device="cuda")]
         import ctypes

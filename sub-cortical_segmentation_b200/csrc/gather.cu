@@ -26,11 +26,16 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(
     const int32_t* __restrict__ xyz, int64_t n, float* __restrict__ ax, float* __restrict__ co,
     float* __restrict__ sa, float* __restrict__ atlas_out) {
   __shared__ int sx[kGroup], sy[kGroup], sz[kGroup];
-  __shared__ float tile[8][32][33];
+  __shared__ float sbuf[8 * 32 * 33];                       // axial: 8 warp-private 32x33 tiles; fast path: the two 32x64 windows
+  float (*tile)[32][33] = reinterpret_cast<float (*)[32][33]>(sbuf);
   __shared__ float satl[kGroup][16];
-  const int64_t base = (int64_t)blockIdx.x * kGroup;
-  const int cnt = (int)min((int64_t)kGroup, n - base);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t ngroups = (n + kGroup - 1) / kGroup;
+  // persistent CTAs: a grid of (resident CTAs per SM) x (SMs) walks the groups, no partial last wave
+  for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  const int64_t base = grp * kGroup;
+  const int cnt = (int)min((int64_t)kGroup, n - base);
+  __syncthreads();                                            // the previous group's shared data is no longer read
   if (tid < kGroup) {
     int64_t c = base + min(tid, cnt - 1);
     sx[tid] = xyz[c * 3 + 0];
@@ -40,8 +45,42 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(
   __syncthreads();
   const int64_t YZ = (int64_t)Y * Z;
 
-  // ---- coronal and saggital: one warp per (candidate, view) ------------------------------
-  for (int job = warp; job < cnt * 2; job += 8) {
+  // ---- coronal and saggital, fast path: a full group of candidates that are consecutive along z (the normal case in
+  // np.nonzero order) shares 31/32 of its rows.  Stage the 32 x 63 window of each view once in shared memory and cut
+  // the 32 patches out of it: the volume is read once per group instead of once per candidate (the kernel is bound by
+  // the bytes moved through L2, reads included).
+  float (*win)[32][64] = reinterpret_cast<float (*)[32][64]>(sbuf);
+  const bool mine_ok = tid >= kGroup || (sx[tid] == sx[0] && sy[tid] == sy[0] && sz[tid] == sz[0] + tid);
+  const bool run = __syncthreads_and(mine_ok && cnt == kGroup) != 0;
+  if (run && (co || sa)) {
+    const int x = sx[0], y = sy[0], z0 = sz[0];
+    for (int e = tid; e < 2 * 32 * 64; e += 256) {
+      const int view = e >> 11, i = (e >> 6) & 31, j = e & 63;
+      const int zz = z0 - 16 + j;
+      const int xx = view ? x : x - 16 + i, yy = view ? y - 16 + i : y;
+      float v = 0.f;
+      if (j < 63 && zz >= 0 && zz < Z && xx >= 0 && xx < X && yy >= 0 && yy < Y) v = __ldg(vol + (int64_t)xx * YZ + (int64_t)yy * Z + zz);
+      win[view][i][j] = v;
+    }
+    __syncthreads();
+    for (int job = warp; job < kGroup * 2; job += 8) {
+      const int c = job >> 1, view = job & 1;
+      float* dst = view ? sa : co;
+      if (!dst) continue;
+      float* out = dst + (base + c) * 1024 + lane;
+      const float* src = &win[view][0][c + lane];
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        __stcs(out, *src);
+        src += 64;
+        out += 32;
+      }
+    }
+    __syncthreads();                                          // the axial tiles reuse the window's shared memory
+  }
+
+  // ---- coronal and saggital, general path: one warp per (candidate, view) ------------------------------
+  for (int job = warp; job < (run ? 0 : cnt * 2); job += 8) {
     const int c = job >> 1, view = job & 1;
     float* dst = view ? sa : co;
     if (!dst) continue;
@@ -112,6 +151,7 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(
     __syncthreads();
     for (int e = tid; e < cnt * 15; e += 256) atlas_out[base * 15 + e] = satl[e / 15][e % 15];
   }
+  }
 }
 
 int launch_gather(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, int bg_fix,
@@ -119,7 +159,9 @@ int launch_gather(sc_ctx* ctx, const float* vol, const int32_t* dims, const floa
                   cudaStream_t st) {
   if (n == 0) return SC_OK;
   SC_CHECK(!atlas_out || atlas, SC_ERR_ARG, "sc_gather_patches: atlas output requested without an atlas");
-  const int64_t blocks = (n + kGroup - 1) / kGroup;
+  int64_t blocks = (n + kGroup - 1) / kGroup;
+  const int64_t cap = (int64_t)ctx->sm_count * ctx->gather_ctas_per_sm;           // persistent CTAs (0 = one CTA per group)
+  if (cap > 0 && blocks > cap) blocks = cap;
   SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "sc_gather_patches: too many candidates in one call");
   ProfScope prof(ctx, PC_GATHER, st);
   gather_patches_kernel<<<(unsigned)blocks, 256, 0, st>>>(vol, dims[0], dims[1], dims[2], atlas, bg_fix, xyz, n, ax,
