@@ -145,6 +145,10 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     if (value >= 0 && !ctx->tc_timing_buf) SC_CUDA(cudaMalloc(&ctx->tc_timing_buf, sizeof(unsigned long long) * 8 * 1024));
     return SC_OK;
   }
+  if (!strcmp(key, "tc_mc")) {
+    ctx->tc_mc = value != 0;
+    return SC_OK;
+  }
   if (!strcmp(key, "gather_ctas_per_sm")) {
     SC_CHECK(value >= 0 && value <= 32, SC_ERR_ARG, "sc_set_option: gather_ctas_per_sm must be 0..32");
     ctx->gather_ctas_per_sm = (int)value;

@@ -541,8 +541,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
 //   * the leader's MMA warp issues tcgen05.mma.cta_group::2 (M = 256) and multicasts its commits to both CTAs
 //   * every CTA's epilogue warps drain their own TMEM half and arrive on the leader's tempty barrier (remote arrive)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
-gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
+// MC = true (FC1, fc_2): a cluster holds one CTA pair per n-tile of the SAME 256 rows; the A blocks are loaded once and
+// multicast to all pairs (the L2 -> SM fabric, not the tensor pipe, bounds these GEMMs); plain (cta_group::1) loads complete
+// bytes on every CTA's own full barrier, the non-leader's idle MMA warp relays its barrier to the leader, and the leaders'
+// commits release a ring slot in every CTA of the cluster.
+template <bool MC>
+__device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcArgs& a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int hb = a.bn >> 1;                               // weight rows held by this CTA
@@ -554,17 +558,26 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint64_t* empty = bars + a.stages;                      // per CTA, arrived by the leader's multicast commit
   uint64_t* tfull = bars + 2 * a.stages;                  // [2] per CTA
   uint64_t* tempty = tfull + 2;                           // [2] leader only: both CTAs' epilogue warps arrive
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_const = reinterpret_cast<float*>(tmem_slot + 4);          // keeps the float4 loads of the constants 16 B aligned
+  uint64_t* pfull = tempty + 2;                           // [stages] MC, leader only: the peer's stage has landed (relayed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + a.stages);
+  float* s_const = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 loads of the constants
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + 2 * 3 * a.bn);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;                          // position inside the CTA pair
+  const uint32_t pi = crank >> 1, lead = crank & ~1u;      // pair index inside the cluster (MC: = n-tile), leader's cluster rank
   const int nepi = (blockDim.x >> 5) - 2;
-  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int csz = MC ? 2 * a.nt : 2;
+  // MC: the cluster walks the m-tiles, pair pi takes n-tile pi of each; otherwise every pair walks the flat tile list
+  const long long pair = MC ? (long long)(blockIdx.x / csz) * a.nt + pi : (long long)(blockIdx.x >> 1);
+  const long long npairs = MC ? (long long)(gridDim.x / csz) * a.nt : (long long)(gridDim.x >> 1);
+  const uint16_t all_mask = (uint16_t)((1u << csz) - 1), pair_mask = (uint16_t)(3u << (2 * pi));
+  uint16_t a_mask = 0;                                      // MC: the CTAs holding the same 128 rows of A
+  for (int j = 0; j < (MC ? a.nt : 0); ++j) a_mask |= (uint16_t)(1u << (2 * j + rank));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MC ? a.nt : 1); mbar_init(&pfull[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * nepi); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -600,15 +613,23 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             mbar_wait(&empty[s], (use - 1) & 1);
             if (a.dbg) w_empty += clock64() - c0;
           }
-          const uint32_t lbar = smem_u32(&full[s]) & 0xFEFFFFFFu;      // the leader's barrier (peer bit cleared)
-          if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));   // both CTAs' bytes land on it
           uint8_t* sp = sStage + s * stage_bytes;
           const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
           const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0 + a.tap_dz[tap];
-          tma_load_4d_2sm(&mapA, lbar, sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
-          tma_load_4d_2sm(&mapA, lbar, sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
-          tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
-          tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
+          if (MC) {
+            mbar_expect_tx(&full[s], (uint32_t)stage_bytes);            // this CTA's own stage: A hi + lo (multicast) + its W halves
+            tma_load_2d(&mapB, &full[s], sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
+            tma_load_2d(&mapB, &full[s], sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
+            if (pi == 0) tma_load_4d_mc(&mapA, &full[s], sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl, a_mask);
+            if (pi == 1) tma_load_4d_mc(&mapA, &full[s], sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl, a_mask);
+          } else {
+            const uint32_t lbar = smem_u32(&full[s]) & 0xFEFFFFFFu;    // the leader's barrier (peer bit cleared)
+            if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));   // both CTAs' bytes land on it
+            tma_load_4d_2sm(&mapA, lbar, sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
+            tma_load_4d_2sm(&mapA, lbar, sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
+            tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
+            tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
+          }
         }
       }
       if (a.dbg && rank == 0) { a.dbg[pair * 8 + 0] = (unsigned long long)w_empty; a.dbg[pair * 8 + 1] = (unsigned long long)(clock64() - tstart); }
@@ -634,6 +655,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const int s = it % a.stages;
           c0 = a.dbg ? clock64() : 0;
           mbar_wait(&full[s], (it / a.stages) & 1);
+          if (MC) mbar_wait(&pfull[s], (it / a.stages) & 1);           // the peer CTA's stage (relayed by its warp 1)
           if (a.dbg) w_full += clock64() - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sp = sStage_u + s * stage_bytes;
@@ -646,16 +668,26 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             umma_bf16_2sm_elect(acc, ah + o, wl + o, idesc, 1, leader);
             umma_bf16_2sm_elect(acc, ah + o, wh + o, idesc, 1, leader);
           }
-          if (leader) umma_commit_2sm(&empty[s]);
+          if (leader) umma_commit_2sm(&empty[s], MC ? all_mask : pair_mask);
           __syncwarp();
         }
-        if (leader) umma_commit_2sm(&tfull[b]);
+        if (leader) umma_commit_2sm(&tfull[b], pair_mask);
         __syncwarp();
       }
       if (a.dbg && leader) {
         a.dbg[pair * 8 + 2] = (unsigned long long)w_full; a.dbg[pair * 8 + 3] = (unsigned long long)w_tempty;
         a.dbg[pair * 8 + 4] = (unsigned long long)(clock64() - tstart);
       }
+    } else if (MC) {
+      // relay: tell the leader when this CTA's stage has landed (its own full barrier counts only its own bytes)
+      uint32_t it = 0;
+      for (long long t = pair; t < a.num_tiles; t += npairs)
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % a.stages;
+          mbar_wait(&full[s], (it / a.stages) & 1);
+          if (lane == 0) mbar_arrive_cta(&pfull[s], lead);
+          __syncwarp();
+        }
     }
   } else {
     const int q = warp & 3;
@@ -776,7 +808,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive_cta(&tempty[b], 0);     // the leader's MMA warp owns the accumulator hand-off
+      if (lane == 0) mbar_arrive_cta(&tempty[b], lead);  // the leader's MMA warp owns the accumulator hand-off
     }
     if (a.dbg && rank == 0 && threadIdx.x == 64) {
       a.dbg[pair * 8 + 5] = (unsigned long long)w_tfull; a.dbg[pair * 8 + 6] = (unsigned long long)(clock64() - tstart);
@@ -790,6 +822,16 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
+  gemm_tc_pair_body<false>(mapA, mapB, a);
+}
+// cluster size 2 * nt is set at launch
+__global__ void __launch_bounds__(576, 1)
+gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
+  gemm_tc_pair_body<true>(mapA, mapB, a);
 }
 
 // plain fp32 [rows][576] -> split bf16 hi|lo blocks (test entry sc_dense_layer only)
@@ -898,11 +940,11 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.num_tiles = (long long)a.mt * a.nt * p.Y * p.Z;
     a.epi_warps = 16;
     stage_bytes = 2 * TC_A_HALF + 2 * (a.bn / 2) * 128;
-    const int budget = 227 * 1024 - 1024 - 128 - 16 - 2 * 3 * a.bn * 4 - a.epi_warps * 2560;
+    const int budget = 227 * 1024 - 1024 - 192 - 16 - 2 * 3 * a.bn * 4 - a.epi_warps * 2560;
     a.stages = budget / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: pair tile too wide");
-    smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 4) * 8 + 32 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
+    smem = 1024 + (size_t)a.stages * stage_bytes + (3 * a.stages + 4) * 8 + 32 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
   } else if (!persistent) {
     a.stages = (108 * 1024) / stage_bytes;
     if (a.stages > 4) a.stages = 4;
@@ -955,10 +997,28 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     SC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     SC_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SC_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SC_CUDA(cudaFuncSetAttribute(gemm_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   ProfScope prof(ctx, p.prof_cls, st);
-  if (pair) {
+  // multicast clusters: plain row GEMMs with 2 or 3 n-tiles (fc_2, FC1): one CTA pair per n-tile, A loaded once per cluster
+  const bool mc = pair && ctx->tc_mc && p.ntaps == 1 && p.Y == 1 && p.Z == 1 && (a.nt == 2 || a.nt == 3) && a.mt >= 1;
+  if (mc) {
+    SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
+    const int csz = 2 * a.nt;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(64 + 32 * a.epi_warps); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(csz);
+    int max_clusters = 0;
+    SC_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tc_mc_kernel, &cfg));
+    SC_CHECK(max_clusters >= 1, SC_ERR_CUDA, "gemm_tc: no cluster of %d CTAs fits", csz);
+    long long ncl = a.mt < max_clusters ? a.mt : max_clusters;
+    cfg.gridDim = dim3((unsigned)(ncl * csz));
+    SC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_mc_kernel, mapA, mapB, a));
+  } else if (pair) {
     SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
     long long pairs = a.num_tiles < ctx->sm_count / 2 ? a.num_tiles : ctx->sm_count / 2;
     gemm_tc_pair_kernel<<<(unsigned)(2 * pairs), 64 + 32 * a.epi_warps, smem, st>>>(mapA, mapB, a);   // __cluster_dims__(2,1,1)

@@ -135,9 +135,17 @@ __device__ __forceinline__ void umma_bf16_2sm_elect(uint32_t tmem_d, uint64_t da
       "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
 }
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on the same barrier offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask = 3) {   // arrives on the same barrier offset in every CTA of `mask`
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// multicast tile load: the box lands at the same shared-memory offset of every CTA in `mask` and completes bytes on the
+// mbarrier at the same offset of each of them
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {   // arrive on `bar` of CTA `cta` of the cluster
   asm volatile(
