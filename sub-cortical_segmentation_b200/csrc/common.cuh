@@ -172,7 +172,7 @@ struct sc_ctx {
   int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
-  int tc_mc = 1;                 // FC1 / fc_2: multicast clusters (one CTA pair per n-tile, A loaded once per cluster)
+  int tc_mc = 0;                 // experiment (measured SLOWER, off): FC1 / fc_2 as multicast clusters, one CTA pair per n-tile, A loaded once per cluster
   int gather_ctas_per_sm = 0;    // > 0: persistent gather grid of that many CTAs per SM; 0 (default, measured fastest) = one CTA per 32-candidate group
   int tc_atlas_fused = 1;        // FC1's CTA-pair epilogue writes the atlas columns of h1 (no separate atlas pass)
   int tc_sweep45 = 7;            // bit 0: conv4 + pool2 as a strip sweep, bit 1: conv5 as a strip sweep, bit 2: CTA pairs for both
