@@ -834,15 +834,16 @@ static int launch_sweep_t(sc_ctx* ctx, const CUtensorMap& mapA, const CUtensorMa
 }
 
 int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
-                      int Pw, int R, int dil, int pool, int prof_cls, cudaStream_t st) {
+                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st) {
   TcState* s = reinterpret_cast<TcState*>(ctx->tc_state);
   SC_CHECK(s != nullptr, SC_ERR_UNSUPPORTED, "tcgen05 back-end not initialised");
   if (Pw <= 0 || R <= 0) return SC_OK;
   SweepArgs a;
-  a.Pw = Pw; a.R = R; a.bn = w.bn;
+  if (rows_out <= 0 || rows_out > R) rows_out = R;                      // rows of the map the next layer actually reads
+  a.Pw = Pw; a.R = rows_out; a.bn = w.bn;
   a.strip_w = 128 - (pool == 1 ? dil : 0);                            // pool: 0 none, 1 stride-1 window {0,d}^2, 2 = 2x2 stride 2
   a.nstrips = (Pw + a.strip_w - 1) / a.strip_w;
-  const int nq = (R + dil - 1) / dil;                                   // class rows of the largest class
+  const int nq = (rows_out + dil - 1) / dil;                            // class rows of the largest class
   // segments: enough items to balance the SMs, rows per item long enough to amortise the 2 (+1) halo rows
   int nseg = (4 * ctx->sm_count + a.nstrips * dil - 1) / (a.nstrips * dil);
   int L = (nq + nseg - 1) / nseg;

@@ -294,10 +294,10 @@ int branch_patches_tc(sc_ctx* ctx, int b, const float* patches, int64_t n, float
     ViewGeo g = {1024, 32, 1, 0, (int)n, 16, 16, 30, 30, 32, 32};   // origin 16 cancels the dense path's zero-pad offset
     SC_TRY(launch_conv1_wide(ctx, patches, g, (int)n, W.c1_host, c1, 30, 32, st));
   }
-  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, c1, 1, p1, 1, (int)(n * 32), 30, 1, 2, PC_CONV2, st));   // conv2 + pool1 -> [15][n][16]
-  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, p1, 1, c3, 0, (int)(n * 16), 15, 1, 0, PC_CONV3, st));   // conv3
-  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, c3, 0, p2, 0, (int)(n * 16), 15, 1, 2, PC_CONV4, st));   // conv4 + pool2 -> [7][n][8]
-  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, p2, 0, c5, 0, (int)(n * 8), 7, 1, 0, PC_CONV5, st));     // conv5
+  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, c1, 1, p1, 1, (int)(n * 32), 30, 28, 1, 2, PC_CONV2, st));   // conv2 + pool1 -> [15][n][16]
+  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, p1, 1, c3, 0, (int)(n * 16), 15, 12, 1, 0, PC_CONV3, st));   // conv3
+  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, c3, 0, p2, 0, (int)(n * 16), 15, 10, 1, 2, PC_CONV4, st));   // conv4 + pool2 -> [7][n][8]
+  SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, p2, 0, c5, 0, (int)(n * 8), 7, 3, 1, 0, PC_CONV5, st));     // conv5
   // d1: rows = patches; tap (ty, tx) of the 3x3 conv5 map is tensor-map coordinate (k, patch, tx, ty); K = tap*64 + c
   GemmProblem p;
   p.A = c5; p.lda = 8 * kC5Ld; p.a_ys = 0; p.a_zs = 0;
@@ -460,19 +460,19 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       float* m1 = carve(cur, 32); float* mp1 = carve(cur, 32);
       float* m3 = carve(cur, 64); float* m4 = carve(cur, 64); float* mp2 = carve(cur, 64);
       SC_TRY(launch_conv1_wide(ctx, vol, g, g.ns, W.c1_host, m1, R1, C1, st));
-      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, Pw, R1, 1, 1, PC_CONV2, st));     // conv2 + pool1
-      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, Pw, R1, 2, 0, PC_CONV3, st));     // conv3
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, Pw, R1, g.br + 26, 1, 1, PC_CONV2, st));     // conv2 + pool1
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, Pw, R1, g.br + 22, 2, 0, PC_CONV3, st));     // conv3
       const int P = (int)npos;
       const unsigned pgrid = (unsigned)((npos * 16 + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (npos * 16 + 255) / 256 : (int64_t)ctx->sm_count * 64);
       if (ctx->tc_sweep45 & 1) {
-        SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, m3, 0, mp2, 0, Pw, R1, 2, 1, PC_CONV4, st));   // conv4 + pool2
+        SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, m3, 0, mp2, 0, Pw, R1, g.br + 16, 2, 1, PC_CONV4, st));   // conv4 + pool2
       } else {
         SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, 1, P, m4, 1, P, 1, 2, 40, PC_CONV4, st, Pw));
         ProfScope prof(ctx, PC_POOL, st);
         pool_flat_kernel<<<pgrid, 256, 0, st>>>(m4, mp2, npos, Pw, 2);
         ctx->launches++;
       }
-      if ((ctx->tc_sweep45 & 6) == 6) SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, mp2, 0, a5[v], 0, Pw, R1, 4, 0, PC_CONV5, st));   // conv5 (CTA pairs)
+      if ((ctx->tc_sweep45 & 6) == 6) SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, mp2, 0, a5[v], 0, Pw, R1, g.br + 8, 4, 0, PC_CONV5, st));   // conv5 (CTA pairs)
       else SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, 1, P, a5[v], 1, P, 1, 4, 40, PC_CONV5, st, Pw));
       SC_CUDA(cudaGetLastError());
     }
