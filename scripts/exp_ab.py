@@ -9,6 +9,7 @@ from cnn_cort import _native, nets
 args = [a for i, a in enumerate(sys.argv[1:], 1) if not a.startswith("--") and not sys.argv[i - 1].startswith("--")]
 size = int(sys.argv[sys.argv.index("--size") + 1]) if "--size" in sys.argv else 256
 rounds = int(sys.argv[sys.argv.index("--rounds") + 1]) if "--rounds" in sys.argv else 4
+mask_frac = float(sys.argv[sys.argv.index("--mask") + 1]) if "--mask" in sys.argv else 0.0   # candidate mask: centred ball with this volume fraction
 configs = []
 for a in args:
     name, _, rest = a.partition(":")
@@ -22,6 +23,13 @@ vol = torch.randn(shape, device="cuda", generator=g)
 atlas = torch.rand(shape + (15,), device="cuda", generator=g) ** 6
 atlas = atlas / atlas.sum(-1, keepdim=True)
 lab = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+mask = None
+if mask_frac > 0:
+    ax = torch.arange(size, device="cuda", dtype=torch.float32) - (size - 1) / 2
+    r2 = ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2
+    rad = size * (3 * mask_frac / (4 * 3.14159265)) ** (1 / 3)
+    mask = (r2 < rad * rad).to(torch.uint8).contiguous()
+    print("mask: %.3f of the voxels" % float(mask.float().mean()))
 ref = None
 tot = {n: [] for n, _ in configs}
 for r in range(rounds + 1):
@@ -30,7 +38,7 @@ for r in range(rounds + 1):
             ctx.set_option(k, v)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ctx.segment_volume(vol, atlas, label_vol=lab)
+        ctx.segment_volume(vol, atlas, cand_mask=mask, label_vol=lab)
         e1.record()
         torch.cuda.synchronize()
         if r > 0:

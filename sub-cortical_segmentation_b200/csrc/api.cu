@@ -122,6 +122,7 @@ int sc_destroy(sc_ctx* ctx) {
   cudaFree(ctx->d_count); cudaFreeHost(ctx->h_count); cudaFree(ctx->train_consts); cudaFree(ctx->tc_timing_buf);
   for (auto& ev : ctx->prof_live) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto& ev : ctx->prof_free) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  if (ctx->h_slab_cnt) { cudaFreeHost(ctx->h_slab_cnt); cudaEventDestroy(ctx->compact_ev); }
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_ev[0]); cudaEventDestroy(ctx->copy_ev[1]); }
   delete ctx;
   return SC_OK;
@@ -143,6 +144,10 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
   if (!strcmp(key, "tc_timing")) {   // value = ProfClass index to instrument, -1 = off
     ctx->tc_timing_cls = (int)value;
     if (value >= 0 && !ctx->tc_timing_buf) SC_CUDA(cudaMalloc(&ctx->tc_timing_buf, sizeof(unsigned long long) * 8 * 1024));
+    return SC_OK;
+  }
+  if (!strcmp(key, "tc_compact")) {
+    ctx->tc_compact = value != 0;
     return SC_OK;
   }
   if (!strcmp(key, "tc_mc")) {

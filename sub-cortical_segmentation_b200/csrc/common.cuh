@@ -172,6 +172,9 @@ struct sc_ctx {
   int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
+  int tc_compact = 1;            // dense path with a candidate mask: the FC head runs on the compacted candidate rows only
+  int32_t* h_slab_cnt = nullptr; // pinned: candidates per slab
+  cudaEvent_t compact_ev = nullptr;
   int tc_mc = 0;                 // experiment (measured SLOWER, off): FC1 / fc_2 as multicast clusters, one CTA pair per n-tile, A loaded once per cluster
   int gather_ctas_per_sm = 0;    // > 0: persistent gather grid of that many CTAs per SM; 0 (default, measured fastest) = one CTA per 32-candidate group
   int tc_atlas_fused = 1;        // FC1's CTA-pair epilogue writes the atlas columns of h1 (no separate atlas pass)
@@ -207,8 +210,15 @@ struct ProfScope {
 };
 
 // gather.cu
+// row m of a box slab <-> voxel (x0 + m / (by*bz), y0 + (m / bz) % by, z0 + m % bz) of a [X][Y][Z] volume
+struct OutGeo { int x0, y0, z0, by, bz, Y, Z; };
+
 int launch_gather(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, int bg_fix,
                   const int32_t* xyz, int64_t n, float* ax, float* co, float* sa, float* atlas_out, cudaStream_t st);
+// ordered compaction of the candidate rows of every slab of a box (slab = nx_per_slab x-planes): rowmap[dense row] = compact
+// row or -1, rowvox[slab base + compact row] = dense row inside the slab, cnt[slab] = candidates; scratch: 2 ints per 2048 rows
+int launch_slab_compact(sc_ctx* ctx, const uint8_t* cand, const OutGeo& box, int bx, int nx_per_slab, int32_t* rowmap, int32_t* rowvox,
+                        int32_t* cnt, int32_t* scratch, cudaStream_t st);
 int launch_center_labels(sc_ctx* ctx, const uint8_t* lab, const int32_t* dims, const int32_t* xyz, int64_t n,
                          uint8_t* y, cudaStream_t st);
 int launch_nonzero(sc_ctx* ctx, const void* vol, int elem_bytes, const int32_t* dims, int32_t* xyz,
@@ -219,9 +229,6 @@ int launch_scatter(sc_ctx* ctx, const int32_t* xyz, int64_t n, const int32_t* la
 
 // weights.cu
 int derive_weights(sc_ctx* ctx, cudaStream_t st);
-
-// row m of a box slab <-> voxel (x0 + m / (by*bz), y0 + (m / bz) % by, z0 + m % bz) of a [X][Y][Z] volume
-struct OutGeo { int x0, y0, z0, by, bz, Y, Z; };
 
 // gemm_simt.cu : C = prelu(A*W + b), implicit-GEMM with taps
 struct GemmProblem {
@@ -245,6 +252,10 @@ struct GemmProblem {
   int n_store;          // columns written (<= w.Npad)
   int c_col0;           // first output column inside the C row (C points at the row start)
   int out_split;        // write C rows in the split bf16 hi|lo block layout (they feed a tcgen05 GEMM)
+  // candidate compaction (tcgen05 pair kernel): d1 writes row r of its dense slab to C row rowmap[r] (skipped when < 0);
+  // FC1 finds the voxel of its compact row m through rowvox[m] (atlas lookup)
+  const int32_t* rowmap = nullptr;
+  const int32_t* rowvox = nullptr;
   const float* atlas = nullptr;            // tcgen05 pair kernel (FC1): write the atlas prior of every row (with the background
   OutGeo ageo;                             // fix of base.py:392-394) into columns 540..554 and zeros up to 575
   const struct SoftmaxOut* sm = nullptr;   // tcgen05 back-end: softmax / argmax epilogue instead of the row store (out_layer)
@@ -265,7 +276,8 @@ inline void gemm_problem_rows(GemmProblem& p, const float* A, int64_t lda, int k
 // geo != nullptr: row m is voxel (ix,iy,iz) of a box slab; results go to the volume-shaped
 // outputs (label8 / proba) at that voxel, skipped where mask[voxel] == 0.
 // out_layer + softmax fused into the tcgen05 GEMM epilogue (N = 16): where the results of row m go
-struct SoftmaxOut { float* proba; int32_t* label32; uint8_t* label8; const uint8_t* mask; OutGeo geo; int use_geo; };
+struct SoftmaxOut { float* proba; int32_t* label32; uint8_t* label8; const uint8_t* mask; OutGeo geo; int use_geo;
+                    const int32_t* rowvox; };   // rowvox != nullptr: GEMM row m is the compacted candidate whose slab row is rowvox[m]
 int launch_out_softmax(sc_ctx* ctx, const float* h2, int64_t n, float* proba, int32_t* label32, uint8_t* label8,
                        const uint8_t* mask, const OutGeo* geo, cudaStream_t st);
 

@@ -426,7 +426,13 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   const size_t h1_bytes = align256(rows_max * kH1Ld * sizeof(float));
   const int h2ld = tc ? kH2LdTc : kH2Ld;
   const size_t h2_bytes = align256(rows_max * h2ld * sizeof(float));
-  const size_t total = a5_bytes + scratch_bytes + feat_bytes + h1_bytes + h2_bytes;
+  // candidate compaction (tensor-core path with a mask): the FC head runs on the candidate rows of each slab only
+  const int nslabs = (bx + slab - 1) / slab;
+  bool compact = tc && cand != nullptr && ctx->tc_compact && ctx->tc_variant == 3 && ctx->tc_atlas_fused && nslabs <= 4096;
+  const size_t nbox = (size_t)bx * plane;
+  const size_t cmp_blocks = (size_t)nslabs * ((rows_max + 2047) / 2048);
+  const size_t cmp_bytes = compact ? align256(nbox * 4) * 2 + align256(cmp_blocks * 8 + 16) + align256((size_t)nslabs * 4) : 0;
+  const size_t total = a5_bytes + scratch_bytes + feat_bytes + h1_bytes + h2_bytes + cmp_bytes;
   SC_TRY(ensure_ws(ctx->ws, total));
   char* wsb = reinterpret_cast<char*>(ctx->ws.ptr);
   float* a5[3] = {reinterpret_cast<float*>(wsb + a5_off[0]), reinterpret_cast<float*>(wsb + a5_off[1]),
@@ -435,6 +441,21 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   float* feats = reinterpret_cast<float*>(scratch + scratch_bytes);
   float* h1 = reinterpret_cast<float*>(reinterpret_cast<char*>(feats) + feat_bytes);
   float* h2 = reinterpret_cast<float*>(reinterpret_cast<char*>(h1) + h1_bytes);
+  int32_t* rowmap = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(h2) + h2_bytes);
+  int32_t* rowvox = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(rowmap) + align256(nbox * 4));
+  int32_t* cmp_scratch = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(rowvox) + align256(nbox * 4));
+  int32_t* d_slab_cnt = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(cmp_scratch) + align256(cmp_blocks * 8 + 16));
+  if (compact) {
+    // enqueue the scan first: its (tiny) result is on the host long before phase 1 has been launched
+    if (!ctx->h_slab_cnt) {
+      SC_CUDA(cudaMallocHost(&ctx->h_slab_cnt, 4096 * sizeof(int32_t)));
+      SC_CUDA(cudaEventCreateWithFlags(&ctx->compact_ev, cudaEventDisableTiming));
+    }
+    OutGeo boxg = {b[0], b[2], b[4], by, bz, Y, Z};
+    SC_TRY(launch_slab_compact(ctx, cand, boxg, bx, slab, rowmap, rowvox, d_slab_cnt, cmp_scratch, st));
+    SC_CUDA(cudaMemcpyAsync(ctx->h_slab_cnt, d_slab_cnt, (size_t)nslabs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaEventRecord(ctx->compact_ev, st));
+  }
 
   // ---- phase 1: conv1..conv5 per view, slices in groups ------------------------------------
   for (int v = 0; v < 3; ++v) {
@@ -515,11 +536,20 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     ctx->atlas_ready = nullptr;
   }
   OutGeo og = {b[0], b[2], b[4], by, bz, Y, Z};
+  if (compact) {
+    SC_CUDA(cudaEventSynchronize(ctx->compact_ev));
+    int64_t ncand = 0;
+    for (int i = 0; i < nslabs; ++i) ncand += ctx->h_slab_cnt[i];
+    if (ncand * 10 >= (int64_t)nbox * 9) compact = false;     // (nearly) every voxel is a candidate: the dense rows are cheaper
+  }
   // tensor-core mode: columns 272..319 of the split h2 rows are never written by fc_2 and must not hold NaN patterns
   if (tc) SC_CUDA(cudaMemsetAsync(h2, 0, h2_bytes, st));
   for (int ix0 = 0; ix0 < bx; ix0 += slab) {
     const int nx = bx - ix0 < slab ? bx - ix0 : slab;
     const int64_t rows = (int64_t)nx * plane;
+    const int64_t slab_base = (int64_t)ix0 * plane;
+    const int64_t rows_fc = compact ? ctx->h_slab_cnt[ix0 / slab] : rows;      // rows of the FC head (compact: candidates only)
+    if (rows_fc == 0) continue;
     for (int v = 0; v < 3; ++v) {
       const ViewGeo& g = vg[v];
       const int64_t c5 = tc ? g.bc + 29 : g.bc + 8, r5 = tc ? g.br + 29 : g.br + 8;   // tensor-core mode: conv1 geometry (see phase 1)
@@ -552,32 +582,33 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
         p.ldc = kFeatLd; p.c_ys = (int64_t)bz * kFeatLd; p.c_zs = plane * kFeatLd;
       }
       p.C = feats;
+      if (compact) p.rowmap = rowmap + slab_base;      // dense row -> compact feature row (or skipped)
       SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->br[v].d1_dense, st) : launch_gemm(ctx, p, ctx->br[v].d1_dense, st));
     }
     GemmProblem p;
     SC_CHECK(rows < (1ll << 31), SC_ERR_ARG, "sc_segment_volume: chunk too large");
-    gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)rows);
+    gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)rows_fc);
     p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
     const bool atlas_fused = tc && ctx->tc_variant == 3 && ctx->tc_atlas_fused;   // the CTA-pair kernel writes the atlas columns in its epilogue
-    if (atlas_fused) { p.atlas = atlas; p.ageo = og; p.ageo.x0 = b[0] + ix0; }
+    if (atlas_fused) { p.atlas = atlas; p.ageo = og; p.ageo.x0 = b[0] + ix0; if (compact) p.rowvox = rowvox + slab_base; }
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
-    p.atlas = nullptr;
+    p.atlas = nullptr; p.rowvox = nullptr;
     if (!atlas_fused) {  // after FC1: the tensor-core epilogue writes whole 16-column chunks (columns 540..543 as zeros)
       ProfScope prof(ctx, PC_ATLAS, st);
       dense_atlas_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(atlas, og, ix0, rows, h1, tc ? 1 : 0);
       ctx->launches++;
     }
     SC_CUDA(cudaGetLastError());
-    gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)rows);
+    gemm_problem_rows(p, h1, kH1Ld, kH1Ld, (int)rows_fc);
     p.C = h2; p.ldc = h2ld; p.n_store = kH2Ld; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC2;
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc2, st) : launch_gemm(ctx, p, ctx->fc2, st));
     OutGeo og2 = og;
     og2.x0 = b[0] + ix0;
     if (tc) {   // out_layer as a 16-column tcgen05 GEMM over the split h2 rows, softmax / argmax in its epilogue
-      SoftmaxOut smo = {proba_vol, nullptr, label_vol, cand, og2, 1};
-      gemm_problem_rows(p, h2, h2ld, h2ld, (int)rows);
+      SoftmaxOut smo = {proba_vol, nullptr, label_vol, cand, og2, 1, compact ? rowvox + slab_base : nullptr};
+      gemm_problem_rows(p, h2, h2ld, h2ld, (int)rows_fc);
       p.C = nullptr; p.ldc = 0; p.n_store = 16; p.out_split = 0; p.sm = &smo;
       p.prof_cls = PC_OUT;
       SC_TRY(launch_gemm_tc(ctx, p, ctx->outl, st));

@@ -321,6 +321,108 @@ int launch_nonzero(sc_ctx* ctx, const void* vol, int elem_bytes, const int32_t* 
   return SC_OK;
 }
 
+// ---- candidate rows of the dense path, compacted per slab (same order as np.nonzero inside the slab) -----------------
+constexpr int kCmpBlock = 2048;          // dense rows per block: 256 threads x 8
+
+__device__ __forceinline__ bool slab_cand(const uint8_t* __restrict__ cand, const OutGeo& g, int64_t plane, int ix0, int64_t m) {
+  const int ix = (int)(m / plane);
+  const int rem = (int)(m - (int64_t)ix * plane);
+  const int iy = rem / g.bz, iz = rem - iy * g.bz;
+  return cand[((int64_t)(g.x0 + ix0 + ix) * g.Y + (g.y0 + iy)) * g.Z + (g.z0 + iz)] != 0;
+}
+
+// pass 1 (emit == 0): candidates per block -> bc;  pass 3 (emit == 1): positions from the scanned block offsets
+__global__ void __launch_bounds__(256) slab_compact_kernel(const uint8_t* __restrict__ cand, OutGeo g, int bx, int nxs, int bps,
+                                                           int32_t* __restrict__ bc, const int32_t* __restrict__ boff,
+                                                           int32_t* __restrict__ rowmap, int32_t* __restrict__ rowvox, int emit) {
+  const int slab = blockIdx.x / bps, blk = blockIdx.x - slab * bps;
+  const int64_t plane = (int64_t)g.by * g.bz;
+  const int ix0 = slab * nxs;
+  const int nx = bx - ix0 < nxs ? bx - ix0 : nxs;
+  const int64_t rows = (int64_t)nx * plane, slab_base = (int64_t)ix0 * plane;
+  const int64_t start = (int64_t)blk * kCmpBlock + (int64_t)threadIdx.x * 8;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (start + k < rows && slab_cand(cand, g, plane, ix0, start + k)) bits |= 1u << k;
+  const int c = __popc(bits);
+  int inc = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += t;
+  }
+  __shared__ int wsum[8];
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  int wbase = 0, total = 0;
+  for (int w = 0; w < 8; ++w) { if (w < (int)(threadIdx.x >> 5)) wbase += wsum[w]; total += wsum[w]; }
+  if (!emit) {
+    if (threadIdx.x == 0) bc[blockIdx.x] = total;
+    return;
+  }
+  int o = boff[blockIdx.x] + wbase + inc - c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (start + k >= rows) break;
+    const bool on = (bits >> k) & 1u;
+    rowmap[slab_base + start + k] = on ? o : -1;
+    if (on) { rowvox[slab_base + o] = (int32_t)(start + k); ++o; }
+  }
+}
+
+// pass 2: exclusive scan of the block counts of one slab (one CTA per slab), candidates of the slab -> cnt
+__global__ void __launch_bounds__(1024) slab_scan_kernel(const int32_t* __restrict__ bc, int bps, int32_t* __restrict__ boff,
+                                                         int32_t* __restrict__ cnt) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int32_t* c = bc + (int64_t)blockIdx.x * bps;
+  int32_t* o = boff + (int64_t)blockIdx.x * bps;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < bps; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < bps ? c[i] : 0;
+    int inc = v;
+    for (int s = 1; s < 32; s <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, s);
+      if ((threadIdx.x & 31) >= s) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int w = wsum[threadIdx.x];
+      int winc = w;
+      for (int s = 1; s < 32; s <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, s);
+        if (threadIdx.x >= s) winc += t;
+      }
+      wsum[threadIdx.x] = winc - w;
+    }
+    __syncthreads();
+    const int excl = carry + wsum[threadIdx.x >> 5] + inc - v;
+    if (i < bps) o[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cnt[blockIdx.x] = carry;
+}
+
+int launch_slab_compact(sc_ctx* ctx, const uint8_t* cand, const OutGeo& box, int bx, int nx_per_slab, int32_t* rowmap, int32_t* rowvox,
+                        int32_t* cnt, int32_t* scratch, cudaStream_t st) {
+  const int64_t plane = (int64_t)box.by * box.bz;
+  const int nslabs = (bx + nx_per_slab - 1) / nx_per_slab;
+  const int bps = (int)(((int64_t)nx_per_slab * plane + kCmpBlock - 1) / kCmpBlock);
+  int32_t* bc = scratch;
+  int32_t* boff = scratch + (int64_t)nslabs * bps;
+  slab_compact_kernel<<<(unsigned)(nslabs * bps), 256, 0, st>>>(cand, box, bx, nx_per_slab, bps, bc, nullptr, nullptr, nullptr, 0);
+  slab_scan_kernel<<<nslabs, 1024, 0, st>>>(bc, bps, boff, cnt);
+  slab_compact_kernel<<<(unsigned)(nslabs * bps), 256, 0, st>>>(cand, box, bx, nx_per_slab, bps, bc, boff, rowmap, rowvox, 1);
+  ctx->launches += 3;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
 // one iteration of scipy.ndimage.binary_dilation with the default (6-connected cross) structuring element and
 // border_value 0: out = in | any face neighbour.  Ten iterations = the reference's crop mask (base.py:369).
 __global__ void dilate6_kernel(const uint8_t* __restrict__ in, int X, int Y, int Z, uint8_t* __restrict__ out) {

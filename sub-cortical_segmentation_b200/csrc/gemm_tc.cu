@@ -63,6 +63,9 @@ struct TcArgs {
   int fuse_w;         // narrow tiles: xh * [wh | wl] as ONE MMA of 2*bn columns (the epilogue adds the halves) + xl * wh:
                       // two instead of three MMAs and A shared-memory reads per product
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
+  const int* rowmap;  // pair kernel, split stores: C row of dense row r = rowmap[r] (skip when < 0); ldc / c_ys / c_zs then count ROWS
+  const int* rowvox;  // pair kernel, atlas epilogue: slab row of compact row m
+  long long crow_ld;  // floats per C row in rowmap mode
   const float* atlas; // pair kernel: atlas prior volume [X][Y][Z][15] -> output columns 540..575 (see GemmProblem::atlas)
   OutGeo ageo;
   int sm_on;          // persistent kernel, bn = 16: softmax / argmax epilogue (out_layer), results scattered through `sm`
@@ -395,8 +398,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                 "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
               : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const long long m = (long long)mw + lane;
+          long long m = (long long)mw + lane;
           bool ok = m < a.M;
+          if (ok && a.sm.rowvox) m = __ldg(a.sm.rowvox + m);      // compact row -> row of the dense slab
           long long o = m;
           if (ok && a.sm.use_geo) {
             const long long plane = (long long)a.sm.geo.by * a.sm.geo.bz;
@@ -748,9 +752,10 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
         if (a.atlas && (ncol == 528 || ncol == 544)) {
           // atlas prior of this thread's row (cnn_cort/base.py:387-394): atlas[x,y,z,:], all-zero rows become one-hot
           // background; the float32 sum follows numpy's pairwise order.  Columns 540..554 of the h1 row.
-          const long long mrow = (long long)mw + lane;
+          long long mrow = (long long)mw + lane;
           float at[15];
           if (mrow < a.M) {
+            if (a.rowvox) mrow = __ldg(a.rowvox + mrow);          // compact row -> row of the dense slab
             const long long plane = (long long)a.ageo.by * a.ageo.bz;
             const int ix = (int)(mrow / plane);
             const int rem = (int)(mrow - (long long)ix * plane);
@@ -788,7 +793,13 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
             const int half = i >> 1, row = (i & 1) * 16 + (lane >> 1), part = lane & 1;
             const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 80 + half * 32 + part * 16);
             if (mw + row < a.M) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ctile + (long long)(mw + row) * a.ldc) + boff + half * 64 + part * 8;
+              float* crow = ctile + (long long)(mw + row) * a.ldc;
+              if (a.rowmap) {      // candidate compaction: strides count rows, the map gives the compact C row (or -1)
+                const int cr = __ldg(a.rowmap + ((long long)z * a.c_zs + (long long)y * a.c_ys + (long long)(mw + row) * a.ldc));
+                if (cr < 0) continue;
+                crow = a.C + (long long)cr * a.crow_ld;
+              }
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(crow) + boff + half * 64 + part * 8;
               *reinterpret_cast<uint4*>(dst) = d;
             }
           }
@@ -895,6 +906,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.bn = pick_bn(p.n_store);
   a.sm_on = 0;
   a.atlas = p.atlas; a.ageo = p.ageo;
+  a.rowmap = p.rowmap; a.rowvox = p.rowvox; a.crow_ld = 0;
   if (p.sm) {
     SC_CHECK(ctx->tc_variant != 1 && p.n_store == 16 && p.ntaps == 1, SC_ERR_ARG, "gemm_tc: the softmax epilogue needs the persistent kernel and a 16-column layer");
     a.bn = 16; a.sm_on = 1; a.sm = *p.sm;
@@ -918,11 +930,16 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.a_y0 = p.a_y0; a.a_z0 = p.a_z0; a.a_swap = p.a_swap;
   for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; a.tap_dz[t] = t < p.ntaps ? p.tap_dz[t] : 0; }
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
+  if (p.rowmap) {   // candidate compaction: the C strides of the dense slab become row counts, rows are kFeatLd floats apart
+    SC_CHECK(p.out_split && p.ldc % kFeatLd == 0 && p.c_ys % kFeatLd == 0 && p.c_zs % kFeatLd == 0, SC_ERR_ARG, "gemm_tc: rowmap needs split rows of kFeatLd floats");
+    a.crow_ld = kFeatLd; a.ldc = p.ldc / kFeatLd; a.c_ys = p.c_ys / kFeatLd; a.c_zs = p.c_zs / kFeatLd;
+  }
   a.bias = w.bias; a.alpha = w.alpha; a.scale = w.scale; a.out_split = p.out_split;
   SC_CHECK(p.c_col0 % 4 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 4");
   const bool persistent = ctx->tc_variant != 1;
   // CTA pairs (cta_group::2) for the wide streaming-weight layers
   const bool pair = ctx->tc_variant == 3 && a.bn >= 128 && a.bn % 16 == 0 && !(p.ntaps == 9 && a.nkb * 2 * a.bn * 128 <= 150 * 1024);
+  SC_CHECK(!p.rowmap || pair, SC_ERR_ARG, "gemm_tc: the row map is implemented in the CTA-pair kernel");
   SC_CHECK(!p.atlas || (pair && p.c_col0 == 0 && p.n_store == 540 && w.Npad == 576), SC_ERR_ARG, "gemm_tc: the atlas epilogue is for FC1 in the CTA-pair kernel");
   const long long blocks = (long long)a.mt * a.nt * p.Y * p.Z;
   SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");

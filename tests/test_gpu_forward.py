@@ -156,6 +156,38 @@ def test_dense_pipeline_variants_agree(ctx, opts):
     assert float((out[0][1] == out[1][1]).float().mean()) >= 0.999
 
 
+@pytest.mark.parametrize("density", [0.02, 0.35, 0.7])
+def test_dense_candidate_compaction(ctx, density):
+    """With a sparse candidate mask the FC head runs on the compacted candidate rows of every slab; same results as the
+    uncompacted pipeline at the candidates, nothing written elsewhere (several slabs, one of them without candidates)."""
+    if ctx.counter("gemm") != 1:
+        pytest.skip("tcgen05 back-end not selected")
+    g = torch.Generator(device="cuda").manual_seed(21)
+    shape = (40, 48, 36)
+    vol = torch.randn(shape, device="cuda", generator=g)
+    atlas = torch.rand(shape + (15,), device="cuda", generator=g) ** 6
+    atlas = atlas / atlas.sum(-1, keepdim=True)
+    atlas[7, 8, 9] = 0
+    cand = (torch.rand(shape, device="cuda", generator=g) < density)
+    cand[7, 8, 9] = True
+    cand[20:26] = False                                      # whole x-planes (and with small chunks whole slabs) without candidates
+    cand = cand.to(torch.uint8).contiguous()
+    ctx.set_option("chunk_voxels", 6000)                     # ~3 x-planes per slab
+    out = []
+    for on in (1, 0):
+        ctx.set_option("tc_compact", on)
+        prob = torch.full(shape + (15,), -1.0, dtype=torch.float32, device="cuda")
+        lab = torch.full(shape, 99, dtype=torch.uint8, device="cuda")
+        ctx.segment_volume(vol, atlas, cand_mask=cand, label_vol=lab, proba_vol=prob)
+        out.append((prob, lab))
+    ctx.set_option("tc_compact", 1)
+    ctx.set_option("chunk_voxels", 1 << 20)
+    sel = cand.bool()
+    assert bool((out[0][1][~sel] == 99).all()) and bool((out[0][0][~sel] == -1.0).all())
+    assert float((out[0][0][sel] - out[1][0][sel]).abs().max()) < 1e-5
+    assert float((out[0][1][sel] == out[1][1][sel]).float().mean()) >= 0.9999
+
+
 def test_dense_equals_patchwise_at_scale(ctx):
     """Size-independent property at a larger size: the dense path and the patchwise path are the
     same function of (volume, atlas, voxel)."""
