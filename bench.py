@@ -295,6 +295,28 @@ def main():
         extra["patchwise"] = {"call": "sc_forward_from_volume (gather + predict_proba on patches, one 100 000-voxel test batch)",
                               "ms_per_batch": p_ms, "voxels_per_s": nb / (p_ms * 1e-3),
                               "algorithmic_tflops": nb * FLOP_PATCHWISE / (p_ms * 1e-3) / 1e12}
+        # brain-like candidate mask (a centred ball holding 35 % of the voxels, its bounding box passed as test_scan does):
+        # the conv phase runs on the box, d1 skips tiles without candidates, the FC head runs on the compacted candidate rows
+        axr = torch.arange(size, device="cuda", dtype=torch.float32) - (size - 1) / 2
+        rad = size * (3 * 0.35 / (4 * np.pi)) ** (1.0 / 3.0)
+        ball = ((axr[:, None, None] ** 2 + axr[None, :, None] ** 2 + axr[None, None, :] ** 2) < rad * rad).to(torch.uint8).contiguous()
+        lo, hi = int(np.floor((size - 1) / 2 - rad)) , int(np.ceil((size - 1) / 2 + rad)) + 1
+        lo, hi = max(lo, 0), min(hi, size)
+        bbox = (lo, hi, lo, hi, lo, hi)
+        n_ball = int(ball.sum())
+        time.sleep(1.0)
+        for _ in range(2):
+            ctx.segment_volume(d_vol, d_atlas, box=bbox, cand_mask=ball, label_vol=d_lab)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            ctx.segment_volume(d_vol, d_atlas, box=bbox, cand_mask=ball, label_vol=d_lab)
+        e1.record()
+        torch.cuda.synchronize()
+        m_ms = e0.elapsed_time(e1) / 3
+        extra["masked_volume"] = {"call": "sc_segment_volume with a candidate mask (centred ball, %.0f %% of the 256^3 voxels) and its bounding box" % (100.0 * n_ball / size ** 3),
+                                  "candidates": n_ball, "ms_per_volume": m_ms, "candidate_voxels_per_s": n_ball / (m_ms * 1e-3)}
+        del ball
         del bufs
 
     if rank != 0:

@@ -174,6 +174,8 @@ struct sc_ctx {
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
   int tc_compact = 1;            // dense path with a candidate mask: the FC head runs on the compacted candidate rows only
   int32_t* h_slab_cnt = nullptr; // pinned: candidates per slab
+  unsigned char* tile_flags = nullptr;   // d1 with a row map: per-tile "has a candidate" flags (device, grow-only)
+  size_t tile_flags_cap = 0;
   cudaEvent_t compact_ev = nullptr;
   int tc_mc = 0;                 // experiment (measured SLOWER, off): FC1 / fc_2 as multicast clusters, one CTA pair per n-tile, A loaded once per cluster
   int gather_ctas_per_sm = 0;    // > 0: persistent gather grid of that many CTAs per SM; 0 (default, measured fastest) = one CTA per 32-candidate group

@@ -66,6 +66,7 @@ struct TcArgs {
   const int* rowmap;  // pair kernel, split stores: C row of dense row r = rowmap[r] (skip when < 0); ldc / c_ys / c_zs then count ROWS
   const int* rowvox;  // pair kernel, atlas epilogue: slab row of compact row m
   long long crow_ld;  // floats per C row in rowmap mode
+  const unsigned char* tile_on;   // pair kernel: tile t is computed only if tile_on[t] != 0 (row map: no candidate row in it)
   const float* atlas; // pair kernel: atlas prior volume [X][Y][Z][15] -> output columns 540..575 (see GemmProblem::atlas)
   OutGeo ageo;
   int sm_on;          // persistent kernel, bn = 16: softmax / argmax epilogue (out_layer), results scattered through `sm`
@@ -603,6 +604,7 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
       long long w_empty = 0;
       const long long tstart = a.dbg ? clock64() : 0;
       for (long long t = pair; t < a.num_tiles; t += npairs) {
+        if (a.tile_on && !a.tile_on[t]) continue;
         long long r = t;
         const int n_tile = (int)(r % a.nt); r /= a.nt;
         const int m_tile = (int)(r % a.mt); r /= a.mt;
@@ -648,7 +650,8 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
       uint32_t it = 0, ti = 0;
       long long w_full = 0, w_tempty = 0;
       const long long tstart = a.dbg ? clock64() : 0;
-      for (long long t = pair; t < a.num_tiles; t += npairs, ++ti) {
+      for (long long t = pair; t < a.num_tiles; t += npairs) {
+        if (a.tile_on && !a.tile_on[t]) continue;
         const uint32_t b = ti & 1, buse = ti >> 1;
         long long c0 = a.dbg ? clock64() : 0;
         mbar_wait(&tempty[b], (buse & 1) ^ 1);
@@ -677,6 +680,7 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
         }
         if (leader) umma_commit_2sm(&tfull[b], pair_mask);
         __syncwarp();
+        ++ti;
       }
       if (a.dbg && leader) {
         a.dbg[pair * 8 + 2] = (unsigned long long)w_full; a.dbg[pair * 8 + 3] = (unsigned long long)w_tempty;
@@ -685,13 +689,15 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
     } else if (MC) {
       // relay: tell the leader when this CTA's stage has landed (its own full barrier counts only its own bytes)
       uint32_t it = 0;
-      for (long long t = pair; t < a.num_tiles; t += npairs)
+      for (long long t = pair; t < a.num_tiles; t += npairs) {
+        if (a.tile_on && !a.tile_on[t]) continue;
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
           const int s = it % a.stages;
           mbar_wait(&full[s], (it / a.stages) & 1);
           if (lane == 0) mbar_arrive_cta(&pfull[s], lead);
           __syncwarp();
         }
+      }
     }
   } else {
     const int q = warp & 3;
@@ -700,7 +706,8 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
     uint32_t ti = 0;
     long long w_tfull = 0;
     const long long tstart = a.dbg ? clock64() : 0;
-    for (long long t = pair; t < a.num_tiles; t += npairs, ++ti) {
+    for (long long t = pair; t < a.num_tiles; t += npairs) {
+      if (a.tile_on && !a.tile_on[t]) continue;
       long long r = t;
       const int n_tile = (int)(r % a.nt); r /= a.nt;
       const int m_tile = (int)(r % a.mt); r /= a.mt;
@@ -820,6 +827,7 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(&tempty[b], lead);  // the leader's MMA warp owns the accumulator hand-off
+      ++ti;
     }
     if (a.dbg && rank == 0 && threadIdx.x == 64) {
       a.dbg[pair * 8 + 5] = (unsigned long long)w_tfull; a.dbg[pair * 8 + 6] = (unsigned long long)(clock64() - tstart);
@@ -860,6 +868,25 @@ int launch_split_rows(sc_ctx* ctx, const float* in, int64_t rows, float* out, cu
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
+}
+
+// row-map mode: which 256-row tiles of the dense slab contain a candidate row at all (one warp per tile)
+__global__ void tile_flags_kernel(const int* __restrict__ rowmap, long long num_tiles, int nt, int mt, int Y, int M, long long ldc,
+                                  long long c_ys, long long c_zs, unsigned char* __restrict__ flags) {
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= num_tiles) return;
+  long long r = t / nt;
+  const int m_tile = (int)(r % mt); r /= mt;
+  const int y = (int)(r % Y);
+  const int z = (int)(r / Y);
+  const int lane = threadIdx.x & 31;
+  bool any = false;
+  for (int k = lane; k < 256; k += 32) {
+    const int m = m_tile * 256 + k;
+    if (m < M && __ldg(rowmap + ((long long)z * c_zs + (long long)y * c_ys + (long long)m * ldc)) >= 0) any = true;
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) flags[t] = any ? 1 : 0;
 }
 
 int tc_init(sc_ctx* ctx) {
@@ -906,7 +933,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.bn = pick_bn(p.n_store);
   a.sm_on = 0;
   a.atlas = p.atlas; a.ageo = p.ageo;
-  a.rowmap = p.rowmap; a.rowvox = p.rowvox; a.crow_ld = 0;
+  a.rowmap = p.rowmap; a.rowvox = p.rowvox; a.crow_ld = 0; a.tile_on = nullptr;
   if (p.sm) {
     SC_CHECK(ctx->tc_variant != 1 && p.n_store == 16 && p.ntaps == 1, SC_ERR_ARG, "gemm_tc: the softmax epilogue needs the persistent kernel and a 16-column layer");
     a.bn = 16; a.sm_on = 1; a.sm = *p.sm;
@@ -1018,6 +1045,18 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     configured = true;
   }
   ProfScope prof(ctx, p.prof_cls, st);
+  if (pair && p.rowmap) {   // skip the tiles of the dense slab without a candidate row
+    if (ctx->tile_flags_cap < (size_t)a.num_tiles) {
+      if (ctx->tile_flags) cudaFree(ctx->tile_flags);
+      ctx->tile_flags = nullptr; ctx->tile_flags_cap = 0;
+      const size_t cap = ((size_t)a.num_tiles + 65535) & ~(size_t)65535;
+      SC_CUDA(cudaMalloc(&ctx->tile_flags, cap));
+      ctx->tile_flags_cap = cap;
+    }
+    tile_flags_kernel<<<(unsigned)((a.num_tiles + 7) / 8), 256, 0, st>>>(p.rowmap, a.num_tiles, a.nt, a.mt, a.Y, a.M, a.ldc, a.c_ys, a.c_zs, ctx->tile_flags);
+    ctx->launches++;
+    a.tile_on = ctx->tile_flags;
+  }
   // multicast clusters: plain row GEMMs with 2 or 3 n-tiles (fc_2, FC1): one CTA pair per n-tile, A loaded once per cluster
   const bool mc = pair && ctx->tc_mc && p.ntaps == 1 && p.Y == 1 && p.Z == 1 && (a.nt == 2 || a.nt == 3) && a.mt >= 1;
   if (mc) {
