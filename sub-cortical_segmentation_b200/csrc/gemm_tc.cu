@@ -66,6 +66,7 @@ struct TcArgs {
   const int* rowmap;  // pair kernel, split stores: C row of dense row r = rowmap[r] (skip when < 0); ldc / c_ys / c_zs then count ROWS
   const int* rowvox;  // pair kernel, atlas epilogue: slab row of compact row m
   long long crow_ld;  // floats per C row in rowmap mode
+  int n_mma;          // pair kernel: columns the MMAs have to produce (real N rounded to 16): the last n-tile issues narrower MMAs
   const unsigned char* tile_on;   // pair kernel: tile t is computed only if tile_on[t] != 0 (row map: no candidate row in it)
   const float* atlas; // pair kernel: atlas prior volume [X][Y][Z][15] -> output columns 540..575 (see GemmProblem::atlas)
   OutGeo ageo;
@@ -610,7 +611,8 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
         const int m_tile = (int)(r % a.mt); r /= a.mt;
         const int y = (int)(r % a.Y);
         const int z = (int)(r / a.Y);
-        const int m0 = m_tile * 256 + (int)rank * TC_BM, n0 = n_tile * a.bn + (int)rank * hb;
+        const int bnj = min(a.bn, a.n_mma - n_tile * a.bn);            // MMA width of this n-tile (the last one may be narrower)
+        const int m0 = m_tile * 256 + (int)rank * TC_BM, n0 = n_tile * a.bn + (int)rank * (bnj >> 1);
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
           const int s = it % a.stages;
           const uint32_t use = it / a.stages;
@@ -645,7 +647,7 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
     if (rank == 0) {
       const uint32_t leader = elect_one();
       // instruction descriptor: D=F32, A=B=BF16, K-major, N = bn, M = 256 (two CTAs x 128 rows)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t sStage_u = smem_u32(sStage);
       uint32_t it = 0, ti = 0;
       long long w_full = 0, w_tempty = 0;
@@ -653,6 +655,8 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
       for (long long t = pair; t < a.num_tiles; t += npairs) {
         if (a.tile_on && !a.tile_on[t]) continue;
         const uint32_t b = ti & 1, buse = ti >> 1;
+        const int bnj = min(a.bn, a.n_mma - (int)(t % a.nt) * a.bn);
+        const uint32_t idesc = idesc0 | ((uint32_t)(bnj >> 3) << 17);   // N = bnj (bnj / 2 weight rows from each CTA)
         long long c0 = a.dbg ? clock64() : 0;
         mbar_wait(&tempty[b], (buse & 1) ^ 1);
         if (a.dbg) w_tempty += clock64() - c0;
@@ -744,6 +748,10 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (n0 + c0 >= a.n_store) continue;
+        if (n0 + c0 >= a.n_mma) {                      // no MMA produced these columns (atlas / zero padding of the row)
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) rr[kk] = 0u;
+        }
         float v[16];
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
@@ -1045,6 +1053,13 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     configured = true;
   }
   ProfScope prof(ctx, p.prof_cls, st);
+  a.n_mma = a.nt * a.bn;
+  if (pair && p.ntaps == 1) {
+    // dense layers: the MMAs only produce the real output columns (rounded to 16, at least 32 in the last tile)
+    int real = (w.N + 15) & ~15;
+    if (real > p.n_store) real = (p.n_store + 15) & ~15;
+    if (real - (a.nt - 1) * a.bn >= 32 && real <= a.nt * a.bn) a.n_mma = real;
+  }
   if (pair && p.rowmap) {   // skip the tiles of the dense slab without a candidate row
     if (ctx->tile_flags_cap < (size_t)a.num_tiles) {
       if (ctx->tile_flags) cudaFree(ctx->tile_flags);
