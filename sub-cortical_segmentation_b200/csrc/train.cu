@@ -373,17 +373,21 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict
 // wgrad, register-tiled: one thread owns 4 output channels x 1 input channel x 9 taps (36 accumulators) and walks the
 // pixels of its CTA's samples four at a time (sliding 6-wide input window per filter row: 22 shared loads per 144 FMA).
 // CTA = (COUT/4) x 20 threads, one tile of 20 input channels, `spc` samples; one atomicAdd per accumulator at the end.
-template <int COUT>
-__global__ void __launch_bounds__((COUT / 4) * 20) conv_wgrad_tiled_kernel(const float* __restrict__ in, int Cin, int inH, int inLd,
-                                                                          const float* __restrict__ dx, int H, int ld, int n, int spc,
-                                                                          float* __restrict__ gW) {
+// PS row splits per CTA (threads = (COUT/4) x 20 x PS): split ps walks the output rows y = ps, ps + PS, ...; the partial sums
+// are reduced through shared memory before the atomics.  Without the split a conv2 CTA has only 100 threads.
+template <int COUT, int PS>
+__global__ void __launch_bounds__((COUT / 4) * 20 * PS) conv_wgrad_tiled_kernel(const float* __restrict__ in, int Cin, int inH, int inLd,
+                                                                               const float* __restrict__ dx, int H, int ld, int n, int spc,
+                                                                               float* __restrict__ gW) {
   extern __shared__ __align__(16) float sm[];
   const int plane = (inH + 1) * inLd + 9;               // odd stride: the 20 channel planes fall into different banks
   const int planep = plane | 1;
   float* in_s = sm;                                      // [20][planep]
   float* dx_s = sm + ((20 * planep + 3) & ~3);           // [H*H][COUT]
-  const int nthr = (COUT / 4) * 20;
-  const int tid = threadIdx.x, cog = tid / 20, ci = tid - cog * 20;
+  constexpr int NT1 = (COUT / 4) * 20;
+  const int nthr = NT1 * PS;
+  const int ps = threadIdx.x / NT1;
+  const int tid = threadIdx.x, t1 = tid - ps * NT1, cog = t1 / 20, ci = t1 - cog * 20;
   const int ci0 = blockIdx.x * 20;
   const int s_begin = blockIdx.y * spc, s_end = min(n, s_begin + spc);
   float acc[4][9];
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__((COUT / 4) * 20) conv_wgrad_tiled_kernel(const
     }
     __syncthreads();
     const float* ip = in_s + ci * planep;
-    for (int y = 0; y < H; ++y) {
+    for (int y = ps; y < H; y += PS) {
       for (int x0 = 0; x0 < H; x0 += 4) {
         float d[4][4];
 #pragma unroll
@@ -431,6 +435,23 @@ __global__ void __launch_bounds__((COUT / 4) * 20) conv_wgrad_tiled_kernel(const
       }
     }
   }
+  if (PS > 1) {   // reduce the row splits through shared memory (the staging buffers are free now)
+    __syncthreads();
+    float* red = sm;                                       // [PS - 1][36][NT1]
+    if (ps > 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) red[((ps - 1) * 36 + c * 9 + t) * NT1 + t1] = acc[c][t];
+    }
+    __syncthreads();
+    if (ps > 0) return;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        for (int q = 0; q < PS - 1; ++q) acc[c][t] += red[(q * 36 + c * 9 + t) * NT1 + t1];
+  }
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -440,9 +461,13 @@ __global__ void __launch_bounds__((COUT / 4) * 20) conv_wgrad_tiled_kernel(const
 template <int COUT>
 static int launch_wgrad_tiled(sc_ctx* ctx, const float* in, int Cin, int inH, int inLd, const float* dx, int H, int ld, int n,
                               float* gW, cudaStream_t st) {
+  constexpr int PS = COUT == 20 ? 4 : (COUT == 40 ? 2 : 1);     // ~400 threads per CTA
   const int planep = ((inH + 1) * inLd + 9) | 1;
-  const size_t smem = ((size_t)((20 * planep + 3) & ~3) + (size_t)COUT * H * H) * sizeof(float);
-  auto kern = conv_wgrad_tiled_kernel<COUT>;
+  size_t smem_f = (size_t)((20 * planep + 3) & ~3) + (size_t)COUT * H * H;
+  const size_t red_f = (size_t)(PS - 1) * 36 * (COUT / 4) * 20;
+  if (PS > 1 && smem_f < red_f) smem_f = red_f;
+  const size_t smem = smem_f * sizeof(float);
+  auto kern = conv_wgrad_tiled_kernel<COUT, PS>;
   static size_t configured = 0;
   if (smem > configured) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
   // samples per CTA: ~2 000 pixels of reduction each, but never fewer than ~2 CTAs per SM
@@ -452,7 +477,7 @@ static int launch_wgrad_tiled(sc_ctx* ctx, const float* in, int Cin, int inH, in
   if (spc < 1) spc = 1;
   dim3 grid(Cin / 20, (n + spc - 1) / spc);
   ProfScope prof(ctx, PC_TRAIN_BWD, st);
-  kern<<<grid, (COUT / 4) * 20, smem, st>>>(in, Cin, inH, inLd, dx, H, ld, n, spc, gW);
+  kern<<<grid, (COUT / 4) * 20 * PS, smem, st>>>(in, Cin, inH, inLd, dx, H, ld, n, spc, gW);
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
