@@ -28,12 +28,9 @@ struct SweepArgs {
   int Pw, R;              // wide-row pitch (pixels) and number of rows of the map geometry
   int bn;                 // accumulator columns per half (output channels rounded up to 16)
   int nstrips, strip_w;   // strips start every strip_w wide columns (128, or 128 - pool reach)
-  int nseg, L;            // row segments per (strip, class); class rows per segment
+  int nseg, L;            // row segments per (strip, class); class rows per segment (output rows of an item)
   int n_items;
   int stages;
-  int in_boxes;           // 1: F32CH input (hi|lo in one 128 B row), 2: F64CH input (hi box, lo box)
-  int lo_off;             // byte offset of the lo operand inside a ring slot (64 or SW_SLOT_HALF)
-  int out_fmt;            // 1: F32CH, 0: F64CH
   int out_bufs;           // output tiles in shared memory (2: double-buffered, 1 when shared memory is short)
   int npanels;            // weight panels (4 k-steps each)
   const float* scale; const float* shift; const float* alpha;
@@ -854,14 +851,11 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   a.L = L; a.nseg = nseg;
   a.n_items = a.nstrips * dil * nseg;
   SC_CHECK(pool != 2 || dil == 1, SC_ERR_ARG, "conv_sweep: the stride-2 pool needs dilation 1");
-  a.in_boxes = in_fmt ? 1 : 2;
-  a.lo_off = in_fmt ? 64 : SW_SLOT_HALF;
-  a.out_fmt = out_fmt;
   a.npanels = w.npanels;
   a.scale = w.scale; a.shift = w.shift; a.alpha = w.alpha;
   a.dbg = (ctx->tc_timing_cls == prof_cls) ? ctx->tc_timing_buf : nullptr;
   SC_CHECK(w.bn <= (out_fmt ? 32 : 64) && w.bn % 16 == 0, SC_ERR_ARG, "conv_sweep: bad channel geometry");
-  const int slot = a.in_boxes * SW_SLOT_HALF;
+  const int slot = (in_fmt ? 1 : 2) * SW_SLOT_HALF;                      // F32CH: one box per row (hi|lo in one 128 B pixel), F64CH: hi box + lo box
   const int w_bytes = w.npanels * 2 * w.bn * 128;
   const int ob_bytes = out_fmt ? 16384 : 32768;
   const int fixed = 1024 + w_bytes + 256 /*barriers, tmem slot*/ + 192 * 4 + 2 * 4 * 4 * 2 * 16 * 4;
