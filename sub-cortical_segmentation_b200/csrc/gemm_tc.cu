@@ -567,7 +567,7 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
   uint64_t* pfull = tempty + 2;                           // [stages] MC, leader only: the peer's stage has landed (relayed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + a.stages);
   float* s_const = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 loads of the constants
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + 2 * 3 * a.bn);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + (a.nt > 2 ? a.nt : 2) * 3 * a.bn);   // constants of every n-tile (<= 4) stay resident
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -709,6 +709,16 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
     const int epi_threads = nepi * 32;
     uint32_t ti = 0;
     long long w_tfull = 0;
+    // epilogue constants (bias / BN shift, PReLU slope, BN scale) of all n-tiles: shared memory, once per kernel
+    for (int i = threadIdx.x - 64; i < a.nt * a.bn; i += epi_threads) {
+      const int j = i / a.bn, c = i - j * a.bn, nn = i;
+      const bool ok = nn < a.npad;
+      float* cbw = s_const + j * 3 * a.bn;
+      cbw[c] = ok ? __ldg(a.bias + nn) : 0.f;
+      cbw[a.bn + c] = ok ? __ldg(a.alpha + nn) : 1.f;
+      cbw[2 * a.bn + c] = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
     const long long tstart = a.dbg ? clock64() : 0;
     for (long long t = pair; t < a.num_tiles; t += npairs) {
       if (a.tile_on && !a.tile_on[t]) continue;
@@ -719,17 +729,7 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
       const int z = (int)(r / a.Y);
       const int m0 = m_tile * 256 + (int)rank * TC_BM, n0 = n_tile * a.bn;
       const uint32_t b = ti & 1, buse = ti >> 1;
-      float* cb = s_const + b * 3 * a.bn;
-      if (ti < 2 || a.nt > 1) {
-        for (int i = threadIdx.x - 64; i < a.bn; i += epi_threads) {
-          const int nn = n0 + i;
-          const bool ok = nn < a.npad;
-          cb[i] = ok ? __ldg(a.bias + nn) : 0.f;
-          cb[a.bn + i] = ok ? __ldg(a.alpha + nn) : 1.f;
-          cb[2 * a.bn + i] = (a.scale && ok) ? __ldg(a.scale + nn) : 1.f;
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
-      }
+      const float* cb = s_const + n_tile * 3 * a.bn;     // loaded once before the tile loop
       const long long c0w = a.dbg ? clock64() : 0;
       mbar_wait(&tfull[b], buse & 1);
       if (a.dbg) w_tfull += clock64() - c0w;
@@ -992,11 +992,13 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.num_tiles = (long long)a.mt * a.nt * p.Y * p.Z;
     a.epi_warps = 16;
     stage_bytes = 2 * TC_A_HALF + 2 * (a.bn / 2) * 128;
-    const int budget = 227 * 1024 - 1024 - 192 - 16 - 2 * 3 * a.bn * 4 - a.epi_warps * 2560;
+    SC_CHECK(a.nt <= 4, SC_ERR_ARG, "gemm_tc: more than 4 n-tiles in the CTA-pair kernel");
+    const int cst = (a.nt > 2 ? a.nt : 2) * 3 * a.bn * 4;     // resident epilogue constants of every n-tile
+    const int budget = 227 * 1024 - 1024 - 192 - 16 - cst - a.epi_warps * 2560;
     a.stages = budget / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: pair tile too wide");
-    smem = 1024 + (size_t)a.stages * stage_bytes + (3 * a.stages + 4) * 8 + 32 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
+    smem = 1024 + (size_t)a.stages * stage_bytes + (3 * a.stages + 4) * 8 + 32 + cst + (size_t)a.epi_warps * 2560;
   } else if (!persistent) {
     a.stages = (108 * 1024) / stage_bytes;
     if (a.stages > 4) a.stages = 4;
