@@ -23,6 +23,7 @@ vol = torch.randn(shape, device="cuda", generator=g)
 atlas = torch.rand(shape + (15,), device="cuda", generator=g) ** 6
 atlas = atlas / atlas.sum(-1, keepdim=True)
 lab = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+proba = torch.zeros(shape + (15,), dtype=torch.float32, device="cuda") if "--proba" in sys.argv else None   # out_probabilities=True
 mask = None
 if mask_frac > 0:
     ax = torch.arange(size, device="cuda", dtype=torch.float32) - (size - 1) / 2
@@ -38,7 +39,7 @@ for r in range(rounds + 1):
             ctx.set_option(k, v)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ctx.segment_volume(vol, atlas, cand_mask=mask, label_vol=lab)
+        ctx.segment_volume(vol, atlas, cand_mask=mask, label_vol=lab, proba_vol=proba)
         e1.record()
         torch.cuda.synchronize()
         if r > 0:
