@@ -124,6 +124,7 @@ int sc_destroy(sc_ctx* ctx) {
   for (auto& ev : ctx->prof_free) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   if (ctx->h_slab_cnt) { cudaFreeHost(ctx->h_slab_cnt); cudaEventDestroy(ctx->compact_ev); }
   cudaFree(ctx->tile_flags);
+  for (int i = 0; i < 64; ++i) if (ctx->atlas_chunk_ev[i]) cudaEventDestroy(ctx->atlas_chunk_ev[i]);
   if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_ev[0]); cudaEventDestroy(ctx->copy_ev[1]); }
   delete ctx;
   return SC_OK;
@@ -388,20 +389,39 @@ int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dim
     SC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) SC_CUDA(cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
   }
-  SC_CUDA(cudaEventRecord(ctx->copy_ev[0], st));                       // earlier work on `st` may still read the staging buffers
-  SC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
-  SC_CUDA(cudaMemcpyAsync(d_atlas, atlas_host, nvox * 60, cudaMemcpyHostToDevice, ctx->copy_stream));
-  SC_CUDA(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
-  ctx->atlas_ready = ctx->copy_ev[1];
+  // the volume and the mask go first: the conv phase waits for them, and host-to-device copies of different streams
+  // are served in issue order -- queued behind the 1 GB atlas they would delay the first kernel by ~20 ms
   SC_CUDA(cudaMemcpyAsync(d_vol, vol_host, nvox * 4, cudaMemcpyHostToDevice, st));
   if (cand_mask_host) SC_CUDA(cudaMemcpyAsync(d_mask, cand_mask_host, nvox, cudaMemcpyHostToDevice, st));
+  SC_CUDA(cudaEventRecord(ctx->copy_ev[0], st));                       // also: earlier work on `st` may still read the staging buffers
+  SC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+  {
+    // in chunks of x-planes (at most 64), each with its own event: the first slab of phase 2 can start as soon as its
+    // planes have arrived, however slow the rest of the upload is under the memory traffic of the kernels
+    const size_t plane_b = (size_t)dims[1] * dims[2] * 60;
+    int cnx = (dims[0] + 63) / 64;
+    const int slab_nx = (int)(ctx->chunk_voxels / ((int64_t)dims[1] * dims[2]));
+    if (cnx < slab_nx) cnx = slab_nx;
+    if (cnx < 1) cnx = 1;
+    const int nch = (dims[0] + cnx - 1) / cnx;
+    for (int i = 0; i < nch; ++i) {
+      if (!ctx->atlas_chunk_ev[i]) SC_CUDA(cudaEventCreateWithFlags(&ctx->atlas_chunk_ev[i], cudaEventDisableTiming));
+      const int x0 = i * cnx, nx = dims[0] - x0 < cnx ? dims[0] - x0 : cnx;
+      SC_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(d_atlas) + (size_t)x0 * plane_b, reinterpret_cast<const char*>(atlas_host) + (size_t)x0 * plane_b,
+                              (size_t)nx * plane_b, cudaMemcpyHostToDevice, ctx->copy_stream));
+      SC_CUDA(cudaEventRecord(ctx->atlas_chunk_ev[i], ctx->copy_stream));
+    }
+    ctx->atlas_chunks = nch; ctx->atlas_chunk_nx = cnx;
+    ctx->atlas_ready = ctx->atlas_chunk_ev[nch - 1];
+  }
   SC_CUDA(cudaMemsetAsync(d_lab, 0, nvox, st));
   if (d_proba) SC_CUDA(cudaMemsetAsync(d_proba, 0, nvox * 60, st));
   const int seg_status = segment_volume(ctx, d_vol, dims, d_atlas, box, cand_mask_host ? d_mask : nullptr, d_lab, d_proba, st);
-  if (ctx->atlas_ready) {                                              // not consumed (empty box or an error): join the side stream anyway
+  if (ctx->atlas_ready) {                                              // join the side stream (the last chunk may not have been waited for)
     cudaStreamWaitEvent(st, ctx->atlas_ready, 0);
     ctx->atlas_ready = nullptr;
   }
+  ctx->atlas_chunks = 0;
   SC_TRY(seg_status);
   if (label_vol_host) SC_CUDA(cudaMemcpyAsync(label_vol_host, d_lab, nvox, cudaMemcpyDeviceToHost, st));
   if (proba_vol_host) SC_CUDA(cudaMemcpyAsync(proba_vol_host, d_proba, nvox * 60, cudaMemcpyDeviceToHost, st));

@@ -186,6 +186,10 @@ struct sc_ctx {
   cudaStream_t copy_stream = nullptr;   // sc_segment_volume_host: the 1 GB atlas upload overlaps the conv phase
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   cudaEvent_t atlas_ready = nullptr;    // when set, segment_volume waits for it before its first use of the atlas (phase 2)
+  // chunked upload: atlas_chunk_ev[i] fires when the x-planes [0, (i + 1) * atlas_chunk_nx) of the atlas are on the device;
+  // a slab of phase 2 only waits for the chunks that cover it (atlas_chunks > 0 replaces the single event above)
+  cudaEvent_t atlas_chunk_ev[64] = {};
+  int atlas_chunks = 0, atlas_chunk_nx = 0;
   bool profile = false;
   std::vector<sc::ProfEvent> prof_live;
   std::vector<sc::ProfEvent> prof_free;

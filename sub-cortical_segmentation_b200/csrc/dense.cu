@@ -531,10 +531,11 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   }
 
   // ---- phase 2: d1 (x3) + FC head per slab of x-planes -------------------------------------
-  if (ctx->atlas_ready) {   // host entry point: the atlas upload ran on a side stream during phase 1
+  if (ctx->atlas_ready && ctx->atlas_chunks == 0) {   // host entry point: the atlas upload ran on a side stream during phase 1
     SC_CUDA(cudaStreamWaitEvent(st, ctx->atlas_ready, 0));
     ctx->atlas_ready = nullptr;
   }
+  int atlas_waited = 0;                                // chunked upload: chunks of x-planes this stream has already waited for
   OutGeo og = {b[0], b[2], b[4], by, bz, Y, Z};
   if (compact) {
     SC_CUDA(cudaEventSynchronize(ctx->compact_ev));
@@ -547,6 +548,14 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   for (int ix0 = 0; ix0 < bx; ix0 += slab) {
     const int nx = bx - ix0 < slab ? bx - ix0 : slab;
     const int64_t rows = (int64_t)nx * plane;
+    if (ctx->atlas_chunks > 0) {                       // the atlas planes of this slab must have arrived
+      int need = (b[0] + ix0 + nx + ctx->atlas_chunk_nx - 1) / ctx->atlas_chunk_nx;
+      if (need > ctx->atlas_chunks) need = ctx->atlas_chunks;
+      if (need > atlas_waited) {
+        SC_CUDA(cudaStreamWaitEvent(st, ctx->atlas_chunk_ev[need - 1], 0));
+        atlas_waited = need;
+      }
+    }
     const int64_t slab_base = (int64_t)ix0 * plane;
     const int64_t rows_fc = compact ? ctx->h_slab_cnt[ix0 / slab] : rows;      // rows of the FC head (compact: candidates only)
     if (rows_fc == 0) continue;
