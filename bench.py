@@ -18,7 +18,14 @@ import argparse
 import json
 import os
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")   # keep NCCL's version banner out of stdout (one JSON line only)
+# stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner ...) is rerouted to stderr
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj):
+    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
+
 import subprocess
 import sys
 import threading
@@ -152,7 +159,7 @@ def run_reference(args, rank, world):
                             "sample": "%d steps x %d voxels of the %d^3 volume" % (args.steps, sample, size)},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "per_step_rates": rates}
-    print(json.dumps(out))
+    emit_json(out)
 
 
 def main():
@@ -376,7 +383,7 @@ def main():
     out.update(extra)
     if cpu_base:
         out["cpu_baseline"] = cpu_base
-    print(json.dumps(out), flush=True)
+    emit_json(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -9,7 +9,14 @@ import argparse
 import json
 import os
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")   # keep NCCL's version banner out of stdout (one JSON line only)
+# stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner ...) is rerouted to stderr
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj):
+    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
+
 import pickle
 import sys
 
@@ -87,7 +94,7 @@ def main():
         ar_ms = e0.elapsed_time(e1) / 50
     if rank == 0:
         per = float(ms) / args.steps
-        print(json.dumps({"metric": "training_samples_per_sec", "value": args.global_batch / (per * 1e-3), "unit": "samples/s",
+        emit_json({"metric": "training_samples_per_sec", "value": args.global_batch / (per * 1e-3), "unit": "samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "training step, patch_size=32, global batch %d, DP over %d GPU(s), per-GPU BN statistics" %
@@ -95,7 +102,7 @@ def main():
                           "e2e": {"value": args.global_batch / (float(ms2) / args.steps * 1e-3), "unit": "samples/s",
                                   "h2d_bytes_per_step": int(n * (3 * 4096 + 60 + 1)), "d2h_bytes_per_step": 4},
                           "allreduce_ms": ar_ms, "allreduce_bytes": 883455 * 4, "gpu_launches": int(launches), "loss": float(loss.item()),
-                          "flops_per_sample_fwd_bwd": 3 * 35407800}))
+                          "flops_per_sample_fwd_bwd": 3 * 35407800})
     if world > 1:
         dist.destroy_process_group()
 
