@@ -11,7 +11,14 @@
 // Activations and weights are stored per 64-wide k block as 64 bf16 hi | 64 bf16 lo, i.e. exactly
 // the bytes of the fp32 row, so one 128 B swizzle row holds one block half.
 //
-// One CTA = one 128-row x BN-column output tile, 192 threads:
+// Three kernels share this file (default pipeline: tc_variant = 3):
+//   gemm_tc_pair_kernel        CTA pairs (cta_group::2, M = 256): d1, FC1 (+ atlas prior columns), fc_2 -- the hot ones
+//   gemm_tc_persistent_kernel  one persistent CTA per SM: the 16-column out_layer GEMM with the softmax / argmax epilogue,
+//                              and the flattened-map conv layers of the pre-sweep pipeline (tc_sweep45 = 0)
+//   gemm_tc_kernel             the first, one-tile-per-CTA version described below (tc_variant = 1), kept as a cross-check
+// (conv2..conv5 of the default pipeline live in conv_sweep.cu.)
+//
+// gemm_tc_kernel: one CTA = one 128-row x BN-column output tile, 192 threads:
 //   warp 0   TMA producer: per k block four tiled loads into one shared-memory stage -- A hi and
 //            A lo (4-D box 64 bf16 x 128 pixels, tap shift applied to the pixel/line coordinates,
 //            zero fill outside) and W hi and W lo (2-D box 64 x BN)
