@@ -17,7 +17,9 @@ mask = torch.ones(shape, dtype=torch.uint8, device="cuda")
 lab = torch.zeros(shape, dtype=torch.uint8, device="cuda")
 h_vol, h_atlas, h_mask = vol.cpu().pin_memory(), atlas.cpu().pin_memory(), mask.cpu().pin_memory()
 h_lab = torch.zeros(shape, dtype=torch.uint8).pin_memory()
-res = {"device": [], "host": [], "host_wall": []}
+res = {"device": [], "host": [], "host_wall": [], "pageable_wall": []}
+p_vol, p_atlas, p_mask = h_vol.numpy().copy(), h_atlas.numpy().copy(), h_mask.numpy().copy()   # plain (pageable) numpy arrays
+p_lab = np.zeros(shape, np.uint8)
 for r in range(6):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); ctx.segment_volume(vol, atlas, cand_mask=mask, label_vol=lab); e1.record(); torch.cuda.synchronize()
@@ -27,5 +29,11 @@ for r in range(6):
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     if r: res["host"].append(e0.elapsed_time(e1)); res["host_wall"].append((t1 - t0) * 1e3)
+    t0 = time.perf_counter()
+    ctx.segment_volume_host(p_vol, p_atlas, cand_mask=p_mask, label_out=p_lab)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if r: res["pageable_wall"].append((t1 - t0) * 1e3)
+    assert np.array_equal(p_lab, h_lab.numpy())
 for k, v in res.items():
     print("%-10s mean %.2f ms (%s)" % (k, sum(v) / len(v), " ".join("%.1f" % x for x in v)))

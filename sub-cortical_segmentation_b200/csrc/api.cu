@@ -3,6 +3,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+
 #include "common.cuh"
 
 namespace sc {
@@ -383,6 +385,9 @@ int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dim
   uint8_t* d_mask = reinterpret_cast<uint8_t*>(base + vb + ab);
   uint8_t* d_lab = d_mask + mb;
   float* d_proba = proba_vol_host ? reinterpret_cast<float*>(base + vb + ab + 2 * mb) : nullptr;
+  std::atomic<int> atlas_recorded(0), upload_err(0);
+  std::thread uploader;
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{uploader};   // on every return path
   // the atlas (15 floats per voxel, 94 % of the upload) is first needed after the conv phase: upload it on a side
   // stream so that the copy engine works while the conv kernels run
   if (!ctx->copy_stream) {
@@ -404,24 +409,46 @@ int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dim
     if (cnx < slab_nx) cnx = slab_nx;
     if (cnx < 1) cnx = 1;
     const int nch = (dims[0] + cnx - 1) / cnx;
-    for (int i = 0; i < nch; ++i) {
+    for (int i = 0; i < nch; ++i)
       if (!ctx->atlas_chunk_ev[i]) SC_CUDA(cudaEventCreateWithFlags(&ctx->atlas_chunk_ev[i], cudaEventDisableTiming));
-      const int x0 = i * cnx, nx = dims[0] - x0 < cnx ? dims[0] - x0 : cnx;
-      SC_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(d_atlas) + (size_t)x0 * plane_b, reinterpret_cast<const char*>(atlas_host) + (size_t)x0 * plane_b,
-                              (size_t)nx * plane_b, cudaMemcpyHostToDevice, ctx->copy_stream));
-      SC_CUDA(cudaEventRecord(ctx->atlas_chunk_ev[i], ctx->copy_stream));
-    }
     ctx->atlas_chunks = nch; ctx->atlas_chunk_nx = cnx;
     ctx->atlas_ready = ctx->atlas_chunk_ev[nch - 1];
+    auto upload = [=, &atlas_recorded, &upload_err]() {
+      cudaSetDevice(ctx->device);
+      for (int i = 0; i < nch; ++i) {
+        const int x0 = i * cnx, nx = dims[0] - x0 < cnx ? dims[0] - x0 : cnx;
+        cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char*>(d_atlas) + (size_t)x0 * plane_b,
+                                        reinterpret_cast<const char*>(atlas_host) + (size_t)x0 * plane_b, (size_t)nx * plane_b,
+                                        cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->atlas_chunk_ev[i], ctx->copy_stream);
+        if (e != cudaSuccess) upload_err.store((int)e);
+        atlas_recorded.store(i + 1, std::memory_order_release);      // (on an error too: the consumer must not spin forever)
+      }
+    };
+    // pinned (or registered) host memory: the copies are asynchronous, issue them right here.  Pageable memory: every
+    // cudaMemcpyAsync blocks its caller while the driver stages the data, so a helper thread issues them and this
+    // thread goes on to launch the conv phase -- the upload still overlaps the kernels
+    cudaPointerAttributes pa;
+    const bool pageable = cudaPointerGetAttributes(&pa, atlas_host) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (pageable) {
+      ctx->atlas_recorded = &atlas_recorded;
+      uploader = std::thread(upload);
+    } else {
+      upload();
+    }
   }
   SC_CUDA(cudaMemsetAsync(d_lab, 0, nvox, st));
   if (d_proba) SC_CUDA(cudaMemsetAsync(d_proba, 0, nvox * 60, st));
   const int seg_status = segment_volume(ctx, d_vol, dims, d_atlas, box, cand_mask_host ? d_mask : nullptr, d_lab, d_proba, st);
+  if (uploader.joinable()) uploader.join();
+  ctx->atlas_recorded = nullptr;
   if (ctx->atlas_ready) {                                              // join the side stream (the last chunk may not have been waited for)
     cudaStreamWaitEvent(st, ctx->atlas_ready, 0);
     ctx->atlas_ready = nullptr;
   }
   ctx->atlas_chunks = 0;
+  SC_CHECK(upload_err.load() == 0, SC_ERR_CUDA, "sc_segment_volume_host: atlas upload failed: %s", cudaGetErrorString((cudaError_t)upload_err.load()));
   SC_TRY(seg_status);
   if (label_vol_host) SC_CUDA(cudaMemcpyAsync(label_vol_host, d_lab, nvox, cudaMemcpyDeviceToHost, st));
   if (proba_vol_host) SC_CUDA(cudaMemcpyAsync(proba_vol_host, d_proba, nvox * 60, cudaMemcpyDeviceToHost, st));

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -190,6 +191,9 @@ struct sc_ctx {
   // a slab of phase 2 only waits for the chunks that cover it (atlas_chunks > 0 replaces the single event above)
   cudaEvent_t atlas_chunk_ev[64] = {};
   int atlas_chunks = 0, atlas_chunk_nx = 0;
+  // pageable host atlas: a helper thread issues the (then blocking) chunk copies; the consumer must not wait for an
+  // event before the helper has recorded it: chunks recorded so far (nullptr = all recorded before the kernels were launched)
+  std::atomic<int>* atlas_recorded = nullptr;
   bool profile = false;
   std::vector<sc::ProfEvent> prof_live;
   std::vector<sc::ProfEvent> prof_free;

@@ -14,6 +14,8 @@
 // This file: the orchestration (segment_volume, branch_patches_tc) and the fp32 SIMT back-end (planar maps
 // [slice][C][rows][ld], pools folded into the load stage of conv3 / conv5, conv5 output NHWC-64 = the A operand of the d1
 // implicit GEMM, K = tap*64 + c).  The default tensor-core back-end runs the conv layers in conv_sweep.cu (wide-row maps).
+#include <thread>
+
 #include "common.cuh"
 
 namespace sc {
@@ -552,6 +554,8 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       int need = (b[0] + ix0 + nx + ctx->atlas_chunk_nx - 1) / ctx->atlas_chunk_nx;
       if (need > ctx->atlas_chunks) need = ctx->atlas_chunks;
       if (need > atlas_waited) {
+        if (ctx->atlas_recorded)       // pageable upload by a helper thread: the event must have been recorded first
+          while (ctx->atlas_recorded->load(std::memory_order_acquire) < need) std::this_thread::yield();
         SC_CUDA(cudaStreamWaitEvent(st, ctx->atlas_chunk_ev[need - 1], 0));
         atlas_waited = need;
       }
