@@ -99,6 +99,25 @@ def test_host_and_from_volume_entry_points_agree(ctx):
     assert np.array_equal(p_dev.cpu().numpy(), p_vol.cpu().numpy()) and np.array_equal(l_dev.cpu().numpy(), l_vol.cpu().numpy())
 
 
+def test_segment_volume_host_pinned_and_pageable(ctx):
+    """sc_segment_volume_host: pinned host buffers (asynchronous chunked atlas upload) and plain numpy arrays (pageable:
+    a helper thread issues the blocking copies) give the result of the device-resident call; several slabs, so that the
+    per-chunk atlas events are exercised."""
+    rng = np.random.RandomState(5)
+    shape = (34, 30, 28)
+    vol = rng.randn(*shape).astype(np.float32)
+    atlas = _soft_atlas(rng, vol.size).reshape(shape + (15,))
+    cand = (rng.rand(*shape) < 0.6).view(np.uint8)
+    ctx.set_option("chunk_voxels", 5000)
+    lab_dev = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+    ctx.segment_volume(dev(vol), dev(atlas), cand_mask=dev(cand), label_vol=lab_dev)
+    lab_page, _ = ctx.segment_volume_host(vol, atlas, cand_mask=cand)
+    pin = [torch.from_numpy(a).pin_memory() for a in (vol, atlas, cand)]
+    lab_pin, _ = ctx.segment_volume_host(pin[0].numpy(), pin[1].numpy(), cand_mask=pin[2].numpy())
+    ctx.set_option("chunk_voxels", 1 << 20)
+    assert np.array_equal(lab_dev.cpu().numpy(), lab_page) and np.array_equal(lab_page, lab_pin)
+
+
 @pytest.mark.parametrize("shape,box", [((20, 24, 18), None), ((37, 29, 41), (5, 30, 0, 29, 7, 33)), ((16, 40, 12), (3, 4, 10, 11, 5, 6))])
 def test_dense_volume_vs_oracle(ctx, P, shape, box):
     rng = np.random.RandomState(sum(shape))
