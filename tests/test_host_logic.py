@@ -155,3 +155,21 @@ def test_no_cpu_fallback_without_gpu():
         _native.Context(0)
     with pytest.raises(_native.NativeError):
         nets.Net({'mode': 'cpu', 'patch_size': [32, 32]}, None, None)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py contract: exactly one JSON line on stdout (library chatter goes to stderr); the reference arm runs the
+    oracle port of the reference's mode=cpu path on the host cores, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-sample", "128", "--size", "48"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "voxels/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
