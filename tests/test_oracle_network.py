@@ -91,3 +91,52 @@ def test_train_step_decreases_loss_and_updates_state():
     assert losses[-1] < losses[0] and state["t"] == 6
     assert len(G) == len(network.trainable_names(P))
     assert not np.allclose(P["axial_ch_conv1_bn"][2], 0)  # running mean moved
+
+
+def test_oracle_agrees_with_an_independent_numpy_scipy_restatement(oracle_params):
+    """Second, independent restatement of nets.py:159-231 in float64 numpy: the convolutions are
+    scipy.signal.convolve2d(mode='valid') -- a TRUE convolution, which is what Lasagne's flip_filters=True computes,
+    so no kernel flip appears anywhere here (the torch oracle cross-correlates with flipped taps); pooling, BN, PReLU,
+    the (C, H, W) flatten order, the concat order and the softmax are written out with plain numpy.  Run on the
+    committed weights."""
+    from scipy.signal import convolve2d
+    P = oracle_params
+    rng = np.random.RandomState(3)
+    n = 3
+    x = [rng.randn(n, 1, 32, 32).astype(np.float32).astype(np.float64) for _ in range(3)]
+    atlas = rng.dirichlet(np.ones(15) * 0.4, size=n).astype(np.float32).astype(np.float64)
+
+    def prelu(v, a):
+        return np.where(v > 0, v, a * v)
+
+    feats = []
+    for b, xin in zip(network.BRANCHES, x):
+        rows = []
+        for s in range(n):
+            maps = [xin[s, 0]]
+            for i in range(1, 6):
+                W = P["%s_ch_conv%d" % (b, i)][0].astype(np.float64)
+                beta, gamma, mean, inv_std = [a.astype(np.float64) for a in P["%s_ch_conv%d_bn" % (b, i)]]
+                alpha = P["%s_ch_prelu%d" % (b, i)][0].astype(np.float64)
+                out = []
+                for co in range(W.shape[0]):
+                    acc = sum(convolve2d(maps[ci], W[co, ci], mode="valid") for ci in range(W.shape[1]))
+                    acc = (acc - mean[co]) * (gamma[co] * inv_std[co]) + beta[co]
+                    out.append(prelu(acc, alpha[co]))
+                if i in (2, 4):   # MaxPool2DLayer(pool_size=2)
+                    out = [o.reshape(o.shape[0] // 2, 2, o.shape[1] // 2, 2).max(axis=(1, 3)) for o in out]
+                maps = out
+            flat = np.stack(maps).reshape(-1)                      # (C, H, W) order
+            Wd, bd = [a.astype(np.float64) for a in P["%s_d1" % b]]
+            rows.append(prelu(flat @ Wd + bd, P["%s_prelu_d1" % b][0].astype(np.float64)))
+        feats.append(np.stack(rows))
+    h = np.concatenate(feats, 1)
+    h = prelu(h @ P["FC1"][0].astype(np.float64) + P["FC1"][1], P["prelu_f1"][0].astype(np.float64))
+    h = np.concatenate([h, atlas], 1)
+    h = prelu(h @ P["fc_2"][0].astype(np.float64) + P["fc_2"][1], P["prelu_f2"][0].astype(np.float64))
+    z = h @ P["out_layer"][0].astype(np.float64) + P["out_layer"][1]
+    e = np.exp(z - z.max(1, keepdims=True))
+    ref = e / e.sum(1, keepdims=True)
+    x32, a32 = [a.astype(np.float32) for a in x], atlas.astype(np.float32)   # the restatement above sees the same rounded inputs
+    got = network.forward(P, *x32, a32, dtype=torch.float64)
+    assert np.abs(got - ref).max() < 1e-9
