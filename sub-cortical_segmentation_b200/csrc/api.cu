@@ -431,12 +431,12 @@ int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dim
     cudaPointerAttributes pa;
     const bool pageable = cudaPointerGetAttributes(&pa, atlas_host) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
     cudaGetLastError();
+    bool threaded = false;
     if (pageable) {
       ctx->atlas_recorded = &atlas_recorded;
-      uploader = std::thread(upload);
-    } else {
-      upload();
+      try { uploader = std::thread(upload); threaded = true; } catch (...) { ctx->atlas_recorded = nullptr; }   // no thread: upload inline
     }
+    if (!threaded) upload();
   }
   SC_CUDA(cudaMemsetAsync(d_lab, 0, nvox, st));
   if (d_proba) SC_CUDA(cudaMemsetAsync(d_proba, 0, nvox * 60, st));
