@@ -33,6 +33,7 @@ struct SweepArgs {
   int stages;
   int out_bufs;           // output tiles in shared memory (2: double-buffered, 1 when shared memory is short)
   int npanels;            // weight panels (4 k-steps each)
+  int pair_fused;         // CTA-pair kernel: 2-MMA form (see conv_sweep_pair_kernel)
   const float* scale; const float* shift; const float* alpha;
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
 };
@@ -512,6 +513,10 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       const uint32_t leader = elect_one();
       // D = F32, A = B = BF16, K-major, N = bn (bn/2 weight rows from each CTA), M = 256
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      // fused form: xh * [wh_a; wl_a | wh_b; wl_b] as ONE MMA of N = 2*bn (a / b = the channel halves held by the two CTAs, every
+      // CTA's panel is [W hi half; W lo half]) into columns [0, 2bn), and xl * [wh_a | wh_b] (N = bn, the first bn/2 rows of
+      // each CTA's panel) into its own columns [2bn, 3bn): two instead of three A reads per k-step; the epilogue adds the pieces
+      const uint32_t idesc2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 2) << 17) | ((uint32_t)(256 >> 4) << 24);
       mbar_wait(wfull, 0);
       const uint32_t w_lo = desc_lo(smem_u32(sW));
       const uint32_t ring_lo = desc_lo(smem_u32(sRing));
@@ -551,9 +556,14 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 const uint32_t a_hi = sl[ky] + (uint32_t)(kx * DIL * 8 + ks * 2);
                 const uint32_t a_lo = a_hi + (uint32_t)(SW_SLOT_HALF >> 4);
                 const uint32_t wh = w_lo + (uint32_t)(gk >> 2) * panel16 + (uint32_t)((gk & 3) * 2);
-                sweep_mma_2sm(acc, a_lo, wh, idesc, gk != 0, leader);
-                sweep_mma_2sm(acc, a_hi, wh + wl_off, idesc, 1, leader);
-                sweep_mma_2sm(acc, a_hi, wh, idesc, 1, leader);
+                if (a.pair_fused) {
+                  sweep_mma_2sm(acc, a_hi, wh, idesc2n, gk != 0, leader);
+                  sweep_mma_2sm(acc + 2 * a.bn, a_lo, wh, idesc, gk != 0, leader);
+                } else {
+                  sweep_mma_2sm(acc, a_lo, wh, idesc, gk != 0, leader);
+                  sweep_mma_2sm(acc, a_hi, wh + wl_off, idesc, 1, leader);
+                  sweep_mma_2sm(acc, a_hi, wh, idesc, 1, leader);
+                }
               }
             }
           }
@@ -603,8 +613,26 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         float v[CW];
         if (real) {
           uint32_t r1[CW];
-          tmem_ld16(tmem_base + b * 256 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, r1);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const uint32_t tb = tmem_base + b * 256 + ((uint32_t)(q4 * 32) << 16);
+          if (a.pair_fused) {
+            // channel c of half h = c / (bn/2): xh*wh at column h*bn + c % (bn/2), xh*wl bn/2 columns further, xl*wh at 2*bn + c
+            const int hb = a.bn >> 1;
+#pragma unroll
+            for (int p8 = 0; p8 < 2; ++p8) {
+              const int ch = c0 + 8 * p8, hf = ch >= hb ? 1 : 0, off = ch - hf * hb;
+              uint32_t x0[8], x1[8], x2[8];
+              tmem_ld8(tb + (uint32_t)(hf * a.bn + off), x0);
+              tmem_ld8(tb + (uint32_t)(hf * a.bn + hb + off), x1);
+              tmem_ld8(tb + (uint32_t)(2 * a.bn + ch), x2);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                r1[8 * p8 + k] = __float_as_uint(__uint_as_float(x0[k]) + __uint_as_float(x1[k]) + __uint_as_float(x2[k]));
+            }
+          } else {
+            tmem_ld16(tb + (uint32_t)c0, r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
 #pragma unroll
           for (int k4 = 0; k4 < CW / 4; ++k4) {
             const float4 sc_ = *reinterpret_cast<const float4*>(s_const + c0 + 4 * k4);
@@ -852,6 +880,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   a.n_items = a.nstrips * dil * nseg;
   SC_CHECK(pool != 2 || dil == 1, SC_ERR_ARG, "conv_sweep: the stride-2 pool needs dilation 1");
   a.npanels = w.npanels;
+  a.pair_fused = ctx->tc_pair_fused;
   a.scale = w.scale; a.shift = w.shift; a.alpha = w.alpha;
   a.dbg = (ctx->tc_timing_cls == prof_cls) ? ctx->tc_timing_buf : nullptr;
   SC_CHECK(w.bn <= (out_fmt ? 32 : 64) && w.bn % 16 == 0, SC_ERR_ARG, "conv_sweep: bad channel geometry");
