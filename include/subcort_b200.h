@@ -55,11 +55,11 @@ SC_API const char* sc_last_error(void);
 /* replaces: THEANO_FLAGS device selection, cnn_cort/load_options.py:54-57 */
 SC_API int sc_create(int device, sc_ctx** out);
 SC_API int sc_destroy(sc_ctx* ctx);
-/* knobs: "gemm" = 0 SIMT fp32 | 1 tcgen05 bf16x3 (default when available);
- *        "chunk_voxels" = voxels per head chunk in sc_segment_volume; "profile" = 0 | 1.
- *        experiment switches of the tensor-core back-end (defaults = the measured-fastest pipeline): "tc_variant" 1..3,
- *        "tc_sweep45" 0..7 (strip-sweep / CTA-pair kernels for conv4, conv5), "tc_atlas_fused" 0 | 1,
- *        "gather_ctas_per_sm" 0..32, "tc_timing" = kernel class whose launches record per-role wait cycles. */
+/* knobs: "gemm" = 1 tcgen05 bf16x3 (the product path, always the default: sc_create fails where it cannot be brought up)
+ *        | 0 exact-fp32 SIMT kernels (cross-check back-end for the parity tests only);
+ *        "chunk_voxels" = voxels per head chunk in sc_segment_volume; "profile" = 0 | 1;
+ *        "tc_compact" 0 | 1 (candidate-row compaction of the FC head, default 1), "gather_ctas_per_sm" 0..32,
+ *        "tc_timing" = kernel class whose launches record per-role wait cycles (debug). */
 SC_API int sc_set_option(sc_ctx* ctx, const char* key, int64_t value);
 SC_API int64_t sc_get_counter(sc_ctx* ctx, const char* key); /* "launches": kernels launched so far */
 /* per-kernel-class device times: after sc_set_option(ctx, "profile", 1) every launch is bracketed by

@@ -38,6 +38,19 @@ int ensure_ws(Workspace& ws, size_t bytes) {
   return SC_OK;
 }
 
+int ensure_smem_attr(sc_ctx* ctx, const void* kernel, int bytes) {
+  for (auto& e : ctx->smem_attr)
+    if (e.first == kernel) {
+      if (e.second >= bytes) return SC_OK;
+      SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      e.second = bytes;
+      return SC_OK;
+    }
+  SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  ctx->smem_attr.emplace_back(kernel, bytes);
+  return SC_OK;
+}
+
 static int need_weights(sc_ctx* ctx, const char* who) {
   SC_CHECK(ctx != nullptr, SC_ERR_ARG, "%s: null context", who);
   SC_CHECK(ctx->weights_loaded, SC_ERR_STATE, "%s: call sc_load_weights first", who);
@@ -109,7 +122,14 @@ int sc_create(int device, sc_ctx** out) {
   }
   SC_CUDA(cudaMalloc(&ctx->d_count, sizeof(int64_t)));
   SC_CUDA(cudaMallocHost(&ctx->h_count, sizeof(int64_t)));
-  ctx->gemm_backend = tc_init(ctx) == SC_OK ? 1 : 0;
+  // the tcgen05 / TMA back-end is the product: a box on which it cannot be brought up is an error, never a silent
+  // switch to the SIMT cross-check kernels
+  const int tcs = tc_init(ctx);
+  if (tcs != SC_OK) {
+    sc_destroy(ctx);
+    return tcs;
+  }
+  ctx->gemm_backend = 1;
   *out = ctx;
   return SC_OK;
 }
@@ -140,54 +160,18 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     ctx->gemm_backend = (int)value;
     return SC_OK;
   }
-  if (!strcmp(key, "tc_variant")) {
-    SC_CHECK(value >= 1 && value <= 3, SC_ERR_ARG, "sc_set_option: tc_variant must be 1, 2 or 3");
-    ctx->tc_variant = (int)value;
-    return SC_OK;
-  }
   if (!strcmp(key, "tc_timing")) {   // value = ProfClass index to instrument, -1 = off
     ctx->tc_timing_cls = (int)value;
     if (value >= 0 && !ctx->tc_timing_buf) SC_CUDA(cudaMalloc(&ctx->tc_timing_buf, sizeof(unsigned long long) * 8 * 1024));
-    return SC_OK;
-  }
-  if (!strcmp(key, "tc_pair_fused")) {
-    ctx->tc_pair_fused = value != 0;
     return SC_OK;
   }
   if (!strcmp(key, "tc_compact")) {
     ctx->tc_compact = value != 0;
     return SC_OK;
   }
-  if (!strcmp(key, "tc_mc")) {
-    ctx->tc_mc = value != 0;
-    return SC_OK;
-  }
   if (!strcmp(key, "gather_ctas_per_sm")) {
     SC_CHECK(value >= 0 && value <= 32, SC_ERR_ARG, "sc_set_option: gather_ctas_per_sm must be 0..32");
     ctx->gather_ctas_per_sm = (int)value;
-    return SC_OK;
-  }
-  if (!strcmp(key, "tc_atlas_fused")) {
-    ctx->tc_atlas_fused = value != 0;
-    return SC_OK;
-  }
-  if (!strcmp(key, "tc_sweep45")) {   // bit 0: conv4 + pool2, bit 1: conv5 run as strip sweeps (conv_sweep.cu)
-    SC_CHECK(value >= 0 && value <= 7, SC_ERR_ARG, "sc_set_option: tc_sweep45 must be 0..7");
-    ctx->tc_sweep45 = (int)value;
-    return SC_OK;
-  }
-  if (!strcmp(key, "tc_fuse_w")) {
-    ctx->tc_fuse_w = value != 0;
-    return SC_OK;
-  }
-  if (!strcmp(key, "tc_nacc")) {
-    SC_CHECK(value == 1 || value == 2 || value == 4, SC_ERR_ARG, "sc_set_option: tc_nacc must be 1, 2 or 4");
-    ctx->tc_nacc = (int)value;
-    return SC_OK;
-  }
-  if (!strcmp(key, "tc_kx_reuse")) {
-    SC_CHECK(value >= 0 && value <= 2, SC_ERR_ARG, "sc_set_option: tc_kx_reuse must be 0, 1 or 2");
-    ctx->tc_kx_reuse = (int)value;
     return SC_OK;
   }
   if (!strcmp(key, "profile")) {
@@ -223,6 +207,9 @@ int64_t sc_get_counter(sc_ctx* ctx, const char* key) {
 static const char* kProfNames[PC_COUNT] = {"gather", "nonzero", "scatter", "patch_branch", "conv1", "conv2", "conv3",
                                            "conv4", "conv5", "gemm_d1", "gemm_fc1", "gemm_fc2", "atlas", "out_softmax", "pool",
                                            "train_fwd", "train_bwd", "adam"};
+}  // extern "C"
+namespace sc { const char* prof_class_name(int cls) { return cls >= 0 && cls < PC_COUNT ? kProfNames[cls] : "subcort"; } }
+extern "C" {
 int sc_profile_classes(void) { return PC_COUNT; }
 const char* sc_profile_name(int cls) { return cls >= 0 && cls < PC_COUNT ? kProfNames[cls] : ""; }
 int sc_profile_read(sc_ctx* ctx, double* ms_out, int64_t* launches_out, int n) {
@@ -391,7 +378,20 @@ int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dim
   float* d_proba = proba_vol_host ? reinterpret_cast<float*>(base + vb + ab + 2 * mb) : nullptr;
   std::atomic<int> atlas_recorded(0), upload_err(0);
   std::thread uploader;
-  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{uploader};   // on every return path
+  // on every return path: join the helper, drop the per-call upload state from the context (it points at this frame),
+  // and on an error path wait for the copies that may still be reading the caller's buffers
+  struct Joiner {
+    std::thread& t; sc_ctx* ctx; cudaStream_t st; bool ok;
+    ~Joiner() {
+      if (t.joinable()) t.join();
+      ctx->atlas_recorded = nullptr; ctx->atlas_chunks = 0; ctx->atlas_ready = nullptr;
+      if (!ok) {
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(st);
+        cudaGetLastError();
+      }
+    }
+  } joiner{uploader, ctx, st, false};
   // the atlas (15 floats per voxel, 94 % of the upload) is first needed after the conv phase: upload it on a side
   // stream so that the copy engine works while the conv kernels run
   if (!ctx->copy_stream) {
@@ -447,16 +447,15 @@ int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dim
   const int seg_status = segment_volume(ctx, d_vol, dims, d_atlas, box, cand_mask_host ? d_mask : nullptr, d_lab, d_proba, st);
   if (uploader.joinable()) uploader.join();
   ctx->atlas_recorded = nullptr;
-  if (ctx->atlas_ready) {                                              // join the side stream (the last chunk may not have been waited for)
-    cudaStreamWaitEvent(st, ctx->atlas_ready, 0);
-    ctx->atlas_ready = nullptr;
-  }
+  if (ctx->atlas_ready) cudaStreamWaitEvent(st, ctx->atlas_ready, 0);  // join the side stream (the last chunk may not have been waited for)
+  ctx->atlas_ready = nullptr;
   ctx->atlas_chunks = 0;
   SC_CHECK(upload_err.load() == 0, SC_ERR_CUDA, "sc_segment_volume_host: atlas upload failed: %s", cudaGetErrorString((cudaError_t)upload_err.load()));
   SC_TRY(seg_status);
   if (label_vol_host) SC_CUDA(cudaMemcpyAsync(label_vol_host, d_lab, nvox, cudaMemcpyDeviceToHost, st));
   if (proba_vol_host) SC_CUDA(cudaMemcpyAsync(proba_vol_host, d_proba, nvox * 60, cudaMemcpyDeviceToHost, st));
   SC_CUDA(cudaStreamSynchronize(st));
+  joiner.ok = true;
   return SC_OK;
 }
 

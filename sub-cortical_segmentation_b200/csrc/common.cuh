@@ -2,10 +2,12 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/subcort_b200.h"
@@ -123,7 +125,6 @@ struct BranchW {
   float* shift[5];      // beta - mean*scale
   float* alpha[5];
   SweepW conv_sw[5];    // l=1..4: conv2..conv5 for the strip-sweep kernel
-  GemmW conv_tc[5];     // l=1..4: conv2..conv5 as implicit GEMMs over NHWC-64 maps (K = tap*64+ci, N padded to 64)
   GemmW d1;             // patchwise: K=540 (c*9+h*3+w order)
   GemmW d1_dense;       // dense: K=576 (tap*64+ci), same N
 };
@@ -146,7 +147,7 @@ struct sc_ctx {
   int device = 0;
   int sm_count = 0;
   bool weights_loaded = false;
-  int gemm_backend = 0;          // 0 SIMT, 1 tcgen05
+  int gemm_backend = 1;          // 1 tcgen05 (the product path); 0 = exact-fp32 SIMT cross-check, tests only
   int64_t chunk_voxels = 1 << 20;
   int64_t launches = 0;
   sc::ParamOff off;
@@ -169,22 +170,14 @@ struct sc_ctx {
   int64_t* d_count = nullptr;    // device scalar for stream compaction
   int64_t* h_count = nullptr;    // pinned
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
-  int tc_variant = 3;            // 1: one tile per CTA (two CTAs / SM), 2: persistent, double-buffered TMEM, 3: 2 + CTA pairs (cta_group::2) for the wide layers
-  int tc_kx_reuse = 1;           // 0 off, 1: one A box per filter row, column taps = descriptor start offsets (verified on B200; 2 = base_offset set is WRONG)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
-  int tc_pair_fused = 0;         // experiment (no measurable gain, off): CTA-pair sweep kernels with xh*[wh|wl] as one double-width MMA + xl*wh into its own accumulator columns
   int tc_compact = 1;            // dense path with a candidate mask: the FC head runs on the compacted candidate rows only
   int32_t* h_slab_cnt = nullptr; // pinned: candidates per slab
   unsigned char* tile_flags = nullptr;   // d1 with a row map: per-tile "has a candidate" flags (device, grow-only)
   size_t tile_flags_cap = 0;
   cudaEvent_t compact_ev = nullptr;
-  int tc_mc = 0;                 // experiment (measured SLOWER, off): FC1 / fc_2 as multicast clusters, one CTA pair per n-tile, A loaded once per cluster
   int gather_ctas_per_sm = 0;    // > 0: persistent gather grid of that many CTAs per SM; 0 (default, measured fastest) = one CTA per 32-candidate group
-  int tc_atlas_fused = 1;        // FC1's CTA-pair epilogue writes the atlas columns of h1 (no separate atlas pass)
-  int tc_sweep45 = 7;            // bit 0: conv4 + pool2 as a strip sweep, bit 1: conv5 as a strip sweep, bit 2: CTA pairs for both
-  int tc_fuse_w = 1;             // conv tiles: fold xh*wh and xh*wl into one double-width MMA
-  int tc_nacc = 1;               // accumulator chains per narrow (<= 64 column) tile: 1, 2 or 4
   cudaStream_t copy_stream = nullptr;   // sc_segment_volume_host: the 1 GB atlas upload overlaps the conv phase
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   cudaEvent_t atlas_ready = nullptr;    // when set, segment_volume waits for it before its first use of the atlas (phase 2)
@@ -199,14 +192,22 @@ struct sc_ctx {
   std::vector<sc::ProfEvent> prof_live;
   std::vector<sc::ProfEvent> prof_free;
   bool derived_dirty = false;    // master parameters changed since the inference layouts were derived
+  // kernels whose MaxDynamicSharedMemorySize has been raised on THIS context's device (the attribute is per device)
+  std::vector<std::pair<const void*, int>> smem_attr;
 };
 
 namespace sc {
 int ensure_ws(Workspace& ws, size_t bytes);
+// cudaFuncAttributeMaxDynamicSharedMemorySize applies per device: remembered per context, never in a process-wide static
+int ensure_smem_attr(sc_ctx* ctx, const void* kernel, int bytes);
 
+const char* prof_class_name(int cls);
+// one scope per kernel launch: an NVTX range named after the kernel class (header-only NVTX v3: a no-op unless a
+// profiler is attached) and, with sc_set_option("profile", 1), a pair of CUDA events on the launching stream
 struct ProfScope {
   sc_ctx* ctx; cudaStream_t st; ProfEvent ev; bool on;
   ProfScope(sc_ctx* c, int cls, cudaStream_t s) : ctx(c), st(s), on(c->profile) {
+    nvtxRangePushA(prof_class_name(cls));
     if (!on) return;
     if (!ctx->prof_free.empty()) { ev = ctx->prof_free.back(); ctx->prof_free.pop_back(); }
     else { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
@@ -214,9 +215,11 @@ struct ProfScope {
     cudaEventRecord(ev.a, st);
   }
   ~ProfScope() {
-    if (!on) return;
-    cudaEventRecord(ev.b, st);
-    ctx->prof_live.push_back(ev);
+    if (on) {
+      cudaEventRecord(ev.b, st);
+      ctx->prof_live.push_back(ev);
+    }
+    nvtxRangePop();
   }
 };
 

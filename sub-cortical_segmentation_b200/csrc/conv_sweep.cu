@@ -33,7 +33,6 @@ struct SweepArgs {
   int stages;
   int out_bufs;           // output tiles in shared memory (2: double-buffered, 1 when shared memory is short)
   int npanels;            // weight panels (4 k-steps each)
-  int pair_fused;         // CTA-pair kernel: 2-MMA form (see conv_sweep_pair_kernel)
   const float* scale; const float* shift; const float* alpha;
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
 };
@@ -513,10 +512,6 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       const uint32_t leader = elect_one();
       // D = F32, A = B = BF16, K-major, N = bn (bn/2 weight rows from each CTA), M = 256
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      // fused form: xh * [wh_a; wl_a | wh_b; wl_b] as ONE MMA of N = 2*bn (a / b = the channel halves held by the two CTAs, every
-      // CTA's panel is [W hi half; W lo half]) into columns [0, 2bn), and xl * [wh_a | wh_b] (N = bn, the first bn/2 rows of
-      // each CTA's panel) into its own columns [2bn, 3bn): two instead of three A reads per k-step; the epilogue adds the pieces
-      const uint32_t idesc2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 2) << 17) | ((uint32_t)(256 >> 4) << 24);
       mbar_wait(wfull, 0);
       const uint32_t w_lo = desc_lo(smem_u32(sW));
       const uint32_t ring_lo = desc_lo(smem_u32(sRing));
@@ -556,14 +551,9 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 const uint32_t a_hi = sl[ky] + (uint32_t)(kx * DIL * 8 + ks * 2);
                 const uint32_t a_lo = a_hi + (uint32_t)(SW_SLOT_HALF >> 4);
                 const uint32_t wh = w_lo + (uint32_t)(gk >> 2) * panel16 + (uint32_t)((gk & 3) * 2);
-                if (a.pair_fused) {
-                  sweep_mma_2sm(acc, a_hi, wh, idesc2n, gk != 0, leader);
-                  sweep_mma_2sm(acc + 2 * a.bn, a_lo, wh, idesc, gk != 0, leader);
-                } else {
-                  sweep_mma_2sm(acc, a_lo, wh, idesc, gk != 0, leader);
-                  sweep_mma_2sm(acc, a_hi, wh + wl_off, idesc, 1, leader);
-                  sweep_mma_2sm(acc, a_hi, wh, idesc, 1, leader);
-                }
+                sweep_mma_2sm(acc, a_lo, wh, idesc, gk != 0, leader);
+                sweep_mma_2sm(acc, a_hi, wh + wl_off, idesc, 1, leader);
+                sweep_mma_2sm(acc, a_hi, wh, idesc, 1, leader);
               }
             }
           }
@@ -614,25 +604,8 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         if (real) {
           uint32_t r1[CW];
           const uint32_t tb = tmem_base + b * 256 + ((uint32_t)(q4 * 32) << 16);
-          if (a.pair_fused) {
-            // channel c of half h = c / (bn/2): xh*wh at column h*bn + c % (bn/2), xh*wl bn/2 columns further, xl*wh at 2*bn + c
-            const int hb = a.bn >> 1;
-#pragma unroll
-            for (int p8 = 0; p8 < 2; ++p8) {
-              const int ch = c0 + 8 * p8, hf = ch >= hb ? 1 : 0, off = ch - hf * hb;
-              uint32_t x0[8], x1[8], x2[8];
-              tmem_ld8(tb + (uint32_t)(hf * a.bn + off), x0);
-              tmem_ld8(tb + (uint32_t)(hf * a.bn + hb + off), x1);
-              tmem_ld8(tb + (uint32_t)(2 * a.bn + ch), x2);
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                r1[8 * p8 + k] = __float_as_uint(__uint_as_float(x0[k]) + __uint_as_float(x1[k]) + __uint_as_float(x2[k]));
-            }
-          } else {
-            tmem_ld16(tb + (uint32_t)c0, r1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          }
+          tmem_ld16(tb + (uint32_t)c0, r1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int k4 = 0; k4 < CW / 4; ++k4) {
             const float4 sc_ = *reinterpret_cast<const float4*>(s_const + c0 + 4 * k4);
@@ -824,11 +797,7 @@ int launch_conv1_wide(sc_ctx* ctx, const float* vol, const ViewGeo& g, int ns, c
   CUresult r = s->encode(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "conv1_wide: cuTensorMapEncodeTiled failed with %d", (int)r);
-  static bool configured = false;
-  if (!configured) {
-    SC_CUDA(cudaFuncSetAttribute(conv1_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768 + 1024));
-    configured = true;
-  }
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(conv1_wide_kernel), 2 * 32768 + 1024));
   const long long n_tiles = (long long)outR * ((ns + bs - 1) / bs) * ((outC + bc - 1) / bc);
   const long long cap = (long long)ctx->sm_count * 3;               // 3 CTAs per SM (66 KB of shared memory each)
   const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
@@ -846,11 +815,7 @@ template <int KSTEPS, int DIL, int POOL, int CW, bool LO64, bool OUT32>
 static int launch_sweep_t(sc_ctx* ctx, const CUtensorMap& mapA, const CUtensorMap& mapW, const CUtensorMap& mapO, const SweepArgs& a,
                           size_t smem, cudaStream_t st) {
   auto kern = conv_sweep_kernel<KSTEPS, DIL, POOL, CW, LO64, OUT32>;
-  static bool configured = false;
-  if (!configured) {
-    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024));
   const int grid = a.n_items < ctx->sm_count ? a.n_items : ctx->sm_count;
   kern<<<grid, 576, smem, st>>>(mapA, mapW, mapO, a);
   ctx->launches++;
@@ -880,7 +845,6 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   a.n_items = a.nstrips * dil * nseg;
   SC_CHECK(pool != 2 || dil == 1, SC_ERR_ARG, "conv_sweep: the stride-2 pool needs dilation 1");
   a.npanels = w.npanels;
-  a.pair_fused = ctx->tc_pair_fused;
   a.scale = w.scale; a.shift = w.shift; a.alpha = w.alpha;
   a.dbg = (ctx->tc_timing_cls == prof_cls) ? ctx->tc_timing_buf : nullptr;
   SC_CHECK(w.bn <= (out_fmt ? 32 : 64) && w.bn % 16 == 0, SC_ERR_ARG, "conv_sweep: bad channel geometry");
@@ -895,7 +859,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     a.stages = (227 * 1024 - fixed - ob_bytes) / slot;
   }
   if (a.stages > 8) a.stages = 8;
-  const bool use_pair = w.ksteps == 3 && !in_fmt && !out_fmt && (ctx->tc_sweep45 & 4);
+  const bool use_pair = w.ksteps == 3 && !in_fmt && !out_fmt;          // 40 input channels: the resident weights need the CTA pair
   SC_CHECK(use_pair || a.stages >= 3, SC_ERR_ARG, "conv_sweep: ring does not fit (layer %d)", layer);
   const size_t smem = (size_t)fixed + (size_t)a.stages * slot + (size_t)a.out_bufs * ob_bytes;
 
@@ -970,23 +934,19 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     ProfScope prof(ctx, prof_cls, st);
     if (dil == 1 && pool == 2) {
       auto kern = conv_sweep_pair_kernel<3, 1, 2>;
-      static bool cfg = false;
-      if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+      SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024));
       kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
     } else if (dil == 1 && !pool) {
       auto kern = conv_sweep_pair_kernel<3, 1, 0>;
-      static bool cfg = false;
-      if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+      SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024));
       kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
     } else if (dil == 2 && pool == 1) {
       auto kern = conv_sweep_pair_kernel<3, 2, 1>;
-      static bool cfg = false;
-      if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+      SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024));
       kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
     } else if (dil == 4 && !pool) {
       auto kern = conv_sweep_pair_kernel<3, 4, 0>;
-      static bool cfg = false;
-      if (!cfg) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+      SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024));
       kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
     } else {
       set_error("conv_sweep: no pair kernel instance for dil=%d pool=%d", dil, pool);
@@ -1000,8 +960,6 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   if (w.ksteps == 2 && dil == 1 && pool == 2 && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 2, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // patch maps: conv2 + 2x2/2 pool
   if (w.ksteps == 2 && dil == 1 && pool == 1 && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 1, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // conv2 + pool1
   if (w.ksteps == 2 && dil == 2 && !pool && i32 && !o32) return launch_sweep_t<2, 2, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);              // conv3
-  if (w.ksteps == 3 && dil == 2 && pool == 1 && !i32 && !o32) return launch_sweep_t<3, 2, 1, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);             // conv4 + pool2
-  if (w.ksteps == 3 && dil == 4 && !pool && !i32 && !o32) return launch_sweep_t<3, 4, 0, 16, false, false>(ctx, mapA, mapW, mapO, a, smem, st);            // conv5
   // patchwise maps (dilation 1 everywhere, stride-2 pools stay separate passes)
   if (w.ksteps == 2 && dil == 1 && !pool && i32 && !o32) return launch_sweep_t<2, 1, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);
   set_error("conv_sweep: no kernel instance for ksteps=%d dil=%d pool=%d in_fmt=%d out_fmt=%d", w.ksteps, dil, pool, in_fmt, out_fmt);

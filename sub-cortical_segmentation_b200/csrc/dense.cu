@@ -206,11 +206,7 @@ template <int CIN, int COUT, int DIL, int POOLD, bool NHWC_OUT>
 static int launch_dense_conv(sc_ctx* ctx, const ConvArgs& a, int prof_cls, cudaStream_t st) {
   using Cfg = ConvCfg<CIN, COUT, DIL, POOLD, NHWC_OUT>;
   auto kern = dense_conv_kernel<CIN, COUT, DIL, POOLD, NHWC_OUT>;
-  static bool configured = false;
-  if (!configured) {
-    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    configured = true;
-  }
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), (int)Cfg::SMEM));
   const int width = NHWC_OUT ? a.outC : a.outLd;
   dim3 grid((width + Cfg::TW - 1) / Cfg::TW, (a.outR + Cfg::TH - 1) / Cfg::TH, a.ns);
   ProfScope prof(ctx, prof_cls, st);
@@ -219,57 +215,6 @@ static int launch_dense_conv(sc_ctx* ctx, const ConvArgs& a, int prof_cls, cudaS
   SC_CUDA(cudaGetLastError());
   return SC_OK;
 }
-
-// ---------------------------------------------------------------------------------------
-// pre-sweep tensor-core pipeline pieces (tc_sweep45 = 0, kept for A/B runs): the stride-1 max-pool as its own (HBM-bound) pass
-// ---------------------------------------------------------------------------------------
-// stride-1 max-pool (window {0,pd}^2) on a flattened NHWC-64 split-bf16 map (positions = slices x rows x pitch, back to
-// back): out[p] = max(in[p], in[p+pd], in[p+pd*pitch], in[p+pd*pitch+pd]); hi + lo is exact in fp32, so the maximum is
-// taken on the reconstructed values and split again (the re-split reproduces the same represented value).  Positions whose window leaves the buffer are skipped (they are never read).
-__global__ void __launch_bounds__(256) pool_flat_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t npos, int pitch, int pd) {
-  const int64_t total = npos * 16;
-  const int64_t reach = (int64_t)pd * pitch + pd;
-  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
-    const int q = (int)(e & 15);
-    const int64_t pos = e >> 4;
-    if (pos + reach >= npos) continue;
-    float best[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(in + (pos + (k >> 1) * (int64_t)pd * pitch + (k & 1) * pd) * kC5Ld) + q * 4;
-      const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
-      const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + 64));
-      const float v0 = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
-      const float v1 = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
-      const float v2 = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
-      const float v3 = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
-      if (k == 0) { best[0] = v0; best[1] = v1; best[2] = v2; best[3] = v3; }
-      else { best[0] = fmaxf(best[0], v0); best[1] = fmaxf(best[1], v1); best[2] = fmaxf(best[2], v2); best[3] = fmaxf(best[3], v3); }
-    }
-    store_split4(out + pos * kC5Ld, q * 4, best[0], best[1], best[2], best[3]);
-  }
-}
-
-static int launch_conv_tc(sc_ctx* ctx, const GemmW& w, const float* in, int inR, int inC, float* out, int outR, int outC, int ns,
-                          int dil, int k_used, int prof_cls, cudaStream_t st, int flat_pitch = 0) {
-  GemmProblem p;
-  p.A = in; p.lda = kC5Ld; p.a_ys = (int64_t)inC * kC5Ld; p.a_zs = (int64_t)inR * inC * kC5Ld;
-  p.ntaps = 9; p.kc = kC5Ld;
-  for (int t = 0; t < 9; ++t) {
-    if (flat_pitch) { p.tap_dx[t] = (t / 3) * dil * flat_pitch + (t % 3) * dil; p.tap_dy[t] = 0; }
-    else { p.tap_dx[t] = (t % 3) * dil; p.tap_dy[t] = (t / 3) * dil; }
-    p.tap_off[t] = ((int64_t)p.tap_dy[t] * inC + p.tap_dx[t]) * kC5Ld;
-  }
-  p.a_base = in; p.a_dims[0] = kC5Ld; p.a_dims[1] = inC; p.a_dims[2] = inR; p.a_dims[3] = ns;
-  p.a_strides[0] = kC5Ld; p.a_strides[1] = p.a_ys; p.a_strides[2] = p.a_zs;
-  p.a_y0 = p.a_z0 = 0;
-  p.C = out; p.ldc = kC5Ld; p.c_ys = (int64_t)outC * kC5Ld; p.c_zs = (int64_t)outR * outC * kC5Ld;
-  p.M = outC; p.Y = outR; p.Z = ns;
-  p.n_store = 64; p.c_col0 = 0; p.out_split = 1; p.prof_cls = prof_cls;
-  p.k_used = k_used;
-  return launch_gemm_tc(ctx, p, w, st);
-}
-
 
 // ---------------------------------------------------------------------------------------
 // Patchwise branch on the tensor cores (predict_proba on patch dicts)
@@ -405,8 +350,8 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   for (int v = 0; v < 3; ++v) {
     const size_t br = vg[v].br, bc = vg[v].bc;
     size_t f;
-    if (tc) {  // strip-sweep pipeline: whole-view wide-row maps conv1 and pool1 (128 B pixels), conv3, conv4, pool2 (256 B pixels)
-      f = (size_t)vg[v].ns * (br + 29) * (bc + 29) * (2 * 32 + 3 * 64) + 5 * 64;
+    if (tc) {  // strip-sweep pipeline: whole-view wide-row maps conv1 and pool1 (128 B pixels), conv3, pool2 (256 B pixels)
+      f = (size_t)vg[v].ns * (br + 29) * (bc + 29) * (2 * 32 + 2 * 64) + 4 * 64;
       view_max = f > view_max ? f : view_max;
       continue;
     }
@@ -430,7 +375,7 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   const size_t h2_bytes = align256(rows_max * h2ld * sizeof(float));
   // candidate compaction (tensor-core path with a mask): the FC head runs on the candidate rows of each slab only
   const int nslabs = (bx + slab - 1) / slab;
-  bool compact = tc && cand != nullptr && ctx->tc_compact && ctx->tc_variant == 3 && ctx->tc_atlas_fused && nslabs <= 4096;
+  bool compact = tc && cand != nullptr && ctx->tc_compact && nslabs <= 4096;
   const size_t nbox = (size_t)bx * plane;
   const size_t cmp_blocks = (size_t)nslabs * ((rows_max + 2047) / 2048);
   const size_t cmp_bytes = compact ? align256(nbox * 4) * 2 + align256(cmp_blocks * 8 + 16) + align256((size_t)nslabs * 4) : 0;
@@ -471,8 +416,8 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     if (tc) {
       // ---- tensor-core pipeline (conv_sweep.cu): whole-view wide-row maps, position = (row * ns + slice) * C1 + col, all
       // with the conv1 geometry (R1 rows, C1 columns per slice).  Positions outside a layer's valid region hold garbage
-      // that valid outputs never read.  conv2 + pool1 and conv3 run as strip sweeps (every input row loaded once, pool
-      // fused into the epilogue); conv4 / pool2 / conv5 still run on the flattened sequence (filter row = shift by Pw).
+      // that valid outputs never read.  Every layer is a strip sweep (every input row loaded once, pools fused into the
+      // epilogues); conv4 + pool2 and conv5 run on CTA pairs.
       const int R1 = g.br + 29, C1 = g.bc + 29;
       const int64_t Pw64 = (int64_t)g.ns * C1;
       const int64_t npos = Pw64 * R1;
@@ -481,22 +426,12 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       auto carve = [&](float*& cur, int px_floats) { float* p = cur; cur += align256((size_t)npos * px_floats * 4) / 4; return p; };
       float* cur = reinterpret_cast<float*>(scratch);
       float* m1 = carve(cur, 32); float* mp1 = carve(cur, 32);
-      float* m3 = carve(cur, 64); float* m4 = carve(cur, 64); float* mp2 = carve(cur, 64);
+      float* m3 = carve(cur, 64); float* mp2 = carve(cur, 64);
       SC_TRY(launch_conv1_wide(ctx, vol, g, g.ns, W.c1_host, m1, R1, C1, st));
       SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, Pw, R1, g.br + 26, 1, 1, PC_CONV2, st));     // conv2 + pool1
       SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, Pw, R1, g.br + 22, 2, 0, PC_CONV3, st));     // conv3
-      const int P = (int)npos;
-      const unsigned pgrid = (unsigned)((npos * 16 + 255) / 256 < (int64_t)ctx->sm_count * 64 ? (npos * 16 + 255) / 256 : (int64_t)ctx->sm_count * 64);
-      if (ctx->tc_sweep45 & 1) {
-        SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, m3, 0, mp2, 0, Pw, R1, g.br + 16, 2, 1, PC_CONV4, st));   // conv4 + pool2
-      } else {
-        SC_TRY(launch_conv_tc(ctx, W.conv_tc[3], m3, 1, P, m4, 1, P, 1, 2, 40, PC_CONV4, st, Pw));
-        ProfScope prof(ctx, PC_POOL, st);
-        pool_flat_kernel<<<pgrid, 256, 0, st>>>(m4, mp2, npos, Pw, 2);
-        ctx->launches++;
-      }
-      if ((ctx->tc_sweep45 & 6) == 6) SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, mp2, 0, a5[v], 0, Pw, R1, g.br + 8, 4, 0, PC_CONV5, st));   // conv5 (CTA pairs)
-      else SC_TRY(launch_conv_tc(ctx, W.conv_tc[4], mp2, 1, P, a5[v], 1, P, 1, 4, 40, PC_CONV5, st, Pw));
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, m3, 0, mp2, 0, Pw, R1, g.br + 16, 2, 1, PC_CONV4, st));     // conv4 + pool2 (CTA pairs)
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, mp2, 0, a5[v], 0, Pw, R1, g.br + 8, 4, 0, PC_CONV5, st));   // conv5 (CTA pairs)
       SC_CUDA(cudaGetLastError());
     }
     for (int sb = 0; sb < g.ns && !tc; sb += group) {
@@ -603,7 +538,7 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     gemm_problem_rows(p, feats, kFeatLd, kFeatLd, (int)rows_fc);
     p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
-    const bool atlas_fused = tc && ctx->tc_variant == 3 && ctx->tc_atlas_fused;   // the CTA-pair kernel writes the atlas columns in its epilogue
+    const bool atlas_fused = tc;   // the CTA-pair kernel writes the atlas columns in its epilogue
     if (atlas_fused) { p.atlas = atlas; p.ageo = og; p.ageo.x0 = b[0] + ix0; if (compact) p.rowvox = rowvox + slab_base; }
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
     p.atlas = nullptr; p.rowvox = nullptr;

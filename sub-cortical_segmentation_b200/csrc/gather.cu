@@ -171,18 +171,20 @@ int launch_gather(sc_ctx* ctx, const float* vol, const int32_t* dims, const floa
   return SC_OK;
 }
 
-__global__ void center_labels_kernel(const uint8_t* __restrict__ lab, int Y, int Z, const int32_t* __restrict__ xyz,
+__global__ void center_labels_kernel(const uint8_t* __restrict__ lab, int X, int Y, int Z, const int32_t* __restrict__ xyz,
                                      int64_t n, uint8_t* __restrict__ y) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int64_t v = ((int64_t)xyz[i * 3] * Y + xyz[i * 3 + 1]) * Z + xyz[i * 3 + 2];
-  y[i] = lab[v];
+  const int cx = xyz[i * 3], cy = xyz[i * 3 + 1], cz = xyz[i * 3 + 2];
+  // a centre outside the volume reads the zero padding get_patches would have produced (base.py:303)
+  if ((unsigned)cx >= (unsigned)X || (unsigned)cy >= (unsigned)Y || (unsigned)cz >= (unsigned)Z) { y[i] = 0; return; }
+  y[i] = lab[((int64_t)cx * Y + cy) * Z + cz];
 }
 
 int launch_center_labels(sc_ctx* ctx, const uint8_t* lab, const int32_t* dims, const int32_t* xyz, int64_t n,
                          uint8_t* y, cudaStream_t st) {
   if (n == 0) return SC_OK;
-  center_labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lab, dims[1], dims[2], xyz, n, y);
+  center_labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lab, dims[0], dims[1], dims[2], xyz, n, y);
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
@@ -463,11 +465,13 @@ int launch_dilate(sc_ctx* ctx, const uint8_t* mask, const int32_t* dims, int ite
 }
 
 __global__ void scatter_kernel(const int32_t* __restrict__ xyz, int64_t n, const int32_t* __restrict__ label,
-                               const float* __restrict__ proba, int Y, int Z, uint8_t* __restrict__ label_vol,
+                               const float* __restrict__ proba, int X, int Y, int Z, uint8_t* __restrict__ label_vol,
                                float* __restrict__ proba_vol) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t v = ((int64_t)xyz[i * 3] * Y + xyz[i * 3 + 1]) * Z + xyz[i * 3 + 2];
+  const int cx = xyz[i * 3], cy = xyz[i * 3 + 1], cz = xyz[i * 3 + 2];
+  if ((unsigned)cx >= (unsigned)X || (unsigned)cy >= (unsigned)Y || (unsigned)cz >= (unsigned)Z) return;   // numpy would raise; never write out of bounds
+  const int64_t v = ((int64_t)cx * Y + cy) * Z + cz;
   if (label_vol && label) label_vol[v] = (uint8_t)label[i];
   if (proba_vol && proba) {
 #pragma unroll
@@ -479,7 +483,7 @@ int launch_scatter(sc_ctx* ctx, const int32_t* xyz, int64_t n, const int32_t* la
                    const int32_t* dims, uint8_t* label_vol, float* proba_vol, cudaStream_t st) {
   if (n == 0) return SC_OK;
   ProfScope prof(ctx, PC_SCATTER, st);
-  scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, n, label, proba, dims[1], dims[2], label_vol,
+  scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, n, label, proba, dims[0], dims[1], dims[2], label_vol,
                                                               proba_vol);
   ctx->launches++;
   SC_CUDA(cudaGetLastError());

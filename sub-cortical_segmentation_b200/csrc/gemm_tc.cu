@@ -11,22 +11,16 @@
 // Activations and weights are stored per 64-wide k block as 64 bf16 hi | 64 bf16 lo, i.e. exactly
 // the bytes of the fp32 row, so one 128 B swizzle row holds one block half.
 //
-// Three kernels share this file (default pipeline: tc_variant = 3):
-//   gemm_tc_pair_kernel        CTA pairs (cta_group::2, M = 256): d1, FC1 (+ atlas prior columns), fc_2 -- the hot ones
-//   gemm_tc_persistent_kernel  one persistent CTA per SM: the 16-column out_layer GEMM with the softmax / argmax epilogue,
-//                              and the flattened-map conv layers of the pre-sweep pipeline (tc_sweep45 = 0)
-//   gemm_tc_kernel             the first, one-tile-per-CTA version described below (tc_variant = 1), kept as a cross-check
-// (conv2..conv5 of the default pipeline live in conv_sweep.cu.)
-//
-// gemm_tc_kernel: one CTA = one 128-row x BN-column output tile, 192 threads:
-//   warp 0   TMA producer: per k block four tiled loads into one shared-memory stage -- A hi and
-//            A lo (4-D box 64 bf16 x 128 pixels, tap shift applied to the pixel/line coordinates,
-//            zero fill outside) and W hi and W lo (2-D box 64 x BN)
-//   warp 1   allocates TMEM; one lane issues 12 x tcgen05.mma (M=128, N=BN, K=16) per stage,
-//            tcgen05.commit releases the stage / signals the accumulator
-//   warps 2-5 epilogue: tcgen05.ld 32x32b.x16 -> bias + PReLU -> plain fp32 or split bf16 rows
-// Two CTAs are co-resident per SM (<= 256 TMEM columns and <= 112 KB shared memory each) so that
-// one tile's loads / epilogue overlap the other's MMAs.
+// Two kernels share this file:
+//   gemm_tc_pair_kernel        CTA pairs (cta_group::2, M = 256): tiles of >= 128 columns -- d1, FC1 (+ atlas prior
+//                              columns), fc_2, the dense layers of the training step: the hot ones
+//   gemm_tc_persistent_kernel  one persistent CTA per SM (M = 128): narrow layers -- the 16-column out_layer GEMM with the
+//                              softmax / argmax epilogue
+// Both: warp 0 = TMA producer (per k block A hi, A lo as 4-D boxes of 64 bf16 x 128 pixels with the tap shift applied to
+// the pixel / line / plane coordinates and zero fill outside, W hi, W lo as 2-D boxes), warp 1 = converged MMA issue
+// (12 x tcgen05.mma K=16 per k block), the other warps = epilogue (tcgen05.ld -> scale / bias / PReLU -> plain fp32 or
+// split bf16 rows); two TMEM accumulators so that the epilogue of tile i overlaps the main loop of tile i + 1.
+// (conv2..conv5 live in conv_sweep.cu.)
 #include "tc_common.cuh"
 
 namespace sc {
@@ -34,8 +28,6 @@ namespace sc {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                    // logical k per block (64 bf16 = one 128 B swizzle row)
 constexpr int TC_A_HALF = TC_BM * 128;       // bytes of the hi (or lo) half of an A stage
-constexpr int TC_THREADS = 192;
-constexpr int TC_TMEM_COLS = 256;
 
 struct TcArgs {
   int kpt;            // k-blocks per tap (kc / 64)
@@ -57,18 +49,7 @@ struct TcArgs {
   int out_split;
   // persistent variant
   long long num_tiles;
-  int w_resident;     // all weight k-blocks stay in shared memory for the CTA's lifetime (conv layers)
-  int kx_reuse;       // 0: one A load per tap; 1/2: one (128+2d)-pixel A load per filter row, the three column taps
-                      // are descriptor start offsets (2: with the descriptor's base_offset field set)
-  int dil;            // tap_dx step (pixels) in kx_reuse mode
-  int a_half;         // bytes reserved for one A half-stage (hi or lo), multiple of 1024
-  int a_tx;           // bytes one A half-load actually delivers (box rows * 128)
-  int zero_to;        // columns [bn, zero_to) of the single column tile are written as zeros (channel padding)
-  int ksteps;         // 16-wide k steps actually issued per 64-wide block (conv layers: ceil(Cin/16); the rest is zero padding)
-  int nacc;           // independent accumulator chains per tile (narrow tiles: back-to-back MMAs into one TMEM tile serialise)
-  int epi_warps;      // epilogue warps of the persistent kernel (4, 8 or 16)
-  int fuse_w;         // narrow tiles: xh * [wh | wl] as ONE MMA of 2*bn columns (the epilogue adds the halves) + xl * wh:
-                      // two instead of three MMAs and A shared-memory reads per product
+  int epi_warps;      // epilogue warps (4, 8 or 16)
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
   const int* rowmap;  // pair kernel, split stores: C row of dense row r = rowmap[r] (skip when < 0); ldc / c_ys / c_zs then count ROWS
   const int* rowvox;  // pair kernel, atlas epilogue: slab row of compact row m
@@ -81,139 +62,10 @@ struct TcArgs {
   SoftmaxOut sm;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  // carve: [stages x (A hi | A lo | W hi | W lo)][barriers][tmem ptr][bias][alpha]
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024 B aligned, still a shared-space pointer
-  const int b_half = a.bn * 128;
-  const int stage_bytes = 2 * TC_A_HALF + 2 * b_half;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + a.stages;
-  uint64_t* accum = bars + 2 * a.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
-  float* s_alpha = s_bias + 192;
-  float* s_scale = s_alpha + 192;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long bid = blockIdx.x;
-  const int n_tile = (int)(bid % a.nt); bid /= a.nt;
-  const int m_tile = (int)(bid % a.mt); bid /= a.mt;
-  const int y = (int)(bid % a.Y);
-  const int z = (int)(bid / a.Y);
-  const int m0 = m_tile * TC_BM, n0 = n_tile * a.bn;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(accum, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  for (int i = threadIdx.x; i < a.bn; i += TC_THREADS) {
-    s_bias[i] = n0 + i < a.npad ? __ldg(a.bias + n0 + i) : 0.f;
-    s_alpha[i] = n0 + i < a.npad ? __ldg(a.alpha + n0 + i) : 1.f;
-    s_scale[i] = (a.scale && n0 + i < a.npad) ? __ldg(a.scale + n0 + i) : 1.f;
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
-      for (int kb = 0; kb < a.nkb; ++kb) {
-        const int s = kb % a.stages, it = kb / a.stages;
-        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-        mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-        uint8_t* st = smem + s * stage_bytes;
-        const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;   // bf16 element offset of the block's hi half
-        const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0 + a.tap_dz[tap];
-        tma_load_4d(&mapA, &full[s], st, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
-        tma_load_4d(&mapA, &full[s], st + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
-        tma_load_2d(&mapB, &full[s], st + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
-        tma_load_2d(&mapB, &full[s], st + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=BF16, both K-major, N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < a.nkb; ++kb) {
-        const int s = kb % a.stages, it = kb / a.stages;
-        mbar_wait(&full[s], it & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = smem_u32(smem + s * stage_bytes);
-        const uint64_t ah = umma_desc(st), al = umma_desc(st + TC_A_HALF);
-        const uint64_t wh = umma_desc(st + 2 * TC_A_HALF), wl = umma_desc(st + 2 * TC_A_HALF + b_half);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {  // 4 x K=16 bf16 (32 B) inside the 128 B swizzle row; small terms first
-          const uint64_t o = (uint64_t)(j * 2);
-          umma_bf16(tmem_base, al + o, wh + o, idesc, (kb | j) != 0);
-          umma_bf16(tmem_base, ah + o, wl + o, idesc, 1);
-          umma_bf16(tmem_base, ah + o, wh + o, idesc, 1);
-        }
-        umma_commit(&empty[s]);
-      }
-      umma_commit(accum);
-    }
-    __syncwarp();
-  } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int q = warp & 3;
-    mbar_wait(accum, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + q * 32 + lane;
-    float* crow = a.C + (long long)z * a.c_zs + (long long)y * a.c_ys + (long long)m * a.ldc;
-    const bool row_ok = m < a.M;
-    for (int c0 = 0; c0 < a.bn; c0 += 16) {
-      uint32_t r[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row_ok) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + c0 + g * 4;
-          if (n < a.n_store) {
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = c0 + g * 4 + k;
-              v[k] = prelu(fmaf(__uint_as_float(r[g * 4 + k]), s_scale[c], s_bias[c]), s_alpha[c]);
-            }
-            store_row4(crow, a.c_col0 + n, a.out_split, v[0], v[1], v[2], v[3]);
-          }
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).
-//   * shared-memory ring of A (+W) stages fed by TMA, decoupled from the MMA warp by full/empty mbarriers
+// Persistent kernel: one CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).
+//   * shared-memory ring of A + W stages fed by TMA, decoupled from the MMA warp by full/empty mbarriers
 //   * two TMEM accumulators (columns 0.. and 256..): the epilogue of tile i overlaps the main loop of tile i+1
-//   * conv layers keep all 9 x (hi|lo) weight blocks resident in shared memory (144 KB), loaded once
-//   * optional kx-reuse: one (128+2d)-pixel A box per filter row serves the three column taps
 // ---------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(576, 1)
@@ -222,27 +74,22 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024 B aligned, still a shared-space pointer
   const int b_half = a.bn * 128;
   const int w_block = 2 * b_half;                               // hi | lo of one 64-wide k block of W
-  const int w_res_bytes = a.w_resident ? a.nkb * w_block : 0;
-  const int stage_bytes = 2 * a.a_half + (a.w_resident ? 0 : w_block);
-  uint8_t* sW = smem;
-  uint8_t* sStage = smem + w_res_bytes;
+  const int stage_bytes = 2 * TC_A_HALF + w_block;
+  uint8_t* sStage = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + a.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + a.stages;
   uint64_t* tfull = bars + 2 * a.stages;     // [2] accumulator ready
   uint64_t* tempty = tfull + 2;              // [2] accumulator drained
-  uint64_t* wfull = tempty + 2;              // resident weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
-  float* s_const = reinterpret_cast<float*>(tmem_slot + 2);   // [2 buffers][bias bn | alpha bn | scale bn]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_const = reinterpret_cast<float*>(tmem_slot + 4);   // [2 buffers][bias bn | alpha bn | scale bn], 16 B aligned (float4 loads)
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + 2 * 3 * a.bn);   // [epilogue warps][32 rows][80 B] store-transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int steps_per_tile = a.kx_reuse ? 3 : a.nkb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], (blockDim.x >> 5) - 2); }
-    mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -258,13 +105,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
-      if (a.w_resident) {
-        mbar_expect_tx(wfull, (uint32_t)w_res_bytes);
-        for (int kb = 0; kb < a.nkb; ++kb) {
-          tma_load_2d(&mapB, wfull, sW + kb * w_block, kb * 2 * TC_BK, 0);
-          tma_load_2d(&mapB, wfull, sW + kb * w_block + b_half, kb * 2 * TC_BK + TC_BK, 0);
-        }
-      }
       uint32_t it = 0;   // global stage-use counter
       long long dbg_acc[1] = {0};
       const long long tstart = a.dbg ? clock64() : 0;
@@ -275,7 +115,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         const int y = (int)(r % a.Y);
         const int z = (int)(r / a.Y);
         const int m0 = m_tile * TC_BM, n0 = n_tile * a.bn;
-        for (int st = 0; st < steps_per_tile; ++st, ++it) {
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
           const int s = it % a.stages;
           const uint32_t use = it / a.stages;
           if (use > 0) {
@@ -283,17 +123,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             mbar_wait(&empty[s], (use - 1) & 1);
             if (a.dbg) dbg_acc[0] += clock64() - c0;
           }
-          mbar_expect_tx(&full[s], (uint32_t)(2 * a.a_tx + (a.w_resident ? 0 : w_block)));
+          mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
           uint8_t* sp = sStage + s * stage_bytes;
-          const int kb = a.kx_reuse ? st * 3 : st;                 // first weight block of this step
           const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
           const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0 + a.tap_dz[tap];
           tma_load_4d(&mapA, &full[s], sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
-          tma_load_4d(&mapA, &full[s], sp + a.a_half, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
-          if (!a.w_resident) {
-            tma_load_2d(&mapB, &full[s], sp + 2 * a.a_half, kb * 2 * TC_BK, n0);
-            tma_load_2d(&mapB, &full[s], sp + 2 * a.a_half + b_half, kb * 2 * TC_BK + TC_BK, n0);
-          }
+          tma_load_4d(&mapA, &full[s], sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
+          tma_load_2d(&mapB, &full[s], sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
+          tma_load_2d(&mapB, &full[s], sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
         }
       }
       if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = (unsigned long long)dbg_acc[0]; a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - tstart); }
@@ -303,11 +140,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     // whole warp converged; one elected lane issues (see umma_bf16_elect)
     const uint32_t leader = elect_one();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 2) << 17) | ((uint32_t)(TC_BM >> 4) << 24);  // N = 2*bn
-    if (a.w_resident) mbar_wait(wfull, 0);
-    const uint32_t sW_u = smem_u32(sW), sStage_u = smem_u32(sStage);
-    const int nsub = a.kx_reuse ? 3 : 1;
-    const uint64_t shift_step = a.kx_reuse ? (uint64_t)(a.dil * 8) : 0ull;   // dil pixels * 128 B, in 16 B descriptor units
+    const uint32_t sStage_u = smem_u32(sStage);
     uint32_t it = 0, ti = 0;
     long long w_full = 0, w_tempty = 0;
     const long long tstart = a.dbg ? clock64() : 0;
@@ -318,32 +151,21 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       if (a.dbg) w_tempty += clock64() - c0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + b * 256;
-      for (int st = 0; st < steps_per_tile; ++st, ++it) {
+      for (int kb = 0; kb < a.nkb; ++kb, ++it) {
         const int s = it % a.stages;
         c0 = a.dbg ? clock64() : 0;
         mbar_wait(&full[s], (it / a.stages) & 1);
         if (a.dbg) w_full += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sp = sStage_u + s * stage_bytes;
-        const uint64_t ah0 = umma_desc(sp), al0 = umma_desc(sp + a.a_half);
-        uint32_t wp = a.w_resident ? sW_u + (a.kx_reuse ? st * 3 : st) * w_block : sp + 2 * a.a_half;
-        uint64_t shift = 0;                                     // kx-reuse: operand starts sub*dil pixels (x 128 B >> 4) into the box
-        for (int sub = 0; sub < nsub; ++sub, wp += w_block, shift += shift_step) {
-          const uint64_t ah = ah0 + shift, al = al0 + shift;
-          const uint64_t wh = umma_desc(wp), wl = umma_desc(wp + b_half);
+        const uint64_t ah = umma_desc(sp), al = umma_desc(sp + TC_A_HALF);
+        const uint64_t wh = umma_desc(sp + 2 * TC_A_HALF), wl = umma_desc(sp + 2 * TC_A_HALF + b_half);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t o = (uint64_t)(j * 2);
-            const uint32_t on = (leader && j < a.ksteps) ? 1u : 0u;
-            if (a.fuse_w) {   // [wh | wl] are adjacent row blocks of the weight stage: one descriptor, N = 2*bn
-              umma_bf16_elect(acc, ah + o, wh + o, idesc2, (st | sub | j) != 0, on);
-              umma_bf16_elect(acc, al + o, wh + o, idesc, 1, on);
-            } else {
-              umma_bf16_elect(acc, al + o, wh + o, idesc, (st | sub | j) != 0, on);
-              umma_bf16_elect(acc, ah + o, wl + o, idesc, 1, on);
-              umma_bf16_elect(acc, ah + o, wh + o, idesc, 1, on);
-            }
-          }
+        for (int j = 0; j < 4; ++j) {   // 4 x K=16 bf16 (32 B) inside the 128 B swizzle row; small terms first
+          const uint64_t o = (uint64_t)(j * 2);
+          umma_bf16_elect(acc, al + o, wh + o, idesc, (kb | j) != 0, leader);
+          umma_bf16_elect(acc, ah + o, wl + o, idesc, 1, leader);
+          umma_bf16_elect(acc, ah + o, wh + o, idesc, 1, leader);
         }
         if (leader) umma_commit(&empty[s]);
         __syncwarp();
@@ -459,17 +281,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
               "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (a.fuse_w) {                                 // second half of the fused accumulator: xh * wl
-          uint32_t r2[16];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]), "=r"(r2[8]),
-                "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
-              : "r"(taddr + (uint32_t)a.bn));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(__uint_as_float(rr[k]) + __uint_as_float(r2[k]));
-        }
         if (n0 + c0 >= a.n_store) continue;             // warp-uniform
         float v[16];
 #pragma unroll
@@ -519,19 +330,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
-      // channel padding of the conv maps: zeros, same coalesced mapping (split layout only)
-      for (int c0 = a.bn + grp * 16; c0 < a.zero_to; c0 += 16 * G) {
-        const int ncol = a.c_col0 + c0;
-        const int boff = (ncol >> 6) * 128 + (ncol & 63);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int half = i >> 1, row = (i & 1) * 16 + (lane >> 1), part = lane & 1;
-          if (mw + row < a.M) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ctile + (long long)(mw + row) * a.ldc) + boff + half * 64 + part * 8;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-      }
     }
     if (a.dbg && threadIdx.x == 64) {
       a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - tstart);
@@ -554,12 +352,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
 //   * the leader's MMA warp issues tcgen05.mma.cta_group::2 (M = 256) and multicasts its commits to both CTAs
 //   * every CTA's epilogue warps drain their own TMEM half and arrive on the leader's tempty barrier (remote arrive)
 // ---------------------------------------------------------------------------------------------------
-// MC = true (FC1, fc_2): a cluster holds one CTA pair per n-tile of the SAME 256 rows; the A blocks are loaded once and
-// multicast to all pairs (the L2 -> SM fabric, not the tensor pipe, bounds these GEMMs); plain (cta_group::1) loads complete
-// bytes on every CTA's own full barrier, the non-leader's idle MMA warp relays its barrier to the leader, and the leaders'
-// commits release a ring slot in every CTA of the cluster.
-template <bool MC>
-__device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcArgs& a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int hb = a.bn >> 1;                               // weight rows held by this CTA
@@ -571,26 +365,17 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
   uint64_t* empty = bars + a.stages;                      // per CTA, arrived by the leader's multicast commit
   uint64_t* tfull = bars + 2 * a.stages;                  // [2] per CTA
   uint64_t* tempty = tfull + 2;                           // [2] leader only: both CTAs' epilogue warps arrive
-  uint64_t* pfull = tempty + 2;                           // [stages] MC, leader only: the peer's stage has landed (relayed)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + a.stages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_const = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 loads of the constants
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + (a.nt > 2 ? a.nt : 2) * 3 * a.bn);   // constants of every n-tile (<= 4) stay resident
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();
-  const uint32_t rank = crank & 1;                          // position inside the CTA pair
-  const uint32_t pi = crank >> 1, lead = crank & ~1u;      // pair index inside the cluster (MC: = n-tile), leader's cluster rank
+  const uint32_t rank = cluster_ctarank();                 // position inside the CTA pair; rank 0 leads
   const int nepi = (blockDim.x >> 5) - 2;
-  const int csz = MC ? 2 * a.nt : 2;
-  // MC: the cluster walks the m-tiles, pair pi takes n-tile pi of each; otherwise every pair walks the flat tile list
-  const long long pair = MC ? (long long)(blockIdx.x / csz) * a.nt + pi : (long long)(blockIdx.x >> 1);
-  const long long npairs = MC ? (long long)(gridDim.x / csz) * a.nt : (long long)(gridDim.x >> 1);
-  const uint16_t all_mask = (uint16_t)((1u << csz) - 1), pair_mask = (uint16_t)(3u << (2 * pi));
-  uint16_t a_mask = 0;                                      // MC: the CTAs holding the same 128 rows of A
-  for (int j = 0; j < (MC ? a.nt : 0); ++j) a_mask |= (uint16_t)(1u << (2 * j + rank));
+  const long long pair = (long long)(blockIdx.x >> 1), npairs = (long long)(gridDim.x >> 1);   // every pair walks the flat tile list
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MC ? a.nt : 1); mbar_init(&pfull[s], 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * nepi); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -631,20 +416,12 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
           uint8_t* sp = sStage + s * stage_bytes;
           const int tap = kb / a.kpt, ka = (kb - tap * a.kpt) * 2 * TC_BK;
           const int px = m0 + a.tap_dx[tap], ln = y + a.a_y0 + a.tap_dy[tap], pl = z + a.a_z0 + a.tap_dz[tap];
-          if (MC) {
-            mbar_expect_tx(&full[s], (uint32_t)stage_bytes);            // this CTA's own stage: A hi + lo (multicast) + its W halves
-            tma_load_2d(&mapB, &full[s], sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
-            tma_load_2d(&mapB, &full[s], sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
-            if (pi == 0) tma_load_4d_mc(&mapA, &full[s], sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl, a_mask);
-            if (pi == 1) tma_load_4d_mc(&mapA, &full[s], sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl, a_mask);
-          } else {
-            const uint32_t lbar = smem_u32(&full[s]) & 0xFEFFFFFFu;    // the leader's barrier (peer bit cleared)
-            if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));   // both CTAs' bytes land on it
-            tma_load_4d_2sm(&mapA, lbar, sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
-            tma_load_4d_2sm(&mapA, lbar, sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
-            tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
-            tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
-          }
+          const uint32_t lbar = smem_u32(&full[s]) & 0xFEFFFFFFu;    // the leader's barrier (peer bit cleared)
+          if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));   // both CTAs' bytes land on it
+          tma_load_4d_2sm(&mapA, lbar, sp, ka, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
+          tma_load_4d_2sm(&mapA, lbar, sp + TC_A_HALF, ka + TC_BK, px, a.a_swap ? pl : ln, a.a_swap ? ln : pl);
+          tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF, kb * 2 * TC_BK, n0);
+          tma_load_2d_2sm(&mapB, lbar, sp + 2 * TC_A_HALF + b_half, kb * 2 * TC_BK + TC_BK, n0);
         }
       }
       if (a.dbg && rank == 0) { a.dbg[pair * 8 + 0] = (unsigned long long)w_empty; a.dbg[pair * 8 + 1] = (unsigned long long)(clock64() - tstart); }
@@ -673,7 +450,6 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
           const int s = it % a.stages;
           c0 = a.dbg ? clock64() : 0;
           mbar_wait(&full[s], (it / a.stages) & 1);
-          if (MC) mbar_wait(&pfull[s], (it / a.stages) & 1);           // the peer CTA's stage (relayed by its warp 1)
           if (a.dbg) w_full += clock64() - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sp = sStage_u + s * stage_bytes;
@@ -686,28 +462,16 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
             umma_bf16_2sm_elect(acc, ah + o, wl + o, idesc, 1, leader);
             umma_bf16_2sm_elect(acc, ah + o, wh + o, idesc, 1, leader);
           }
-          if (leader) umma_commit_2sm(&empty[s], MC ? all_mask : pair_mask);
+          if (leader) umma_commit_2sm(&empty[s]);
           __syncwarp();
         }
-        if (leader) umma_commit_2sm(&tfull[b], pair_mask);
+        if (leader) umma_commit_2sm(&tfull[b]);
         __syncwarp();
         ++ti;
       }
       if (a.dbg && leader) {
         a.dbg[pair * 8 + 2] = (unsigned long long)w_full; a.dbg[pair * 8 + 3] = (unsigned long long)w_tempty;
         a.dbg[pair * 8 + 4] = (unsigned long long)(clock64() - tstart);
-      }
-    } else if (MC) {
-      // relay: tell the leader when this CTA's stage has landed (its own full barrier counts only its own bytes)
-      uint32_t it = 0;
-      for (long long t = pair; t < a.num_tiles; t += npairs) {
-        if (a.tile_on && !a.tile_on[t]) continue;
-        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-          const int s = it % a.stages;
-          mbar_wait(&full[s], (it / a.stages) & 1);
-          if (lane == 0) mbar_arrive_cta(&pfull[s], lead);
-          __syncwarp();
-        }
       }
     }
   } else {
@@ -841,7 +605,7 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive_cta(&tempty[b], lead);  // the leader's MMA warp owns the accumulator hand-off
+      if (lane == 0) mbar_arrive_cta(&tempty[b], 0);     // the leader's MMA warp owns the accumulator hand-off
       ++ti;
     }
     if (a.dbg && rank == 0 && threadIdx.x == 64) {
@@ -856,16 +620,6 @@ __device__ __forceinline__ void gemm_tc_pair_body(const CUtensorMap& mapA, const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
-gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
-  gemm_tc_pair_body<false>(mapA, mapB, a);
-}
-// cluster size 2 * nt is set at launch
-__global__ void __launch_bounds__(576, 1)
-gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
-  gemm_tc_pair_body<true>(mapA, mapB, a);
 }
 
 // plain fp32 [rows][576] -> split bf16 hi|lo blocks (test entry sc_dense_layer only)
@@ -950,25 +704,15 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   a.atlas = p.atlas; a.ageo = p.ageo;
   a.rowmap = p.rowmap; a.rowvox = p.rowvox; a.crow_ld = 0; a.tile_on = nullptr;
   if (p.sm) {
-    SC_CHECK(ctx->tc_variant != 1 && p.n_store == 16 && p.ntaps == 1, SC_ERR_ARG, "gemm_tc: the softmax epilogue needs the persistent kernel and a 16-column layer");
+    SC_CHECK(p.n_store == 16 && p.ntaps == 1, SC_ERR_ARG, "gemm_tc: the softmax epilogue needs a 16-column layer");
     a.bn = 16; a.sm_on = 1; a.sm = *p.sm;
   }
-  a.zero_to = 0;
-  if (ctx->tc_variant != 1 && p.ntaps == 9 && w.N < p.n_store && p.n_store <= 64) {
-    // conv layers: compute only the real output channels (rounded to 16), zero-fill the channel padding;
-    // the narrower resident weight block leaves room for more A stages
-    a.bn = (w.N + 15) & ~15;
-    a.zero_to = p.n_store;
-  }
   a.nt = (p.n_store + a.bn - 1) / a.bn;
-  if (a.zero_to) a.nt = 1;
   a.mt = (p.M + TC_BM - 1) / TC_BM;
-  a.Y = p.Y; a.M = p.M; a.n_store = a.zero_to ? a.bn : p.n_store; a.npad = w.Npad;
-  if (ctx->tc_variant != 1) {
-    a.n_store = (a.n_store + 15) & ~15;   // whole 16-column chunks: the caller lets pad columns be overwritten with zeros
-    if (p.atlas) a.n_store = 576;
-    SC_CHECK(p.c_col0 % 16 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 16 for the persistent kernel");
-  }
+  a.Y = p.Y; a.M = p.M; a.npad = w.Npad;
+  a.n_store = (p.n_store + 15) & ~15;     // whole 16-column chunks: the caller lets pad columns be overwritten with zeros
+  if (p.atlas) a.n_store = 576;
+  SC_CHECK(p.c_col0 % 16 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 16");
   a.a_y0 = p.a_y0; a.a_z0 = p.a_z0; a.a_swap = p.a_swap;
   for (int t = 0; t < 9; ++t) { a.tap_dx[t] = t < p.ntaps ? p.tap_dx[t] : 0; a.tap_dy[t] = t < p.ntaps ? p.tap_dy[t] : 0; a.tap_dz[t] = t < p.ntaps ? p.tap_dz[t] : 0; }
   a.C = p.C; a.ldc = p.ldc; a.c_ys = p.c_ys; a.c_zs = p.c_zs;
@@ -977,22 +721,15 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.crow_ld = kFeatLd; a.ldc = p.ldc / kFeatLd; a.c_ys = p.c_ys / kFeatLd; a.c_zs = p.c_zs / kFeatLd;
   }
   a.bias = w.bias; a.alpha = w.alpha; a.scale = w.scale; a.out_split = p.out_split;
-  SC_CHECK(p.c_col0 % 4 == 0, SC_ERR_ARG, "gemm_tc: c_col0 must be a multiple of 4");
-  const bool persistent = ctx->tc_variant != 1;
-  // CTA pairs (cta_group::2) for the wide streaming-weight layers
-  const bool pair = ctx->tc_variant == 3 && a.bn >= 128 && a.bn % 16 == 0 && !(p.ntaps == 9 && a.nkb * 2 * a.bn * 128 <= 150 * 1024);
+  // CTA pairs (cta_group::2) for the wide streaming-weight tiles, the persistent single-CTA kernel for the narrow ones
+  const bool pair = a.bn >= 128 && a.bn % 16 == 0 && !p.sm;
   SC_CHECK(!p.rowmap || pair, SC_ERR_ARG, "gemm_tc: the row map is implemented in the CTA-pair kernel");
   SC_CHECK(!p.atlas || (pair && p.c_col0 == 0 && p.n_store == 540 && w.Npad == 576), SC_ERR_ARG, "gemm_tc: the atlas epilogue is for FC1 in the CTA-pair kernel");
   const long long blocks = (long long)a.mt * a.nt * p.Y * p.Z;
   SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
   a.num_tiles = blocks;
-  a.w_resident = 0; a.kx_reuse = 0; a.dil = 0; a.a_half = TC_A_HALF; a.a_tx = TC_A_HALF;
-  a.ksteps = 4;
-  if (p.ntaps == 9 && a.kpt == 1 && p.k_used > 0) a.ksteps = (p.k_used + 15) / 16;
-  a.nacc = 1; a.epi_warps = 4;
-  a.fuse_w = (ctx->tc_variant != 1 && p.ntaps == 9 && a.nt == 1 && 2 * a.bn <= 256 && ctx->tc_fuse_w) ? 1 : 0;
   a.dbg = (ctx->tc_timing_cls == p.prof_cls) ? ctx->tc_timing_buf : nullptr;
-  int stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
+  int stage_bytes;
   size_t smem = 0;
   if (pair) {
     a.mt = (p.M + 255) / 256;
@@ -1005,29 +742,15 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     a.stages = budget / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: pair tile too wide");
-    smem = 1024 + (size_t)a.stages * stage_bytes + (3 * a.stages + 4) * 8 + 32 + cst + (size_t)a.epi_warps * 2560;
-  } else if (!persistent) {
-    a.stages = (108 * 1024) / stage_bytes;
-    if (a.stages > 4) a.stages = 4;
-    SC_CHECK(a.stages >= 1, SC_ERR_ARG, "gemm_tc: tile too wide for one stage");
-    smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 3 * 192 * 4;
+    smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 4) * 8 + 32 + cst + (size_t)a.epi_warps * 2560;
   } else {
-    // epilogue warps: 16 for wide tiles, 8 for conv tiles, 4 when the resident weights leave no room (conv5)
-    int epi_warps = a.bn > 64 ? 16 : 8;
-    if (p.ntaps == 9 && a.nt == 1 && a.nkb * 2 * a.bn * 128 + 2 * 2 * 17408 + 2 * 3 * a.bn * 4 + 1168 + epi_warps * 2560 > 227 * 1024 - 1024)
-      epi_warps = 4;
-    a.epi_warps = epi_warps;
-    const int budget = 227 * 1024 - 1024 - 128 - 16 - 2 * 3 * a.bn * 4 - epi_warps * 2560;   // alignment slack, barriers, epilogue constants, store tiles
-    const int w_all = a.nkb * 2 * a.bn * 128;
-    a.w_resident = (a.nt == 1 && p.ntaps == 9 && w_all + 2 * 2 * 17408 <= budget) ? 1 : 0;
-    if (a.w_resident && ctx->tc_kx_reuse && a.kpt == 1 && p.tap_dx[1] > 0 && p.tap_dx[2] == 2 * p.tap_dx[1] && p.tap_dx[1] <= 4) {
-      a.kx_reuse = ctx->tc_kx_reuse; a.dil = p.tap_dx[1]; a.a_half = 17408; a.a_tx = (TC_BM + 2 * a.dil) * 128;
-    }
-    stage_bytes = 2 * a.a_half + (a.w_resident ? 0 : 2 * a.bn * 128);
-    a.stages = (budget - (a.w_resident ? w_all : 0)) / stage_bytes;
+    a.epi_warps = a.bn > 64 ? 16 : 8;
+    const int budget = 227 * 1024 - 1024 - 128 - 16 - 2 * 3 * a.bn * 4 - a.epi_warps * 2560;   // alignment slack, barriers, epilogue constants, store tiles
+    stage_bytes = 2 * TC_A_HALF + 2 * a.bn * 128;
+    a.stages = budget / stage_bytes;
     if (a.stages > 6) a.stages = 6;
     SC_CHECK(a.stages >= 2, SC_ERR_ARG, "gemm_tc: tile too wide for two stages (bn=%d)", a.bn);
-    smem = 1024 + (size_t)(a.w_resident ? w_all : 0) + (size_t)a.stages * stage_bytes + (2 * a.stages + 5) * 8 + 16 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
+    smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 4) * 8 + 16 + 2 * 3 * a.bn * 4 + (size_t)a.epi_warps * 2560;
   }
 
   CUtensorMap mapA, mapB;
@@ -1035,7 +758,7 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     // a row of kc logical columns is 2*kc bf16 (hi | lo per 64-wide block)
     cuuint64_t dims[4] = {(cuuint64_t)p.a_dims[0] * 2, (cuuint64_t)p.a_dims[1], (cuuint64_t)p.a_dims[2], (cuuint64_t)p.a_dims[3]};
     cuuint64_t strides[3] = {(cuuint64_t)p.a_strides[0] * 4, (cuuint64_t)p.a_strides[1] * 4, (cuuint64_t)p.a_strides[2] * 4};
-    cuuint32_t box[4] = {TC_BK, (cuuint32_t)(a.kx_reuse ? TC_BM + 2 * a.dil : TC_BM), 1, 1};
+    cuuint32_t box[4] = {TC_BK, TC_BM, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = s->encode(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<float*>(p.a_base), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1053,14 +776,9 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
-  static bool configured = false;
-  if (!configured) {
-    SC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    SC_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SC_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SC_CUDA(cudaFuncSetAttribute(gemm_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(gemm_tc_persistent_kernel), 227 * 1024));
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(gemm_tc_pair_kernel), 227 * 1024));
+  SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
   ProfScope prof(ctx, p.prof_cls, st);
   a.n_mma = a.nt * a.bn;
   if (pair && p.ntaps == 1) {
@@ -1081,32 +799,10 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
     ctx->launches++;
     a.tile_on = ctx->tile_flags;
   }
-  // multicast clusters: plain row GEMMs with 2 or 3 n-tiles (fc_2, FC1): one CTA pair per n-tile, A loaded once per cluster
-  const bool mc = pair && ctx->tc_mc && p.ntaps == 1 && p.Y == 1 && p.Z == 1 && (a.nt == 2 || a.nt == 3) && a.mt >= 1;
-  if (mc) {
-    SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
-    const int csz = 2 * a.nt;
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(64 + 32 * a.epi_warps); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.gridDim = dim3(csz);
-    int max_clusters = 0;
-    SC_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_tc_mc_kernel, &cfg));
-    SC_CHECK(max_clusters >= 1, SC_ERR_CUDA, "gemm_tc: no cluster of %d CTAs fits", csz);
-    long long ncl = a.mt < max_clusters ? a.mt : max_clusters;
-    cfg.gridDim = dim3((unsigned)(ncl * csz));
-    SC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_mc_kernel, mapA, mapB, a));
-  } else if (pair) {
-    SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
+  if (pair) {
     long long pairs = a.num_tiles < ctx->sm_count / 2 ? a.num_tiles : ctx->sm_count / 2;
     gemm_tc_pair_kernel<<<(unsigned)(2 * pairs), 64 + 32 * a.epi_warps, smem, st>>>(mapA, mapB, a);   // __cluster_dims__(2,1,1)
-  } else if (!persistent) {
-    SC_CHECK(smem <= 112 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
-    gemm_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, st>>>(mapA, mapB, a);
   } else {
-    SC_CHECK(smem <= 227 * 1024, SC_ERR_ARG, "gemm_tc: shared memory budget exceeded (%zu)", smem);
     const unsigned grid = (unsigned)(blocks < ctx->sm_count ? blocks : ctx->sm_count);
     gemm_tc_persistent_kernel<<<grid, 64 + 32 * a.epi_warps, smem, st>>>(mapA, mapB, a);
   }

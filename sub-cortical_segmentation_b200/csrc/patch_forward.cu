@@ -211,11 +211,7 @@ __global__ void __launch_bounds__(256) branch_patch_kernel(const float* __restri
 
 int launch_branch_patches(sc_ctx* ctx, int b, const float* patches, int64_t n, float* c5_out, cudaStream_t st) {
   if (n == 0) return SC_OK;
-  static bool configured = false;
-  if (!configured) {
-    SC_CUDA(cudaFuncSetAttribute(branch_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATCH_SMEM));
-    configured = true;
-  }
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(branch_patch_kernel), (int)PATCH_SMEM));
   PatchW W;
   W.c1_w = ctx->br[b].c1_w;
   for (int l = 0; l < 5; ++l) {

@@ -248,7 +248,7 @@ __global__ void softmax_ce_kernel(const float* __restrict__ z, const uint8_t* __
     float v[15], mx = -INFINITY, s = 0.f;
 #pragma unroll
     for (int c = 0; c < 15; ++c) { v[c] = z[i * 15 + c]; mx = fmaxf(mx, v[c]); }
-    const int t = y[i];
+    const int t = y[i] < 15 ? y[i] : 0;   // raw label 15 (the boundary ring, base.py:89 maps it to 0) never indexes out of bounds
     const float zt = z[i * 15 + t] - mx;
 #pragma unroll
     for (int c = 0; c < 15; ++c) { v[c] = expf(v[c] - mx); s += v[c]; }
@@ -468,8 +468,7 @@ static int launch_wgrad_tiled(sc_ctx* ctx, const float* in, int Cin, int inH, in
   if (PS > 1 && smem_f < red_f) smem_f = red_f;
   const size_t smem = smem_f * sizeof(float);
   auto kern = conv_wgrad_tiled_kernel<COUT, PS>;
-  static size_t configured = 0;
-  if (smem > configured) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), (int)smem));
   // samples per CTA: ~2 000 pixels of reduction each, but never fewer than ~2 CTAs per SM
   int spc = 2048 / (H * H);
   const int fill = (n * (Cin / 20) + 2 * ctx->sm_count - 1) / (2 * ctx->sm_count);
@@ -564,8 +563,7 @@ static int launch_tconv(sc_ctx* ctx, const float* in, int inR, int inLd, float* 
                         int cls, cudaStream_t st) {
   using Cfg = TConvCfg<CIN, COUT, NS, TH, SEG>;
   auto kern = train_conv_kernel<CIN, COUT, NS, TH, SEG>;
-  static bool configured = false;
-  if (!configured) { SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); configured = true; }
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), (int)Cfg::SMEM));
   dim3 grid((outLd + SEG * 8 - 1) / (SEG * 8), (outR + TH - 1) / TH, (n + NS - 1) / NS);
   ProfScope prof(ctx, cls, st);
   kern<<<grid, 320, Cfg::SMEM, st>>>(in, inR, inLd, out, outR, outLd, w, n);
@@ -812,8 +810,9 @@ __global__ void eval_reduce_kernel(const float* __restrict__ proba, const uint8_
     const float* p = proba + (int64_t)i * 15;
     int best = 0;
     for (int k = 1; k < 15; ++k) if (p[k] > p[best]) best = k;
-    l = -logf(fmaxf(p[y[i]], 1e-38f));
-    c = best == y[i] ? 1.f : 0.f;
+    const int t = y[i] < 15 ? y[i] : 0;
+    l = -logf(fmaxf(p[t], 1e-38f));
+    c = best == t ? 1.f : 0.f;
   }
   for (int o = 16; o; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
   if ((threadIdx.x & 31) == 0) { atomicAdd(out2, l); atomicAdd(out2 + 1, c); }

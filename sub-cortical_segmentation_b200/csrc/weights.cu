@@ -68,7 +68,7 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
   SC_CUDA(cudaStreamSynchronize(st));
 
   Arena A;
-  struct BOff { size_t c1, conv[5], scale[5], shift[5], alpha[5], sw[5], swp[5]; GemmOff d1, d1d, ctc[5]; } bo[3];
+  struct BOff { size_t c1, conv[5], scale[5], shift[5], alpha[5], sw[5], swp[5]; GemmOff d1, d1d; } bo[3];
   GemmOff fc1o, fc2o, outo;
   size_t outw, outb;
   for (int b = 0; b < 3; ++b) {
@@ -88,7 +88,6 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
       bo[b].scale[l] = A.alloc(64);
       bo[b].shift[l] = A.alloc(64);
       bo[b].alpha[l] = A.alloc(64);
-      if (l > 0) bo[b].ctc[l] = make_gemm(A, ctx->br[b].conv_tc[l], 9 * kC5Ld, co_n, 9 * kC5Ld, 64);
       if (l > 0) {   // strip-sweep kernel: k-step-packed weight panels, W hi rows then W lo rows
         SweepW& S = ctx->br[b].conv_sw[l];
         S.ksteps = (ci_n + 15) / 16; S.bn = (co_n + 15) & ~15; S.npanels = (9 * S.ksteps + 3) / 4;
@@ -118,14 +117,6 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
         A.host[bo[b].shift[l] + c] = beta - mean * s;
         A.host[bo[b].alpha[l] + c] = h[B.alpha[l] + c];
         if (l == 0) { ctx->br[b].c1_host.scale[c] = s; ctx->br[b].c1_host.shift[c] = beta - mean * s; ctx->br[b].c1_host.alpha[c] = h[B.alpha[l] + c]; }
-        if (l > 0) {
-          A.host[bo[b].ctc[l].scale + c] = s;
-          A.host[bo[b].ctc[l].bias + c] = beta - mean * s;
-          A.host[bo[b].ctc[l].alpha + c] = h[B.alpha[l] + c];
-          for (int ci = 0; ci < ci_n; ++ci)
-            for (int t = 0; t < 9; ++t)   // flipped taps (true convolution), k = tap*64 + ci
-              set_w(A, bo[b].ctc[l], ctx->br[b].conv_tc[l], t * kC5Ld + ci, c, h[B.convW[l] + ((size_t)c * ci_n + ci) * 9 + (8 - t)]);
-        }
       }
     }
     bo[b].d1 = make_gemm(A, ctx->br[b].d1, 540, 180, kFeatLd, 192);
@@ -184,7 +175,6 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
       ctx->br[b].shift[l] = base + bo[b].shift[l];
       ctx->br[b].alpha[l] = base + bo[b].alpha[l];
     }
-    for (int l = 1; l < 5; ++l) bind(ctx->br[b].conv_tc[l], bo[b].ctc[l], base);
     for (int l = 1; l < 5; ++l) {
       SweepW& S = ctx->br[b].conv_sw[l];
       S.panels = base + bo[b].sw[l]; S.panels_pair = base + bo[b].swp[l]; S.scale = ctx->br[b].scale[l]; S.shift = ctx->br[b].shift[l]; S.alpha = ctx->br[b].alpha[l];
