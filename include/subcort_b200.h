@@ -90,6 +90,28 @@ SC_API int sc_nonzero_coords(sc_ctx* ctx, const void* vol_dev, int elem_bytes, c
 SC_API int sc_dilate_mask(sc_ctx* ctx, const uint8_t* mask_dev, const int32_t dims[3], int iterations,
                    uint8_t* out_dev, void* stream);
 
+/* ---- scan preparation on the device ---------------------------------------------------
+ * replaces: the host-side head of load_patch_batch / test_scan (base.py:357-372).  A scan is uploaded once in the
+ * array order the NIfTI file has; everything up to the label volume stays on the device. */
+typedef enum { SC_DT_U8 = 1, SC_DT_I8, SC_DT_U16, SC_DT_I16, SC_DT_U32, SC_DT_I32, SC_DT_F32, SC_DT_F64 } sc_dtype;
+/* NIfTI (Fortran) order -> the C order used everywhere else: src is [channels][Z][Y][X] (x fastest, what nibabel's
+ * get_data() holds in memory), dst is [X][Y][Z][channels]; bit-preserving for elements of 1, 2, 4 or 8 bytes. */
+SC_API int sc_import_volume(sc_ctx* ctx, const void* src_dev, int elem_bytes, const int32_t dims[3], int channels,
+                     void* dst_dev, void* stream);
+/* replaces: image_norm = (image - image[np.nonzero(image)].mean()) / image[np.nonzero(image)].std() (base.py:358),
+ * cast to float32 as the patches are (base.py:383).  numpy's result bit for bit: same dtype promotion, same pairwise
+ * summation order (csrc/prep.cu).  vol_dev: C-ordered raw volume of `dtype`; out_dev float32 (NULL: statistics only);
+ * mean_std_host (nullable): the two scalars.  Synchronises the stream. */
+SC_API int sc_normalise_volume(sc_ctx* ctx, const void* vol_dev, int dtype, const int32_t dims[3], float* out_dev,
+                        double* mean_std_host, void* stream);
+/* replaces: image.astype('bool') (base.py:372) / the truth value scipy's binary_dilation takes of the registered mask
+ * (base.py:369): mask_dev[v] = vol[v] != 0 as uint8. */
+SC_API int sc_candidate_mask(sc_ctx* ctx, const void* vol_dev, int dtype, const int32_t dims[3], uint8_t* mask_dev, void* stream);
+/* half-open bounding box {x0,x1,y0,y1,z0,z1} and number of the non-zero voxels of a uint8 mask (all zeros when empty):
+ * the box sc_segment_volume restricts its convolutions to.  Synchronises the stream. */
+SC_API int sc_mask_bbox(sc_ctx* ctx, const uint8_t* mask_dev, const int32_t dims[3], int32_t box_host[6],
+                 int64_t* count_host, void* stream);
+
 /* ---- orthogonal patch gather ---------------------------------------------------------
  * replaces: get_patches x3 views (base.py:272-308) + the atlas vector with background fix
  * (base.py:387-394) of one load_patch_batch batch.  Outputs are [n][1][32][32] float32 per

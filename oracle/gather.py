@@ -19,11 +19,18 @@ def normalise(image, dtype=None):
     dtype the NIfTI holds (integer T1 -> float64, float32 T1 -> float32); the
     patches are cast to float32 afterwards (:383-385), which is bit-identical to
     casting the normalised volume once.  Train path ``base.py:146`` casts the
-    image to float32 first: pass ``dtype=np.float32``.
+    image to float32 first: pass ``dtype=np.float32``.  Under the reference's numpy
+    1.12.1 (requirements.txt:18) a float32 ARRAY combined with float64 SCALARS stays
+    float32 (value-based casting: the scalars are rounded to float32), whereas an
+    integer array with a float64 scalar promotes to float64 -- so the train path is
+    float32 arithmetic and the test path on an integer T1 is float64 arithmetic.
+    NumPy 2 (NEP 50) would promote the train path to float64; the casts below
+    restore the reference's result.
     """
     nz = image[np.nonzero(image)]
     if dtype is not None:
-        return (image.astype(dtype) - nz.mean()) / nz.std()
+        dt = np.dtype(dtype).type
+        return (image.astype(dtype) - dt(nz.mean())) / dt(nz.std())
     return (image - nz.mean()) / nz.std()
 
 

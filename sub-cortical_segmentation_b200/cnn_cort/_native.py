@@ -12,6 +12,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsubcort_b200.so")
 PARAM_FLOATS = 883455
+# sc_dtype codes of raw (un-normalised) volumes, include/subcort_b200.h
+DTYPE_CODES = {"u1": 1, "i1": 2, "u2": 3, "i2": 4, "u4": 5, "i4": 6, "f4": 7, "f8": 8}
 
 _lib = None
 
@@ -42,6 +44,10 @@ PROTOTYPES = {
     "sc_get_params": (ctypes.c_int, [_vp, _vp, _c_i64]),
     "sc_nonzero_coords": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _c_i64, _p(_c_i64), _vp]),
     "sc_dilate_mask": (ctypes.c_int, [_vp, _vp, _p(_c_i32), ctypes.c_int, _vp, _vp]),
+    "sc_import_volume": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), ctypes.c_int, _vp, _vp]),
+    "sc_normalise_volume": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _p(ctypes.c_double), _vp]),
+    "sc_candidate_mask": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _vp]),
+    "sc_mask_bbox": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _p(_c_i32), _p(_c_i64), _vp]),
     "sc_gather_patches": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, ctypes.c_int, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp]),
     "sc_gather_center_labels": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _c_i64, _vp, _vp]),
     "sc_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp]),
@@ -166,6 +172,51 @@ class Context(object):
         out = torch.empty_like(mask)
         _check(self.lib.sc_dilate_mask(self.h, _ptr(mask), _dims(mask.shape), int(iterations), _ptr(out), _stream()))
         return out
+
+    # -- scan preparation (device-resident head of load_patch_batch / test_scan) ------------------
+    def upload_volume(self, arr, channels=1):
+        """numpy volume [X,Y,Z(,C)] of any supported dtype and memory order -> (uint8 CUDA tensor holding the C-ordered
+        bytes, dtype).  A Fortran-ordered array (what a NIfTI file holds) is uploaded as it lies in memory -- no host
+        transposition -- and reordered on the device (sc_import_volume)."""
+        import torch
+        arr = np.asarray(arr)
+        if arr.dtype == np.bool_:
+            arr = arr.view(np.uint8)
+        if arr.dtype.str[1:] not in DTYPE_CODES:
+            raise NativeError("unsupported volume dtype %s" % arr.dtype)
+        shape = tuple(int(s) for s in arr.shape[:3])
+        dev = "cuda:%d" % self.device
+        if arr.flags["C_CONTIGUOUS"]:
+            return torch.from_numpy(arr.reshape(-1).view(np.uint8)).to(dev, non_blocking=True), arr.dtype
+        if not arr.flags["F_CONTIGUOUS"]:
+            arr = np.asfortranarray(arr)
+        raw = torch.from_numpy(arr.reshape(-1, order="F").view(np.uint8)).to(dev, non_blocking=True)
+        out = torch.empty_like(raw)
+        _check(self.lib.sc_import_volume(self.h, _ptr(raw), arr.dtype.itemsize, _dims(shape), int(channels), _ptr(out), _stream()))
+        return out, arr.dtype
+
+    def normalise_volume(self, raw, dtype, shape, want_volume=True):
+        """C-ordered raw volume bytes on the device -> (float32 CUDA tensor [X,Y,Z], mean_nz, std_nz) == numpy's
+        (image - image[nz].mean()) / image[nz].std() cast to float32, bit for bit (base.py:358)."""
+        import torch
+        out = torch.empty(tuple(shape), dtype=torch.float32, device=raw.device) if want_volume else None
+        ms = (ctypes.c_double * 2)()
+        _check(self.lib.sc_normalise_volume(self.h, _ptr(raw), DTYPE_CODES[np.dtype(dtype).str[1:]], _dims(shape), _ptr(out), ms, _stream()))
+        return out, ms[0], ms[1]
+
+    def candidate_mask(self, raw, dtype, shape):
+        """raw != 0 as a uint8 CUDA mask [X,Y,Z] (base.py:372)"""
+        import torch
+        mask = torch.empty(tuple(shape), dtype=torch.uint8, device=raw.device)
+        _check(self.lib.sc_candidate_mask(self.h, _ptr(raw), DTYPE_CODES[np.dtype(dtype).str[1:]], _dims(shape), _ptr(mask), _stream()))
+        return mask
+
+    def mask_bbox(self, mask):
+        """(half-open box (x0,x1,y0,y1,z0,z1) or None, number of non-zero voxels) of a uint8 CUDA mask"""
+        box = (_c_i32 * 6)()
+        n = _c_i64(0)
+        _check(self.lib.sc_mask_bbox(self.h, _ptr(mask), _dims(mask.shape), box, ctypes.byref(n), _stream()))
+        return (tuple(int(b) for b in box) if n.value else None), int(n.value)
 
     def gather_patches(self, vol, xyz, atlas=None, bg_fix=True, views=(True, True, True)):
         import torch

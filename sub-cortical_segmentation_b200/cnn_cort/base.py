@@ -107,24 +107,34 @@ def load_patch_batch(scan_name, options, datatype=np.float32):
     Arrays are float32 [n,1,32,32] / [n,15] numpy like the reference's.  The volume and the
     atlas are uploaded once and stay on the device for the whole scan.
     """
+    import torch
     ctx = get_context(options.get('device'))
     dir_name, name = os.path.split(scan_name)
     image = load_nii(scan_name).get_data()
-    image_norm = normalise_test(image)
     atlas_name = os.path.join(dir_name, 'tmp', 'MNI_sub_probabilities.nii.gz')
     _require_registered(atlas_name)
-    cand = candidate_mask(image, dir_name, options)
-    centers = get_mask_voxels(cand, device=ctx.device, as_array=True)
+    shape = tuple(int(s) for s in image.shape[:3])
+    raw, dt = ctx.upload_volume(image)
+    vol, _, _ = ctx.normalise_volume(raw, dt, shape)                       # base.py:358, numpy's result bit for bit
+    if _crop_enabled(options):                                             # base.py:367-372
+        mraw, mdt = ctx.upload_volume(nib.load(os.path.join(dir_name, 'tmp', 'MNI_subcortical_mask.nii.gz')).get_data())
+        cand = ctx.dilate_mask(ctx.candidate_mask(mraw, mdt, shape), 10)
+    else:
+        cand = ctx.candidate_mask(raw, dt, shape)
+    centers = ctx.nonzero_coords(cand)                                     # np.nonzero order, stays on the device
     if options['debug'] == 'True':
         print("    -->  num of samples to test:", len(centers))
-    vol = _dev(image_norm, ctx.device, np.float32)
-    atlas = _dev(load_nii(atlas_name).get_data(), ctx.device, np.float32)
+    atlas = np.asarray(load_nii(atlas_name).get_data())
+    if atlas.dtype != np.float32:
+        atlas = atlas.astype(np.float32, order='K')
+    d_atlas, _ = ctx.upload_volume(atlas, channels=15)
+    d_atlas = d_atlas.view(torch.float32).view(shape + (15,))
     batch_size = options['test_batch_size']
     for i in range(0, len(centers), batch_size):
-        c = centers[i:i + batch_size]
-        ax, co, sa, at = ctx.gather_patches(vol, _centers_tensor(c, ctx.device), atlas=atlas, bg_fix=True)
+        c = centers[i:i + batch_size].contiguous()
+        ax, co, sa, at = ctx.gather_patches(vol, c, atlas=d_atlas, bg_fix=True)
         yield (ax.cpu().numpy().astype(datatype, copy=False), co.cpu().numpy().astype(datatype, copy=False),
-               sa.cpu().numpy().astype(datatype, copy=False), at.cpu().numpy(), [tuple(int(v) for v in r) for r in c])
+               sa.cpu().numpy().astype(datatype, copy=False), at.cpu().numpy(), [tuple(int(v) for v in r) for r in c.cpu().numpy()])
 
 
 def normalise_test(image):
@@ -133,12 +143,16 @@ def normalise_test(image):
     return (image - nz.mean()) / nz.std()
 
 
-def candidate_mask(image, dir_name, options):
-    """bool volume of the voxels to classify. [base.py:367-372]"""
+def _crop_enabled(options):
     crop = options.get('crop_bool')
     if crop is None:
         crop = str(options.get('crop', 'True')).strip().lower() in ('true', '1', 'yes', 'on')
-    if crop:
+    return bool(crop)
+
+
+def candidate_mask(image, dir_name, options):
+    """bool volume of the voxels to classify. [base.py:367-372]"""
+    if _crop_enabled(options):
         mask_atlas = nib.load(os.path.join(dir_name, 'tmp', 'MNI_subcortical_mask.nii.gz')).get_data()
         ctx = get_context(options.get('device'))
         m = _dev(np.ascontiguousarray(mask_atlas != 0).view(np.uint8), ctx.device)
@@ -165,10 +179,11 @@ def test_scan(net, test_scan, options):
     """
     s_time = time.time()
     image_path, name = os.path.split(test_scan)
-    t1_nii = nib.load(test_scan)
+    mode = options.get('inference', 'dense')
+    # I/O: in the dense mode the files are read straight into page-locked memory, in the array order they have on disk
+    t1_nii = nib.load(test_scan, pinned=(mode != 'patchwise'))
     t1 = t1_nii.get_data()
     want_proba = options['out_probabilities'] == 'True'
-    mode = options.get('inference', 'dense')
     if mode == 'patchwise':
         image = np.zeros_like(t1)
         image_proba = np.zeros(t1_nii.shape + (15,)) if want_proba else None
@@ -182,23 +197,17 @@ def test_scan(net, test_scan, options):
             else:
                 image[x, y, z] = net.predict(X)
     else:
-        ctx = net.ctx
         atlas_name = os.path.join(image_path, 'tmp', 'MNI_sub_probabilities.nii.gz')
         _require_registered(atlas_name)
-        image_norm = np.ascontiguousarray(normalise_test(t1), dtype=np.float32)
-        atlas = np.ascontiguousarray(load_nii(atlas_name).get_data(), dtype=np.float32)
-        cand = candidate_mask(t1, image_path, options)
-        box = bounding_box(cand)
+        atlas = nib.load(atlas_name, pinned=True).get_data()
+        crop_mask = None
+        if _crop_enabled(options):
+            crop_mask = nib.load(os.path.join(image_path, 'tmp', 'MNI_subcortical_mask.nii.gz'), pinned=True).get_data()
+        timings = options.get('timings')
+        labels, image_proba, n_cand = segment_arrays(net.ctx, t1, atlas, crop_mask, want_proba, timings)
         if options['debug'] == 'True':
-            print("    -->  num of samples to test:", int(cand.sum()))
-        if box is None:
-            labels, proba = np.zeros(t1.shape, np.uint8), (np.zeros(t1.shape + (15,), np.float32) if want_proba else None)
-        else:
-            labels, proba = ctx.segment_volume_host(image_norm, atlas, box=box,
-                                                    cand_mask=np.ascontiguousarray(cand).view(np.uint8),
-                                                    want_proba=want_proba)
+            print("    -->  num of samples to test:", n_cand)
         image = labels.astype(t1.dtype)
-        image_proba = proba
 
     if want_proba:
         nib.Nifti1Image(image_proba, affine=t1_nii.affine).to_filename(os.path.join(image_path, 'out_subcortical_prob.nii.gz'))
@@ -208,6 +217,60 @@ def test_scan(net, test_scan, options):
     else:
         nib.Nifti1Image(image, affine=t1_nii.affine).to_filename(os.path.join(image_path, 'out_subcortical_rawseg.nii.gz'))
     return (time.time() - s_time) / 60.0
+
+
+def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=None):
+    """The timed part of test_scan for one scan, device-resident from the first byte [base.py:357-372, 401-440]:
+    raw T1 / atlas priors (/ registered mask) as host arrays in -> uint8 label volume (+ float32 [X,Y,Z,15] probabilities,
+    number of candidates) out.  One upload per array (Fortran-ordered NIfTI arrays are reordered on the device), then
+    normalisation over the non-zero voxels (numpy's result bit for bit), candidate mask (non-zero T1 voxels, or the
+    registered mask dilated 10 times), its bounding box, the dense network pass and the scatter, all without the mask,
+    the normalised volume or the coordinates ever visiting the host; one download of the result."""
+    import torch
+    t0 = time.time()
+    shape = tuple(int(s) for s in t1.shape[:3])
+    raw, dt = ctx.upload_volume(t1)
+    atlas = np.asarray(atlas)
+    if atlas.dtype != np.float32:          # a scaled NIfTI comes back as float64: the priors are consumed as float32 (base.py:388)
+        atlas = atlas.astype(np.float32, order='K')
+    d_atlas, _ = ctx.upload_volume(atlas, channels=15)
+    d_atlas = d_atlas.view(torch.float32).view(shape + (15,))
+    vol, mean, std = ctx.normalise_volume(raw, dt, shape)
+    if crop_mask is not None:
+        mraw, mdt = ctx.upload_volume(crop_mask)
+        cand = ctx.dilate_mask(ctx.candidate_mask(mraw, mdt, shape), 10)   # == ndimage.binary_dilation(mask, iterations=10)
+    else:
+        cand = ctx.candidate_mask(raw, dt, shape)                          # == image.astype('bool')
+    box, n_cand = ctx.mask_bbox(cand)
+    lab = torch.zeros(shape, dtype=torch.uint8, device=vol.device)
+    prob = torch.zeros(shape + (15,), dtype=torch.float32, device=vol.device) if want_proba else None
+    if box is not None:
+        ctx.segment_volume(vol, d_atlas, box=box, cand_mask=cand, label_vol=lab, proba_vol=prob)
+    h_lab = _pinned_out('lab', shape, torch.uint8)
+    h_lab.copy_(lab, non_blocking=True)
+    h_prob = None
+    if want_proba:
+        h_prob = _pinned_out('prob', shape + (15,), torch.float32)
+        h_prob.copy_(prob, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    if timings is not None:
+        timings.update({'hot_s': time.time() - t0, 'n_candidates': n_cand, 'mean_nz': mean, 'std_nz': std, 'box': box})
+    # views of reusable page-locked buffers: valid until the next call
+    return h_lab.numpy(), (h_prob.numpy() if want_proba else None), n_cand
+
+
+_pinned_cache = {}
+
+
+def _pinned_out(key, shape, dtype):
+    """reusable page-locked result buffers (allocating 1 GB of pinned memory per scan would cost more than the scan)"""
+    import torch
+    t = _pinned_cache.get(key)
+    n = int(np.prod(shape))
+    if t is None or t.dtype != dtype or t.numel() < n:
+        t = torch.empty(n, dtype=dtype, pin_memory=True)
+        _pinned_cache[key] = t
+    return t[:n].view(shape)
 
 
 def bounding_box(mask):
@@ -283,7 +346,9 @@ def load_patch_vectors(name, label_name, dir_name, size, random_state=42, balanc
     for image_name, lab_name in zip(image_names, label_names):
         im = load_nii(image_name).get_data()
         nz = im[np.nonzero(im)]
-        im_norm = (im.astype(np.float32) - nz.mean()) / nz.std()          # base.py:146
+        # base.py:146 under the reference's numpy 1.12: a float32 array combined with float64 *scalars* stays float32
+        # (value-based casting), i.e. the mean and std are rounded to float32 first; NumPy 2 would promote to float64
+        im_norm = (im.astype(np.float32) - np.float32(nz.mean())) / np.float32(nz.std())
         mask = load_nii(lab_name).get_data()
         pos = get_mask_voxels(np.logical_and(mask > 0, mask < 15), device=ctx.device, as_array=True)
         neg = get_mask_voxels(mask == 15, size=len(pos) if balance_neg else None, device=ctx.device, as_array=True)

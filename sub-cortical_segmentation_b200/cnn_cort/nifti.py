@@ -17,7 +17,10 @@ _CODES = {np.dtype(v).str[1:]: k for k, v in _DTYPES.items()}
 
 
 def _open(path, mode):
-    return gzip.open(path, mode) if str(path).endswith(".gz") else open(path, mode)
+    if str(path).endswith(".gz"):
+        # nibabel writes .nii.gz at compresslevel 1 (its Opener default); 9 would cost minutes on a 1 GB prior volume
+        return gzip.open(path, mode, compresslevel=1) if "w" in mode else gzip.open(path, mode)
+    return open(path, mode)
 
 
 def _quat_affine(b, c, d, qx, qy, qz, dx, dy, dz, qfac):
@@ -75,15 +78,62 @@ class Nifti1Image(object):
             f.write(np.asfortranarray(data).tobytes(order="F"))
 
 
-def load(path):
+_PINNED_KEEPALIVE = {}
+
+
+def _pinned_bytes(n):
+    """page-locked host buffer of n bytes as a numpy uint8 array (None when CUDA is not usable)"""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        t = torch.empty(int(n), dtype=torch.uint8, pin_memory=True)
+        a = t.numpy()
+        _PINNED_KEEPALIVE[a.__array_interface__["data"][0]] = t      # the tensor owns the allocation
+        if len(_PINNED_KEEPALIVE) > 8:
+            _PINNED_KEEPALIVE.pop(next(iter(_PINNED_KEEPALIVE)))
+        return a
+    except Exception:
+        return None
+
+
+def _endianness(head, path):
+    if struct.unpack_from("<i", head, 0)[0] == 348:
+        return "<"
+    if struct.unpack_from(">i", head, 0)[0] == 348:
+        return ">"
+    raise ValueError("%s: not a NIfTI-1 file" % path)
+
+
+def load(path, pinned=False):
+    """pinned=True reads the file straight into page-locked memory (when CUDA is available), so that the later
+    host-to-device copy of the scan runs at full PCIe speed without a staging copy; the array is otherwise identical."""
     with _open(path, "rb") as f:
-        raw = f.read()
-    end = "<"
-    if struct.unpack_from("<i", raw, 0)[0] != 348:
-        end = ">"
-        if struct.unpack_from(">i", raw, 0)[0] != 348:
+        head = f.read(352)
+        if len(head) < 348:
             raise ValueError("%s: not a NIfTI-1 file" % path)
-    if raw[344:347] not in (b"n+1",):
+        end = _endianness(head, path)
+        raw = None
+        if pinned:
+            dim = struct.unpack_from(end + "8h", head, 40)
+            code = struct.unpack_from(end + "h", head, 70)[0]
+            off = int(struct.unpack_from(end + "f", head, 108)[0])
+            if code in _DTYPES and 1 <= dim[0] <= 7 and off >= len(head):
+                nbytes = int(np.prod([int(d) for d in dim[1:1 + dim[0]]])) * np.dtype(_DTYPES[code]).itemsize
+                buf = _pinned_bytes(off + nbytes)
+                if buf is not None:
+                    buf[:len(head)] = np.frombuffer(head, np.uint8)
+                    view = memoryview(buf)[len(head):]
+                    got = 0
+                    while got < len(view):
+                        k = f.readinto(view[got:])
+                        if not k:
+                            break
+                        got += k
+                    raw = buf
+        if raw is None:
+            raw = head + f.read()
+    if bytes(raw[344:347]) not in (b"n+1",):
         raise ValueError("%s: only single-file NIfTI-1 (magic n+1) is supported" % path)
     dim = struct.unpack_from(end + "8h", raw, 40)
     ndim = dim[0]
@@ -102,9 +152,13 @@ def load(path):
     data = np.frombuffer(raw, dtype=dt, count=n, offset=vox_offset).reshape(shape, order="F")
     if end == ">":
         data = data.astype(dt.newbyteorder("<"))
-    if slope not in (0.0, 1.0) or inter != 0.0:
-        if not np.isnan(slope):
+    # nibabel: scl_slope == 0 (or non-finite) means "no scaling" and scl_inter is then ignored; a non-finite inter counts as 0
+    if np.isfinite(slope) and slope != 0.0:
+        inter = inter if np.isfinite(inter) else 0.0
+        if slope != 1.0 or inter != 0.0:
             data = data * np.float64(slope) + np.float64(inter)
+    if not data.flags.writeable:
+        data = data.copy(order="F")      # np.frombuffer views are read-only; callers edit volumes in place
     if scode > 0:
         A = np.eye(4)
         for r in range(3):

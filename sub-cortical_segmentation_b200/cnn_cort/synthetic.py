@@ -68,11 +68,13 @@ def make_labels(atlas):
 
 
 def write_subject(root, name, shape=(256, 256, 256), seed=1234, with_labels=False, t1_name="T1.nii.gz",
-                  roi_name="gt_15_classes.nii.gz", zoom=1.0):
+                  roi_name="gt_15_classes.nii.gz", zoom=1.0, t1_dtype=np.float32):
     d = os.path.join(root, name)
     os.makedirs(os.path.join(d, "tmp"), exist_ok=True)
     aff = np.diag([zoom, zoom, zoom, 1.0])
     t1 = make_t1(shape, seed)
+    if np.dtype(t1_dtype).kind in "iu":       # scanner-style integer intensities (the usual on-disk type of a T1)
+        t1 = np.rint(t1).astype(t1_dtype)
     atlas, _, _ = make_atlas(shape, seed)
     nifti.Nifti1Image(t1, aff).to_filename(os.path.join(d, t1_name))
     nifti.Nifti1Image(atlas, aff).to_filename(os.path.join(d, "tmp", "MNI_sub_probabilities.nii.gz"))

@@ -268,6 +268,34 @@ int sc_dilate_mask(sc_ctx* ctx, const uint8_t* mask_dev, const int32_t dims[3], 
   return launch_dilate(ctx, mask_dev, dims, iterations, out_dev, (cudaStream_t)stream);
 }
 
+int sc_import_volume(sc_ctx* ctx, const void* src_dev, int elem_bytes, const int32_t dims[3], int channels, void* dst_dev, void* stream) {
+  SC_CHECK(ctx && src_dev && dst_dev && src_dev != dst_dev && channels >= 1, SC_ERR_ARG, "sc_import_volume: bad argument");
+  SC_TRY(check_dims(dims, "sc_import_volume"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return import_volume(ctx, src_dev, elem_bytes, dims, channels, dst_dev, (cudaStream_t)stream);
+}
+
+int sc_normalise_volume(sc_ctx* ctx, const void* vol_dev, int dtype, const int32_t dims[3], float* out_dev, double* mean_std_host, void* stream) {
+  SC_CHECK(ctx && vol_dev && (out_dev || mean_std_host), SC_ERR_ARG, "sc_normalise_volume: bad argument");
+  SC_TRY(check_dims(dims, "sc_normalise_volume"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return normalise_volume(ctx, vol_dev, dtype, dims, out_dev, mean_std_host, (cudaStream_t)stream);
+}
+
+int sc_candidate_mask(sc_ctx* ctx, const void* vol_dev, int dtype, const int32_t dims[3], uint8_t* mask_dev, void* stream) {
+  SC_CHECK(ctx && vol_dev && mask_dev, SC_ERR_ARG, "sc_candidate_mask: bad argument");
+  SC_TRY(check_dims(dims, "sc_candidate_mask"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return candidate_mask(ctx, vol_dev, dtype, dims, mask_dev, (cudaStream_t)stream);
+}
+
+int sc_mask_bbox(sc_ctx* ctx, const uint8_t* mask_dev, const int32_t dims[3], int32_t box_host[6], int64_t* count_host, void* stream) {
+  SC_CHECK(ctx && mask_dev && box_host, SC_ERR_ARG, "sc_mask_bbox: bad argument");
+  SC_TRY(check_dims(dims, "sc_mask_bbox"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return mask_bbox(ctx, mask_dev, dims, box_host, count_host, (cudaStream_t)stream);
+}
+
 int sc_gather_patches(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3], const float* atlas_dev, int bg_fix,
                       const int32_t* xyz_dev, int64_t n, float* axial_dev, float* coronal_dev, float* saggital_dev,
                       float* atlas_out_dev, void* stream) {

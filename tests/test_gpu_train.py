@@ -121,13 +121,15 @@ def test_fit_loop_history_checkpoint_and_early_stopping(tmp_path):
     assert net2.predict({'in1': x[0], 'in2': x[1], 'in3': x[2], 'in4': at}).dtype == np.int64
 
 
-def test_load_data_and_generate_training_set(tmp_path):
-    """a-8: load_data -> generate_training_set on synthetic subjects (boundary-restricted sampling) vs the oracle."""
+@pytest.mark.parametrize("t1_dtype", [np.float32, np.int16])
+def test_load_data_and_generate_training_set(tmp_path, t1_dtype):
+    """a-8: load_data -> generate_training_set on synthetic subjects (boundary-restricted sampling) vs the oracle.
+    int16 T1: the train-path normalisation is float32 arithmetic under the reference's numpy 1.12 (base.py:146)."""
     from cnn_cort import base, nifti, synthetic
     from oracle import gather as og
     root = str(tmp_path)
     for i, name in enumerate(("s01", "s02")):
-        synthetic.write_subject(root, name, shape=(44, 40, 36), seed=20 + i, with_labels=True)
+        synthetic.write_subject(root, name, shape=(44, 40, 36), seed=20 + i, with_labels=True, t1_dtype=t1_dtype)
     options = {'train_folder': root, 't1_name': 'T1.nii.gz', 'roi_name': 'gt_15_classes.nii.gz', 'patch_size': [32, 32],
                'debug': 'False', 'device': 0}
     x_axial, x_cor, x_sag, y_axial, x_atlas, names = base.load_data(options)
@@ -137,6 +139,7 @@ def test_load_data_and_generate_training_set(tmp_path):
         lab = nifti.load(os.path.join(root, name, "gt_15_classes.nii.gz")).get_data()
         atlas = nifti.load(os.path.join(root, name, "tmp", "MNI_sub_probabilities.nii.gz")).get_data()
         norm = og.normalise(t1, np.float32)
+        assert t1.dtype == t1_dtype and norm.dtype == np.float32
         pos = og.get_mask_voxels(np.logical_and(lab > 0, lab < 15))
         n_pos = len(pos)
         n_neg = min(n_pos, int((lab == 15).sum()))          # shuffled list truncated to len(positives), base.py:327-329

@@ -78,6 +78,22 @@ def test_atlas_vectors_bg_fix():
     assert gather.atlas_vectors_train(atlas, c)[0].sum() == 0  # quirk Q4: no fix at train time
 
 
+def test_normalise_dtype_rules_of_the_reference_numpy():
+    """numpy 1.12 (requirements.txt:18): float32 array (op) float64 scalar stays float32 -> the train path (base.py:146) is
+    float32 arithmetic; an integer array (op) float64 scalar is float64 -> the test path (base.py:358) on an int16 T1."""
+    rng = np.random.RandomState(4)
+    vol = rng.randint(0, 1500, size=(9, 8, 7)).astype(np.int16)
+    nz = vol[vol != 0]
+    tr = gather.normalise(vol, np.float32)
+    assert tr.dtype == np.float32
+    assert np.array_equal(tr, (vol.astype(np.float32) - np.float32(nz.mean())) / np.float32(nz.std()))
+    te = gather.normalise(vol)
+    assert te.dtype == np.float64 and np.array_equal(te, (vol.astype(np.float64) - nz.mean()) / nz.std())
+    # the float64-promoted result (what NumPy 2 would compute for the train path) differs in the last bit somewhere
+    wide = ((vol.astype(np.float32) - nz.mean()) / nz.std()).astype(np.float32)
+    assert np.abs(wide - tr).max() < 1e-6
+
+
 def test_patch_batches_and_candidates():
     rng = np.random.RandomState(1)
     vol = rng.rand(12, 10, 9) + 0.5
