@@ -227,11 +227,47 @@ class Net(object):
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank() if world > 1 else 0
         y = np.asarray(y).astype(np.uint8)
+        if y.size and int(y.max()) > 14:
+            raise ValueError("fit: labels must be in 0..14 (generate_training_set maps the boundary label 15 to 0, base.py:89)")
         tr, va = self.train_split.indices(y)
         xs = [np.ascontiguousarray(X[k], dtype=np.float32) for k in ('in1', 'in2', 'in3', 'in4')]
+        if world > 1:
+            # data parallel: every rank must hold the SAME training set in the same order (shard_batch strides through the
+            # global minibatch) and start from the SAME parameters; neither is true by construction (the reference's
+            # negative sampling and its weight initialisation are unseeded), so check the first and enforce the second
+            parallel.assert_same_dataset(xs, y, dev)
+            p = ctx.param_tensor()
+            dist.broadcast(p, 0)
+            ctx.load_weights(p.cpu().numpy())          # re-derives the inference layouts from the broadcast parameters
+            ctx.reset_optimizer()
 
-        def to_dev(idx):
-            return [torch.from_numpy(a[idx]).to(dev) for a in xs] + [torch.from_numpy(y[idx]).to(dev)]
+        # the training set lives on the device when it fits (a minibatch is then one index_select per input instead of five
+        # pageable host-to-device copies per step); otherwise minibatches are staged through page-locked buffers
+        nbytes = sum(a.nbytes for a in xs) + y.nbytes
+        free_b = torch.cuda.mem_get_info(dev)[0]
+        resident = nbytes < 0.5 * free_b
+        if resident:
+            d_xs = [torch.from_numpy(a).to(dev) for a in xs]
+            d_y = torch.from_numpy(y).to(dev)
+
+            def to_dev(idx):
+                di = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(dev)
+                return [a.index_select(0, di) for a in d_xs] + [d_y.index_select(0, di)]
+        else:
+            stage = {}
+
+            def to_dev(idx):
+                out = []
+                for k, a in enumerate(xs + [y]):
+                    need = (len(idx),) + a.shape[1:]
+                    buf = stage.get(k)
+                    if buf is None or buf.shape[0] < len(idx):
+                        buf = torch.empty((max(len(idx), self.batch_size),) + a.shape[1:], dtype=torch.from_numpy(a[:1]).dtype, pin_memory=True)
+                        stage[k] = buf
+                    np.take(a, idx, axis=0, out=buf.numpy()[:len(idx)])
+                    out.append(buf[:len(idx)].to(dev, non_blocking=True))
+                torch.cuda.current_stream().synchronize()      # the staging buffers are reused by the next minibatch
+                return out
 
         best_valid, best_train = np.inf, np.inf
         best_epoch, best_weights = 0, None
@@ -254,7 +290,9 @@ class Net(object):
                     grads.zero_()
                     loss_buf.zero_()
                 parallel.allreduce_gradients(grads, loss_buf)
-                ctx.adam_step(lr=self.update_learning_rate, stat_scale=1.0 / world)
+                # the BN-statistics slots hold the SUM of the batch statistics of the ranks that had samples: rank r of
+                # shard_batch has some iff r < len(gidx)
+                ctx.adam_step(lr=self.update_learning_rate, stat_scale=1.0 / min(world, len(gidx)))
                 losses.append(loss_buf.clone())
                 sizes.append(len(gidx))
             train_loss = float(np.average(torch.cat(losses).cpu().numpy(), weights=sizes)) if losses else float('nan')

