@@ -162,6 +162,183 @@ def run_reference(args, rank, world):
     emit_json(out)
 
 
+# ------------------------------------------------------------------------------------------------
+# secondary sections (BASELINE.json configs[3], [4] and the N > 1 paths); none of them may cost the headline line
+# ------------------------------------------------------------------------------------------------
+FLOP_TRAIN_SAMPLE = 3 * FLOP_PATCHWISE       # forward + backward ~ 3 x forward = 106.2 MFLOP per sample
+
+
+def bench_train(ctx, torch, dist, rank, world, peaks, steps=20, warmup=5):
+    """configs[3] (global batch 256 split over the ranks, strong scaling) and configs[4] (1024 samples per GPU, i.e. global
+    batch 8192 at 8 GPUs): one training step = forward + backward + gradient all-reduce + Adam, timed on the device."""
+    from cnn_cort import parallel
+    out = {}
+    grads = ctx.grad_tensor()
+    for name, per_gpu in (("global_batch_256", max(1, 256 // world)), ("per_gpu_batch_1024", 1024)):
+        gb = per_gpu * world
+        g = torch.Generator(device="cuda").manual_seed(100 + rank)
+        x = [torch.randn((per_gpu, 1, 32, 32), device="cuda", generator=g) for _ in range(3)]
+        at = torch.softmax(3 * torch.randn((per_gpu, 15), device="cuda", generator=g), 1)
+        y = torch.randint(0, 15, (per_gpu,), device="cuda", generator=g, dtype=torch.uint8)
+        hx = [t.cpu().pin_memory() for t in x] + [at.cpu().pin_memory(), y.cpu().pin_memory()]
+        loss = torch.zeros(1, device="cuda")
+
+        def step(i, from_host=False):
+            d = [t.cuda(non_blocking=True) for t in hx] if from_host else x + [at, y]
+            ctx.train_forward_backward(*d, n_global=gb, seed=i, loss_out=loss)
+            parallel.allreduce_gradients(grads, loss)
+            ctx.adam_step(lr=1e-3, stat_scale=1.0 / world)
+
+        def sync():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for i in range(warmup):
+            step(i)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.counter("launches")
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        sync()
+        launches = (ctx.counter("launches") - l0) / steps
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        e0.record()
+        for i in range(steps):
+            step(i, from_host=True)
+            float(loss.item())
+        e1.record()
+        sync()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        ar_ms = None
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+            sync()
+            e0.record()
+            for _ in range(50):
+                dist.all_reduce(grads)
+            e1.record()
+            sync()
+            ar_ms = e0.elapsed_time(e1) / 50
+        per = float(ms) / steps
+        tfl = gb * FLOP_TRAIN_SAMPLE / (per * 1e-3) / 1e12
+        out[name] = {"global_batch": gb, "per_gpu_batch": per_gpu, "ms_per_step": per, "samples_per_s": gb / (per * 1e-3),
+                     "e2e_samples_per_s": gb / (float(ms2) / steps * 1e-3), "h2d_bytes_per_step": int(per_gpu * (3 * 4096 + 60 + 1)),
+                     "allreduce_ms": ar_ms, "allreduce_bytes": 883455 * 4, "gpu_launches_per_step": launches, "loss": float(loss.item()),
+                     "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tflops"] * world, "unit": "TFLOP/s",
+                                  "frac": tfl / (peaks["tflops"] * world), "flops_per_sample": FLOP_TRAIN_SAMPLE}}
+    out["scaling"] = {"global_batch_256": "strong (256 / N samples per GPU)", "per_gpu_batch_1024": "weak"}
+    out["bn"] = "per-GPU batch statistics"
+    return out
+
+
+def bench_single_volume_sharded(ctx, torch, dist, rank, world, d_vol, d_atlas, d_mask, nvox, steps=3):
+    """the metric's 'seconds per 256^3 volume at N GPUs': ONE volume, every rank segments its x-slab of the candidate box
+    (parallel.segment_volume_sharded: no collective on the data path), the label slabs are gathered to rank 0 by
+    NCCL point-to-point copies over NVLink.  The volume / atlas are rank 0's, broadcast once outside the timed region."""
+    from cnn_cort import parallel
+    vol, atlas, mask = d_vol.clone(), d_atlas.clone(), d_mask.clone()
+    dist.broadcast(vol, 0); dist.broadcast(atlas, 0); dist.broadcast(mask, 0)
+    shape = tuple(vol.shape)
+    lab = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+    box = (0, shape[0], 0, shape[1], 0, shape[2])
+
+    def one():
+        lab.zero_()
+        mine = parallel.segment_volume_sharded(ctx, vol, atlas, box=box, cand_mask=mask, label_vol=lab)
+        reqs = []
+        if rank == 0:
+            for r in range(1, world):
+                s = parallel.shard_box(box, r, world)
+                if s is not None:
+                    reqs.append(dist.irecv(lab[s[0]:s[1]], src=r))
+        elif mine is not None:
+            reqs.append(dist.isend(lab[mine[0]:mine[1]], dst=0))
+        for q in reqs:
+            q.wait()
+
+    one()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # union check against the unsharded result on rank 0
+    ok = None
+    if rank == 0:
+        ref = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+        ctx.segment_volume(vol, atlas, cand_mask=mask, label_vol=ref)
+        ok = bool((ref == lab).all())
+    ms = float(t.item())
+    return {"ms_per_volume": ms, "seconds_per_volume": ms * 1e-3, "voxels_per_s": nvox / (ms * 1e-3), "union_equals_unsharded": ok,
+            "note": "x-slab split of one %s volume over %d GPUs, each slab recomputes a 16-plane halo in the saggital view and the full "
+                    "planes of the axial / coronal views' conv phase is restricted to its slab +- 16; labels gathered to rank 0" % (shape, world)}
+
+
+def bench_test_scan_hot(ctx, torch, t1, atlas, steps=3):
+    """the drop-in call's timed part (cnn_cort.base.segment_arrays = test_scan minus NIfTI I/O): raw T1 + atlas priors in
+    page-locked Fortran-ordered host arrays (what nifti.load(pinned=True) yields) -> label volume on the host; device-side
+    import, normalisation, candidate mask, bounding box, dense network pass."""
+    from cnn_cort import base, synthetic
+    def pinned_f(a):
+        t = torch.empty(a.size * a.itemsize, dtype=torch.uint8, pin_memory=True)
+        v = t.numpy().view(a.dtype).reshape(a.shape, order="F")
+        v[...] = a
+        return t, v
+    keep1, t1f = pinned_f(t1)
+    keep2, atf = pinned_f(atlas)
+    keep3, mkf = pinned_f(synthetic.make_mask(atlas))
+    out = {}
+    for name, crop in (("full_brain", None), ("crop", mkf)):
+        tm = {}
+        base.segment_arrays(ctx, t1f, atf, crop, False, tm)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            base.segment_arrays(ctx, t1f, atf, crop, False, tm)
+        wall = (time.perf_counter() - t0) / steps
+        out[name] = {"wall_ms": wall * 1e3, "candidates": tm["n_candidates"], "candidate_voxels_per_s": tm["n_candidates"] / wall,
+                     "box": list(tm["box"]) if tm["box"] else None}
+    out["call"] = ("cnn_cort.base.segment_arrays (the body of test_scan between reading the NIfTI files into page-locked memory and "
+                   "writing the outputs), host wall clock")
+    return out
+
+
+def bench_volume_320_proba(ctx, torch, dist, rank, world, steps=2):
+    """configs[4]: out_probabilities=True over a 0.7 mm 320^3 volume per GPU (32 768 000 voxels, 1.97 GB probability volume)"""
+    _, norm, atlas = synthetic_volume(320, 4321 + rank)
+    dv, da = torch.from_numpy(norm).cuda(), torch.from_numpy(atlas).cuda()
+    lab = torch.zeros(norm.shape, dtype=torch.uint8, device="cuda")
+    prob = torch.zeros(norm.shape + (15,), dtype=torch.float32, device="cuda")
+    ctx.segment_volume(dv, da, label_vol=lab, proba_vol=prob)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ctx.segment_volume(dv, da, label_vol=lab, proba_vol=prob)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    n = norm.size
+    del dv, da, lab, prob
+    torch.cuda.empty_cache()
+    return {"ms_per_volume": ms, "voxels_per_s": world * n / (ms * 1e-3), "voxels_per_volume": n, "proba_volume_bytes": n * 60,
+            "volumes": world, "workspace_bytes": ctx.counter("workspace_bytes")}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,6 +350,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=16384)
     ap.add_argument("--cpu-sample", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="headline + e2e only (skip train / sharded / 320^3 / dp_check sections)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -329,9 +507,39 @@ def main():
         except Exception as exc:          # the secondary sections must never cost the headline line
             extra["secondary_error"] = repr(exc)[:300]
 
+    # ---- sections every rank takes part in: training (configs[3], [4]), the N > 1 checks, one volume sharded over the ranks,
+    # the 320^3 probability sweep (configs[4]) ----
+    if not args.no_secondary:
+        del h_vol, h_atlas, h_mask, h_lab
+        def section(name, fn):
+            try:
+                extra[name] = fn()
+            except Exception as exc:
+                extra[name] = {"error": repr(exc)[:300]}
+        time.sleep(1.0)
+        section("train", lambda: bench_train(ctx, torch, dist, rank, world, peaks))
+        ctx.load_weights(nets.pack_params(pickle.load(open(WEIGHTS, "rb"), encoding="latin1")))   # the steps above moved the weights
+        if world > 1:
+            def dp():
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import dp_check
+                res = dp_check.run_checks(ctx, rank, world, local_rank, fit=True)
+                res["result"] = "ok"
+                return res
+            section("dp_check", dp)
+            ctx.load_weights(nets.pack_params(pickle.load(open(WEIGHTS, "rb"), encoding="latin1")))
+            section("single_volume_sharded", lambda: bench_single_volume_sharded(ctx, torch, dist, rank, world, d_vol, d_atlas, d_mask, nvox))
+        if rank == 0:
+            section("test_scan_hot", lambda: bench_test_scan_hot(ctx, torch, t1, atlas))
+            if "wall_ms" in extra["test_scan_hot"].get("full_brain", {}):
+                extra["test_scan_hot"]["full_brain"]["vs_e2e"] = extra["test_scan_hot"]["full_brain"]["wall_ms"] / (1e3 * n_cand * world / e2e_value)
+        del d_vol, d_atlas, d_mask, d_lab
+        torch.cuda.empty_cache()
+        section("volume_320_proba", lambda: bench_volume_320_proba(ctx, torch, dist, rank, world))
+
     if rank != 0:
         if world > 1:
-            dist.barrier()            # rank 0 is still measuring its secondary sections / CPU baseline
+            dist.barrier()            # rank 0 is still measuring its CPU baseline
             dist.destroy_process_group()
         return
 

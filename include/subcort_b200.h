@@ -159,6 +159,10 @@ SC_API int sc_dense_layer(sc_ctx* ctx, int which, const float* in_dev, int64_t n
 SC_API int sc_segment_volume(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3],
                       const float* atlas_dev, const int32_t* box, const uint8_t* cand_mask_dev,
                       uint8_t* label_vol_dev, float* proba_vol_dev, void* stream);
+/* The atlas priors are first read after the convolution phase.  A caller that uploads them on a side stream passes the
+ * cudaEvent_t recorded behind that upload here; the NEXT sc_segment_volume call makes its stream wait for the event right
+ * before the FC head instead of the caller serialising upload and convolutions.  One-shot (cleared by that call). */
+SC_API int sc_atlas_ready_event(sc_ctx* ctx, void* cuda_event);
 /* host-buffer form: copies volume + atlas (+mask) in and the label (+proba) volume out. */
 SC_API int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dims[3],
                            const float* atlas_host, const int32_t* box, const uint8_t* cand_mask_host,

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "sc_dense_layer": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _c_i64, _vp, ctypes.c_int, _vp]),
     "sc_forward_from_volume": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _vp, _c_i64, _vp, _vp, _vp]),
     "sc_segment_volume": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _p(_c_i32), _vp, _vp, _vp, _vp]),
+    "sc_atlas_ready_event": (ctypes.c_int, [_vp, _vp]),
     "sc_segment_volume_host": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _p(_c_i32), _vp, _vp, _vp, _vp]),
     "sc_scatter": (ctypes.c_int, [_vp, _vp, _c_i64, _vp, _vp, _p(_c_i32), _vp, _vp, _vp]),
     "sc_train_forward_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, ctypes.c_uint64, _vp, _vp, _vp]),
@@ -266,8 +267,12 @@ class Context(object):
                                                _ptr(proba), _ptr(label), _stream()))
         return proba, label
 
-    def segment_volume(self, vol, atlas, box=None, cand_mask=None, label_vol=None, proba_vol=None):
+    def segment_volume(self, vol, atlas, box=None, cand_mask=None, label_vol=None, proba_vol=None, atlas_ready=None):
+        """atlas_ready: a torch.cuda.Event recorded behind an upload of `atlas` on another stream; the call waits for it
+        only when the FC head first reads the priors, so the upload overlaps the convolution phase."""
         cbox = (_c_i32 * 6)(*[int(b) for b in box]) if box is not None else None
+        if atlas_ready is not None:
+            _check(self.lib.sc_atlas_ready_event(self.h, atlas_ready.cuda_event))
         _check(self.lib.sc_segment_volume(self.h, _ptr(vol), _dims(vol.shape), _ptr(atlas), cbox, _ptr(cand_mask),
                                           _ptr(label_vol), _ptr(proba_vol), _stream()))
 

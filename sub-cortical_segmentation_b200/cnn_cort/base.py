@@ -233,7 +233,15 @@ def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=Non
     atlas = np.asarray(atlas)
     if atlas.dtype != np.float32:          # a scaled NIfTI comes back as float64: the priors are consumed as float32 (base.py:388)
         atlas = atlas.astype(np.float32, order='K')
-    d_atlas, _ = ctx.upload_volume(atlas, channels=15)
+    # the priors (94 % of the upload) are first needed by the FC head: upload and reorder them on a side stream while the
+    # normalisation, the candidate selection and the convolution phase run
+    main = torch.cuda.current_stream()
+    side = _side_stream(ctx.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        d_atlas, _ = ctx.upload_volume(atlas, channels=15)
+        atlas_ready = torch.cuda.Event()
+        atlas_ready.record(side)
     d_atlas = d_atlas.view(torch.float32).view(shape + (15,))
     vol, mean, std = ctx.normalise_volume(raw, dt, shape)
     if crop_mask is not None:
@@ -245,7 +253,8 @@ def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=Non
     lab = torch.zeros(shape, dtype=torch.uint8, device=vol.device)
     prob = torch.zeros(shape + (15,), dtype=torch.float32, device=vol.device) if want_proba else None
     if box is not None:
-        ctx.segment_volume(vol, d_atlas, box=box, cand_mask=cand, label_vol=lab, proba_vol=prob)
+        ctx.segment_volume(vol, d_atlas, box=box, cand_mask=cand, label_vol=lab, proba_vol=prob, atlas_ready=atlas_ready)
+    main.wait_stream(side)
     h_lab = _pinned_out('lab', shape, torch.uint8)
     h_lab.copy_(lab, non_blocking=True)
     h_prob = None
@@ -260,6 +269,14 @@ def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=Non
 
 
 _pinned_cache = {}
+_side_streams = {}
+
+
+def _side_stream(device):
+    import torch
+    if device not in _side_streams:
+        _side_streams[device] = torch.cuda.Stream(device=device)
+    return _side_streams[device]
 
 
 def _pinned_out(key, shape, dtype):

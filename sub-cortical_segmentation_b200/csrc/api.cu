@@ -387,6 +387,13 @@ int sc_segment_volume(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3], 
   return segment_volume(ctx, vol_dev, dims, atlas_dev, box, cand_mask_dev, label_vol_dev, proba_vol_dev, (cudaStream_t)stream);
 }
 
+int sc_atlas_ready_event(sc_ctx* ctx, void* cuda_event) {
+  SC_CHECK(ctx, SC_ERR_ARG, "sc_atlas_ready_event: null context");
+  ctx->atlas_ready = (cudaEvent_t)cuda_event;
+  ctx->atlas_chunks = 0;
+  return SC_OK;
+}
+
 int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int32_t dims[3], const float* atlas_host,
                            const int32_t* box, const uint8_t* cand_mask_host, uint8_t* label_vol_host,
                            float* proba_vol_host, void* stream) {
