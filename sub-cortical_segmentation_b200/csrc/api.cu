@@ -140,7 +140,10 @@ int sc_destroy(sc_ctx* ctx) {
   cudaDeviceSynchronize();
   tc_destroy(ctx);
   cudaFree(ctx->params); cudaFree(ctx->grads); cudaFree(ctx->adam_m); cudaFree(ctx->adam_v);
-  cudaFree(ctx->trainable); cudaFree(ctx->derived); cudaFree(ctx->ws.ptr); cudaFree(ctx->ws_train.ptr);
+  cudaFree(ctx->trainable); cudaFree(ctx->derived); cudaFree(ctx->ws.ptr); cudaFree(ctx->ws_train.ptr); cudaFree(ctx->ws_fit.ptr);
+  for (auto& g : ctx->train_graphs) cudaGraphExecDestroy(g.exec);
+  for (int i = 0; i < 2; ++i) if (ctx->train_side[i]) cudaStreamDestroy(ctx->train_side[i]);
+  for (int i = 0; i < 8; ++i) if (ctx->train_ev[i]) cudaEventDestroy(ctx->train_ev[i]);
   cudaFree(ctx->d_count); cudaFreeHost(ctx->h_count); cudaFree(ctx->train_consts); cudaFree(ctx->tc_timing_buf);
   for (auto& ev : ctx->prof_live) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto& ev : ctx->prof_free) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -172,6 +175,10 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
   if (!strcmp(key, "gather_ctas_per_sm")) {
     SC_CHECK(value >= 0 && value <= 32, SC_ERR_ARG, "sc_set_option: gather_ctas_per_sm must be 0..32");
     ctx->gather_ctas_per_sm = (int)value;
+    return SC_OK;
+  }
+  if (!strcmp(key, "train_graph")) {
+    ctx->train_graph_on = value != 0;
     return SC_OK;
   }
   if (!strcmp(key, "profile")) {

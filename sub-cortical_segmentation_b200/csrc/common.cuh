@@ -165,7 +165,15 @@ struct sc_ctx {
   float* out_w = nullptr;        // [270][16]
   float* out_b = nullptr;        // [16]
   sc::Workspace ws;              // inference scratch (grow-only)
-  sc::Workspace ws_train;        // training scratch
+  sc::Workspace ws_train;        // staging of the host entry points, scan preparation, eval scratch
+  sc::Workspace ws_fit;          // training step: staged inputs, saved activations, gradients of activations
+  // training step as a CUDA graph (one per (batch, global batch, injected masks) shape): the three branches run on
+  // three captured streams; rebuilt when the arena moves
+  struct TrainGraph { int n; long long n_global; int injected; void* arena; cudaGraphExec_t exec; int launches; };
+  std::vector<TrainGraph> train_graphs;
+  cudaStream_t train_side[2] = {nullptr, nullptr};
+  cudaEvent_t train_ev[8] = {};
+  int train_graph_on = 1;        // sc_set_option("train_graph", 0): launch the step kernel by kernel (profiling, debugging)
   float* train_consts = nullptr; // 64 ones | 64 zeros (identity BN epilogue of the conv1 kernel)
   int64_t* d_count = nullptr;    // device scalar for stream compaction
   int64_t* h_count = nullptr;    // pinned

@@ -109,9 +109,9 @@ __global__ void bn_act_kernel(const float* __restrict__ x, int n, int C, int H, 
 
 // ---- dropout ------------------------------------------------------------------------------------------
 // mask layout per sample: [3][540] branch (c*9+h*3+w) | [540] f1_drop | [540] f2_drop
-__global__ void make_masks_kernel(uint8_t* __restrict__ m, int64_t total, uint64_t seed) {
+__global__ void make_masks_kernel(uint8_t* __restrict__ m, int64_t total, const unsigned long long* __restrict__ seed) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) m[i] = (uint8_t)(hash3(seed, (uint64_t)i) & 1u);
+  if (i < total) m[i] = (uint8_t)(hash3(*seed, (uint64_t)i) & 1u);   // the seed lives in device memory: the launch is graph-replayable
 }
 
 // conv5 activation [n][60][3][ld=8] -> F5 [n][540] with dropout
@@ -627,178 +627,258 @@ struct Bump {
 
 static unsigned ew_grid(int64_t total) { return (unsigned)((total + 255) / 256 < 65535 * 8 ? (total + 255) / 256 : 65535 * 8); }
 
-int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, const uint8_t* y,
-                           int64_t n64, int64_t n_global, uint64_t seed, const uint8_t* masks_in, float* loss, cudaStream_t st) {
-  SC_CHECK(n64 <= 16384, SC_ERR_ARG, "sc_train_forward_backward: per-GPU batch %lld too large (max 16384)", (long long)n64);
-  const int n = (int)n64;
-  const ParamOff& O = ctx->off;
-  float* P = ctx->params;
-  float* G = ctx->grads;
-  const float* ins[3] = {in1, in2, in3};
-
-  // ---- workspace (two passes over the same carve-up: size, then pointers) ----
+// The step body.  Every pointer it touches lives in the context (staged inputs, arena, parameter / gradient buffers), every
+// scalar that changes from step to step is read from device memory (the dropout seed), so the same sequence of launches is
+// valid as a captured CUDA graph.  The three branches are independent between the patches and the concatenation (forward)
+// and after the gradient of the concatenation (backward): they run on three streams forked from / joined into `st`.
+struct StepBuf {
   struct BranchBuf {
     float* X[5]; float* A[5]; uint8_t* idx[2]; float* mean[5]; float* istd[5];
     float* F5; float* Z1;
     float* wf[5]; float* wd[5];
+    float *dZ1, *dF5, *dA, *dX, *dXpad;
+    double* sums;
   } bb[3];
-  float *CAT, *ZF1, *CAT2, *ZF2, *H2, *ZO, *dZO, *dH2, *dZF2, *dCAT2, *dZF1, *dCAT, *dZ1, *dF5, *dA, *dX, *dXpad, *ones, *zeros;
+  float *in[3], *in4; uint8_t* y;
+  float *CAT, *ZF1, *CAT2, *ZF2, *H2, *ZO, *dZO, *dH2, *dZF2, *dCAT2, *dZF1, *dCAT;
   uint8_t* masks;
-  double* sums;
-  auto carve = [&](Bump& B) {
-    for (int b = 0; b < 3; ++b) {
-      for (int l = 0; l < 5; ++l) {
-        bb[b].X[l] = B.take<float>((size_t)n * kConvCout[l] * kH[l] * kLd[l]);
-        const int oh = (l == 1 || l == 3) ? kH[l] / 2 : kH[l];
-        const int old = (l == 1) ? 16 : (l == 3) ? 8 : kLd[l];
-        bb[b].A[l] = B.take<float>((size_t)n * kConvCout[l] * oh * old);
-        bb[b].mean[l] = B.take<float>(64); bb[b].istd[l] = B.take<float>(64);
-        bb[b].wf[l] = B.take<float>((size_t)kConvCout[l] * kConvCin[l] * 9);
-        bb[b].wd[l] = l > 0 ? B.take<float>((size_t)kConvCout[l] * kConvCin[l] * 9) : nullptr;
-      }
-      bb[b].idx[0] = B.take<uint8_t>((size_t)n * 20 * 14 * 16);
-      bb[b].idx[1] = B.take<uint8_t>((size_t)n * 40 * 5 * 8);
-      bb[b].F5 = B.take<float>((size_t)n * 540);
-      bb[b].Z1 = B.take<float>((size_t)n * 180);
+  unsigned long long* seed;
+  float* loss;
+};
+
+static size_t carve_step(StepBuf& S, char* base, int n) {
+  Bump B{base, 0};
+  for (int b = 0; b < 3; ++b) {
+    auto& bb = S.bb[b];
+    S.in[b] = B.take<float>((size_t)n * 1024);
+    for (int l = 0; l < 5; ++l) {
+      bb.X[l] = B.take<float>((size_t)n * kConvCout[l] * kH[l] * kLd[l]);
+      const int oh = (l == 1 || l == 3) ? kH[l] / 2 : kH[l];
+      const int old = (l == 1) ? 16 : (l == 3) ? 8 : kLd[l];
+      bb.A[l] = B.take<float>((size_t)n * kConvCout[l] * oh * old);
+      bb.mean[l] = B.take<float>(64); bb.istd[l] = B.take<float>(64);
+      bb.wf[l] = B.take<float>((size_t)kConvCout[l] * kConvCin[l] * 9);
+      bb.wd[l] = l > 0 ? B.take<float>((size_t)kConvCout[l] * kConvCin[l] * 9) : nullptr;
     }
-    CAT = B.take<float>((size_t)n * 540);     // [D1_ax | D1_cor | D1_sag], f1_drop applied
-    ZF1 = B.take<float>((size_t)n * 540);
-    CAT2 = B.take<float>((size_t)n * 555);    // [prelu(ZF1) with f2_drop | atlas]
-    ZF2 = B.take<float>((size_t)n * 270);
-    H2 = B.take<float>((size_t)n * 270);
-    ZO = B.take<float>((size_t)n * 15);
-    dZO = B.take<float>((size_t)n * 15);
-    dH2 = B.take<float>((size_t)n * 270);
-    dZF2 = B.take<float>((size_t)n * 270);
-    dCAT2 = B.take<float>((size_t)n * 555);
-    dZF1 = B.take<float>((size_t)n * 540);
-    dCAT = B.take<float>((size_t)n * 540);
-    dZ1 = B.take<float>((size_t)n * 180);
-    dF5 = B.take<float>((size_t)n * 540);
-    dA = B.take<float>((size_t)n * 20 * 30 * 32);      // incoming activation gradient of the current layer
-    dX = B.take<float>((size_t)n * 20 * 30 * 32);      // compact conv-output gradient
-    dXpad = B.take<float>((size_t)n * 20 * 34 * 32);   // zero-padded copy for dgrad
-    masks = B.take<uint8_t>((size_t)n * 2700);
-    sums = B.take<double>(64 * 3);
-    ones = B.take<float>(64);
-    zeros = B.take<float>(64);
-  };
-  Bump sizing{nullptr, 0};
-  carve(sizing);
-  SC_TRY(ensure_ws(ctx->ws_train, sizing.off + 4096));
-  Bump B{reinterpret_cast<char*>(ctx->ws_train.ptr), 0};
-  carve(B);
+    bb.idx[0] = B.take<uint8_t>((size_t)n * 20 * 14 * 16);
+    bb.idx[1] = B.take<uint8_t>((size_t)n * 40 * 5 * 8);
+    bb.F5 = B.take<float>((size_t)n * 540);
+    bb.Z1 = B.take<float>((size_t)n * 180);
+    bb.dZ1 = B.take<float>((size_t)n * 180);
+    bb.dF5 = B.take<float>((size_t)n * 540);
+    bb.dA = B.take<float>((size_t)n * 20 * 30 * 32);      // incoming activation gradient of the current layer
+    bb.dX = B.take<float>((size_t)n * 20 * 30 * 32);      // compact conv-output gradient
+    bb.dXpad = B.take<float>((size_t)n * 20 * 34 * 32);   // zero-padded copy for dgrad
+    bb.sums = B.take<double>(64 * 3);
+  }
+  S.in4 = B.take<float>((size_t)n * 15);
+  S.y = B.take<uint8_t>((size_t)n);
+  S.CAT = B.take<float>((size_t)n * 540);     // [D1_ax | D1_cor | D1_sag], f1_drop applied
+  S.ZF1 = B.take<float>((size_t)n * 540);
+  S.CAT2 = B.take<float>((size_t)n * 555);    // [prelu(ZF1) with f2_drop | atlas]
+  S.ZF2 = B.take<float>((size_t)n * 270);
+  S.H2 = B.take<float>((size_t)n * 270);
+  S.ZO = B.take<float>((size_t)n * 15);
+  S.dZO = B.take<float>((size_t)n * 15);
+  S.dH2 = B.take<float>((size_t)n * 270);
+  S.dZF2 = B.take<float>((size_t)n * 270);
+  S.dCAT2 = B.take<float>((size_t)n * 555);
+  S.dZF1 = B.take<float>((size_t)n * 540);
+  S.dCAT = B.take<float>((size_t)n * 540);
+  S.masks = B.take<uint8_t>((size_t)n * 2700);
+  S.seed = B.take<unsigned long long>(1);
+  S.loss = B.take<float>(1);
+  return B.off;
+}
+
+static int train_body(sc_ctx* ctx, const StepBuf& S, int n, int64_t n_global, bool injected_masks, cudaStream_t st) {
+  const ParamOff& O = ctx->off;
+  float* P = ctx->params;
+  float* G = ctx->grads;
+  const float* ones = ctx->train_consts;
+  const float* zeros = ctx->train_consts + 64;
+  cudaStream_t sb[3] = {st, ctx->train_side[0], ctx->train_side[1]};
+  cudaEvent_t* ev = ctx->train_ev;
 
   SC_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * SC_PARAM_FLOATS, st));
-  SC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  SC_CUDA(cudaMemsetAsync(S.loss, 0, sizeof(float), st));
+  if (!injected_masks) { make_masks_kernel<<<ew_grid((int64_t)n * 2700), 256, 0, st>>>(S.masks, (int64_t)n * 2700, S.seed); ctx->launches++; }
+  SC_CUDA(cudaEventRecord(ev[0], st));
+  for (int b = 1; b < 3; ++b) SC_CUDA(cudaStreamWaitEvent(sb[b], ev[0], 0));
+
+  // ================= forward =================
+  for (int b = 0; b < 3; ++b) {
+    const BranchOff& Ob = O.br[b];
+    const auto& bb = S.bb[b];
+    cudaStream_t s = sb[b];
+    for (int l = 0; l < 5; ++l) {
+      const int co = kConvCout[l], ci = kConvCin[l];
+      repack_conv_kernel<<<(co * ci * 9 + 255) / 256, 256, 0, s>>>(P + Ob.convW[l], co, ci, bb.wf[l], bb.wd[l]);
+      ctx->launches++;
+      if (l == 0) {
+        SC_TRY(launch_conv1_patches(ctx, S.in[b], n, bb.wf[0], ones, zeros, ones, bb.X[0], s));
+      } else {
+        SC_TRY(train_conv(ctx, ci, co, bb.A[l - 1], kInH[l], kInLd[l], bb.X[l], kH[l], kLd[l], bb.wf[l], n, PC_TRAIN_FWD, s));
+      }
+      SC_CUDA(cudaMemsetAsync(bb.sums, 0, 64 * 3 * sizeof(double), s));
+      bn_stats_kernel<<<dim3(co, 32), 256, 0, s>>>(bb.X[l], n, co, kH[l], kH[l], kLd[l], bb.sums);
+      bn_finalize_kernel<<<1, 64, 0, s>>>(bb.sums, co, (double)n * kH[l] * kH[l], bb.mean[l], bb.istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3]);
+      const int pool = (l == 1 || l == 3);
+      const int oh = pool ? kH[l] / 2 : kH[l];
+      const int old = (l == 1) ? 16 : (l == 3) ? 8 : kLd[l];
+      bn_act_kernel<<<ew_grid((int64_t)n * co * oh * oh), 256, 0, s>>>(bb.X[l], n, co, kH[l], kH[l], kLd[l], bb.mean[l], bb.istd[l],
+                                                                     P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], pool, bb.A[l], oh, oh, old,
+                                                                     pool ? bb.idx[l == 1 ? 0 : 1] : nullptr);
+      ctx->launches += 3;
+    }
+    flatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, s>>>(bb.A[4], n, S.masks + b * 540, bb.F5);
+    ctx->launches++;
+    SC_TRY((sgemm<false, false>(ctx, bb.F5, 540, P + Ob.d1W, 180, bb.Z1, 180, n, 180, 540, P + Ob.d1b, 0, PC_TRAIN_FWD, s)));
+    dense_act_kernel<<<ew_grid((int64_t)n * 180), 256, 0, s>>>(bb.Z1, n, 180, P + Ob.d1alpha, S.masks + 1620 + b * 180, 2700, S.CAT, 540, b * 180);
+    ctx->launches++;
+    if (b > 0) { SC_CUDA(cudaEventRecord(ev[b], s)); SC_CUDA(cudaStreamWaitEvent(st, ev[b], 0)); }
+  }
+  SC_TRY((sgemm<false, false>(ctx, S.CAT, 540, P + O.fc1W, 540, S.ZF1, 540, n, 540, 540, P + O.fc1b, 0, PC_TRAIN_FWD, st)));
+  dense_act_kernel<<<ew_grid((int64_t)n * 540), 256, 0, st>>>(S.ZF1, n, 540, P + O.a1, S.masks + 2160, 2700, S.CAT2, 555, 0);
+  SC_CUDA(cudaMemcpy2DAsync(S.CAT2 + 540, 555 * 4, S.in4, 15 * 4, 15 * 4, n, cudaMemcpyDeviceToDevice, st));
+  SC_TRY((sgemm<false, false>(ctx, S.CAT2, 555, P + O.fc2W, 270, S.ZF2, 270, n, 270, 555, P + O.fc2b, 0, PC_TRAIN_FWD, st)));
+  dense_act_kernel<<<ew_grid((int64_t)n * 270), 256, 0, st>>>(S.ZF2, n, 270, P + O.a2, nullptr, 0, S.H2, 270, 0);
+  SC_TRY((sgemm<false, false>(ctx, S.H2, 270, P + O.outW, 15, S.ZO, 15, n, 15, 270, P + O.outb, 0, PC_TRAIN_FWD, st)));
+  softmax_ce_kernel<<<(n + 127) / 128, 128, 0, st>>>(S.ZO, S.y, n, 1.f / (float)n_global, S.dZO, S.loss);
+  ctx->launches += 3;
+
+  // ================= backward =================
+  // out layer
+  SC_TRY((sgemm<true, false>(ctx, S.H2, 270, S.dZO, 15, G + O.outW, 15, 270, 15, n, nullptr, 0, PC_TRAIN_BWD, st)));
+  colsum_kernel<<<dim3(1, 32), 32, 0, st>>>(S.dZO, n, 15, G + O.outb);
+  SC_TRY((sgemm<false, true>(ctx, S.dZO, 15, P + O.outW, 15, S.dH2, 270, n, 270, 15, nullptr, 0, PC_TRAIN_BWD, st)));
+  // fc_2
+  dense_act_bwd_kernel<<<dim3((270 + 31) / 32, 16), 256, 0, st>>>(S.dH2, 270, 0, S.ZF2, n, 270, P + O.a2, nullptr, 0, S.dZF2, G + O.a2, G + O.fc2b);
+  SC_TRY((sgemm<true, false>(ctx, S.CAT2, 555, S.dZF2, 270, G + O.fc2W, 270, 555, 270, n, nullptr, 0, PC_TRAIN_BWD, st)));
+  SC_TRY((sgemm<false, true>(ctx, S.dZF2, 270, P + O.fc2W, 270, S.dCAT2, 555, n, 555, 270, nullptr, 0, PC_TRAIN_BWD, st)));
+  // FC1 (dropout f2_drop sits on its activation)
+  dense_act_bwd_kernel<<<dim3((540 + 31) / 32, 16), 256, 0, st>>>(S.dCAT2, 555, 0, S.ZF1, n, 540, P + O.a1, S.masks + 2160, 2700, S.dZF1, G + O.a1, G + O.fc1b);
+  SC_TRY((sgemm<true, false>(ctx, S.CAT, 540, S.dZF1, 540, G + O.fc1W, 540, 540, 540, n, nullptr, 0, PC_TRAIN_BWD, st)));
+  SC_TRY((sgemm<false, true>(ctx, S.dZF1, 540, P + O.fc1W, 540, S.dCAT, 540, n, 540, 540, nullptr, 0, PC_TRAIN_BWD, st)));
+  ctx->launches += 3;
+  SC_CUDA(cudaEventRecord(ev[3], st));
+  for (int b = 1; b < 3; ++b) SC_CUDA(cudaStreamWaitEvent(sb[b], ev[3], 0));
+
+  for (int b = 0; b < 3; ++b) {
+    const BranchOff& Ob = O.br[b];
+    const auto& bb = S.bb[b];
+    cudaStream_t s = sb[b];
+    // d1 (dropout f1_drop sits on the concatenated d1 activations)
+    dense_act_bwd_kernel<<<dim3((180 + 31) / 32, 16), 256, 0, s>>>(S.dCAT, 540, b * 180, bb.Z1, n, 180, P + Ob.d1alpha, S.masks + 1620 + b * 180, 2700,
+                                                                  bb.dZ1, G + Ob.d1alpha, G + Ob.d1b);
+    SC_TRY((sgemm<true, false>(ctx, bb.F5, 540, bb.dZ1, 180, G + Ob.d1W, 180, 540, 180, n, nullptr, 0, PC_TRAIN_BWD, s)));
+    SC_TRY((sgemm<false, true>(ctx, bb.dZ1, 180, P + Ob.d1W, 180, bb.dF5, 540, n, 540, 180, nullptr, 0, PC_TRAIN_BWD, s)));
+    unflatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, s>>>(bb.dF5, n, S.masks + b * 540, bb.dA);
+    ctx->launches += 2;
+    for (int l = 4; l >= 0; --l) {
+      const int co = kConvCout[l], ci = kConvCin[l], H = kH[l], ld = kLd[l];
+      const int pool = (l == 1 || l == 3);
+      const int pld = (l == 1) ? 16 : 8;
+      const uint8_t* idx = pool ? bb.idx[l == 1 ? 0 : 1] : nullptr;
+      const double count = (double)n * H * H;
+      SC_CUDA(cudaMemsetAsync(bb.sums, 0, 64 * 3 * sizeof(double), s));
+      bn_bwd_reduce_kernel<<<dim3(co, 32), 256, 0, s>>>(bb.X[l], bb.dA, idx, n, co, H, H, ld, pool, pld, bb.mean[l], bb.istd[l],
+                                                        P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], bb.sums);
+      bn_bwd_params_kernel<<<1, 64, 0, s>>>(bb.sums, co, G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l]);
+      const int pld2 = kInLd[l];   // padded map has the size of this layer's input (H+4 >= inH, same row stride)
+      if (l > 0) SC_CUDA(cudaMemsetAsync(bb.dXpad, 0, (size_t)n * co * (H + 4) * pld2 * 4, s));
+      bn_bwd_dx_kernel<<<ew_grid((int64_t)n * co * H * H), 256, 0, s>>>(bb.X[l], bb.dA, idx, n, co, H, H, ld, pool, pld, bb.mean[l], bb.istd[l],
+                                                                       P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], bb.sums, count, bb.dX,
+                                                                       l > 0 ? bb.dXpad : nullptr, pld2);
+      // wgrad against this layer's input (the previous activation, or the patches for conv1)
+      const float* lin = l == 0 ? S.in[b] : bb.A[l - 1];
+      if (l == 0) {
+        int zc = n < 32 ? n : 32;
+        conv_wgrad_kernel<<<dim3(co, ci, zc), 128, 0, s>>>(lin, ci, kInH[l], kInLd[l], bb.dX, co, H, H, ld, n, G + Ob.convW[l]);
+        ctx->launches++;
+      } else if (co == 20) {
+        SC_TRY(launch_wgrad_tiled<20>(ctx, lin, ci, kInH[l], kInLd[l], bb.dX, H, ld, n, G + Ob.convW[l], s));
+      } else if (co == 40) {
+        SC_TRY(launch_wgrad_tiled<40>(ctx, lin, ci, kInH[l], kInLd[l], bb.dX, H, ld, n, G + Ob.convW[l], s));
+      } else {
+        SC_TRY(launch_wgrad_tiled<60>(ctx, lin, ci, kInH[l], kInLd[l], bb.dX, H, ld, n, G + Ob.convW[l], s));
+      }
+      ctx->launches += 3;
+      if (l > 0) {
+        // dgrad: d(input) = valid conv of the zero-padded dx with the raw taps, channel roles swapped
+        SC_TRY(train_conv(ctx, co, ci, bb.dXpad, H + 4, pld2, bb.dA, kInH[l], kInLd[l], bb.wd[l], n, PC_TRAIN_BWD, s));
+      }
+    }
+    if (b > 0) { SC_CUDA(cudaEventRecord(ev[3 + b], s)); SC_CUDA(cudaStreamWaitEvent(st, ev[3 + b], 0)); }
+  }
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4, const uint8_t* y,
+                           int64_t n64, int64_t n_global, uint64_t seed, const uint8_t* masks_in, float* loss, cudaStream_t st) {
+  SC_CHECK(n64 <= 16384, SC_ERR_ARG, "sc_train_forward_backward: per-GPU batch %lld too large (max 16384)", (long long)n64);
+  const int n = (int)n64;
+  StepBuf S;
+  const size_t need = carve_step(S, nullptr, n);
+  SC_TRY(ensure_ws(ctx->ws_fit, need + 4096));
+  carve_step(S, reinterpret_cast<char*>(ctx->ws_fit.ptr), n);
   if (!ctx->train_consts) {
     SC_CUDA(cudaMalloc(&ctx->train_consts, 128 * sizeof(float)));
     float h1[128];
     for (int i = 0; i < 128; ++i) h1[i] = i < 64 ? 1.f : 0.f;
     SC_CUDA(cudaMemcpy(ctx->train_consts, h1, sizeof(h1), cudaMemcpyHostToDevice));
   }
-  ones = ctx->train_consts; zeros = ctx->train_consts + 64;
-  if (masks_in) SC_CUDA(cudaMemcpyAsync(masks, masks_in, (size_t)n * 2700, cudaMemcpyDeviceToDevice, st));
-  else { make_masks_kernel<<<ew_grid((int64_t)n * 2700), 256, 0, st>>>(masks, (int64_t)n * 2700, seed); ctx->launches++; }
-
-  // ================= forward =================
-  for (int b = 0; b < 3; ++b) {
-    const BranchOff& Ob = O.br[b];
-    for (int l = 0; l < 5; ++l) {
-      const int co = kConvCout[l], ci = kConvCin[l];
-      repack_conv_kernel<<<(co * ci * 9 + 255) / 256, 256, 0, st>>>(P + Ob.convW[l], co, ci, bb[b].wf[l], bb[b].wd[l]);
-      ctx->launches++;
-      if (l == 0) {
-        SC_TRY(launch_conv1_patches(ctx, ins[b], n, bb[b].wf[0], ones, zeros, ones, bb[b].X[0], st));
-      } else {
-        SC_TRY(train_conv(ctx, ci, co, bb[b].A[l - 1], kInH[l], kInLd[l], bb[b].X[l], kH[l], kLd[l], bb[b].wf[l], n, PC_TRAIN_FWD, st));
-      }
-      SC_CUDA(cudaMemsetAsync(sums, 0, 64 * 3 * sizeof(double), st));
-      bn_stats_kernel<<<dim3(co, 32), 256, 0, st>>>(bb[b].X[l], n, co, kH[l], kH[l], kLd[l], sums);
-      bn_finalize_kernel<<<1, 64, 0, st>>>(sums, co, (double)n * kH[l] * kH[l], bb[b].mean[l], bb[b].istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3]);
-      const int pool = (l == 1 || l == 3);
-      const int oh = pool ? kH[l] / 2 : kH[l];
-      const int old = (l == 1) ? 16 : (l == 3) ? 8 : kLd[l];
-      bn_act_kernel<<<ew_grid((int64_t)n * co * oh * oh), 256, 0, st>>>(bb[b].X[l], n, co, kH[l], kH[l], kLd[l], bb[b].mean[l], bb[b].istd[l],
-                                                                      P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], pool, bb[b].A[l], oh, oh, old,
-                                                                      pool ? bb[b].idx[l == 1 ? 0 : 1] : nullptr);
-      ctx->launches += 3;
-    }
-    flatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, st>>>(bb[b].A[4], n, masks + b * 540, bb[b].F5);
-    ctx->launches++;
-    SC_TRY((sgemm<false, false>(ctx, bb[b].F5, 540, P + Ob.d1W, 180, bb[b].Z1, 180, n, 180, 540, P + Ob.d1b, 0, PC_TRAIN_FWD, st)));
-    dense_act_kernel<<<ew_grid((int64_t)n * 180), 256, 0, st>>>(bb[b].Z1, n, 180, P + Ob.d1alpha, masks + 1620 + b * 180, 2700, CAT, 540, b * 180);
-    ctx->launches++;
+  if (!ctx->train_side[0]) {
+    for (int i = 0; i < 2; ++i) SC_CUDA(cudaStreamCreateWithFlags(&ctx->train_side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) SC_CUDA(cudaEventCreateWithFlags(&ctx->train_ev[i], cudaEventDisableTiming));
   }
-  SC_TRY((sgemm<false, false>(ctx, CAT, 540, P + O.fc1W, 540, ZF1, 540, n, 540, 540, P + O.fc1b, 0, PC_TRAIN_FWD, st)));
-  dense_act_kernel<<<ew_grid((int64_t)n * 540), 256, 0, st>>>(ZF1, n, 540, P + O.a1, masks + 2160, 2700, CAT2, 555, 0);
-  SC_CUDA(cudaMemcpy2DAsync(CAT2 + 540, 555 * 4, in4, 15 * 4, 15 * 4, n, cudaMemcpyDeviceToDevice, st));
-  SC_TRY((sgemm<false, false>(ctx, CAT2, 555, P + O.fc2W, 270, ZF2, 270, n, 270, 555, P + O.fc2b, 0, PC_TRAIN_FWD, st)));
-  dense_act_kernel<<<ew_grid((int64_t)n * 270), 256, 0, st>>>(ZF2, n, 270, P + O.a2, nullptr, 0, H2, 270, 0);
-  SC_TRY((sgemm<false, false>(ctx, H2, 270, P + O.outW, 15, ZO, 15, n, 15, 270, P + O.outb, 0, PC_TRAIN_FWD, st)));
-  softmax_ce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ZO, y, n, 1.f / (float)n_global, dZO, loss);
-  ctx->launches += 3;
+  // stage the caller's batch into the arena: the step itself only ever sees context-owned addresses
+  const float* ins[3] = {in1, in2, in3};
+  for (int b = 0; b < 3; ++b) SC_CUDA(cudaMemcpyAsync(S.in[b], ins[b], (size_t)n * 4096, cudaMemcpyDeviceToDevice, st));
+  SC_CUDA(cudaMemcpyAsync(S.in4, in4, (size_t)n * 60, cudaMemcpyDeviceToDevice, st));
+  SC_CUDA(cudaMemcpyAsync(S.y, y, (size_t)n, cudaMemcpyDeviceToDevice, st));
+  if (masks_in) SC_CUDA(cudaMemcpyAsync(S.masks, masks_in, (size_t)n * 2700, cudaMemcpyDeviceToDevice, st));
+  const unsigned long long seed_h = seed;
+  SC_CUDA(cudaMemcpyAsync(S.seed, &seed_h, sizeof(seed_h), cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
 
-  // ================= backward =================
-  // out layer
-  SC_TRY((sgemm<true, false>(ctx, H2, 270, dZO, 15, G + O.outW, 15, 270, 15, n, nullptr, 0, PC_TRAIN_BWD, st)));
-  colsum_kernel<<<dim3(1, 32), 32, 0, st>>>(dZO, n, 15, G + O.outb);
-  SC_TRY((sgemm<false, true>(ctx, dZO, 15, P + O.outW, 15, dH2, 270, n, 270, 15, nullptr, 0, PC_TRAIN_BWD, st)));
-  // fc_2
-  dense_act_bwd_kernel<<<dim3((270 + 31) / 32, 16), 256, 0, st>>>(dH2, 270, 0, ZF2, n, 270, P + O.a2, nullptr, 0, dZF2, G + O.a2, G + O.fc2b);
-  SC_TRY((sgemm<true, false>(ctx, CAT2, 555, dZF2, 270, G + O.fc2W, 270, 555, 270, n, nullptr, 0, PC_TRAIN_BWD, st)));
-  SC_TRY((sgemm<false, true>(ctx, dZF2, 270, P + O.fc2W, 270, dCAT2, 555, n, 555, 270, nullptr, 0, PC_TRAIN_BWD, st)));
-  // FC1 (dropout f2_drop sits on its activation)
-  dense_act_bwd_kernel<<<dim3((540 + 31) / 32, 16), 256, 0, st>>>(dCAT2, 555, 0, ZF1, n, 540, P + O.a1, masks + 2160, 2700, dZF1, G + O.a1, G + O.fc1b);
-  SC_TRY((sgemm<true, false>(ctx, CAT, 540, dZF1, 540, G + O.fc1W, 540, 540, 540, n, nullptr, 0, PC_TRAIN_BWD, st)));
-  SC_TRY((sgemm<false, true>(ctx, dZF1, 540, P + O.fc1W, 540, dCAT, 540, n, 540, 540, nullptr, 0, PC_TRAIN_BWD, st)));
-  ctx->launches += 3;
-
-  for (int b = 0; b < 3; ++b) {
-    const BranchOff& Ob = O.br[b];
-    // d1 (dropout f1_drop sits on the concatenated d1 activations)
-    dense_act_bwd_kernel<<<dim3((180 + 31) / 32, 16), 256, 0, st>>>(dCAT, 540, b * 180, bb[b].Z1, n, 180, P + Ob.d1alpha, masks + 1620 + b * 180, 2700,
-                                                                   dZ1, G + Ob.d1alpha, G + Ob.d1b);
-    SC_TRY((sgemm<true, false>(ctx, bb[b].F5, 540, dZ1, 180, G + Ob.d1W, 180, 540, 180, n, nullptr, 0, PC_TRAIN_BWD, st)));
-    SC_TRY((sgemm<false, true>(ctx, dZ1, 180, P + Ob.d1W, 180, dF5, 540, n, 540, 180, nullptr, 0, PC_TRAIN_BWD, st)));
-    unflatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, st>>>(dF5, n, masks + b * 540, dA);
-    ctx->launches += 2;
-    for (int l = 4; l >= 0; --l) {
-      const int co = kConvCout[l], ci = kConvCin[l], H = kH[l], ld = kLd[l];
-      const int pool = (l == 1 || l == 3);
-      const int pld = (l == 1) ? 16 : 8;
-      const uint8_t* idx = pool ? bb[b].idx[l == 1 ? 0 : 1] : nullptr;
-      const double count = (double)n * H * H;
-      SC_CUDA(cudaMemsetAsync(sums, 0, 64 * 3 * sizeof(double), st));
-      bn_bwd_reduce_kernel<<<dim3(co, 32), 256, 0, st>>>(bb[b].X[l], dA, idx, n, co, H, H, ld, pool, pld, bb[b].mean[l], bb[b].istd[l],
-                                                         P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], sums);
-      bn_bwd_params_kernel<<<1, 64, 0, st>>>(sums, co, G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l]);
-      const int pld2 = kInLd[l];   // padded map has the size of this layer's input (H+4 >= inH, same row stride)
-      if (l > 0) SC_CUDA(cudaMemsetAsync(dXpad, 0, (size_t)n * co * (H + 4) * pld2 * 4, st));
-      bn_bwd_dx_kernel<<<ew_grid((int64_t)n * co * H * H), 256, 0, st>>>(bb[b].X[l], dA, idx, n, co, H, H, ld, pool, pld, bb[b].mean[l], bb[b].istd[l],
-                                                                        P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], sums, count, dX,
-                                                                        l > 0 ? dXpad : nullptr, pld2);
-      // wgrad against this layer's input (the previous activation, or the patches for conv1)
-      const float* lin = l == 0 ? ins[b] : bb[b].A[l - 1];
-      if (l == 0) {
-        int zc = n < 32 ? n : 32;
-        conv_wgrad_kernel<<<dim3(co, ci, zc), 128, 0, st>>>(lin, ci, kInH[l], kInLd[l], dX, co, H, H, ld, n, G + Ob.convW[l]);
-        ctx->launches++;
-      } else if (co == 20) {
-        SC_TRY(launch_wgrad_tiled<20>(ctx, lin, ci, kInH[l], kInLd[l], dX, H, ld, n, G + Ob.convW[l], st));
-      } else if (co == 40) {
-        SC_TRY(launch_wgrad_tiled<40>(ctx, lin, ci, kInH[l], kInLd[l], dX, H, ld, n, G + Ob.convW[l], st));
-      } else {
-        SC_TRY(launch_wgrad_tiled<60>(ctx, lin, ci, kInH[l], kInLd[l], dX, H, ld, n, G + Ob.convW[l], st));
+  const bool use_graph = ctx->train_graph_on && !ctx->profile;
+  if (!use_graph) {
+    SC_TRY(train_body(ctx, S, n, n_global, masks_in != nullptr, st));
+  } else {
+    sc_ctx::TrainGraph* g = nullptr;
+    for (auto& e : ctx->train_graphs)
+      if (e.n == n && e.n_global == (long long)n_global && e.injected == (masks_in ? 1 : 0) && e.arena == ctx->ws_fit.ptr) g = &e;
+    if (!g) {
+      // a moved arena invalidates every captured address
+      for (size_t i = 0; i < ctx->train_graphs.size();) {
+        if (ctx->train_graphs[i].arena != ctx->ws_fit.ptr) { cudaGraphExecDestroy(ctx->train_graphs[i].exec); ctx->train_graphs.erase(ctx->train_graphs.begin() + i); }
+        else ++i;
       }
-      ctx->launches += 3;
-      if (l > 0) {
-        // dgrad: d(input) = valid conv of the zero-padded dx with the raw taps, channel roles swapped
-        SC_TRY(train_conv(ctx, co, ci, dXpad, H + 4, pld2, dA, kInH[l], kInLd[l], bb[b].wd[l], n, PC_TRAIN_BWD, st));
-      }
+      if (ctx->train_graphs.size() >= 8) { cudaGraphExecDestroy(ctx->train_graphs[0].exec); ctx->train_graphs.erase(ctx->train_graphs.begin()); }
+      cudaStream_t cap;
+      SC_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));   // capture on a private stream: `st` may be the legacy default stream
+      const int64_t l0 = ctx->launches;
+      SC_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
+      const int bs = train_body(ctx, S, n, n_global, masks_in != nullptr, cap);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+      cudaStreamDestroy(cap);
+      const int launches = (int)(ctx->launches - l0);
+      ctx->launches = l0;
+      if (bs != SC_OK) { if (graph) cudaGraphDestroy(graph); return bs; }
+      SC_CUDA(ce);
+      cudaGraphExec_t exec = nullptr;
+      const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      SC_CUDA(ie);
+      ctx->train_graphs.push_back({n, (long long)n_global, masks_in ? 1 : 0, ctx->ws_fit.ptr, exec, launches});
+      g = &ctx->train_graphs.back();
     }
+    SC_CUDA(cudaGraphLaunch(g->exec, st));
+    ctx->launches += g->launches;
   }
-  SC_CUDA(cudaGetLastError());
+  SC_CUDA(cudaMemcpyAsync(loss, S.loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
   return SC_OK;
 }
 
