@@ -144,7 +144,7 @@ int sc_destroy(sc_ctx* ctx) {
   for (auto& g : ctx->train_graphs) cudaGraphExecDestroy(g.exec);
   for (int i = 0; i < 2; ++i) if (ctx->train_side[i]) cudaStreamDestroy(ctx->train_side[i]);
   for (int i = 0; i < 8; ++i) if (ctx->train_ev[i]) cudaEventDestroy(ctx->train_ev[i]);
-  cudaFree(ctx->d_count); cudaFreeHost(ctx->h_count); cudaFree(ctx->train_consts); cudaFree(ctx->tc_timing_buf);
+  cudaFree(ctx->d_count); cudaFreeHost(ctx->h_count); cudaFree(ctx->train_consts); cudaFree(ctx->tc_timing_buf); cudaFree(ctx->train_panels); cudaFree(ctx->train_dense_w);
   for (auto& ev : ctx->prof_live) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto& ev : ctx->prof_free) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   if (ctx->h_slab_cnt) { cudaFreeHost(ctx->h_slab_cnt); cudaEventDestroy(ctx->compact_ev); }

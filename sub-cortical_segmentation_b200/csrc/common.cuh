@@ -169,12 +169,17 @@ struct sc_ctx {
   sc::Workspace ws_fit;          // training step: staged inputs, saved activations, gradients of activations
   // training step as a CUDA graph (one per (batch, global batch, injected masks) shape): the three branches run on
   // three captured streams; rebuilt when the arena moves
-  struct TrainGraph { int n; long long n_global; int injected; void* arena; cudaGraphExec_t exec; int launches; };
+  struct TrainGraph { int n; long long n_global; int injected; int backend; void* arena; cudaGraphExec_t exec; int launches; };
   std::vector<TrainGraph> train_graphs;
   cudaStream_t train_side[2] = {nullptr, nullptr};
   cudaEvent_t train_ev[8] = {};
   int train_graph_on = 1;        // sc_set_option("train_graph", 0): launch the step kernel by kernel (profiling, debugging)
-  float* train_consts = nullptr; // 64 ones | 64 zeros (identity BN epilogue of the conv1 kernel)
+  void* train_panels = nullptr;  // sweep weight panels of the training step, re-derived on the device every step
+  void* train_dense_w = nullptr; // dense weights of the training step in the two GEMM operand layouts, re-derived every step
+  struct TrainDenseW { float* wnk; float* wkn; float* bias; };
+  TrainDenseW train_dw[6];       // d1 x3, FC1, fc_2, out_layer
+  sc::SweepW train_sw[3][5][2];  // [branch][layer 1..4][forward | dgrad]
+  float* train_consts = nullptr; // 1024 ones | 1024 zeros (identity epilogue constants of the training kernels)
   int64_t* d_count = nullptr;    // device scalar for stream compaction
   int64_t* h_count = nullptr;    // pinned
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
@@ -354,6 +359,37 @@ int branch_patches_tc(sc_ctx* ctx, int branch, const float* patches, int64_t n, 
                       cudaStream_t st);
 int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const float* atlas, const int32_t* box,
                    const uint8_t* cand, uint8_t* label_vol, float* proba_vol, cudaStream_t st);
+
+// train_tc.cu : the convolutional part of the training step on the tensor cores (split-bf16 wide-row maps)
+constexpr float kBnEps = 1e-4f;
+struct TcBranchBuf {
+  float* X[5]; float* A[5]; uint16_t* AT[5]; uint8_t* idx[5]; float* mean[5]; float* istd[5];
+  float* frame; float* dA; uint16_t* DT; float* dX0; double* sums;
+};
+size_t tc_branch_bytes(int n);
+int tc_carve_branch(TcBranchBuf& T, char* base, int n);
+int tc_branch_forward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* patches, const float* wf0, int n, const uint8_t* masks,
+                      float* F5, cudaStream_t s);
+int tc_branch_backward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* patches, const float* dF5, int dF5_ld, const uint8_t* masks, int n,
+                       cudaStream_t s);
+// train_dense.cu : the dense layers of the training step as split-bf16 tcgen05 GEMMs
+constexpr int kTrainZeros = 1024;   // ctx->train_consts: 1024 ones | 1024 zeros (identity epilogue constants)
+struct TcDenseBuf {
+  int npad;                                  // batch rounded up to 64: K of the wgrad GEMMs
+  char* zero_begin; size_t zero_bytes;       // split operands whose padding must read as zero: cleared every step
+  float *F5s[3], *F5T[3], *Z1[3], *dZ1s[3], *dZ1T[3], *dF5[3], *gW1[3];
+  float *CATs, *CATT, *ZF1, *CAT2s, *CAT2T, *ZF2, *H2s, *H2T, *ZO, *dZOs, *dZOT, *dH2, *dZF2s, *dZF2T, *dCAT2, *dZF1s, *dZF1T, *dCAT;
+  float *gWfc1, *gWfc2, *gWout;
+};
+int tc_train_prepare(sc_ctx* ctx);      // persistent buffers: allocated outside any stream capture
+int tdense_prepare(sc_ctx* ctx);
+size_t tdense_bytes(int n);
+void tdense_carve(TcDenseBuf& D, char* base, int n);
+int tdense_branch_forward(sc_ctx* ctx, int b, const TcDenseBuf& D, const float* F5, int n, const uint8_t* masks, cudaStream_t s);
+int tdense_head(sc_ctx* ctx, const TcDenseBuf& D, const float* in4, const uint8_t* y, int n, int64_t n_global, const uint8_t* masks, float* loss,
+                cudaStream_t s);
+int tdense_branch_backward(sc_ctx* ctx, int b, const TcDenseBuf& D, int n, const uint8_t* masks, cudaStream_t s);
+int launch_conv1_wgrad(sc_ctx* ctx, const float* patches, const float* dx_planar, int n, int zc, float* gW, cudaStream_t st);
 
 // train.cu
 int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4,

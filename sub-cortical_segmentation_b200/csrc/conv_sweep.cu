@@ -859,7 +859,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     a.stages = (227 * 1024 - fixed - ob_bytes) / slot;
   }
   if (a.stages > 8) a.stages = 8;
-  const bool use_pair = w.ksteps == 3 && !in_fmt && !out_fmt;          // 40 input channels: the resident weights need the CTA pair
+  const bool use_pair = w.ksteps >= 3 && !in_fmt && !out_fmt;          // >= 40 input channels: the resident weights need the CTA pair
   SC_CHECK(use_pair || a.stages >= 3, SC_ERR_ARG, "conv_sweep: ring does not fit (layer %d)", layer);
   const size_t smem = (size_t)fixed + (size_t)a.stages * slot + (size_t)a.out_bufs * ob_bytes;
 
@@ -936,6 +936,10 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
       auto kern = conv_sweep_pair_kernel<3, 1, 2>;
       SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024));
       kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
+    } else if (dil == 1 && !pool && w.ksteps == 4) {   // training: dgrad of conv5 (60 input channels)
+      auto kern = conv_sweep_pair_kernel<4, 1, 0>;
+      SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024));
+      kern<<<2 * npairs, 576, smem_p, st>>>(mapA, mapWp, mapO, a);
     } else if (dil == 1 && !pool) {
       auto kern = conv_sweep_pair_kernel<3, 1, 0>;
       SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(kern), 227 * 1024));
@@ -962,6 +966,8 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   if (w.ksteps == 2 && dil == 2 && !pool && i32 && !o32) return launch_sweep_t<2, 2, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);              // conv3
   // patchwise maps (dilation 1 everywhere, stride-2 pools stay separate passes)
   if (w.ksteps == 2 && dil == 1 && !pool && i32 && !o32) return launch_sweep_t<2, 1, 0, 16, true, false>(ctx, mapA, mapW, mapO, a, smem, st);
+  // training: raw conv2 forward and its dgrad (20 -> 20 channels, 128 B pixels in and out)
+  if (w.ksteps == 2 && dil == 1 && !pool && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 0, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);
   set_error("conv_sweep: no kernel instance for ksteps=%d dil=%d pool=%d in_fmt=%d out_fmt=%d", w.ksteps, dil, pool, in_fmt, out_fmt);
   return SC_ERR_ARG;
 }

@@ -17,7 +17,6 @@
 
 namespace sc {
 
-constexpr float kBnEps = 1e-4f;
 constexpr int kH[5] = {30, 28, 12, 10, 3};      // conv output size per layer
 constexpr int kLd[5] = {32, 32, 16, 16, 8};     // row stride of the conv output maps
 constexpr int kInH[5] = {32, 30, 14, 12, 5};    // conv input size
@@ -632,6 +631,8 @@ static unsigned ew_grid(int64_t total) { return (unsigned)((total + 255) / 256 <
 // valid as a captured CUDA graph.  The three branches are independent between the patches and the concatenation (forward)
 // and after the gradient of the concatenation (backward): they run on three streams forked from / joined into `st`.
 struct StepBuf {
+  TcBranchBuf tc[3];
+  TcDenseBuf td;
   struct BranchBuf {
     float* X[5]; float* A[5]; uint8_t* idx[2]; float* mean[5]; float* istd[5];
     float* F5; float* Z1;
@@ -646,30 +647,39 @@ struct StepBuf {
   float* loss;
 };
 
-static size_t carve_step(StepBuf& S, char* base, int n) {
+static size_t carve_step(StepBuf& S, char* base, int n, bool tc) {
   Bump B{base, 0};
   for (int b = 0; b < 3; ++b) {
     auto& bb = S.bb[b];
     S.in[b] = B.take<float>((size_t)n * 1024);
     for (int l = 0; l < 5; ++l) {
-      bb.X[l] = B.take<float>((size_t)n * kConvCout[l] * kH[l] * kLd[l]);
+      // the tensor-core path keeps its activations in the split-bf16 maps of S.tc; the planar fp32 maps are the SIMT path's
+      bb.X[l] = tc ? nullptr : B.take<float>((size_t)n * kConvCout[l] * kH[l] * kLd[l]);
       const int oh = (l == 1 || l == 3) ? kH[l] / 2 : kH[l];
       const int old = (l == 1) ? 16 : (l == 3) ? 8 : kLd[l];
-      bb.A[l] = B.take<float>((size_t)n * kConvCout[l] * oh * old);
+      bb.A[l] = tc ? nullptr : B.take<float>((size_t)n * kConvCout[l] * oh * old);
       bb.mean[l] = B.take<float>(64); bb.istd[l] = B.take<float>(64);
       bb.wf[l] = B.take<float>((size_t)kConvCout[l] * kConvCin[l] * 9);
       bb.wd[l] = l > 0 ? B.take<float>((size_t)kConvCout[l] * kConvCin[l] * 9) : nullptr;
     }
-    bb.idx[0] = B.take<uint8_t>((size_t)n * 20 * 14 * 16);
-    bb.idx[1] = B.take<uint8_t>((size_t)n * 40 * 5 * 8);
+    bb.idx[0] = tc ? nullptr : B.take<uint8_t>((size_t)n * 20 * 14 * 16);
+    bb.idx[1] = tc ? nullptr : B.take<uint8_t>((size_t)n * 40 * 5 * 8);
     bb.F5 = B.take<float>((size_t)n * 540);
     bb.Z1 = B.take<float>((size_t)n * 180);
     bb.dZ1 = B.take<float>((size_t)n * 180);
     bb.dF5 = B.take<float>((size_t)n * 540);
-    bb.dA = B.take<float>((size_t)n * 20 * 30 * 32);      // incoming activation gradient of the current layer
-    bb.dX = B.take<float>((size_t)n * 20 * 30 * 32);      // compact conv-output gradient
-    bb.dXpad = B.take<float>((size_t)n * 20 * 34 * 32);   // zero-padded copy for dgrad
+    bb.dA = tc ? nullptr : B.take<float>((size_t)n * 20 * 30 * 32);      // incoming activation gradient of the current layer
+    bb.dX = tc ? nullptr : B.take<float>((size_t)n * 20 * 30 * 32);      // compact conv-output gradient
+    bb.dXpad = tc ? nullptr : B.take<float>((size_t)n * 20 * 34 * 32);   // zero-padded copy for dgrad
     bb.sums = B.take<double>(64 * 3);
+    if (tc) {
+      char* t = B.take<char>(tc_branch_bytes(n));
+      tc_carve_branch(S.tc[b], t, n);
+    }
+  }
+  if (tc) {
+    char* t = B.take<char>(tdense_bytes(n));
+    tdense_carve(S.td, t, n);
   }
   S.in4 = B.take<float>((size_t)n * 15);
   S.y = B.take<uint8_t>((size_t)n);
@@ -691,18 +701,28 @@ static size_t carve_step(StepBuf& S, char* base, int n) {
   return B.off;
 }
 
+int launch_conv1_wgrad(sc_ctx* ctx, const float* patches, const float* dx_planar, int n, int zc, float* gW, cudaStream_t st) {
+  ProfScope prof(ctx, PC_TRAIN_BWD, st);
+  conv_wgrad_kernel<<<dim3(20, 1, zc), 128, 0, st>>>(patches, 1, 32, 32, dx_planar, 20, 30, 30, 32, n, gW);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
 static int train_body(sc_ctx* ctx, const StepBuf& S, int n, int64_t n_global, bool injected_masks, cudaStream_t st) {
+  const bool tc = ctx->gemm_backend == 1;
   const ParamOff& O = ctx->off;
   float* P = ctx->params;
   float* G = ctx->grads;
   const float* ones = ctx->train_consts;
-  const float* zeros = ctx->train_consts + 64;
+  const float* zeros = ctx->train_consts + kTrainZeros;
   cudaStream_t sb[3] = {st, ctx->train_side[0], ctx->train_side[1]};
   cudaEvent_t* ev = ctx->train_ev;
 
   SC_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * SC_PARAM_FLOATS, st));
   SC_CUDA(cudaMemsetAsync(S.loss, 0, sizeof(float), st));
   if (!injected_masks) { make_masks_kernel<<<ew_grid((int64_t)n * 2700), 256, 0, st>>>(S.masks, (int64_t)n * 2700, S.seed); ctx->launches++; }
+  if (tc) SC_CUDA(cudaMemsetAsync(S.td.zero_begin, 0, S.td.zero_bytes, st));
   SC_CUDA(cudaEventRecord(ev[0], st));
   for (int b = 1; b < 3; ++b) SC_CUDA(cudaStreamWaitEvent(sb[b], ev[0], 0));
 
@@ -711,7 +731,12 @@ static int train_body(sc_ctx* ctx, const StepBuf& S, int n, int64_t n_global, bo
     const BranchOff& Ob = O.br[b];
     const auto& bb = S.bb[b];
     cudaStream_t s = sb[b];
-    for (int l = 0; l < 5; ++l) {
+    if (tc) {   // conv1..conv5 with their BatchNorm / PReLU / pools on the split-bf16 maps (train_tc.cu)
+      repack_conv_kernel<<<1, 256, 0, s>>>(P + Ob.convW[0], 20, 1, bb.wf[0], nullptr);
+      ctx->launches++;
+      SC_TRY(tc_branch_forward(ctx, b, S.tc[b], S.in[b], bb.wf[0], n, S.masks, bb.F5, s));
+    }
+    for (int l = 0; l < 5 && !tc; ++l) {
       const int co = kConvCout[l], ci = kConvCin[l];
       repack_conv_kernel<<<(co * ci * 9 + 255) / 256, 256, 0, s>>>(P + Ob.convW[l], co, ci, bb.wf[l], bb.wd[l]);
       ctx->launches++;
@@ -731,13 +756,18 @@ static int train_body(sc_ctx* ctx, const StepBuf& S, int n, int64_t n_global, bo
                                                                      pool ? bb.idx[l == 1 ? 0 : 1] : nullptr);
       ctx->launches += 3;
     }
-    flatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, s>>>(bb.A[4], n, S.masks + b * 540, bb.F5);
-    ctx->launches++;
-    SC_TRY((sgemm<false, false>(ctx, bb.F5, 540, P + Ob.d1W, 180, bb.Z1, 180, n, 180, 540, P + Ob.d1b, 0, PC_TRAIN_FWD, s)));
-    dense_act_kernel<<<ew_grid((int64_t)n * 180), 256, 0, s>>>(bb.Z1, n, 180, P + Ob.d1alpha, S.masks + 1620 + b * 180, 2700, S.CAT, 540, b * 180);
-    ctx->launches++;
+    if (tc) {
+      SC_TRY(tdense_branch_forward(ctx, b, S.td, bb.F5, n, S.masks, s));
+    } else {
+      flatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, s>>>(bb.A[4], n, S.masks + b * 540, bb.F5);
+      SC_TRY((sgemm<false, false>(ctx, bb.F5, 540, P + Ob.d1W, 180, bb.Z1, 180, n, 180, 540, P + Ob.d1b, 0, PC_TRAIN_FWD, s)));
+      dense_act_kernel<<<ew_grid((int64_t)n * 180), 256, 0, s>>>(bb.Z1, n, 180, P + Ob.d1alpha, S.masks + 1620 + b * 180, 2700, S.CAT, 540, b * 180);
+      ctx->launches += 2;
+    }
     if (b > 0) { SC_CUDA(cudaEventRecord(ev[b], s)); SC_CUDA(cudaStreamWaitEvent(st, ev[b], 0)); }
   }
+  if (tc) SC_TRY(tdense_head(ctx, S.td, S.in4, S.y, n, n_global, S.masks, S.loss, st));
+  if (!tc) {
   SC_TRY((sgemm<false, false>(ctx, S.CAT, 540, P + O.fc1W, 540, S.ZF1, 540, n, 540, 540, P + O.fc1b, 0, PC_TRAIN_FWD, st)));
   dense_act_kernel<<<ew_grid((int64_t)n * 540), 256, 0, st>>>(S.ZF1, n, 540, P + O.a1, S.masks + 2160, 2700, S.CAT2, 555, 0);
   SC_CUDA(cudaMemcpy2DAsync(S.CAT2 + 540, 555 * 4, S.in4, 15 * 4, 15 * 4, n, cudaMemcpyDeviceToDevice, st));
@@ -761,6 +791,7 @@ static int train_body(sc_ctx* ctx, const StepBuf& S, int n, int64_t n_global, bo
   SC_TRY((sgemm<true, false>(ctx, S.CAT, 540, S.dZF1, 540, G + O.fc1W, 540, 540, 540, n, nullptr, 0, PC_TRAIN_BWD, st)));
   SC_TRY((sgemm<false, true>(ctx, S.dZF1, 540, P + O.fc1W, 540, S.dCAT, 540, n, 540, 540, nullptr, 0, PC_TRAIN_BWD, st)));
   ctx->launches += 3;
+  }
   SC_CUDA(cudaEventRecord(ev[3], st));
   for (int b = 1; b < 3; ++b) SC_CUDA(cudaStreamWaitEvent(sb[b], ev[3], 0));
 
@@ -769,13 +800,19 @@ static int train_body(sc_ctx* ctx, const StepBuf& S, int n, int64_t n_global, bo
     const auto& bb = S.bb[b];
     cudaStream_t s = sb[b];
     // d1 (dropout f1_drop sits on the concatenated d1 activations)
-    dense_act_bwd_kernel<<<dim3((180 + 31) / 32, 16), 256, 0, s>>>(S.dCAT, 540, b * 180, bb.Z1, n, 180, P + Ob.d1alpha, S.masks + 1620 + b * 180, 2700,
-                                                                  bb.dZ1, G + Ob.d1alpha, G + Ob.d1b);
-    SC_TRY((sgemm<true, false>(ctx, bb.F5, 540, bb.dZ1, 180, G + Ob.d1W, 180, 540, 180, n, nullptr, 0, PC_TRAIN_BWD, s)));
-    SC_TRY((sgemm<false, true>(ctx, bb.dZ1, 180, P + Ob.d1W, 180, bb.dF5, 540, n, 540, 180, nullptr, 0, PC_TRAIN_BWD, s)));
-    unflatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, s>>>(bb.dF5, n, S.masks + b * 540, bb.dA);
-    ctx->launches += 2;
-    for (int l = 4; l >= 0; --l) {
+    if (tc) {
+      SC_TRY(tdense_branch_backward(ctx, b, S.td, n, S.masks, s));
+      SC_TRY(tc_branch_backward(ctx, b, S.tc[b], S.in[b], S.td.dF5[b], 576, S.masks, n, s));
+    } else {
+      dense_act_bwd_kernel<<<dim3((180 + 31) / 32, 16), 256, 0, s>>>(S.dCAT, 540, b * 180, bb.Z1, n, 180, P + Ob.d1alpha, S.masks + 1620 + b * 180, 2700,
+                                                                    bb.dZ1, G + Ob.d1alpha, G + Ob.d1b);
+      SC_TRY((sgemm<true, false>(ctx, bb.F5, 540, bb.dZ1, 180, G + Ob.d1W, 180, 540, 180, n, nullptr, 0, PC_TRAIN_BWD, s)));
+      SC_TRY((sgemm<false, true>(ctx, bb.dZ1, 180, P + Ob.d1W, 180, bb.dF5, 540, n, 540, 180, nullptr, 0, PC_TRAIN_BWD, s)));
+      ctx->launches++;
+      unflatten_drop_kernel<<<ew_grid((int64_t)n * 540), 256, 0, s>>>(bb.dF5, n, S.masks + b * 540, bb.dA);
+      ctx->launches++;
+    }
+    for (int l = 4; l >= 0 && !tc; --l) {
       const int co = kConvCout[l], ci = kConvCin[l], H = kH[l], ld = kLd[l];
       const int pool = (l == 1 || l == 3);
       const int pld = (l == 1) ? 16 : 8;
@@ -820,19 +857,21 @@ int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, cons
   SC_CHECK(n64 <= 16384, SC_ERR_ARG, "sc_train_forward_backward: per-GPU batch %lld too large (max 16384)", (long long)n64);
   const int n = (int)n64;
   StepBuf S;
-  const size_t need = carve_step(S, nullptr, n);
+  const bool tc = ctx->gemm_backend == 1;
+  const size_t need = carve_step(S, nullptr, n, tc);
   SC_TRY(ensure_ws(ctx->ws_fit, need + 4096));
-  carve_step(S, reinterpret_cast<char*>(ctx->ws_fit.ptr), n);
+  carve_step(S, reinterpret_cast<char*>(ctx->ws_fit.ptr), n, tc);
   if (!ctx->train_consts) {
-    SC_CUDA(cudaMalloc(&ctx->train_consts, 128 * sizeof(float)));
-    float h1[128];
-    for (int i = 0; i < 128; ++i) h1[i] = i < 64 ? 1.f : 0.f;
-    SC_CUDA(cudaMemcpy(ctx->train_consts, h1, sizeof(h1), cudaMemcpyHostToDevice));
+    SC_CUDA(cudaMalloc(&ctx->train_consts, 2 * kTrainZeros * sizeof(float)));
+    std::vector<float> h1(2 * kTrainZeros);
+    for (int i = 0; i < 2 * kTrainZeros; ++i) h1[i] = i < kTrainZeros ? 1.f : 0.f;
+    SC_CUDA(cudaMemcpy(ctx->train_consts, h1.data(), h1.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   if (!ctx->train_side[0]) {
     for (int i = 0; i < 2; ++i) SC_CUDA(cudaStreamCreateWithFlags(&ctx->train_side[i], cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) SC_CUDA(cudaEventCreateWithFlags(&ctx->train_ev[i], cudaEventDisableTiming));
   }
+  if (tc) { SC_TRY(tc_train_prepare(ctx)); SC_TRY(tdense_prepare(ctx)); }
   // stage the caller's batch into the arena: the step itself only ever sees context-owned addresses
   const float* ins[3] = {in1, in2, in3};
   for (int b = 0; b < 3; ++b) SC_CUDA(cudaMemcpyAsync(S.in[b], ins[b], (size_t)n * 4096, cudaMemcpyDeviceToDevice, st));
@@ -848,7 +887,8 @@ int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, cons
   } else {
     sc_ctx::TrainGraph* g = nullptr;
     for (auto& e : ctx->train_graphs)
-      if (e.n == n && e.n_global == (long long)n_global && e.injected == (masks_in ? 1 : 0) && e.arena == ctx->ws_fit.ptr) g = &e;
+      if (e.n == n && e.n_global == (long long)n_global && e.injected == (masks_in ? 1 : 0) && e.backend == ctx->gemm_backend &&
+          e.arena == ctx->ws_fit.ptr) g = &e;
     if (!g) {
       // a moved arena invalidates every captured address
       for (size_t i = 0; i < ctx->train_graphs.size();) {
@@ -872,7 +912,7 @@ int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, cons
       const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       SC_CUDA(ie);
-      ctx->train_graphs.push_back({n, (long long)n_global, masks_in ? 1 : 0, ctx->ws_fit.ptr, exec, launches});
+      ctx->train_graphs.push_back({n, (long long)n_global, masks_in ? 1 : 0, ctx->gemm_backend, ctx->ws_fit.ptr, exec, launches});
       g = &ctx->train_graphs.back();
     }
     SC_CUDA(cudaGraphLaunch(g->exec, st));

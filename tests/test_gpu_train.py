@@ -27,12 +27,24 @@ def _batch(n, seed):
     return x, at, y, masks, np.ascontiguousarray(packed)
 
 
+# Gradient tolerances per back-end, relative to the largest entry of each tensor.  The exact-fp32 SIMT cross-check agrees with
+# the fp64 oracle to 2e-3.  The tensor-core path stores activations as bf16 hi+lo pairs (2^-17 relative) and the network is
+# piecewise linear: a pre-activation within ~1e-5 of a PReLU kink or a max-pool tie may take the other branch, which moves ONE
+# term of a sum of ~10^4 terms by its full size; such rare single-element flips are allowed for by the looser max-norm bound,
+# while the relative L2 bound keeps the tensor as a whole within 3e-3.
+# (which elements flip varies from run to run: the BatchNorm sums are accumulated with floating-point atomics)
+TOL = {0: dict(maxnorm=2e-3, l2=2e-3, well=1e-5), 1: dict(maxnorm=3e-2, l2=1e-2, well=None)}
+
+
+@pytest.mark.parametrize("backend", [1, 0])
 @pytest.mark.parametrize("source,n", [("committed", 24), ("random", 17)])
-def test_train_step_matches_autograd_oracle(weights_path, source, n):
+def test_train_step_matches_autograd_oracle(weights_path, source, n, backend):
     from cnn_cort import nets
     P = on.load_params(weights_path) if source == "committed" else on.init_params(3)
     ctx = cuda_ctx()
     ctx.load_weights(nets.pack_params(P))
+    ctx.set_option("gemm", backend)
+    tol = TOL[backend]
     x, at, y, masks, packed = _batch(n, 5)
     loss_ref, G_ref, P_ref, state = on.train_step(P, *x, at, y, masks=masks, lr=1e-3)
     loss = ctx.train_forward_backward(*[dev(a) for a in x], dev(at), dev(y), drop_masks=dev(packed))
@@ -43,8 +55,10 @@ def test_train_step_matches_autograd_oracle(weights_path, source, n):
         g = G[name][k].astype(np.float64)
         denom = max(np.abs(g_ref).max(), 1e-6)
         err = np.abs(g - g_ref).max() / denom
+        l2 = np.linalg.norm(g - g_ref) / max(np.linalg.norm(g_ref), 1e-6)
         worst = max(worst, err)
-        assert err < 2e-3, "%s[%d]: rel err %g (|g|max %g)" % (name, k, err, denom)
+        assert err < tol["maxnorm"], "%s[%d]: rel err %g (|g|max %g)" % (name, k, err, denom)
+        assert l2 < tol["l2"], "%s[%d]: relative L2 err %g" % (name, k, l2)
     # BN batch statistics ride in the gradient slots of the running statistics
     ctx.adam_step(lr=1e-3)
     P_new = nets.unpack_params(ctx.get_params())
@@ -55,7 +69,8 @@ def test_train_step_matches_autograd_oracle(weights_path, source, n):
                 assert diff.max() < 2e-5 + 2e-4 * np.abs(a).max(), "%s[%d]: %g" % (name, k, diff.max())
             else:
                 # Adam's first step is lr*g/(|g| + 3.2e-7): only entries with |g| >> 3e-7 are well conditioned
-                ok = np.abs(G_ref[(name, k)]) > 1e-5
+                g_ref = np.abs(G_ref[(name, k)])
+                ok = g_ref > (tol["well"] if tol["well"] else 0.05 * g_ref.max())
                 assert ok.any() and diff[ok].max() < 5e-5, "%s[%d]: %g" % (name, k, diff[ok].max())
                 assert diff.max() < 2.1e-3
     assert ctx.counter("adam_t") == 1
