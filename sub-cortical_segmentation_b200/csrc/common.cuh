@@ -335,7 +335,7 @@ int launch_conv1_wide(sc_ctx* ctx, const float* vol, const ViewGeo& g, int ns, c
 // conv_sweep.cu : strip-sweep 3x3 dilated conv (+ fused stride-1 max-pool) over wide-row maps.
 // in_fmt / out_fmt: 1 = 128 B pixels (32 bf16 hi | 32 lo), 0 = 256 B pixels (64 hi | 64 lo)
 int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
-                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st);
+                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx = 0, int in_dy = 0);
 
 // patch_forward.cu
 int launch_branch_patches(sc_ctx* ctx, int branch, const float* patches, int64_t n, float* c5_out /*[n][540]*/,

@@ -33,6 +33,8 @@ struct SweepArgs {
   int stages;
   int out_bufs;           // output tiles in shared memory (2: double-buffered, 1 when shared memory is short)
   int npanels;            // weight panels (4 k-steps each)
+  int in_dx, in_dy;       // offset (pixels, rows) of the input window against the output position: 0 for a valid convolution,
+                          // -2 for the full correlation of a dgrad (what lies outside the map is zero-filled by the TMA unit)
   const float* scale; const float* shift; const float* alpha;
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
 };
@@ -167,8 +169,8 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           mbar_expect_tx(&full[s], (uint32_t)(NBOX * BOX_BYTES));
           uint8_t* sp = sRing + s * SLOT;
           const int r = q + DIL * (n0 + m);          // rows beyond the map are zero-filled by the TMA unit
-          tma_load_3d(&mapA, &full[s], sp, 0, w0, r);
-          if (NBOX == 2) tma_load_3d(&mapA, &full[s], sp + SW_SLOT_HALF, 64, w0, r);
+          tma_load_3d(&mapA, &full[s], sp, 0, w0 + a.in_dx, r + a.in_dy);
+          if (NBOX == 2) tma_load_3d(&mapA, &full[s], sp + SW_SLOT_HALF, 64, w0 + a.in_dx, r + a.in_dy);
         }
       }
       if (a.dbg) { a.dbg[blockIdx.x * 8 + 0] = (unsigned long long)w_empty; a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - tstart); }
@@ -501,8 +503,8 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           if (rank == 0) mbar_expect_tx(&full[s], (uint32_t)(2 * 2 * BOX_BYTES));   // both CTAs' boxes land on it
           uint8_t* sp = sRing + s * SLOT;
           const int r = q + DIL * (n0 + m);
-          tma_load_3d_2sm(&mapA, lbar, sp, 0, w0, r);
-          tma_load_3d_2sm(&mapA, lbar, sp + SW_SLOT_HALF, 64, w0, r);
+          tma_load_3d_2sm(&mapA, lbar, sp, 0, w0 + a.in_dx, r + a.in_dy);
+          tma_load_3d_2sm(&mapA, lbar, sp + SW_SLOT_HALF, 64, w0 + a.in_dx, r + a.in_dy);
         }
       }
     }
@@ -824,7 +826,7 @@ static int launch_sweep_t(sc_ctx* ctx, const CUtensorMap& mapA, const CUtensorMa
 }
 
 int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
-                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st) {
+                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx, int in_dy) {
   TcState* s = reinterpret_cast<TcState*>(ctx->tc_state);
   SC_CHECK(s != nullptr, SC_ERR_UNSUPPORTED, "tcgen05 back-end not initialised");
   if (Pw <= 0 || R <= 0) return SC_OK;
@@ -845,6 +847,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   a.n_items = a.nstrips * dil * nseg;
   SC_CHECK(pool != 2 || dil == 1, SC_ERR_ARG, "conv_sweep: the stride-2 pool needs dilation 1");
   a.npanels = w.npanels;
+  a.in_dx = in_dx; a.in_dy = in_dy;
   a.scale = w.scale; a.shift = w.shift; a.alpha = w.alpha;
   a.dbg = (ctx->tc_timing_cls == prof_cls) ? ctx->tc_timing_buf : nullptr;
   SC_CHECK(w.bn <= (out_fmt ? 32 : 64) && w.bn % 16 == 0, SC_ERR_ARG, "conv_sweep: bad channel geometry");

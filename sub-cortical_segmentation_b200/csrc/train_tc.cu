@@ -145,6 +145,12 @@ __global__ void __launch_bounds__(256) tbn_stats_kernel(const float* __restrict_
 #pragma unroll
       for (int k = 0; k < 8; ++k) { s[k] += x[k]; q[k] = fmaf(x[k], x[k], q[k]); }
     }
+  }
+  // lanes with the same chunk are NCH apart: fold them with shuffles, then one shared-memory atomic per warp and channel
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    for (int o = NCH; o < 32; o <<= 1) { s[k] += __shfl_xor_sync(0xffffffffu, s[k], o); q[k] += __shfl_xor_sync(0xffffffffu, q[k], o); }
+  if ((threadIdx.x & 31) < NCH && chunk * 8 < C) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { atomicAdd(&red[chunk * 8 + k][0], s[k]); atomicAdd(&red[chunk * 8 + k][1], q[k]); }
   }
@@ -313,14 +319,16 @@ __global__ void __launch_bounds__(256) tbn_bwd_reduce_kernel(const float* __rest
   __syncthreads();
   const int chunk = threadIdx.x % NCH, slot = threadIdx.x / NCH;
   const int64_t total = (int64_t)H * n * H;
+  float s1[8], s2[8], s3[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = s3[k] = 0.f;
   if (chunk * 8 < C) {
-    float mu[8], is[8], ga[8], be[8], al[8], s1[8], s2[8], s3[8];
+    float mu[8], is[8], ga[8], be[8], al[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int ch = chunk * 8 + k;
       const bool on = ch < C;
       mu[k] = on ? mean[ch] : 0.f; is[k] = on ? istd[ch] : 0.f; ga[k] = on ? gamma[ch] : 0.f; be[k] = on ? beta[ch] : 0.f; al[k] = on ? alpha[ch] : 0.f;
-      s1[k] = s2[k] = s3[k] = 0.f;
     }
     for (int64_t v = (int64_t)blockIdx.x * (256 / NCH) + slot; v < total; v += (int64_t)gridDim.x * (256 / NCH)) {
       const int c = (int)(v % H);
@@ -337,6 +345,13 @@ __global__ void __launch_bounds__(256) tbn_bwd_reduce_kernel(const float* __rest
         if (yv <= 0.f) s3[k] = fmaf(g[k], yv, s3[k]);
       }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    for (int o = NCH; o < 32; o <<= 1) {
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o); s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o); s3[k] += __shfl_xor_sync(0xffffffffu, s3[k], o);
+    }
+  if ((threadIdx.x & 31) < NCH && chunk * 8 < C) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       atomicAdd(&red[chunk * 8 + k][0], s1[k]); atomicAdd(&red[chunk * 8 + k][1], s2[k]); atomicAdd(&red[chunk * 8 + k][2], s3[k]);
@@ -357,7 +372,8 @@ __global__ void tbn_bwd_params_kernel(const double* __restrict__ sums, int C, fl
 }
 
 // pass 2 over ALL positions of the conv-output map (64 consecutive positions per CTA):
-//   frame   (l >= 1): dx at (r + 2, c + 2) of a zeroed split map of the same geometry = the dgrad sweep's input
+//   frame   (l >= 1): dx as a split map of the same geometry, zeros outside the valid region = the dgrad sweep's input
+//                     (the sweep reads it with a window offset of (-2, -2): full correlation, zero fill by the TMA unit)
 //   DT      (l >= 1): three planar transposed copies [3][2 * CP][Npix], copy k shifted right by k positions
 //                     (DT_k[p] = dx[p - k]), zeros outside the valid region = the wgrad operand of filter column k
 //   planar  (l == 0): fp32 [n][C][H][ld] for the CUDA-core conv1 wgrad
@@ -413,7 +429,7 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float*
   }
   uint4 h, l;
   split8(dx, h, l);
-  if (valid && frame) store8<FMT>(frame, (int64_t)(r + 2) * Pw + (int64_t)s * pitch + c + 2, chunk, h, l);   // r + 2 < R, c + 2 < pitch by geometry
+  if (q < npix) store8<FMT>(frame, q, chunk, h, l);
   const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -441,10 +457,82 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// conv1 backward in one pass: dx of the BatchNorm / PReLU block and, fused, the conv1 weight gradient (1 -> 20 channels,
+// K = 9: CUDA cores).  gW[co][8 - t] += sum over pixels dx[co] * patch[r + ky][c + kx]; 72 accumulators per thread (8 channels
+// x 9 taps), folded with shuffles and shared-memory atomics.  conv1 has no dgrad, so dx is never written.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tbn_bwd_conv1_kernel(const float* __restrict__ X, const float* __restrict__ dA, const float* __restrict__ patches,
+                                                            int n, const float* __restrict__ mean, const float* __restrict__ istd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ alpha, const double* __restrict__ sums, double count,
+                                                            float* __restrict__ gW) {
+  constexpr int C = 20, H = 30;
+  __shared__ float red[24][9];
+  for (int i = threadIdx.x; i < 24 * 9; i += 256) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  const int chunk = threadIdx.x & 3, slot = threadIdx.x >> 2;
+  const int Pw = n * 32;
+  float acc[8][9];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+  if (chunk < 3) {
+    float mu[8], is[8], ga[8], be[8], al[8], m1[8], m2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = chunk * 8 + k;
+      const bool on = ch < C;
+      mu[k] = on ? mean[ch] : 0.f; is[k] = on ? istd[ch] : 0.f; ga[k] = on ? gamma[ch] : 0.f; be[k] = on ? beta[ch] : 0.f; al[k] = on ? alpha[ch] : 0.f;
+      m1[k] = on ? (float)(sums[ch * 3] / count) : 0.f; m2[k] = on ? (float)(sums[ch * 3 + 1] / count) : 0.f;
+    }
+    const int64_t total = (int64_t)H * n * H;
+    for (int64_t v = (int64_t)blockIdx.x * 64 + slot; v < total; v += (int64_t)gridDim.x * 64) {
+      const int c = (int)(v % H);
+      const int s = (int)((v / H) % n);
+      const int r = (int)(v / ((int64_t)H * n));
+      const int64_t p = (int64_t)r * Pw + (int64_t)s * 32 + c;
+      float x[8], g[8];
+      load8<32>(X, p, chunk, x);
+      load8<32>(dA, p, chunk, g);
+      const float* src = patches + (int64_t)s * 1024 + r * 32 + c;
+      float w[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) w[ky * 3 + kx] = __ldg(src + ky * 32 + kx);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (x[k] - mu[k]) * is[k];
+        const float yv = fmaf(xh, ga[k], be[k]);
+        const float dy = yv > 0.f ? g[k] : al[k] * g[k];
+        const float dx = ga[k] * is[k] * (dy - m1[k] - xh * m2[k]);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[k][t] = fmaf(dx, w[t], acc[k][t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float v = acc[k][t];
+      v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 3) atomicAdd(&red[chunk * 8 + k][t], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 9; i += 256) {
+    const int co = i / 9, t = i - co * 9;
+    atomicAdd(&gW[co * 9 + (8 - t)], red[co][t]);     // correlation tap t = element 8 - t of the (true-convolution) filter
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // wgrad on the tensor cores.  With p' = p + tx:
 //   gW[ty][tx][ci][co] = sum_p A[ci][p + ty*Pw + tx] * dX[co][p] = sum_p' A[ci][p' + ty*Pw] * DT_tx[co][p']
 //   A operand (M): the three row-shifted windows of the planar input map, stacked: 3 x CIN8 <= 120 rows of one M = 128 tile
-//   B operands (N): the three column-shifted copies DT_tx of the planar output gradient, NCO rows each -> three accumulators
+//   B operand (N): the three column-shifted copies DT_tx of the planar output gradient stacked, 3 x NCO rows: ONE MMA per
+//                   k-step and split term produces all three filter columns (the A tile is fetched once instead of thrice)
 //   K: 64 pixels per stage; the CTAs split the pixel range (split-K) and add their partial sums atomically
 // warp 0: TMA producer (12 boxes per stage), warp 1: MMA issue (3 accumulators x 4 k-steps x 3 split products), warps 2-5: epilogue
 // ---------------------------------------------------------------------------------------------------------------
@@ -511,24 +599,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       __syncwarp();
     } else if (warp == 1) {
       const uint32_t leader = elect_one();
-      // D = F32, A = B = BF16, both K-major, N = nco, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.nco >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // D = F32, A = B = BF16, both K-major, N = 3 * nco (the three shifted copies are adjacent row blocks), M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * a.nco) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       for (int i = 0; i < nk; ++i) {
         const int s = i % a.stages;
         mbar_wait(&full[s], (i / a.stages) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sp = smem_u32(smem + s * stage_bytes);
         const uint64_t ah = umma_desc(sp), al = umma_desc(sp + a_half);
-        for (int t = 0; t < 3; ++t) {
-          const uint64_t dh = umma_desc(sp + 2 * a_half + t * d_one), dl = umma_desc(sp + 2 * a_half + d_half + t * d_one);
-          const uint32_t acc = tmem_base + (uint32_t)(t * 64);
+        const uint64_t dh = umma_desc(sp + 2 * a_half), dl = umma_desc(sp + 2 * a_half + d_half);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t o = (uint64_t)(j * 2);
-            umma_bf16_elect(acc, al + o, dh + o, idesc, (i | j) != 0, leader);
-            umma_bf16_elect(acc, ah + o, dl + o, idesc, 1, leader);
-            umma_bf16_elect(acc, ah + o, dh + o, idesc, 1, leader);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t o = (uint64_t)(j * 2);
+          umma_bf16_elect(tmem_base, al + o, dh + o, idesc, (i | j) != 0, leader);
+          umma_bf16_elect(tmem_base, ah + o, dl + o, idesc, 1, leader);
+          umma_bf16_elect(tmem_base, ah + o, dh + o, idesc, 1, leader);
         }
         if (leader) umma_commit(&empty[s]);
         __syncwarp();
@@ -545,7 +630,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       for (int tx = 0; tx < 3; ++tx) {
         for (int c0 = 0; c0 < a.nco; c0 += 16) {
           uint32_t rr[16];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tx * 64 + c0);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tx * a.nco + c0);
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
               : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
@@ -788,7 +873,6 @@ static int bwd_layer(sc_ctx* ctx, int b, int l, const TcBranchBuf& T, const floa
       P + Ob.alpha[l], T.sums);
   tbn_bwd_params_kernel<<<1, 64, 0, s>>>(T.sums, L.cout, G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l]);
   const int64_t npix = (int64_t)L.R * Pw;
-  if (frame) SC_CUDA(cudaMemsetAsync(frame, 0, (size_t)npix * FMT * 4, s));
   tbn_bwd_dx_kernel<FMT, DFMT><<<(unsigned)((npix + 63) / 64), 64 * NCH, 0, s>>>(
       T.X[l], dA, T.idx[l], dF5, dF5_ld, mask, n, L.cout, L.H, L.R, Pw, L.pitch, L.pool, dPw, dPitch, T.mean[l], T.istd[l], P + Ob.bn[l][1], P + Ob.bn[l][0],
       P + Ob.alpha[l], T.sums, (double)vpix, frame, DT, pad16(L.cout), planar, 32);
@@ -811,11 +895,19 @@ int tc_branch_backward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pa
     else if (l == 3) SC_TRY((bwd_layer<64, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, T.DT, nullptr, s)));
     else if (l == 2) SC_TRY((bwd_layer<64, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, T.DT, nullptr, s)));
     else if (l == 1) SC_TRY((bwd_layer<32, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, T.DT, nullptr, s)));
-    else SC_TRY((bwd_layer<32, 32>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, nullptr, nullptr, T.dX0, s)));
-    if (l == 0) {
-      // conv1 wgrad (K = 9) on CUDA cores: planar fp32 gradient against the patches
-      const int zc = n < 32 ? n : 32;
-      launch_conv1_wgrad(ctx, patches, T.dX0, n, zc, G + Ob.convW[0], s);
+    else {
+      // conv1: reduction pass, then dx and the weight gradient in one fused pass (no dgrad below conv1)
+      float* P = ctx->params;
+      const int64_t vpix = (int64_t)30 * n * 30;
+      SC_CUDA(cudaMemsetAsync(T.sums, 0, 64 * 3 * sizeof(double), s));
+      tbn_bwd_reduce_kernel<32, 32><<<cap_grid(ctx, (vpix * 4 + 255) / 256 / 4 + 1, 2), 256, 0, s>>>(
+          T.X[0], T.dA, nullptr, nullptr, 0, nullptr, n, 20, 30, Pw, 32, 0, Pw, 32, T.mean[0], T.istd[0], P + Ob.bn[0][1], P + Ob.bn[0][0],
+          P + Ob.alpha[0], T.sums);
+      tbn_bwd_params_kernel<<<1, 64, 0, s>>>(T.sums, 20, G + Ob.bn[0][0], G + Ob.bn[0][1], G + Ob.alpha[0]);
+      ProfScope prof(ctx, PC_TRAIN_BWD, s);
+      tbn_bwd_conv1_kernel<<<cap_grid(ctx, (vpix + 63) / 64 / 8 + 1, 2), 256, 0, s>>>(T.X[0], T.dA, patches, n, T.mean[0], T.istd[0], P + Ob.bn[0][1],
+                                                                                    P + Ob.bn[0][0], P + Ob.alpha[0], T.sums, (double)vpix, G + Ob.convW[0]);
+      ctx->launches += 3;
       break;
     }
     const TLayer& Li = kTL[l - 1];
@@ -823,7 +915,7 @@ int tc_branch_backward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pa
     SC_TRY(launch_wgrad_tc(ctx, T.AT[l - 1], T.DT, L.cin, L.cout, pad8(L.cin), pad16(L.cout), Pw, npix, L.H, G + Ob.convW[l], s));
     // dgrad: the gradient of this layer's input = sweep over the zero-framed dx with the raw taps; valid Li.oH x Li.oH
     SC_TRY(launch_conv_sweep(ctx, ctx->train_sw[b][l][1], l, T.frame, L.fmt == 32 ? 1 : 0, T.dA, (l == 1) ? 1 : 0, Pw, L.R, Li.oH, 1, 0,
-                             PC_TRAIN_BWD, s));
+                             PC_TRAIN_BWD, s, -2, -2));
   }
   SC_CUDA(cudaGetLastError());
   return SC_OK;
