@@ -103,6 +103,7 @@ struct GemmW {      // one dense layer prepared for both GEMM back-ends
   float* alpha;     // [Npad] (PReLU; 1 where identity)
   float* scale;     // [Npad] multiplies the accumulator before the bias (BN scale), or nullptr = 1
   int K, N, Kpad, Npad;
+  int k_used = 0;   // columns of the padded K row that can be non-zero (0 = all of Kpad): the tcgen05 GEMM skips the k-steps beyond
 };
 
 struct SweepW {     // one conv layer prepared for the strip-sweep tcgen05 kernel (conv_sweep.cu)

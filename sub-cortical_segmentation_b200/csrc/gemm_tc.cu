@@ -50,6 +50,7 @@ struct TcArgs {
   // persistent variant
   long long num_tiles;
   int epi_warps;      // epilogue warps (4, 8 or 16)
+  int last_ksteps;    // 16-wide k-steps issued in the LAST k block (dense layers: the K padding beyond the real fan-in is skipped)
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
   const int* rowmap;  // pair kernel, split stores: C row of dense row r = rowmap[r] (skip when < 0); ldc / c_ys / c_zs then count ROWS
   const int* rowvox;  // pair kernel, atlas epilogue: slab row of compact row m
@@ -455,12 +456,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const uint32_t sp = sStage_u + s * stage_bytes;
           const uint64_t ah = umma_desc(sp), al = umma_desc(sp + TC_A_HALF);
           const uint64_t wh = umma_desc(sp + 2 * TC_A_HALF), wl = umma_desc(sp + 2 * TC_A_HALF + b_half);
+          const int nj = kb == a.nkb - 1 ? a.last_ksteps : 4;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint64_t o = (uint64_t)(j * 2);
-            umma_bf16_2sm_elect(acc, al + o, wh + o, idesc, (kb | j) != 0, leader);
-            umma_bf16_2sm_elect(acc, ah + o, wl + o, idesc, 1, leader);
-            umma_bf16_2sm_elect(acc, ah + o, wh + o, idesc, 1, leader);
+            const uint32_t on = (leader && j < nj) ? 1u : 0u;
+            umma_bf16_2sm_elect(acc, al + o, wh + o, idesc, (kb | j) != 0, on);
+            umma_bf16_2sm_elect(acc, ah + o, wl + o, idesc, 1, on);
+            umma_bf16_2sm_elect(acc, ah + o, wh + o, idesc, 1, on);
           }
           if (leader) umma_commit_2sm(&empty[s]);
           __syncwarp();
@@ -729,6 +732,8 @@ int launch_gemm_tc(sc_ctx* ctx, const GemmProblem& p, const GemmW& w, cudaStream
   SC_CHECK(blocks < (1ll << 31), SC_ERR_ARG, "gemm_tc: grid too large");
   a.num_tiles = blocks;
   a.dbg = (ctx->tc_timing_cls == p.prof_cls) ? ctx->tc_timing_buf : nullptr;
+  a.last_ksteps = 4;
+  if (p.ntaps == 1 && w.k_used > w.Kpad - TC_BK && w.k_used <= w.Kpad) a.last_ksteps = (w.k_used - (w.Kpad - TC_BK) + 15) / 16;   // real fan-in inside the last block
   int stage_bytes;
   size_t smem = 0;
   if (pair) {

@@ -536,8 +536,13 @@ __global__ void __launch_bounds__(256) tbn_bwd_conv1_kernel(const float* __restr
 //   K: 64 pixels per stage; the CTAs split the pixel range (split-K) and add their partial sums atomically
 // warp 0: TMA producer (12 boxes per stage), warp 1: MMA issue (3 accumulators x 4 k-steps x 3 split products), warps 2-5: epilogue
 // ---------------------------------------------------------------------------------------------------------------
+static inline int pad8(int c) { return (c + 7) & ~7; }
+static inline int pad16(int c) { return (c + 15) & ~15; }
+
 struct WgradArgs {
-  int cin, cout, cin8, nco;      // real channels, input rows per window (multiple of 8), gradient rows (multiple of 16)
+  int cin, cout, cin8, nco;      // real channels, input rows per window (multiple of 8), gradient rows per copy in shared memory (multiple of 16)
+  int co8;                       // gradient rows per copy as stored / loaded (multiple of 8): the rows [co8, nco) of a slot are never
+                                 // written and only feed accumulator columns nobody reads
   int Pw;                        // wide-row pitch in pixels: filter row = shift by Pw
   int nkb;                       // 64-pixel blocks to reduce over
   int stages;
@@ -551,6 +556,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int a_half = 3 * a.cin8 * 128;                    // bytes of the stacked hi (or lo) windows
   const int d_one = a.nco * 128, d_half = 3 * d_one;      // one shifted copy; the three hi (or lo) copies
   const int stage_bytes = 2 * a_half + 2 * d_half;        // (the M = 128 tile of the lo windows reads on into the gradient boxes)
+  const int tx_bytes = 2 * a_half + 2 * 3 * a.co8 * 128;  // bytes the TMA unit actually delivers per stage
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + a.stages;
@@ -584,15 +590,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int i = 0; i < nk; ++i) {
           const int s = i % a.stages, use = i / a.stages;
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-          mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+          mbar_expect_tx(&full[s], (uint32_t)tx_bytes);
           uint8_t* sp = smem + s * stage_bytes;
           const int p0 = (kb0 + i) * 64;
 #pragma unroll 1
           for (int t = 0; t < 3; ++t) {
             tma_load_2d(&mapA, &full[s], sp + t * a.cin8 * 128, p0 + t * a.Pw, 0);                 // window of filter row t, hi rows
             tma_load_2d(&mapA, &full[s], sp + a_half + t * a.cin8 * 128, p0 + t * a.Pw, a.cin8);   // lo rows
-            tma_load_2d(&mapD, &full[s], sp + 2 * a_half + t * d_one, p0, t * 2 * a.nco);          // copy shifted by t, hi rows
-            tma_load_2d(&mapD, &full[s], sp + 2 * a_half + d_half + t * d_one, p0, t * 2 * a.nco + a.nco);
+            tma_load_2d(&mapD, &full[s], sp + 2 * a_half + t * d_one, p0, t * 2 * a.co8);          // copy shifted by t, hi rows
+            tma_load_2d(&mapD, &full[s], sp + 2 * a_half + d_half + t * d_one, p0, t * 2 * a.co8 + a.co8);
           }
         }
       }
@@ -665,6 +671,7 @@ static int launch_wgrad_tc(sc_ctx* ctx, const uint16_t* AT, const uint16_t* DT, 
   SC_CHECK(3 * cin8 <= 128 && nco <= 64 && nco % 16 == 0 && cin8 % 8 == 0, SC_ERR_ARG, "wgrad_tc: bad channel geometry");
   WgradArgs a;
   a.cin = cin; a.cout = cout; a.cin8 = cin8; a.nco = nco; a.Pw = Pw; a.gW = gW;
+  a.co8 = pad8(cout);
   a.nkb = (int)(((int64_t)rows_valid * Pw + 2 + 63) / 64);  // the (shifted) gradient is zero beyond its valid rows
   const int stage_bytes = 2 * 3 * cin8 * 128 + 2 * 3 * nco * 128;
   a.stages = (227 * 1024 - 2048) / stage_bytes;
@@ -683,9 +690,9 @@ static int launch_wgrad_tc(sc_ctx* ctx, const uint16_t* AT, const uint16_t* DT, 
     SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)npix, (cuuint64_t)(3 * 2 * nco)};
+    cuuint64_t dims[2] = {(cuuint64_t)npix, (cuuint64_t)(3 * 2 * a.co8)};
     cuuint64_t strides[1] = {(cuuint64_t)npix * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)nco};
+    cuuint32_t box[2] = {64, (cuuint32_t)a.co8};
     cuuint32_t es[2] = {1, 1};
     CUresult r = s->encode(&mapD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(DT), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -715,8 +722,6 @@ static const TLayer kTL[5] = {
     {40, 40, 15, 16, 64, 10, 1, 7, 8, 5},
     {40, 60, 7, 8, 64, 3, 0, 0, 0, 0},
 };
-static inline int pad8(int c) { return (c + 7) & ~7; }
-static inline int pad16(int c) { return (c + 15) & ~15; }
 
 size_t tc_branch_bytes(int n) {
   size_t b = 0;
@@ -875,7 +880,7 @@ static int bwd_layer(sc_ctx* ctx, int b, int l, const TcBranchBuf& T, const floa
   const int64_t npix = (int64_t)L.R * Pw;
   tbn_bwd_dx_kernel<FMT, DFMT><<<(unsigned)((npix + 63) / 64), 64 * NCH, 0, s>>>(
       T.X[l], dA, T.idx[l], dF5, dF5_ld, mask, n, L.cout, L.H, L.R, Pw, L.pitch, L.pool, dPw, dPitch, T.mean[l], T.istd[l], P + Ob.bn[l][1], P + Ob.bn[l][0],
-      P + Ob.alpha[l], T.sums, (double)vpix, frame, DT, pad16(L.cout), planar, 32);
+      P + Ob.alpha[l], T.sums, (double)vpix, frame, DT, pad8(L.cout), planar, 32);
   ctx->launches += 3;
   SC_CUDA(cudaGetLastError());
   return SC_OK;

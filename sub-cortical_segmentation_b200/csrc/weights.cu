@@ -142,6 +142,9 @@ int derive_weights(sc_ctx* ctx, cudaStream_t st) {
     A.host[fc1o.alpha + n] = n < 540 ? h[P.a1 + n] : 1.f;
   }
   fc2o = make_gemm(A, ctx->fc2, 555, 270, kH1Ld, kH2Ld);
+  ctx->fc2.k_used = 555;                     // h1 rows: 540 FC1 outputs | 15 atlas priors | zeros: the last k block needs 3 of its 4 k-steps
+  for (int b = 0; b < 3; ++b) ctx->br[b].d1.k_used = 540;   // patchwise d1 over the flattened (c, h, w) features
+  ctx->fc1.k_used = 0;                       // feature rows hold 192 columns per view (180 used): the last block is used up to column 563
   for (int k = 0; k < 555; ++k)
     for (int n = 0; n < 270; ++n) set_w(A, fc2o, ctx->fc2, k, n, h[P.fc2W + (size_t)k * 270 + n]);
   for (int n = 0; n < kH2Ld; ++n) {
