@@ -168,6 +168,13 @@ SC_API int sc_segment_volume_host(sc_ctx* ctx, const float* vol_host, const int3
                            const float* atlas_host, const int32_t* box, const uint8_t* cand_mask_host,
                            uint8_t* label_vol_host, float* proba_vol_host, void* stream);
 
+/* ---- post-processing ------------------------------------------------------------------
+ * replaces: post_process_segmentation (base.py:460-480): per class 1..14 keep the 6-connected component that overlaps the
+ * registered sub-cortical mask most (first maximum in scipy.ndimage.label's raster order; the reference's argmax == 0
+ * quirk included, see csrc/postproc.cu).  seg / mask / out: uint8 [X][Y][Z]; mask non-zero = inside; out != seg. */
+SC_API int sc_post_process(sc_ctx* ctx, const uint8_t* seg_dev, const uint8_t* mask_dev, const int32_t dims[3],
+                    uint8_t* out_dev, void* stream);
+
 /* ---- scatter -------------------------------------------------------------------------
  * replaces: image[x,y,z] = y_pred and image_proba[x,y,z,c] = proba[:,c] (base.py:430-440) */
 SC_API int sc_scatter(sc_ctx* ctx, const int32_t* xyz_dev, int64_t n, const int32_t* label_dev,
@@ -197,6 +204,14 @@ SC_API int sc_param_buffer(sc_ctx* ctx, float** params_dev);
  * Marks the inference layouts stale; they are re-derived lazily by the next inference call. */
 SC_API int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, float stat_scale, void* stream);
 SC_API int sc_reset_optimizer(sc_ctx* ctx);
+/* Synchronised BatchNorm for data-parallel training: the reference normalises over the whole batch of its
+ * single device; with the hook set, the per-channel BatchNorm sums of the forward pass ({sum x, sum x^2}) and of the backward
+ * pass ({sum dy, sum dy*xhat}) plus the element count are handed to `fn` as one small float64 device buffer right after they
+ * are reduced locally; `fn` must sum it over all ranks IN PLACE, ordered on `stream` (an all-reduce of torch.distributed /
+ * NCCL).  N ranks then reproduce the single-device step on the same global batch.  fn == NULL (default): per-GPU statistics.
+ * With a hook the step is launched kernel by kernel (no CUDA graph). */
+typedef int (*sc_allreduce_fn)(void* user, void* buf_dev /* double[count] */, int64_t count, void* stream);
+SC_API int sc_set_allreduce_hook(sc_ctx* ctx, sc_allreduce_fn fn, void* user);
 /* evaluation pass of nolearn's eval_fn: mean CE loss and accuracy numerators over a batch
  * in deterministic mode; out2_dev = {sum of -log p[y], number of correct argmax}. */
 SC_API int sc_eval_batch(sc_ctx* ctx, const float* in1_dev, const float* in2_dev, const float* in3_dev,

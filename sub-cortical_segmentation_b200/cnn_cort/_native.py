@@ -48,6 +48,7 @@ PROTOTYPES = {
     "sc_normalise_volume": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _p(ctypes.c_double), _vp]),
     "sc_candidate_mask": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _vp]),
     "sc_mask_bbox": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _p(_c_i32), _p(_c_i64), _vp]),
+    "sc_post_process": (ctypes.c_int, [_vp, _vp, _vp, _p(_c_i32), _vp, _vp]),
     "sc_gather_patches": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, ctypes.c_int, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp]),
     "sc_gather_center_labels": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _vp, _c_i64, _vp, _vp]),
     "sc_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp]),
@@ -63,6 +64,7 @@ PROTOTYPES = {
     "sc_param_buffer": (ctypes.c_int, [_vp, _p(_vp)]),
     "sc_adam_step": (ctypes.c_int, [_vp, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _vp]),
     "sc_reset_optimizer": (ctypes.c_int, [_vp]),
+    "sc_set_allreduce_hook": (ctypes.c_int, [_vp, _vp, _vp]),
     "sc_eval_batch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp]),
 }
 
@@ -219,6 +221,13 @@ class Context(object):
         _check(self.lib.sc_mask_bbox(self.h, _ptr(mask), _dims(mask.shape), box, ctypes.byref(n), _stream()))
         return (tuple(int(b) for b in box) if n.value else None), int(n.value)
 
+    def post_process(self, seg, mask):
+        """uint8 CUDA label volume + uint8 CUDA mask [X,Y,Z] -> filtered uint8 label volume (base.py:460-480)"""
+        import torch
+        out = torch.empty_like(seg)
+        _check(self.lib.sc_post_process(self.h, _ptr(seg), _ptr(mask), _dims(seg.shape), _ptr(out), _stream()))
+        return out
+
     def gather_patches(self, vol, xyz, atlas=None, bg_fix=True, views=(True, True, True)):
         import torch
         n = xyz.shape[0]
@@ -315,6 +324,37 @@ class Context(object):
     def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, stat_scale=1.0):
         _check(self.lib.sc_adam_step(self.h, lr, beta1, beta2, eps, grad_scale, stat_scale, _stream()))
 
+    def set_sync_bn(self, enable=True):
+        """Synchronised BatchNorm for data-parallel training: the BN reduction buffers are all-reduced over the ranks of
+        torch.distributed's default group (sc_set_allreduce_hook), so that N ranks reproduce the single-device step on the
+        same global batch.  Off (default): per-GPU batch statistics."""
+        if not enable:
+            _check(self.lib.sc_set_allreduce_hook(self.h, None, None))
+            self._ar_cb = None
+            return
+        import torch
+        import torch.distributed as dist
+        device = self.device
+
+        def hook(user, ptr, count, stream):
+            try:
+                t = torch.as_tensor(_CudaArrayHolder(ptr, int(count), "<f8"), device="cuda:%d" % device)
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream or 0, device=device)):
+                    if dist.get_backend() == "nccl":
+                        dist.all_reduce(t)
+                    else:                      # gloo reduces host tensors
+                        h = t.cpu()
+                        dist.all_reduce(h)
+                        t.copy_(h)
+                return 0
+            except Exception:                  # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        self._ar_cb = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, _c_i64, _vp)(hook)
+        _check(self.lib.sc_set_allreduce_hook(self.h, ctypes.cast(self._ar_cb, _vp), None))
+
     def reset_optimizer(self):
         _check(self.lib.sc_reset_optimizer(self.h))
 
@@ -326,8 +366,8 @@ class Context(object):
 
 
 class _CudaArrayHolder(object):
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 def _as_tensor(ptr, n, device):

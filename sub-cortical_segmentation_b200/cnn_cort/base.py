@@ -204,7 +204,10 @@ def test_scan(net, test_scan, options):
         if _crop_enabled(options):
             crop_mask = nib.load(os.path.join(image_path, 'tmp', 'MNI_subcortical_mask.nii.gz'), pinned=True).get_data()
         timings = options.get('timings')
-        labels, image_proba, n_cand = segment_arrays(net.ctx, t1, atlas, crop_mask, want_proba, timings)
+        post_mask = None
+        if options['post_process'] == 'True':      # filtered on the device, before the label volume is downloaded
+            post_mask = crop_mask if crop_mask is not None else nib.load(os.path.join(image_path, 'tmp', 'MNI_subcortical_mask.nii.gz'), pinned=True).get_data()
+        labels, image_proba, n_cand = segment_arrays(net.ctx, t1, atlas, crop_mask, want_proba, timings, post_mask=post_mask)
         if options['debug'] == 'True':
             print("    -->  num of samples to test:", n_cand)
         image = labels.astype(t1.dtype)
@@ -212,14 +215,14 @@ def test_scan(net, test_scan, options):
     if want_proba:
         nib.Nifti1Image(image_proba, affine=t1_nii.affine).to_filename(os.path.join(image_path, 'out_subcortical_prob.nii.gz'))
     if options['post_process'] == 'True':
-        filtered = post_process_segmentation(image_path, image)
+        filtered = image if mode != 'patchwise' else post_process_segmentation(image_path, image, device=options.get('device'))
         nib.Nifti1Image(filtered, affine=t1_nii.affine).to_filename(os.path.join(image_path, 'out_subcortical_seg_prec.nii.gz'))
     else:
         nib.Nifti1Image(image, affine=t1_nii.affine).to_filename(os.path.join(image_path, 'out_subcortical_rawseg.nii.gz'))
     return (time.time() - s_time) / 60.0
 
 
-def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=None):
+def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=None, post_mask=None):
     """The timed part of test_scan for one scan, device-resident from the first byte [base.py:357-372, 401-440]:
     raw T1 / atlas priors (/ registered mask) as host arrays in -> uint8 label volume (+ float32 [X,Y,Z,15] probabilities,
     number of candidates) out.  One upload per array (Fortran-ordered NIfTI arrays are reordered on the device), then
@@ -255,6 +258,13 @@ def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=Non
     if box is not None:
         ctx.segment_volume(vol, d_atlas, box=box, cand_mask=cand, label_vol=lab, proba_vol=prob, atlas_ready=atlas_ready)
     main.wait_stream(side)
+    if post_mask is not None:        # post_process_segmentation (base.py:460-480) on the device-resident label volume
+        if post_mask is crop_mask and crop_mask is not None:
+            pm = ctx.candidate_mask(mraw, mdt, shape)
+        else:
+            praw, pdt = ctx.upload_volume(post_mask)
+            pm = ctx.candidate_mask(praw, pdt, shape)
+        lab = ctx.post_process(lab, pm)
     h_lab = _pinned_out('lab', shape, torch.uint8)
     h_lab.copy_(lab, non_blocking=True)
     h_prob = None
@@ -302,20 +312,19 @@ def bounding_box(mask):
     return tuple(box)
 
 
-def post_process_segmentation(image_folder, input_mask):
-    """Per label 1..14 keep the connected component overlapping the atlas mask most.
-    [base.py:460-480] -- host-side scipy, same quirks (a class with no voxels selects
-    component 0, i.e. the background of that class)."""
-    filtered_mask = np.zeros_like(input_mask)
+def post_process_segmentation(image_folder, input_mask, device=None):
+    """Per label 1..14 keep the 6-connected component overlapping the registered sub-cortical mask most. [base.py:460-480]
+    Runs on the device (sc_post_process: one union-find labelling pass for all classes), with the reference's quirks: a
+    class without any component inside the mask selects "component 0", i.e. everything that is not of that class."""
+    import torch
+    ctx = get_context(device)
     atlas = load_nii(os.path.join(image_folder, 'tmp', 'MNI_subcortical_mask.nii.gz')).get_data()
-    for l in range(1, 15):
-        th_label = input_mask == l
-        labels, num_labels = ndimage.label(th_label)
-        label_list = np.unique(labels)
-        overlap = ndimage.labeled_comprehension(np.logical_and(th_label, atlas), labels, label_list, np.sum, float, 0)
-        keep = np.argmax(overlap)
-        filtered_mask[labels == keep] = l
-    return filtered_mask
+    shape = tuple(int(s) for s in input_mask.shape[:3])
+    seg = torch.from_numpy(np.ascontiguousarray(input_mask).astype(np.uint8)).to('cuda:%d' % ctx.device)
+    mraw, mdt = ctx.upload_volume(atlas)
+    mask = ctx.candidate_mask(mraw, mdt, shape)
+    out = ctx.post_process(seg, mask)
+    return out.cpu().numpy().astype(input_mask.dtype)
 
 
 def register_masks(input_mask):

@@ -240,6 +240,9 @@ class Net(object):
             dist.broadcast(p, 0)
             ctx.load_weights(p.cpu().numpy())          # re-derives the inference layouts from the broadcast parameters
             ctx.reset_optimizer()
+        # options['sync_bn'] = 'True': BatchNorm statistics over the GLOBAL batch like the single-device reference (30 tiny
+        # all-reduces per step); default: per-GPU statistics, the usual data-parallel practice
+        ctx.set_sync_bn(world > 1 and str(self.options.get('sync_bn', 'False')) == 'True')
 
         # the training set lives on the device when it fits (a minibatch is then one index_select per input instead of five
         # pageable host-to-device copies per step); otherwise minibatches are staged through page-locked buffers

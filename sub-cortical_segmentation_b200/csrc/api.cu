@@ -303,6 +303,13 @@ int sc_mask_bbox(sc_ctx* ctx, const uint8_t* mask_dev, const int32_t dims[3], in
   return mask_bbox(ctx, mask_dev, dims, box_host, count_host, (cudaStream_t)stream);
 }
 
+int sc_post_process(sc_ctx* ctx, const uint8_t* seg_dev, const uint8_t* mask_dev, const int32_t dims[3], uint8_t* out_dev, void* stream) {
+  SC_CHECK(ctx && seg_dev && mask_dev && out_dev && out_dev != seg_dev, SC_ERR_ARG, "sc_post_process: bad argument");
+  SC_TRY(check_dims(dims, "sc_post_process"));
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return post_process(ctx, seg_dev, mask_dev, dims, out_dev, (cudaStream_t)stream);
+}
+
 int sc_gather_patches(sc_ctx* ctx, const float* vol_dev, const int32_t dims[3], const float* atlas_dev, int bg_fix,
                       const int32_t* xyz_dev, int64_t n, float* axial_dev, float* coronal_dev, float* saggital_dev,
                       float* atlas_out_dev, void* stream) {
@@ -563,6 +570,12 @@ int sc_param_buffer(sc_ctx* ctx, float** params_dev) {
 int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, float stat_scale, void* stream) {
   SC_TRY(need_weights(ctx, "sc_adam_step"));
   return adam_step(ctx, lr, beta1, beta2, eps, grad_scale, stat_scale, (cudaStream_t)stream);
+}
+
+int sc_set_allreduce_hook(sc_ctx* ctx, sc_allreduce_fn fn, void* user) {
+  SC_CHECK(ctx, SC_ERR_ARG, "sc_set_allreduce_hook: null context");
+  ctx->ar_hook = fn; ctx->ar_user = user;
+  return SC_OK;
 }
 
 int sc_reset_optimizer(sc_ctx* ctx) {

@@ -175,6 +175,8 @@ struct sc_ctx {
   cudaStream_t train_side[2] = {nullptr, nullptr};
   cudaEvent_t train_ev[8] = {};
   int train_graph_on = 1;        // sc_set_option("train_graph", 0): launch the step kernel by kernel (profiling, debugging)
+  sc_allreduce_fn ar_hook = nullptr;   // synchronised BatchNorm: sums the BN reduction buffers over the ranks (sc_set_allreduce_hook)
+  void* ar_user = nullptr;
   void* train_panels = nullptr;  // sweep weight panels of the training step, re-derived on the device every step
   void* train_dense_w = nullptr; // dense weights of the training step in the two GEMM operand layouts, re-derived every step
   struct TrainDenseW { float* wnk; float* wkn; float* bias; };
@@ -260,6 +262,9 @@ int import_volume(sc_ctx* ctx, const void* src, int elem_bytes, const int32_t* d
 int normalise_volume(sc_ctx* ctx, const void* vol, int dtype, const int32_t* dims, float* out, double* mean_std_host, cudaStream_t st);
 int candidate_mask(sc_ctx* ctx, const void* vol, int dtype, const int32_t* dims, uint8_t* mask, cudaStream_t st);
 int mask_bbox(sc_ctx* ctx, const uint8_t* mask, const int32_t* dims, int32_t* box_host, int64_t* count_host, cudaStream_t st);
+
+// postproc.cu : connected-component post-processing of a label volume
+int post_process(sc_ctx* ctx, const uint8_t* seg, const uint8_t* mask, const int32_t* dims, uint8_t* out, cudaStream_t st);
 
 // weights.cu
 int derive_weights(sc_ctx* ctx, cudaStream_t st);

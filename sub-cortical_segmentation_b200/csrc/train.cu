@@ -881,7 +881,7 @@ int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, cons
   const unsigned long long seed_h = seed;
   SC_CUDA(cudaMemcpyAsync(S.seed, &seed_h, sizeof(seed_h), cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
 
-  const bool use_graph = ctx->train_graph_on && !ctx->profile;
+  const bool use_graph = ctx->train_graph_on && !ctx->profile && !(tc && ctx->ar_hook);   // the sync-BN hook runs host code between kernels
   if (!use_graph) {
     SC_TRY(train_body(ctx, S, n, n_global, masks_in != nullptr, st));
   } else {

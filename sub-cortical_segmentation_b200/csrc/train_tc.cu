@@ -161,10 +161,26 @@ __global__ void __launch_bounds__(256) tbn_stats_kernel(const float* __restrict_
   }
 }
 
-__global__ void tbn_finalize_kernel(const double* __restrict__ sums, int C, double count, float* __restrict__ mean,
+// sums[kCountSlot] carries the element count when the sums are all-reduced over the ranks (synchronised BatchNorm)
+constexpr int kCountSlot = 192;
+__global__ void tset_count_kernel(double* __restrict__ sums, double count) { sums[kCountSlot] = count; }
+
+// all-reduce the local BatchNorm sums (+ count) over the ranks through the caller's hook; `cnt` then points at the global count
+static int sync_sums(sc_ctx* ctx, double* sums, double count, const double** cnt, cudaStream_t s) {
+  *cnt = nullptr;
+  if (!ctx->ar_hook) return SC_OK;
+  tset_count_kernel<<<1, 1, 0, s>>>(sums, count);
+  ctx->launches++;
+  SC_CHECK(ctx->ar_hook(ctx->ar_user, sums, kCountSlot + 1, s) == 0, SC_ERR_STATE, "the all-reduce hook of sc_set_allreduce_hook failed");
+  *cnt = sums + kCountSlot;
+  return SC_OK;
+}
+
+__global__ void tbn_finalize_kernel(const double* __restrict__ sums, int C, double count, const double* __restrict__ cnt, float* __restrict__ mean,
                                     float* __restrict__ istd, float* __restrict__ g_mean_slot, float* __restrict__ g_istd_slot) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (cnt) count = *cnt;
   const double m = sums[c * 2] / count;
   double var = sums[c * 2 + 1] / count - m * m;
   if (var < 0) var = 0;
@@ -384,9 +400,11 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float*
                                                                      const float* __restrict__ mean, const float* __restrict__ istd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      const float* __restrict__ alpha, const double* __restrict__ sums, double count,
+                                                                     const double* __restrict__ cnt,
                                                                      float* __restrict__ frame, uint16_t* __restrict__ DT, int CP,
                                                                      float* __restrict__ planar, int pld) {
   constexpr int NCH = FMT / 8;
+  if (cnt) count = *cnt;
   __shared__ uint16_t tile[2][FMT][66];
   const int chunk = threadIdx.x % NCH, px = threadIdx.x / NCH;
   const int64_t npix = (int64_t)R * Pw;
@@ -465,8 +483,9 @@ __global__ void __launch_bounds__(256) tbn_bwd_conv1_kernel(const float* __restr
                                                             int n, const float* __restrict__ mean, const float* __restrict__ istd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ alpha, const double* __restrict__ sums, double count,
-                                                            float* __restrict__ gW) {
+                                                            const double* __restrict__ cnt, float* __restrict__ gW) {
   constexpr int C = 20, H = 30;
+  if (cnt) count = *cnt;
   __shared__ float red[24][9];
   for (int i = threadIdx.x; i < 24 * 9; i += 256) (&red[0][0])[i] = 0.f;
   __syncthreads();
@@ -771,7 +790,7 @@ int tc_carve_branch(TcBranchBuf& T, char* base, int n) {
   T.dA = reinterpret_cast<float*>(take(big));
   T.DT = reinterpret_cast<uint16_t*>(take((size_t)30 * n * 32 * 3 * 2 * 32 * 2));
   T.dX0 = reinterpret_cast<float*>(take((size_t)n * 20 * 30 * 32 * 4));
-  T.sums = reinterpret_cast<double*>(take(64 * 3 * 8));
+  T.sums = reinterpret_cast<double*>(take(256 * 8));            // [64][3] sums + the count slot
   return (int)0;
 }
 
@@ -841,7 +860,9 @@ int tc_branch_forward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pat
     const int64_t vpix = (int64_t)L.H * n * L.H;
     if (L.fmt == 32) tbn_stats_kernel<32><<<cap_grid(ctx, (vpix + 63) / 64 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, T.sums);
     else tbn_stats_kernel<64><<<cap_grid(ctx, (vpix + 31) / 32 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, T.sums);
-    tbn_finalize_kernel<<<1, 64, 0, s>>>(T.sums, L.cout, (double)vpix, T.mean[l], T.istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3]);
+    const double* cnt;
+    SC_TRY(sync_sums(ctx, T.sums, (double)vpix, &cnt, s));
+    tbn_finalize_kernel<<<1, 64, 0, s>>>(T.sums, L.cout, (double)vpix, cnt, T.mean[l], T.istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3]);
     ctx->launches += 2;
     if (l < 4) {
       const int64_t opix = (int64_t)L.oR * n * L.oPitch;
@@ -876,11 +897,13 @@ static int bwd_layer(sc_ctx* ctx, int b, int l, const TcBranchBuf& T, const floa
   tbn_bwd_reduce_kernel<FMT, DFMT><<<cap_grid(ctx, (vpix * NCH + 255) / 256 / 4 + 1, 2), 256, 0, s>>>(
       T.X[l], dA, T.idx[l], dF5, dF5_ld, mask, n, L.cout, L.H, Pw, L.pitch, L.pool, dPw, dPitch, T.mean[l], T.istd[l], P + Ob.bn[l][1], P + Ob.bn[l][0],
       P + Ob.alpha[l], T.sums);
-  tbn_bwd_params_kernel<<<1, 64, 0, s>>>(T.sums, L.cout, G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l]);
+  tbn_bwd_params_kernel<<<1, 64, 0, s>>>(T.sums, L.cout, G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l]);   // LOCAL sums: the gradient all-reduce adds the ranks
+  const double* cnt;
+  SC_TRY(sync_sums(ctx, T.sums, (double)vpix, &cnt, s));
   const int64_t npix = (int64_t)L.R * Pw;
   tbn_bwd_dx_kernel<FMT, DFMT><<<(unsigned)((npix + 63) / 64), 64 * NCH, 0, s>>>(
       T.X[l], dA, T.idx[l], dF5, dF5_ld, mask, n, L.cout, L.H, L.R, Pw, L.pitch, L.pool, dPw, dPitch, T.mean[l], T.istd[l], P + Ob.bn[l][1], P + Ob.bn[l][0],
-      P + Ob.alpha[l], T.sums, (double)vpix, frame, DT, pad8(L.cout), planar, 32);
+      P + Ob.alpha[l], T.sums, (double)vpix, cnt, frame, DT, pad8(L.cout), planar, 32);
   ctx->launches += 3;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
@@ -909,9 +932,11 @@ int tc_branch_backward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pa
           T.X[0], T.dA, nullptr, nullptr, 0, nullptr, n, 20, 30, Pw, 32, 0, Pw, 32, T.mean[0], T.istd[0], P + Ob.bn[0][1], P + Ob.bn[0][0],
           P + Ob.alpha[0], T.sums);
       tbn_bwd_params_kernel<<<1, 64, 0, s>>>(T.sums, 20, G + Ob.bn[0][0], G + Ob.bn[0][1], G + Ob.alpha[0]);
+      const double* cnt;
+      SC_TRY(sync_sums(ctx, T.sums, (double)vpix, &cnt, s));
       ProfScope prof(ctx, PC_TRAIN_BWD, s);
       tbn_bwd_conv1_kernel<<<cap_grid(ctx, (vpix + 63) / 64 / 8 + 1, 2), 256, 0, s>>>(T.X[0], T.dA, patches, n, T.mean[0], T.istd[0], P + Ob.bn[0][1],
-                                                                                    P + Ob.bn[0][0], P + Ob.alpha[0], T.sums, (double)vpix, G + Ob.convW[0]);
+                                                                                    P + Ob.bn[0][0], P + Ob.alpha[0], T.sums, (double)vpix, cnt, G + Ob.convW[0]);
       ctx->launches += 3;
       break;
     }

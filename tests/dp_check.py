@@ -81,6 +81,37 @@ def check_dp_step(ctx, rank, world, n=32):
     return float(loss)
 
 
+def check_sync_bn(ctx, rank, world, n=48):
+    """N ranks with synchronised BatchNorm statistics == one rank on the same global batch: the all-reduced gradient, the
+    loss and the BN running statistics of the sharded step match the single-device step (run on this rank's own GPU)."""
+    x, at, y = _batch(n, seed=17)
+    rng = np.random.RandomState(23)
+    masks = (rng.rand(n, 2700) < 0.5).astype(np.uint8)
+    full = [torch.from_numpy(a).cuda() for a in x] + [torch.from_numpy(at).cuda(), torch.from_numpy(y).cuda()]
+    ctx.set_sync_bn(False)
+    loss_ref = float(ctx.train_forward_backward(*full, n_global=n, drop_masks=torch.from_numpy(masks).cuda()))
+    g_ref = ctx.grad_tensor().clone()
+    idx = parallel.shard_batch(np.arange(n), rank, world)
+    part = [torch.from_numpy(np.ascontiguousarray(a[idx])).cuda() for a in x] + [torch.from_numpy(at[idx]).cuda(), torch.from_numpy(y[idx]).cuda()]
+    ctx.set_sync_bn(True)
+    loss = ctx.train_forward_backward(*part, n_global=n, drop_masks=torch.from_numpy(np.ascontiguousarray(masks[idx])).cuda())
+    grads = ctx.grad_tensor()
+    parallel.allreduce_gradients(grads, loss)
+    ctx.set_sync_bn(False)
+    assert abs(float(loss) - loss_ref) < 2e-4 * max(1.0, abs(loss_ref)), (float(loss), loss_ref)
+    G, R = nets.unpack_params(grads.cpu().numpy()), nets.unpack_params(g_ref.cpu().numpy())
+    worst = 0.0
+    for name, arrs in R.items():
+        for k, a in enumerate(arrs):
+            g = G[name][k]
+            if name.endswith("_bn") and k >= 2:
+                g = g / world                       # the statistics slots carry one (identical) copy per rank
+            l2 = np.linalg.norm(g - a) / max(np.linalg.norm(a), 1e-6)
+            worst = max(worst, l2)
+            assert l2 < 1e-2, "sync-BN %s[%d]: relative L2 err %g" % (name, k, l2)
+    return worst
+
+
 def check_fit_replicas(rank, world, device):
     """Net.fit from DIFFERENT initial parameters on every rank (seed None -> the unseeded Glorot init of the reference):
     fit broadcasts rank 0's, so the replicas must end bit-identical; a rank holding a different training set must raise."""
@@ -119,6 +150,9 @@ def run_checks(ctx, rank, world, device, fit=True):
     check_sharded_inference(ctx, rank, world)
     loss = check_dp_step(ctx, rank, world)
     out = {"sharded_inference": "ok", "dp_step": "ok", "loss": loss}
+    ctx.load_weights(_committed())
+    out["sync_bn_worst_rel_l2"] = check_sync_bn(ctx, rank, world)
+    out["sync_bn"] = "ok"
     if fit:
         check_fit_replicas(rank, world, device)
         out["fit_replicas"] = "ok"
