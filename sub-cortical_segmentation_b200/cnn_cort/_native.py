@@ -339,13 +339,21 @@ class Context(object):
         def hook(user, ptr, count, stream):
             try:
                 t = torch.as_tensor(_CudaArrayHolder(ptr, int(count), "<f8"), device="cuda:%d" % device)
-                with torch.cuda.stream(torch.cuda.ExternalStream(stream or 0, device=device)):
+                # the library's stream: torch's default stream object when it is the legacy stream (wrapping handle 0 in an
+                # ExternalStream does not order reliably against it)
+                cur = torch.cuda.ExternalStream(stream, device=device) if stream else torch.cuda.default_stream(device)
+                with torch.cuda.stream(cur):
                     if dist.get_backend() == "nccl":
                         dist.all_reduce(t)
                     else:                      # gloo reduces host tensors
                         h = t.cpu()
+                        if os.environ.get("SC_DEBUG_HOOK"):
+                            before = (float(h[0]), float(h[1]), float(h[192]))
                         dist.all_reduce(h)
                         t.copy_(h)
+                        if os.environ.get("SC_DEBUG_HOOK"):
+                            import sys
+                            sys.stderr.write("hook rank %d stream %s: %r -> %r\n" % (dist.get_rank(), stream, before, (float(h[0]), float(h[1]), float(h[192]))))
                 return 0
             except Exception:                  # never let an exception cross the C boundary
                 import traceback
