@@ -204,6 +204,17 @@ SC_API int sc_param_buffer(sc_ctx* ctx, float** params_dev);
  * Marks the inference layouts stale; they are re-derived lazily by the next inference call. */
 SC_API int sc_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, float grad_scale, float stat_scale, void* stream);
 SC_API int sc_reset_optimizer(sc_ctx* ctx);
+/* Data-parallel step as ONE kernel over NVLink peer memory: sum-all-reduce of the gradient buffers fused with sc_adam_step
+ * (each rank reduces and updates its 1/world slice out of the peers' buffers and stores the new parameters into every peer;
+ * csrc/fused_adam.cu).  One process per GPU: sc_fused_export writes 3 CUDA IPC handles (192 bytes: gradients, parameters,
+ * flag page); the caller gathers the handles of all ranks (torch.distributed all_gather) and passes the world x 192 bytes,
+ * in rank order, to sc_fused_attach on every rank (world <= 8).  sc_allreduce_adam_step must then be called by every rank
+ * once per step, after sc_train_forward_backward on the same stream; it replaces all_reduce + sc_adam_step (the statistics
+ * slots are averaged over the ranks).  All ranks end every step with bit-identical parameters. */
+#define SC_IPC_BYTES 192
+SC_API int sc_fused_export(sc_ctx* ctx, unsigned char* handles_out);
+SC_API int sc_fused_attach(sc_ctx* ctx, int rank, int world, const unsigned char* all_handles);
+SC_API int sc_allreduce_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, void* stream);
 /* Synchronised BatchNorm for data-parallel training: the reference normalises over the whole batch of its
  * single device; with the hook set, the per-channel BatchNorm sums of the forward pass ({sum x, sum x^2}) and of the backward
  * pass ({sum dy, sum dy*xhat}) plus the element count are handed to `fn` as one small float64 device buffer right after they

@@ -64,6 +64,9 @@ PROTOTYPES = {
     "sc_param_buffer": (ctypes.c_int, [_vp, _p(_vp)]),
     "sc_adam_step": (ctypes.c_int, [_vp, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _vp]),
     "sc_reset_optimizer": (ctypes.c_int, [_vp]),
+    "sc_fused_export": (ctypes.c_int, [_vp, _vp]),
+    "sc_fused_attach": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "sc_allreduce_adam_step": (ctypes.c_int, [_vp, _c_f, _c_f, _c_f, _c_f, _vp]),
     "sc_set_allreduce_hook": (ctypes.c_int, [_vp, _vp, _vp]),
     "sc_eval_batch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp]),
 }
@@ -362,6 +365,31 @@ class Context(object):
 
         self._ar_cb = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, _c_i64, _vp)(hook)
         _check(self.lib.sc_set_allreduce_hook(self.h, ctypes.cast(self._ar_cb, _vp), None))
+
+    def fused_attach(self):
+        """Exchange the CUDA IPC handles of the gradient / parameter / flag buffers over torch.distributed's default group and
+        open the peers' buffers: afterwards allreduce_adam_step() replaces all_reduce + adam_step (one kernel over NVLink)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        mine = np.zeros(192, np.uint8)
+        _check(self.lib.sc_fused_export(self.h, mine.ctypes.data))
+        if dist.get_backend() == "nccl":
+            t = torch.from_numpy(mine).to("cuda:%d" % self.device)
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            allh = np.concatenate([p.cpu().numpy() for p in parts])
+        else:
+            t = torch.from_numpy(mine)
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            allh = np.concatenate([p.numpy() for p in parts])
+        allh = np.ascontiguousarray(allh, dtype=np.uint8)
+        _check(self.lib.sc_fused_attach(self.h, rank, world, allh.ctypes.data))
+        dist.barrier()
+
+    def allreduce_adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        _check(self.lib.sc_allreduce_adam_step(self.h, lr, beta1, beta2, eps, _stream()))
 
     def reset_optimizer(self):
         _check(self.lib.sc_reset_optimizer(self.h))

@@ -139,6 +139,7 @@ int sc_destroy(sc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   tc_destroy(ctx);
+  fused_detach(ctx);
   cudaFree(ctx->params); cudaFree(ctx->grads); cudaFree(ctx->adam_m); cudaFree(ctx->adam_v);
   cudaFree(ctx->trainable); cudaFree(ctx->derived); cudaFree(ctx->ws.ptr); cudaFree(ctx->ws_train.ptr); cudaFree(ctx->ws_fit.ptr);
   for (auto& g : ctx->train_graphs) cudaGraphExecDestroy(g.exec);
@@ -576,6 +577,19 @@ int sc_set_allreduce_hook(sc_ctx* ctx, sc_allreduce_fn fn, void* user) {
   SC_CHECK(ctx, SC_ERR_ARG, "sc_set_allreduce_hook: null context");
   ctx->ar_hook = fn; ctx->ar_user = user;
   return SC_OK;
+}
+
+int sc_fused_export(sc_ctx* ctx, unsigned char* handles_out) {
+  SC_CHECK(ctx && handles_out, SC_ERR_ARG, "sc_fused_export: null argument");
+  return fused_export(ctx, handles_out);
+}
+int sc_fused_attach(sc_ctx* ctx, int rank, int world, const unsigned char* all_handles) {
+  SC_CHECK(ctx && all_handles, SC_ERR_ARG, "sc_fused_attach: null argument");
+  return fused_attach(ctx, rank, world, all_handles);
+}
+int sc_allreduce_adam_step(sc_ctx* ctx, float lr, float beta1, float beta2, float eps, void* stream) {
+  SC_TRY(need_weights(ctx, "sc_allreduce_adam_step"));
+  return fused_allreduce_adam(ctx, lr, beta1, beta2, eps, (cudaStream_t)stream);
 }
 
 int sc_reset_optimizer(sc_ctx* ctx) {

@@ -175,6 +175,10 @@ struct sc_ctx {
   cudaStream_t train_side[2] = {nullptr, nullptr};
   cudaEvent_t train_ev[8] = {};
   int train_graph_on = 1;        // sc_set_option("train_graph", 0): launch the step kernel by kernel (profiling, debugging)
+  // fused all-reduce + Adam over peer memory (fused_adam.cu): peers' buffers opened through CUDA IPC
+  unsigned* peer_flags = nullptr;
+  float* peer_grads[8] = {}; float* peer_params[8] = {}; unsigned* peer_flagp[8] = {};
+  int peer_rank = 0, peer_world = 0; unsigned peer_step = 0;
   sc_allreduce_fn ar_hook = nullptr;   // synchronised BatchNorm: sums the BN reduction buffers over the ranks (sc_set_allreduce_hook)
   void* ar_user = nullptr;
   void* train_panels = nullptr;  // sweep weight panels of the training step, re-derived on the device every step
@@ -396,6 +400,12 @@ int tdense_head(sc_ctx* ctx, const TcDenseBuf& D, const float* in4, const uint8_
                 cudaStream_t s);
 int tdense_branch_backward(sc_ctx* ctx, int b, const TcDenseBuf& D, int n, const uint8_t* masks, cudaStream_t s);
 int launch_conv1_wgrad(sc_ctx* ctx, const float* patches, const float* dx_planar, int n, int zc, float* gW, cudaStream_t st);
+
+// fused_adam.cu
+int fused_export(sc_ctx* ctx, unsigned char* handles);
+int fused_attach(sc_ctx* ctx, int rank, int world, const unsigned char* all);
+void fused_detach(sc_ctx* ctx);
+int fused_allreduce_adam(sc_ctx* ctx, float lr, float b1, float b2, float eps, cudaStream_t st);
 
 // train.cu
 int train_forward_backward(sc_ctx* ctx, const float* in1, const float* in2, const float* in3, const float* in4,

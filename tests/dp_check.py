@@ -112,6 +112,37 @@ def check_sync_bn(ctx, rank, world, n=48):
     return worst
 
 
+def check_fused_adam(ctx, rank, world, n=32):
+    """the fused all-reduce + Adam kernel over peer memory == all_reduce + sc_adam_step, and leaves bit-identical replicas"""
+    x, at, y = _batch(n, seed=29)
+    idx = parallel.shard_batch(np.arange(n), rank, world)
+    d = [torch.from_numpy(a[idx]).cuda() for a in x] + [torch.from_numpy(at[idx]).cuda(), torch.from_numpy(y[idx]).cuda()]
+    masks = torch.from_numpy((np.random.RandomState(31).rand(n, 2700) < 0.5).astype(np.uint8)[idx]).cuda()
+    grads = ctx.grad_tensor()
+    out = []
+    for fused in (False, True):
+        ctx.load_weights(_committed())
+        ctx.reset_optimizer()
+        if fused:
+            ctx.fused_attach()
+        for step in range(3):
+            ctx.train_forward_backward(*d, n_global=n, drop_masks=masks)
+            if fused:
+                ctx.allreduce_adam_step(lr=1e-3)
+            else:
+                parallel.allreduce_gradients(grads)
+                ctx.adam_step(lr=1e-3, stat_scale=1.0 / world)
+        torch.cuda.synchronize()
+        out.append(ctx.param_tensor().clone())
+    ref = out[1].clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(out[1], ref), "fused step: parameters differ across ranks"
+    # same update up to the summation order of the reduction (and the kink flips it can trigger in the following steps)
+    rel = float((out[0] - out[1]).norm() / out[0].norm())
+    assert rel < 1e-4, "fused all-reduce + Adam differs from all_reduce + adam_step: relative L2 %g" % rel
+    return rel
+
+
 def check_fit_replicas(rank, world, device):
     """Net.fit from DIFFERENT initial parameters on every rank (seed None -> the unseeded Glorot init of the reference):
     fit broadcasts rank 0's, so the replicas must end bit-identical; a rank holding a different training set must raise."""
@@ -143,7 +174,7 @@ def check_fit_replicas(rank, world, device):
     net.ctx.close()
 
 
-def run_checks(ctx, rank, world, device, fit=True):
+def run_checks(ctx, rank, world, device, fit=True, fused=True):
     """-> dict of results; raises AssertionError on the first failed check"""
     ctx.load_weights(_committed())
     ctx.reset_optimizer()
@@ -153,6 +184,9 @@ def run_checks(ctx, rank, world, device, fit=True):
     ctx.load_weights(_committed())
     out["sync_bn_worst_rel_l2"] = check_sync_bn(ctx, rank, world)
     out["sync_bn"] = "ok"
+    if fused:
+        out["fused_adam_rel_l2"] = check_fused_adam(ctx, rank, world)
+        out["fused_adam"] = "ok"
     if fit:
         check_fit_replicas(rank, world, device)
         out["fit_replicas"] = "ok"
@@ -176,7 +210,7 @@ def main():
     else:
         dist.init_process_group(backend)
     ctx = _native.Context(device)
-    res = run_checks(ctx, rank, world, device)
+    res = run_checks(ctx, rank, world, device, fused="--no-fused" not in sys.argv)
     if rank == 0:
         print("dp_check ok: world=%d backend=%s %s" % (world, backend, res))
     dist.destroy_process_group()
