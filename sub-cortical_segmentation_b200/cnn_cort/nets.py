@@ -243,6 +243,11 @@ class Net(object):
         # options['sync_bn'] = 'True': BatchNorm statistics over the GLOBAL batch like the single-device reference (30 tiny
         # all-reduces per step); default: per-GPU statistics, the usual data-parallel practice
         ctx.set_sync_bn(world > 1 and str(self.options.get('sync_bn', 'False')) == 'True')
+        # options['fused_adam'] = 'True': the gradient all-reduce and the Adam update run as ONE kernel over NVLink peer memory
+        # (sc_allreduce_adam_step) instead of NCCL all_reduce + sc_adam_step
+        fused = world > 1 and str(self.options.get('fused_adam', 'False')) == 'True'
+        if fused:
+            ctx.fused_attach()
 
         # the training set lives on the device when it fits (a minibatch is then one index_select per input instead of five
         # pageable host-to-device copies per step); otherwise minibatches are staged through page-locked buffers
@@ -292,10 +297,15 @@ class Net(object):
                 else:                      # a last partial batch smaller than the world size: contribute zeros
                     grads.zero_()
                     loss_buf.zero_()
-                parallel.allreduce_gradients(grads, loss_buf)
-                # the BN-statistics slots hold the SUM of the batch statistics of the ranks that had samples: rank r of
-                # shard_batch has some iff r < len(gidx)
-                ctx.adam_step(lr=self.update_learning_rate, stat_scale=1.0 / min(world, len(gidx)))
+                if fused:
+                    ctx.allreduce_adam_step(lr=self.update_learning_rate)
+                    if world > 1:
+                        dist.all_reduce(loss_buf)
+                else:
+                    parallel.allreduce_gradients(grads, loss_buf)
+                    # the BN-statistics slots hold the SUM of the batch statistics of the ranks that had samples: rank r of
+                    # shard_batch has some iff r < len(gidx)
+                    ctx.adam_step(lr=self.update_learning_rate, stat_scale=1.0 / min(world, len(gidx)))
                 losses.append(loss_buf.clone())
                 sizes.append(len(gidx))
             train_loss = float(np.average(torch.cat(losses).cpu().numpy(), weights=sizes)) if losses else float('nan')
