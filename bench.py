@@ -174,6 +174,8 @@ def bench_train(ctx, torch, dist, rank, world, peaks, steps=20, warmup=5):
     from cnn_cort import parallel
     out = {}
     grads = ctx.grad_tensor()
+    if world > 1:
+        ctx.fused_attach()          # CUDA IPC handles of the gradient / parameter buffers: the fused all-reduce + Adam kernel
     for name, per_gpu in (("global_batch_256", max(1, 256 // world)), ("per_gpu_batch_1024", 1024)):
         gb = per_gpu * world
         g = torch.Generator(device="cuda").manual_seed(100 + rank)
@@ -214,6 +216,7 @@ def bench_train(ctx, torch, dist, rank, world, peaks, steps=20, warmup=5):
         sync()
         ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         ar_ms = None
+        fused_ms = None
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
@@ -224,11 +227,27 @@ def bench_train(ctx, torch, dist, rank, world, peaks, steps=20, warmup=5):
             e1.record()
             sync()
             ar_ms = e0.elapsed_time(e1) / 50
+            # the same step with the gradient all-reduce fused into the Adam kernel over NVLink peer memory (sc_allreduce_adam_step)
+            def fstep(i):
+                ctx.train_forward_backward(*(x + [at, y]), n_global=gb, seed=i, loss_out=loss)
+                ctx.allreduce_adam_step(lr=1e-3)
+            for i in range(warmup):
+                fstep(i)
+            sync()
+            e0.record()
+            for i in range(steps):
+                fstep(i)
+            e1.record()
+            sync()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fused_ms = float(t) / steps
         per = float(ms) / steps
         tfl = gb * FLOP_TRAIN_SAMPLE / (per * 1e-3) / 1e12
         out[name] = {"global_batch": gb, "per_gpu_batch": per_gpu, "ms_per_step": per, "samples_per_s": gb / (per * 1e-3),
                      "e2e_samples_per_s": gb / (float(ms2) / steps * 1e-3), "h2d_bytes_per_step": int(per_gpu * (3 * 4096 + 60 + 1)),
-                     "allreduce_ms": ar_ms, "allreduce_bytes": 883455 * 4, "gpu_launches_per_step": launches, "loss": float(loss.item()),
+                     "allreduce_ms": ar_ms, "allreduce_bytes": 883455 * 4, "ms_per_step_fused_allreduce_adam": fused_ms,
+                     "samples_per_s_fused": (gb / (fused_ms * 1e-3)) if fused_ms else None, "gpu_launches_per_step": launches, "loss": float(loss.item()),
                      "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tflops"] * world, "unit": "TFLOP/s",
                                   "frac": tfl / (peaks["tflops"] * world), "flops_per_sample": FLOP_TRAIN_SAMPLE}}
     out["scaling"] = {"global_batch_256": "strong (256 / N samples per GPU)", "per_gpu_batch_1024": "weak"}
