@@ -23,8 +23,15 @@ _JSON_FD = os.dup(1)
 os.dup2(2, 1)
 
 
+def _plain(o):
+    """numpy scalars / arrays (a float32 from a parity check ...) -> plain Python for json"""
+    if hasattr(o, "tolist"):
+        return o.tolist()
+    return str(o)
+
+
 def emit_json(obj):
-    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
+    os.write(_JSON_FD, (json.dumps(obj, default=_plain) + "\n").encode())
 
 import subprocess
 import sys
