@@ -25,6 +25,14 @@
 
 namespace sc {
 
+__device__ __forceinline__ void tmem_ld16(uint32_t (&r)[16], uint32_t taddr) {   // 32 lanes x 16 consecutive 32-bit columns
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                    // logical k per block (64 bf16 = one 128 B swizzle row)
 constexpr int TC_A_HALF = TC_BM * 128;       // bytes of the hi (or lo) half of an A stage
@@ -367,7 +375,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint64_t* tfull = bars + 2 * a.stages;                  // [2] per CTA
   uint64_t* tempty = tfull + 2;                           // [2] leader only: both CTAs' epilogue warps arrive
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_const = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 loads of the constants
+  // float4 loads of the constants need 16 B alignment; plain pointer arithmetic on `smem` keeps the shared address space (LDS / STS)
+  float* s_const = reinterpret_cast<float*>(smem + (((size_t)a.stages * stage_bytes + (2 * a.stages + 4) * 8 + 16 + 15) & ~(size_t)15));
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_const + (a.nt > 2 ? a.nt : 2) * 3 * a.bn);   // constants of every n-tile (<= 4) stay resident
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -512,30 +521,52 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const int mw = m0 + q * 32;
       uint8_t* stg = s_stage + (warp - 2) * 2560;
       uint8_t* mine = stg + lane * 80;
-      for (int c0 = grp * 16; c0 < a.bn; c0 += 16 * G) {
-        uint32_t rr[16];
-        const uint32_t taddr = tmem_base + b * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
-              "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (n0 + c0 >= a.n_store) continue;
+      // The warp's (up to three) 16-column chunks of the accumulator go to registers first; the accumulator is handed back
+      // to the MMA warp right after that, so the arithmetic and the stores of this tile overlap the MMAs of the tile after next.
+      uint32_t rr[3][16];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c0 = grp * 16 + i * 16 * G;
+        if (c0 < a.bn) tmem_ld16(rr[i], tmem_base + b * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0);
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tempty[b], 0);     // the leader's MMA warp owns the accumulator hand-off
+      // destination row of this lane's accumulator row (the transposed stores below fetch it by shuffle)
+      float* myrow = nullptr;
+      if (a.out_split && mw + lane < a.M) {
+        myrow = ctile + (long long)(mw + lane) * a.ldc;
+        if (a.rowmap) {        // candidate compaction: strides count rows, the map gives the compact C row (or -1)
+          const int cr = __ldg(a.rowmap + ((long long)z * a.c_zs + (long long)y * a.c_ys + (long long)(mw + lane) * a.ldc));
+          myrow = cr < 0 ? nullptr : a.C + (long long)cr * a.crow_ld;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c0 = grp * 16 + i * 16 * G;
+        if (c0 >= a.bn || n0 + c0 >= a.n_store) continue;     // warp-uniform
         if (n0 + c0 >= a.n_mma) {                      // no MMA produced these columns (atlas / zero padding of the row)
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk) rr[kk] = 0u;
+          for (int kk = 0; kk < 16; ++kk) rr[i][kk] = 0u;
         }
         float v[16];
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const float4 bi = *reinterpret_cast<const float4*>(cb + c0 + 4 * k4);
           const float4 al = *reinterpret_cast<const float4*>(cb + a.bn + c0 + 4 * k4);
-          const float4 sc_ = *reinterpret_cast<const float4*>(cb + 2 * a.bn + c0 + 4 * k4);
-          v[4 * k4 + 0] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 0]), sc_.x, bi.x), al.x);
-          v[4 * k4 + 1] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 1]), sc_.y, bi.y), al.y);
-          v[4 * k4 + 2] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 2]), sc_.z, bi.z), al.z);
-          v[4 * k4 + 3] = prelu(fmaf(__uint_as_float(rr[4 * k4 + 3]), sc_.w, bi.w), al.w);
+          if (a.scale) {
+            const float4 sc_ = *reinterpret_cast<const float4*>(cb + 2 * a.bn + c0 + 4 * k4);
+            v[4 * k4 + 0] = prelu(fmaf(__uint_as_float(rr[i][4 * k4 + 0]), sc_.x, bi.x), al.x);
+            v[4 * k4 + 1] = prelu(fmaf(__uint_as_float(rr[i][4 * k4 + 1]), sc_.y, bi.y), al.y);
+            v[4 * k4 + 2] = prelu(fmaf(__uint_as_float(rr[i][4 * k4 + 2]), sc_.z, bi.z), al.z);
+            v[4 * k4 + 3] = prelu(fmaf(__uint_as_float(rr[i][4 * k4 + 3]), sc_.w, bi.w), al.w);
+          } else {
+            v[4 * k4 + 0] = prelu(__uint_as_float(rr[i][4 * k4 + 0]) + bi.x, al.x);
+            v[4 * k4 + 1] = prelu(__uint_as_float(rr[i][4 * k4 + 1]) + bi.y, al.y);
+            v[4 * k4 + 2] = prelu(__uint_as_float(rr[i][4 * k4 + 2]) + bi.z, al.z);
+            v[4 * k4 + 3] = prelu(__uint_as_float(rr[i][4 * k4 + 3]) + bi.w, al.w);
+          }
         }
         const int ncol = a.c_col0 + n0 + c0;
         if (a.atlas && (ncol == 528 || ncol == 544)) {
@@ -578,19 +609,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           __syncwarp();
           const int boff = (ncol >> 6) * 128 + (ncol & 63);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int half = i >> 1, row = (i & 1) * 16 + (lane >> 1), part = lane & 1;
+          for (int j = 0; j < 4; ++j) {
+            const int half = j >> 1, row = (j & 1) * 16 + (lane >> 1), part = lane & 1;
             const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 80 + half * 32 + part * 16);
-            if (mw + row < a.M) {
-              float* crow = ctile + (long long)(mw + row) * a.ldc;
-              if (a.rowmap) {      // candidate compaction: strides count rows, the map gives the compact C row (or -1)
-                const int cr = __ldg(a.rowmap + ((long long)z * a.c_zs + (long long)y * a.c_ys + (long long)(mw + row) * a.ldc));
-                if (cr < 0) continue;
-                crow = a.C + (long long)cr * a.crow_ld;
-              }
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(crow) + boff + half * 64 + part * 8;
-              *reinterpret_cast<uint4*>(dst) = d;
-            }
+            float* crow = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myrow), row));
+            if (crow) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + boff + half * 64 + part * 8) = d;
           }
         } else {
 #pragma unroll
@@ -598,17 +621,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             *reinterpret_cast<float4*>(mine + 16 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = i * 8 + (lane >> 2), part = lane & 3;
+          for (int j = 0; j < 4; ++j) {
+            const int row = j * 8 + (lane >> 2), part = lane & 3;
             const float4 d = *reinterpret_cast<const float4*>(stg + row * 80 + part * 16);
             if (mw + row < a.M) *reinterpret_cast<float4*>(ctile + (long long)(mw + row) * a.ldc + ncol + part * 4) = d;
           }
         }
         __syncwarp();
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cta(&tempty[b], 0);     // the leader's MMA warp owns the accumulator hand-off
       ++ti;
     }
     if (a.dbg && rank == 0 && threadIdx.x == 64) {
