@@ -98,6 +98,13 @@ typedef enum { SC_DT_U8 = 1, SC_DT_I8, SC_DT_U16, SC_DT_I16, SC_DT_U32, SC_DT_I3
  * get_data() holds in memory), dst is [X][Y][Z][channels]; bit-preserving for elements of 1, 2, 4 or 8 bytes. */
 SC_API int sc_import_volume(sc_ctx* ctx, const void* src_dev, int elem_bytes, const int32_t dims[3], int channels,
                      void* dst_dev, void* stream);
+/* Crop mode (base.py:367-369): the atlas priors are only read at the candidate voxels, so only the candidates' bounding
+ * box {x0,x1,y0,y1,z0,z1} of the HOST array (94 % of a scan's bytes are priors) is uploaded: strided DMA copies into
+ * staging_dev (Fortran-ordered source: >= box voxels * channels * elem_bytes bytes; NULL for a C-ordered source) and a
+ * reorder into the box region of dst_dev, the full-size C-ordered [X][Y][Z][channels] device volume.  Voxels outside
+ * the box keep whatever dst_dev held.  src_host should be page-locked (pageable memory makes the copies synchronous). */
+SC_API int sc_upload_volume_box(sc_ctx* ctx, const void* src_host, int elem_bytes, const int32_t dims[3], int channels,
+                         int fortran_order, const int32_t box[6], void* staging_dev, void* dst_dev, void* stream);
 /* replaces: image_norm = (image - image[np.nonzero(image)].mean()) / image[np.nonzero(image)].std() (base.py:358),
  * cast to float32 as the patches are (base.py:383).  numpy's result bit for bit: same dtype promotion, same pairwise
  * summation order (csrc/prep.cu).  vol_dev: C-ordered raw volume of `dtype`; out_dev float32 (NULL: statistics only);

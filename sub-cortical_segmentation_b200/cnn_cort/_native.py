@@ -45,6 +45,7 @@ PROTOTYPES = {
     "sc_nonzero_coords": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _c_i64, _p(_c_i64), _vp]),
     "sc_dilate_mask": (ctypes.c_int, [_vp, _vp, _p(_c_i32), ctypes.c_int, _vp, _vp]),
     "sc_import_volume": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), ctypes.c_int, _vp, _vp]),
+    "sc_upload_volume_box": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), ctypes.c_int, ctypes.c_int, _p(_c_i32), _vp, _vp, _vp]),
     "sc_normalise_volume": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _p(ctypes.c_double), _vp]),
     "sc_candidate_mask": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _p(_c_i32), _vp, _vp]),
     "sc_mask_bbox": (ctypes.c_int, [_vp, _vp, _p(_c_i32), _p(_c_i32), _p(_c_i64), _vp]),
@@ -200,6 +201,31 @@ class Context(object):
         out = torch.empty_like(raw)
         _check(self.lib.sc_import_volume(self.h, _ptr(raw), arr.dtype.itemsize, _dims(shape), int(channels), _ptr(out), _stream()))
         return out, arr.dtype
+
+    def upload_volume_box(self, arr, box, channels=1, out=None):
+        """only the box (x0,x1,y0,y1,z0,z1) of a host volume [X,Y,Z(,C)] goes to the device (strided DMA, no host copy): ->
+        C-ordered CUDA tensor of the array's dtype and FULL shape whose box region holds the data; the rest is uninitialised
+        (or keeps the contents of `out`).  The crop path uploads the atlas priors this way (sc_upload_volume_box)."""
+        import torch
+        arr = np.asarray(arr)
+        if arr.dtype.str[1:] not in DTYPE_CODES:
+            raise NativeError("unsupported volume dtype %s" % arr.dtype)
+        fortran = not arr.flags["C_CONTIGUOUS"]
+        if fortran and not arr.flags["F_CONTIGUOUS"]:
+            arr = np.asfortranarray(arr)
+        shape = tuple(int(s) for s in arr.shape[:3])
+        dev = "cuda:%d" % self.device
+        tdt = torch.from_numpy(np.zeros(1, arr.dtype)).dtype
+        full = shape + ((int(channels),) if arr.ndim == 4 else ())
+        if out is None:
+            out = torch.empty(full, dtype=tdt, device=dev)
+        staging = None
+        if fortran:
+            n = (box[1] - box[0]) * (box[3] - box[2]) * (box[5] - box[4]) * int(channels)
+            staging = torch.empty(n, dtype=tdt, device=dev)
+        _check(self.lib.sc_upload_volume_box(self.h, ctypes.c_void_p(arr.ctypes.data), arr.dtype.itemsize, _dims(shape), int(channels),
+                                             1 if fortran else 0, (_c_i32 * 6)(*[int(b) for b in box]), _ptr(staging), _ptr(out), _stream()))
+        return out
 
     def normalise_volume(self, raw, dtype, shape, want_volume=True):
         """C-ordered raw volume bytes on the device -> (float32 CUDA tensor [X,Y,Z], mean_nz, std_nz) == numpy's

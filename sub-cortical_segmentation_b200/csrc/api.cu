@@ -283,6 +283,17 @@ int sc_import_volume(sc_ctx* ctx, const void* src_dev, int elem_bytes, const int
   return import_volume(ctx, src_dev, elem_bytes, dims, channels, dst_dev, (cudaStream_t)stream);
 }
 
+int sc_upload_volume_box(sc_ctx* ctx, const void* src_host, int elem_bytes, const int32_t dims[3], int channels, int fortran_order,
+                         const int32_t box[6], void* staging_dev, void* dst_dev, void* stream) {
+  SC_CHECK(ctx && src_host && dst_dev && box && channels >= 1, SC_ERR_ARG, "sc_upload_volume_box: bad argument");
+  SC_CHECK(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8, SC_ERR_ARG, "sc_upload_volume_box: elem_bytes must be 1, 2, 4 or 8");
+  SC_TRY(check_dims(dims, "sc_upload_volume_box"));
+  SC_CHECK(box[0] >= 0 && box[0] < box[1] && box[1] <= dims[0] && box[2] >= 0 && box[2] < box[3] && box[3] <= dims[1] &&
+           box[4] >= 0 && box[4] < box[5] && box[5] <= dims[2], SC_ERR_ARG, "sc_upload_volume_box: empty box or box outside the volume");
+  SC_CUDA(cudaSetDevice(ctx->device));
+  return upload_volume_box(ctx, src_host, elem_bytes, dims, channels, fortran_order, box, staging_dev, dst_dev, (cudaStream_t)stream);
+}
+
 int sc_normalise_volume(sc_ctx* ctx, const void* vol_dev, int dtype, const int32_t dims[3], float* out_dev, double* mean_std_host, void* stream) {
   SC_CHECK(ctx && vol_dev && (out_dev || mean_std_host), SC_ERR_ARG, "sc_normalise_volume: bad argument");
   SC_TRY(check_dims(dims, "sc_normalise_volume"));

@@ -263,6 +263,8 @@ int launch_scatter(sc_ctx* ctx, const int32_t* xyz, int64_t n, const int32_t* la
 
 // prep.cu : scan preparation on the device (array-order import, normalisation, candidate mask, bounding box)
 int import_volume(sc_ctx* ctx, const void* src, int elem_bytes, const int32_t* dims, int channels, void* dst, cudaStream_t st);
+int upload_volume_box(sc_ctx* ctx, const void* src_host, int elem_bytes, const int32_t* dims, int channels, int fortran_order,
+                      const int32_t* box, void* staging_dev, void* dst, cudaStream_t st);
 int normalise_volume(sc_ctx* ctx, const void* vol, int dtype, const int32_t* dims, float* out, double* mean_std_host, cudaStream_t st);
 int candidate_mask(sc_ctx* ctx, const void* vol, int dtype, const int32_t* dims, uint8_t* mask, cudaStream_t st);
 int mask_bbox(sc_ctx* ctx, const uint8_t* mask, const int32_t* dims, int32_t* box_host, int64_t* count_host, cudaStream_t st);

@@ -22,8 +22,10 @@ namespace sc {
 // ---------------------------------------------------------------------------------------------------------------
 // F-order (NIfTI: x fastest, channel slowest) -> C-order [X][Y][Z][C] (z fastest, channels innermost), bit-preserving
 // ---------------------------------------------------------------------------------------------------------------
+// in: [C][Zi][Yi][Xi] (x fastest), the whole volume or the compact copy of a box; out: [X][Y][Z][C] at origin (ox, oy, oz)
 template <typename E, int ZT>
-__global__ void __launch_bounds__(256) f2c_kernel(const E* __restrict__ in, E* __restrict__ out, int X, int Y, int Z, int C) {
+__global__ void __launch_bounds__(256) f2c_kernel(const E* __restrict__ in, E* __restrict__ out, int Xi, int Yi, int Zi, int C,
+                                                  int Y, int Z, int ox, int oy, int oz) {
   extern __shared__ __align__(16) unsigned char f2c_smem[];
   E* tile = reinterpret_cast<E*>(f2c_smem);                       // [C][ZT][33]
   const int x0 = blockIdx.x * 32, z0 = blockIdx.y * ZT, y = blockIdx.z;
@@ -33,7 +35,7 @@ __global__ void __launch_bounds__(256) f2c_kernel(const E* __restrict__ in, E* _
     const int c = line / ZT, zz = line - c * ZT;
     const int x = x0 + lane, z = z0 + zz;
     E v = E(0);
-    if (x < X && z < Z) v = in[(((int64_t)c * Z + z) * Y + y) * X + x];
+    if (x < Xi && z < Zi) v = in[(((int64_t)c * Zi + z) * Yi + y) * Xi + x];
     tile[(c * ZT + zz) * 33 + lane] = v;
   }
   __syncthreads();
@@ -43,32 +45,78 @@ __global__ void __launch_bounds__(256) f2c_kernel(const E* __restrict__ in, E* _
     const int xx = e / run, r = e - xx * run;
     const int zz = r / C, c = r - zz * C;
     const int x = x0 + xx, z = z0 + zz;
-    if (x < X && z < Z) out[(((int64_t)x * Y + y) * Z + z) * C + c] = tile[(c * ZT + zz) * 33 + xx];
+    if (x < Xi && z < Zi) out[(((int64_t)(ox + x) * Y + (oy + y)) * Z + (oz + z)) * C + c] = tile[(c * ZT + zz) * 33 + xx];
   }
 }
 
+// idims: extents of the input array; odims / origin: the C-ordered output volume and where the input's corner goes in it
 template <typename E>
-static int launch_f2c(sc_ctx* ctx, const void* src, const int32_t* dims, int C, void* dst, cudaStream_t st) {
+static int launch_f2c(sc_ctx* ctx, const void* src, const int32_t* idims, int C, void* dst, const int32_t* odims, const int32_t* origin,
+                      cudaStream_t st) {
   constexpr int ZT = 8;
   const size_t smem = (size_t)C * ZT * 33 * sizeof(E);
   SC_CHECK(smem <= 48 * 1024, SC_ERR_ARG, "sc_import_volume: too many channels (%d)", C);
-  dim3 grid((dims[0] + 31) / 32, (dims[2] + ZT - 1) / ZT, dims[1]);
+  dim3 grid((idims[0] + 31) / 32, (idims[2] + ZT - 1) / ZT, idims[1]);
   SC_CHECK(grid.y <= 65535 && grid.z <= 65535, SC_ERR_ARG, "sc_import_volume: volume too large");
-  f2c_kernel<E, ZT><<<grid, 256, smem, st>>>(reinterpret_cast<const E*>(src), reinterpret_cast<E*>(dst), dims[0], dims[1], dims[2], C);
+  f2c_kernel<E, ZT><<<grid, 256, smem, st>>>(reinterpret_cast<const E*>(src), reinterpret_cast<E*>(dst), idims[0], idims[1], idims[2], C,
+                                             odims[1], odims[2], origin[0], origin[1], origin[2]);
   ctx->launches++;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
 }
 
-int import_volume(sc_ctx* ctx, const void* src, int elem_bytes, const int32_t* dims, int channels, void* dst, cudaStream_t st) {
+static int import_box(sc_ctx* ctx, const void* src, int elem_bytes, const int32_t* idims, int channels, void* dst, const int32_t* odims,
+                      const int32_t* origin, cudaStream_t st) {
   switch (elem_bytes) {
-    case 1: return launch_f2c<uint8_t>(ctx, src, dims, channels, dst, st);
-    case 2: return launch_f2c<uint16_t>(ctx, src, dims, channels, dst, st);
-    case 4: return launch_f2c<uint32_t>(ctx, src, dims, channels, dst, st);
-    case 8: return launch_f2c<unsigned long long>(ctx, src, dims, channels, dst, st);
+    case 1: return launch_f2c<uint8_t>(ctx, src, idims, channels, dst, odims, origin, st);
+    case 2: return launch_f2c<uint16_t>(ctx, src, idims, channels, dst, odims, origin, st);
+    case 4: return launch_f2c<uint32_t>(ctx, src, idims, channels, dst, odims, origin, st);
+    case 8: return launch_f2c<unsigned long long>(ctx, src, idims, channels, dst, odims, origin, st);
   }
   set_error("sc_import_volume: elem_bytes must be 1, 2, 4 or 8");
   return SC_ERR_ARG;
+}
+
+int import_volume(sc_ctx* ctx, const void* src, int elem_bytes, const int32_t* dims, int channels, void* dst, cudaStream_t st) {
+  const int32_t origin[3] = {0, 0, 0};
+  return import_box(ctx, src, elem_bytes, dims, channels, dst, dims, origin, st);
+}
+
+// Only the box {x0,x1,y0,y1,z0,z1} of a host volume [X,Y,Z(,C)] goes to the device: strided DMA copies (cudaMemcpy3DAsync), one per
+// channel for a Fortran-ordered array (runs of x), one for a C-ordered array (runs of z * C), land in / are reordered into the
+// box region of the C-ordered device volume `dst`; everything outside the box is left untouched.
+int upload_volume_box(sc_ctx* ctx, const void* src_host, int elem_bytes, const int32_t* dims, int channels, int fortran_order,
+                      const int32_t* box, void* staging_dev, void* dst, cudaStream_t st) {
+  const int X = dims[0], Y = dims[1], Z = dims[2];
+  const int bx = box[1] - box[0], by = box[3] - box[2], bz = box[5] - box[4];
+  const size_t eb = (size_t)elem_bytes;
+  if (!fortran_order) {
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    const size_t row = (size_t)Z * channels * eb;
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src_host), row, row, (size_t)Y);
+    p.dstPtr = make_cudaPitchedPtr(dst, row, row, (size_t)Y);
+    p.srcPos = make_cudaPos((size_t)box[4] * channels * eb, (size_t)box[2], (size_t)box[0]);
+    p.dstPos = p.srcPos;
+    p.extent = make_cudaExtent((size_t)bz * channels * eb, (size_t)by, (size_t)bx);
+    p.kind = cudaMemcpyHostToDevice;
+    SC_CUDA(cudaMemcpy3DAsync(&p, st));
+    return SC_OK;
+  }
+  SC_CHECK(staging_dev != nullptr, SC_ERR_ARG, "sc_upload_volume_box: a Fortran-ordered source needs the staging buffer");
+  for (int c = 0; c < channels; ++c) {
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    p.srcPtr = make_cudaPitchedPtr(const_cast<char*>(reinterpret_cast<const char*>(src_host)) + (size_t)c * X * Y * Z * eb, (size_t)X * eb, (size_t)X * eb, (size_t)Y);
+    p.dstPtr = make_cudaPitchedPtr(reinterpret_cast<char*>(staging_dev) + (size_t)c * bx * by * bz * eb, (size_t)bx * eb, (size_t)bx * eb, (size_t)by);
+    p.srcPos = make_cudaPos((size_t)box[0] * eb, (size_t)box[2], (size_t)box[4]);
+    p.dstPos = make_cudaPos(0, 0, 0);
+    p.extent = make_cudaExtent((size_t)bx * eb, (size_t)by, (size_t)bz);
+    p.kind = cudaMemcpyHostToDevice;
+    SC_CUDA(cudaMemcpy3DAsync(&p, st));
+  }
+  const int32_t idims[3] = {bx, by, bz}, origin[3] = {box[0], box[2], box[4]};
+  return import_box(ctx, staging_dev, elem_bytes, idims, channels, dst, dims, origin, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -35,6 +35,31 @@ def test_import_volume_is_a_bit_exact_reorder(ctx, dtype, shape, channels):
     assert torch.equal(raw, raw2)
 
 
+@pytest.mark.parametrize("order", ["F", "C"])
+@pytest.mark.parametrize("dtype,shape,channels,box", [
+    (np.float32, (40, 35, 70), 15, (3, 29, 0, 35, 11, 64)),        # box touching two faces
+    (np.float32, (40, 35, 70), 15, (0, 40, 0, 35, 0, 70)),         # the whole volume
+    (np.float32, (33, 17, 9), 15, (32, 33, 16, 17, 8, 9)),         # one voxel in the far corner
+    (np.int16, (64, 48, 40), 1, (5, 50, 7, 41, 2, 39)),
+    (np.float64, (20, 24, 28), 3, (1, 19, 2, 3, 0, 28)),
+])
+def test_upload_volume_box_writes_exactly_the_box(ctx, order, dtype, shape, channels, box):
+    """crop mode: only the candidates' bounding box of the (page-locked or pageable) host priors is uploaded"""
+    rng = np.random.RandomState(sum(box))
+    full = shape + ((channels,) if channels > 1 else ())
+    a = (rng.rand(*full) * 200 - 20).astype(dtype)
+    a = np.asfortranarray(a) if order == "F" else np.ascontiguousarray(a)
+    tdt = torch.from_numpy(np.zeros(1, dtype)).dtype
+    out = torch.full(full, 7, dtype=tdt, device="cuda")
+    got = ctx.upload_volume_box(a, box, channels=channels, out=out)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    ref = np.full(full, 7, dtype)
+    sl = (slice(box[0], box[1]), slice(box[2], box[3]), slice(box[4], box[5]))
+    ref[sl] = a[sl]
+    assert np.array_equal(got, ref)
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int16, np.uint8, np.int32])
 @pytest.mark.parametrize("shape,zero_frac", [((3, 2, 1), 0.0), ((4, 4, 4), 0.5), ((16, 9, 11), 0.3), ((37, 41, 29), 0.2),
                                              ((128, 96, 80), 0.45), ((64, 64, 64), 0.0)])
