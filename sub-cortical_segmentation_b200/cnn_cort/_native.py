@@ -197,7 +197,11 @@ class Context(object):
             return torch.from_numpy(arr.reshape(-1).view(np.uint8)).to(dev, non_blocking=True), arr.dtype
         if not arr.flags["F_CONTIGUOUS"]:
             arr = np.asfortranarray(arr)
-        raw = torch.from_numpy(arr.reshape(-1, order="F").view(np.uint8)).to(dev, non_blocking=True)
+        host = torch.from_numpy(arr.reshape(-1, order="F").view(np.uint8))
+        raw = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
+        step = 64 << 20           # pieces of 64 MB: small copies of other streams (statistics, counts) slip in between them
+        for o in range(0, host.numel(), step):
+            raw[o:o + step].copy_(host[o:o + step], non_blocking=True)
         out = torch.empty_like(raw)
         _check(self.lib.sc_import_volume(self.h, _ptr(raw), arr.dtype.itemsize, _dims(shape), int(channels), _ptr(out), _stream()))
         return out, arr.dtype

@@ -236,19 +236,6 @@ def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=Non
     atlas = np.asarray(atlas)
     if atlas.dtype != np.float32:          # a scaled NIfTI comes back as float64: the priors are consumed as float32 (base.py:388)
         atlas = atlas.astype(np.float32, order='K')
-    # the priors (94 % of the upload) are first needed by the FC head: upload and reorder them on a side stream while the
-    # normalisation, the candidate selection and the convolution phase run.  Crop mode reads them at the candidates only:
-    # once the bounding box of the dilated mask is known, just that box of the host array is uploaded (strided DMA).
-    main = torch.cuda.current_stream()
-    side = _side_stream(ctx.device)
-    side.wait_stream(main)
-    atlas_ready = torch.cuda.Event()
-    d_atlas = None
-    if crop_mask is None:
-        with torch.cuda.stream(side):
-            d_atlas, _ = ctx.upload_volume(atlas, channels=15)
-            atlas_ready.record(side)
-        d_atlas = d_atlas.view(torch.float32).view(shape + (15,))
     vol, mean, std = ctx.normalise_volume(raw, dt, shape)
     if crop_mask is not None:
         mraw, mdt = ctx.upload_volume(crop_mask)
@@ -256,9 +243,22 @@ def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=Non
     else:
         cand = ctx.candidate_mask(raw, dt, shape)                          # == image.astype('bool')
     box, n_cand = ctx.mask_bbox(cand)
-    if crop_mask is not None and box is not None:
+    # the priors (94 % of the upload) are first needed by the FC head: they are uploaded and reordered on a side stream while
+    # the convolution phase runs -- enqueued only now, behind the host-synchronous steps above, whose small device -> host
+    # copies would otherwise queue up behind the gigabyte.  Crop mode reads the priors at the candidates only: just the
+    # bounding box of the dilated mask is uploaded (strided DMA from the host array).
+    main = torch.cuda.current_stream()
+    side = _side_stream(ctx.device)
+    side.wait_stream(main)
+    atlas_ready = torch.cuda.Event()
+    d_atlas = None
+    if box is not None:
         with torch.cuda.stream(side):
-            d_atlas = ctx.upload_volume_box(atlas, box, channels=15)
+            if crop_mask is not None:
+                d_atlas = ctx.upload_volume_box(atlas, box, channels=15)
+            else:
+                d_atlas, _ = ctx.upload_volume(atlas, channels=15)
+                d_atlas = d_atlas.view(torch.float32).view(shape + (15,))
             atlas_ready.record(side)
     lab = torch.zeros(shape, dtype=torch.uint8, device=vol.device)
     prob = torch.zeros(shape + (15,), dtype=torch.float32, device=vol.device) if want_proba else None
