@@ -215,6 +215,9 @@ def bench_train(ctx, torch, dist, rank, world, peaks, steps=20, warmup=5):
         sync()
         launches = (ctx.counter("launches") - l0) / steps
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        for i in range(2):                      # the first copy out of a fresh page-locked buffer costs tens of ms once
+            step(i, from_host=True)
+        sync()
         e0.record()
         for i in range(steps):
             step(i, from_host=True)
