@@ -136,14 +136,25 @@ __global__ void __launch_bounds__(256) tbn_stats_kernel(const float* __restrict_
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
   if (chunk * 8 < C) {
-    for (int64_t v = (int64_t)blockIdx.x * (256 / NCH) + slot; v < total; v += (int64_t)gridDim.x * (256 / NCH)) {
+    const int64_t stride = (int64_t)gridDim.x * (256 / NCH);
+    auto pos = [&](int64_t v) {
       const int c = (int)(v % H);
       const int sidx = (int)((v / H) % n);
       const int r = (int)(v / ((int64_t)H * n));
-      float x[8];
-      load8<FMT>(X, (int64_t)r * Pw + (int64_t)sidx * pitch + c, chunk, x);
+      return (int64_t)r * Pw + (int64_t)sidx * pitch + c;
+    };
+    // two points per iteration: both loads are issued before either is consumed
+    for (int64_t v = (int64_t)blockIdx.x * (256 / NCH) + slot; v < total; v += 2 * stride) {
+      float x[8], x2[8];
+      load8<FMT>(X, pos(v), chunk, x);
+      const bool two = v + stride < total;
+      if (two) load8<FMT>(X, pos(v + stride), chunk, x2);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { s[k] += x[k]; q[k] = fmaf(x[k], x[k], q[k]); }
+      if (two) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += x2[k]; q[k] = fmaf(x2[k], x2[k], q[k]); }
+      }
     }
   }
   // lanes with the same chunk are NCH apart: fold them with shuffles, then one shared-memory atomic per warp and channel
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(256) tbn_bwd_reduce_kernel(const float* __rest
       const bool on = ch < C;
       mu[k] = on ? mean[ch] : 0.f; is[k] = on ? istd[ch] : 0.f; ga[k] = on ? gamma[ch] : 0.f; be[k] = on ? beta[ch] : 0.f; al[k] = on ? alpha[ch] : 0.f;
     }
-    for (int64_t v = (int64_t)blockIdx.x * (256 / NCH) + slot; v < total; v += (int64_t)gridDim.x * (256 / NCH)) {
+for (int64_t v = (int64_t)blockIdx.x * (256 / NCH) + slot; v < total; v += (int64_t)gridDim.x * (256 / NCH)) {
       const int c = (int)(v % H);
       const int s = (int)((v / H) % n);
       const int r = (int)(v / ((int64_t)H * n));
@@ -405,36 +416,46 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float*
                                                                      float* __restrict__ planar, int pld) {
   constexpr int NCH = FMT / 8;
   if (cnt) count = *cnt;
-  __shared__ uint16_t tile[2][FMT][66];
+  __shared__ uint16_t tile[2][FMT][68];     // columns 0..63: this CTA's positions; 64, 65: the two positions to their left
   const int chunk = threadIdx.x % NCH, px = threadIdx.x / NCH;
   const int64_t npix = (int64_t)R * Pw;
-  const int64_t q = (int64_t)blockIdx.x * 64 + px;
-  float dx[8];
+  const int64_t q0 = (int64_t)blockIdx.x * 64;
+  // dx of position q (zeros outside the valid region / the map) -> returns whether q is a valid position of this chunk
+  auto point = [&](int64_t q, float (&dx)[8], int& r, int& s, int& c) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) dx[k] = 0.f;
-  bool valid = false;
-  int r = 0, s = 0, c = 0;
-  if (q < npix) {
+    for (int k = 0; k < 8; ++k) dx[k] = 0.f;
+    if (q < 0 || q >= npix) return false;
     c = (int)(q % pitch);
     s = (int)((q / pitch) % n);
     r = (int)(q / Pw);
-    valid = r < H && c < H && chunk * 8 < C;
-    if (valid) {
-      float x[8], g[8];
-      bwd_point<FMT, DFMT>(X, dA, idx, dF5, dF5_ld, mask, n, C, Pw, pitch, pool, dPw, dPitch, r, s, c, chunk, x, g);
+    if (!(r < H && c < H && chunk * 8 < C)) return false;
+    float x[8], g[8];
+    bwd_point<FMT, DFMT>(X, dA, idx, dF5, dF5_ld, mask, n, C, Pw, pitch, pool, dPw, dPitch, r, s, c, chunk, x, g);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int ch = chunk * 8 + k;
-        if (ch < C) {
-          const float is = istd[ch], ga = gamma[ch];
-          const float xh = (x[k] - mean[ch]) * is;
-          const float yv = fmaf(xh, ga, beta[ch]);
-          const float dy = yv > 0.f ? g[k] : alpha[ch] * g[k];
-          dx[k] = ga * is * (dy - (float)(sums[ch * 3] / count) - xh * (float)(sums[ch * 3 + 1] / count));
-        }
+    for (int k = 0; k < 8; ++k) {
+      const int ch = chunk * 8 + k;
+      if (ch < C) {
+        const float is = istd[ch], ga = gamma[ch];
+        const float xh = (x[k] - mean[ch]) * is;
+        const float yv = fmaf(xh, ga, beta[ch]);
+        const float dy = yv > 0.f ? g[k] : alpha[ch] * g[k];
+        dx[k] = ga * is * (dy - (float)(sums[ch * 3] / count) - xh * (float)(sums[ch * 3 + 1] / count));
       }
     }
-  }
+    return true;
+  };
+  auto to_tile = [&](const uint4& h, const uint4& l, int col) {
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      tile[0][chunk * 8 + 2 * k][col] = (uint16_t)(hh[k] & 0xffffu); tile[0][chunk * 8 + 2 * k + 1][col] = (uint16_t)(hh[k] >> 16);
+      tile[1][chunk * 8 + 2 * k][col] = (uint16_t)(ll[k] & 0xffffu); tile[1][chunk * 8 + 2 * k + 1][col] = (uint16_t)(ll[k] >> 16);
+    }
+  };
+  const int64_t q = q0 + px;
+  float dx[8];
+  int r = 0, s = 0, c = 0;
+  const bool valid = point(q, dx, r, s, c);
   if (planar) {
     if (valid) {
 #pragma unroll
@@ -448,28 +469,27 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float*
   uint4 h, l;
   split8(dx, h, l);
   if (q < npix) store8<FMT>(frame, q, chunk, h, l);
-  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    tile[0][chunk * 8 + 2 * k][px] = (uint16_t)(hh[k] & 0xffffu); tile[0][chunk * 8 + 2 * k + 1][px] = (uint16_t)(hh[k] >> 16);
-    tile[1][chunk * 8 + 2 * k][px] = (uint16_t)(ll[k] & 0xffffu); tile[1][chunk * 8 + 2 * k + 1][px] = (uint16_t)(ll[k] >> 16);
+  to_tile(h, l, px);
+  if (px < 2) {          // the shifted copies of this CTA's 64 positions start one / two positions to the left: recompute those two
+    float dh[8];
+    int r2, s2, c2;
+    point(q0 - 2 + px, dh, r2, s2, c2);
+    uint4 h2, l2;
+    split8(dh, h2, l2);
+    to_tile(h2, l2, 64 + px);
   }
   __syncthreads();
+  // DT_k[p] = dx[p - k]: every copy is written as whole aligned 128 B rows (two positions per lane)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int64_t q0 = (int64_t)blockIdx.x * 64;
-  for (int row = warp; row < 2 * CP; row += nw) {
-    const int half = row / CP, ch = row - half * CP;
-    const int64_t qa = q0 + 2 * lane;
-    if (qa < npix) {
-      const uint16_t v0 = tile[half][ch][2 * lane], v1 = tile[half][ch][2 * lane + 1];
-      uint16_t* d0 = DT + (int64_t)row * npix;
-      uint16_t* d1 = DT + ((int64_t)2 * CP + row) * npix;
-      uint16_t* d2 = DT + ((int64_t)4 * CP + row) * npix;
-      *reinterpret_cast<uint32_t*>(d0 + qa) = (uint32_t)v0 | ((uint32_t)v1 << 16);
-      d1[qa + 1] = v0;
-      if (qa + 2 < npix) { d1[qa + 2] = v1; d2[qa + 2] = v0; }
-      if (qa + 3 < npix) d2[qa + 3] = v1;
-      if (qa == 0) { d1[0] = 0; d2[0] = 0; d2[1] = 0; }     // nothing lies to the left of position 0
+  const int64_t qa = q0 + 2 * lane;
+  if (qa < npix) {     // npix is even
+    for (int row = warp; row < 2 * CP; row += nw) {
+      const int half = row / CP, ch = row - half * CP;
+      const uint16_t* t = tile[half][ch];
+      const uint32_t m2 = lane ? t[2 * lane - 2] : t[64], m1 = lane ? t[2 * lane - 1] : t[65], v0 = t[2 * lane], v1 = t[2 * lane + 1];
+      *reinterpret_cast<uint32_t*>(DT + (int64_t)row * npix + qa) = v0 | (v1 << 16);
+      *reinterpret_cast<uint32_t*>(DT + ((int64_t)2 * CP + row) * npix + qa) = m1 | (v0 << 16);
+      *reinterpret_cast<uint32_t*>(DT + ((int64_t)4 * CP + row) * npix + qa) = m2 | (m1 << 16);
     }
   }
 }
