@@ -86,10 +86,31 @@ def _q(x, mode):
     raise ValueError(mode)
 
 
+def _q8(x):
+    """e4m3 (4 significant bits, |x| <= 448, saturating) -- the cross-term operands of the 'fp16+e4m3' scheme"""
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+
+
 def _contract(op, x, w, mode):
-    """op(x, w) with both operands rounded as ``mode`` says; '<m>x3' = hi/lo split, 3 products."""
+    """op(x, w) with both operands rounded as ``mode`` says; '<m>x3' = hi/lo split, 3 products.
+
+    Two-MMA candidates examined for the FC head (none is shipped):
+    'fp16_w2'   single fp16 activations x fp16 hi/lo weights        (xh*wh + xh*wl)
+    'fp16_x2'   fp16 hi/lo activations x single fp16 weights        (xh*wh + xl*wh)
+    'fp16+e4m3' fp16 hi product + both cross terms in e4m3 with a uniform 2^-11 block scale (tcgen05 kind::mxf8f6f4)
+    """
     if mode is None:
         return op(x, w)
+    if mode == "fp16_w2":
+        xh, wh = _q(x, "fp16"), _q(w, "fp16")
+        return op(xh, wh) + op(xh, _q(w - wh, "fp16"))
+    if mode == "fp16_x2":
+        xh, wh = _q(x, "fp16"), _q(w, "fp16")
+        return op(xh, wh) + op(_q(x - xh, "fp16"), wh)
+    if mode == "fp16+e4m3":
+        s = 2.0 ** 11
+        xh, wh = _q(x, "fp16"), _q(w, "fp16")
+        return op(xh, wh) + op(_q8(x), _q8((w - wh) * s) / s) + op(_q8((x - xh) * s) / s, _q8(w))
     if mode.endswith("x3"):
         m = mode[:-2]
         xh, wh = _q(x, m), _q(w, m)
