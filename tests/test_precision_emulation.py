@@ -1,6 +1,6 @@
 """Design validation of the product precision, oracle emulation on the CPU: which contractions may
 drop from three MMAs to two.  Inputs are the harsh case of the GPU parity tests -- zero patches + soft atlas priors
-(unsaturated softmax).  Run as a script for the whole table: python tests/test_precision_emulation.py [n]"""
+(unsaturated softmax).  Run as a script for the whole table: PYTHONPATH=. python tests/test_precision_emulation.py [n]"""
 import sys
 
 import numpy as np
