@@ -92,28 +92,45 @@ __global__ void tsoftmax_ce_kernel(const float* __restrict__ z, const uint8_t* _
 }
 
 // PReLU (+ dropout) backward of a dense layer: dz = dy * (2 mask) * (z > 0 ? 1 : alpha) as split rows and transposed split;
-// galpha[j] += sum_m dy' * z * [z <= 0]; gbias[j] += sum_m dz.  One warp per output unit j (lanes run over the batch).
+// galpha[j] += sum_m dy' * z * [z <= 0]; gbias[j] += sum_m dz (the gradient buffer is cleared at the start of the step).
+// One thread per element, visited twice like tsplit_kernel: j fastest for the row-major copy, m fastest for the transposed copy
+// and the two column sums (a warp then holds 32 rows of one unit: shuffle reduction, one atomic per warp).
 __global__ void __launch_bounds__(256) tsplit_bwd_kernel(const float* __restrict__ dy, int ld_dy, int col0, const float* __restrict__ z, int ldz, int n,
                                                          int N, const float* __restrict__ alpha, const uint8_t* __restrict__ mask, int mask_ld,
                                                          float* __restrict__ dz, int ld_dz, float* __restrict__ dzT, int npad,
                                                          float* __restrict__ galpha, float* __restrict__ gbias) {
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (j >= N) return;
-  const float al = alpha[j];
-  float sa = 0.f, sb = 0.f;
-  for (int m = lane; m < n; m += 32) {
-    float g = dy[(int64_t)m * ld_dy + col0 + j];
+  const int64_t total = (int64_t)n * N;
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool on = e < total;
+  auto point = [&](int m, int j, float& g, float& zz) {
+    g = dy[(int64_t)m * ld_dy + col0 + j];
     if (mask) g = mask[(int64_t)m * mask_ld + j] ? 2.f * g : 0.f;
-    const float zz = z[(int64_t)m * ldz + j];
-    const float d = zz > 0.f ? g : al * g;
-    put_split(dz, ld_dz, m, j, d);
-    put_split(dzT, npad, j, m, d);
-    if (zz <= 0.f) sa = fmaf(g, zz, sa);
-    sb += d;
+    zz = z[(int64_t)m * ldz + j];
+    return zz > 0.f ? g : alpha[j] * g;
+  };
+  if (on) {   // j fastest: coalesced reads, row-major split writes
+    const int m = (int)(e / N), j = (int)(e - (int64_t)m * N);
+    float g, zz;
+    put_split(dz, ld_dz, m, j, point(m, j, g, zz));
   }
-  for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
-  if (lane == 0) { galpha[j] = sa; gbias[j] = sb; }
+  int j2 = -1;
+  float sa = 0.f, sb = 0.f;
+  if (on) {   // m fastest: contiguous transposed writes, column sums
+    j2 = (int)(e / n);
+    const int m = (int)(e - (int64_t)j2 * n);
+    float g, zz;
+    const float d = point(m, j2, g, zz);
+    put_split(dzT, npad, j2, m, d);
+    if (zz <= 0.f) sa = g * zz;
+    sb = d;
+  }
+  const int j0 = __shfl_sync(0xffffffffu, j2, 0);
+  if (__all_sync(0xffffffffu, j2 == j0)) {
+    for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+    if ((threadIdx.x & 31) == 0 && j0 >= 0) { atomicAdd(&galpha[j0], sa); atomicAdd(&gbias[j0], sb); }
+  } else if (on) {
+    atomicAdd(&galpha[j2], sa); atomicAdd(&gbias[j2], sb);
+  }
 }
 
 __global__ void tcopy_grad_kernel(const float* __restrict__ scratch, int ld, int K, int N, float* __restrict__ g) {
@@ -273,13 +290,13 @@ int tdense_head(sc_ctx* ctx, const TcDenseBuf& D, const float* in4, const uint8_
   tcopy_grad_kernel<<<g256(270 * 15), 256, 0, s>>>(D.gWout, 16, 270, 15, G + O.outW);
   SC_TRY(tgemm(ctx, D.dZOs, n, 64, W[5].wkn, 270, 272, ctx->train_consts + kTrainZeros, D.dH2, 272, 272, PC_TRAIN_BWD, s));
   // fc_2
-  tsplit_bwd_kernel<<<(270 + 7) / 8, 256, 0, s>>>(D.dH2, 272, 0, D.ZF2, 272, n, 270, P + O.a2, nullptr, 0, D.dZF2s, 320, D.dZF2T, D.npad,
+  tsplit_bwd_kernel<<<g256((int64_t)n * 270), 256, 0, s>>>(D.dH2, 272, 0, D.ZF2, 272, n, 270, P + O.a2, nullptr, 0, D.dZF2s, 320, D.dZF2T, D.npad,
                                                   G + O.a2, G + O.fc2b);
   SC_TRY(tgemm(ctx, D.CAT2T, 555, D.npad, D.dZF2T, 270, 272, ctx->train_consts + kTrainZeros, D.gWfc2, 272, 272, PC_TRAIN_BWD, s));
   tcopy_grad_kernel<<<g256(555 * 270), 256, 0, s>>>(D.gWfc2, 272, 555, 270, G + O.fc2W);
   SC_TRY(tgemm(ctx, D.dZF2s, n, 320, W[4].wkn, 555, 576, ctx->train_consts + kTrainZeros, D.dCAT2, 576, 556, PC_TRAIN_BWD, s));
   // FC1 (f2_drop sits on its activation)
-  tsplit_bwd_kernel<<<(540 + 7) / 8, 256, 0, s>>>(D.dCAT2, 576, 0, D.ZF1, 576, n, 540, P + O.a1, masks + 2160, 2700, D.dZF1s, 576, D.dZF1T, D.npad,
+  tsplit_bwd_kernel<<<g256((int64_t)n * 540), 256, 0, s>>>(D.dCAT2, 576, 0, D.ZF1, 576, n, 540, P + O.a1, masks + 2160, 2700, D.dZF1s, 576, D.dZF1T, D.npad,
                                                   G + O.a1, G + O.fc1b);
   SC_TRY(tgemm(ctx, D.CATT, 540, D.npad, D.dZF1T, 540, 576, ctx->train_consts + kTrainZeros, D.gWfc1, 576, 540, PC_TRAIN_BWD, s));
   tcopy_grad_kernel<<<g256(540 * 540), 256, 0, s>>>(D.gWfc1, 576, 540, 540, G + O.fc1W);
@@ -294,7 +311,7 @@ int tdense_branch_backward(sc_ctx* ctx, int b, const TcDenseBuf& D, int n, const
   const BranchOff& Ob = ctx->off.br[b];
   float* P = ctx->params;
   float* G = ctx->grads;
-  tsplit_bwd_kernel<<<(180 + 7) / 8, 256, 0, s>>>(D.dCAT, 576, b * 180, D.Z1[b], 192, n, 180, P + Ob.d1alpha, masks + 1620 + b * 180, 2700,
+  tsplit_bwd_kernel<<<g256((int64_t)n * 180), 256, 0, s>>>(D.dCAT, 576, b * 180, D.Z1[b], 192, n, 180, P + Ob.d1alpha, masks + 1620 + b * 180, 2700,
                                                   D.dZ1s[b], 192, D.dZ1T[b], D.npad, G + Ob.d1alpha, G + Ob.d1b);
   SC_TRY(tgemm(ctx, D.F5T[b], 540, D.npad, D.dZ1T[b], 180, 192, ctx->train_consts + kTrainZeros, D.gW1[b], 192, 180, PC_TRAIN_BWD, s));
   tcopy_grad_kernel<<<g256(540 * 180), 256, 0, s>>>(D.gW1[b], 192, 540, 180, G + Ob.d1W);

@@ -54,12 +54,16 @@ __device__ __forceinline__ void store8(float* map, int64_t pixel, int chunk, con
 // weight panels of the sweep kernels, re-derived from the master parameters on the device every step
 // (same layout as weights.cu builds on the host for inference)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void derive_panels_kernel(const float* __restrict__ W, int cout, int cin, int dgrad, int ksteps, int bn,
-                                     uint16_t* __restrict__ plain, uint16_t* __restrict__ pair) {
+struct PanelJob { const float* W; int cout, cin, dgrad, ksteps, bn; uint16_t* plain; uint16_t* pair; };
+struct PanelJobs { PanelJob j[8]; };
+// one launch per branch: blockIdx.y = (layer 1..4) x (forward | dgrad)
+__global__ void derive_panels_kernel(const PanelJobs jobs) {
+  const PanelJob& J = jobs.j[blockIdx.y];
+  const int cout = J.cout, cin = J.cin, dgrad = J.dgrad, ksteps = J.ksteps, bn = J.bn;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cout * cin * 9) return;
   const int t = i % 9, ci = (i / 9) % cin, co = i / (9 * cin);
-  const float v = W[i];
+  const float v = J.W[i];
   // forward: true convolution -> correlation taps (tap 8 - t), rows = output channels, k = input channels
   // dgrad:   raw taps, rows = the layer's INPUT channels, k = its output channels
   const int o = dgrad ? ci : co, k = dgrad ? co : ci, tap = dgrad ? t : 8 - t;
@@ -67,12 +71,12 @@ __global__ void derive_panels_kernel(const float* __restrict__ W, int cout, int 
   const __nv_bfloat16 hb16 = __float2bfloat16_rn(v);
   const uint16_t hi = __bfloat16_as_ushort(hb16);
   const uint16_t lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hb16)));
-  plain[((size_t)panel * 2 * bn + o) * 64 + kk] = hi;
-  plain[((size_t)panel * 2 * bn + bn + o) * 64 + kk] = lo;
+  J.plain[((size_t)panel * 2 * bn + o) * 64 + kk] = hi;
+  J.plain[((size_t)panel * 2 * bn + bn + o) * 64 + kk] = lo;
   const int hb = bn >> 1;
   const size_t prow = ((size_t)panel * 2 + o / hb) * bn + o % hb;
-  pair[prow * 64 + kk] = hi;
-  pair[(prow + hb) * 64 + kk] = lo;
+  J.pair[prow * 64 + kk] = hi;
+  J.pair[(prow + hb) * 64 + kk] = lo;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -143,18 +147,22 @@ __global__ void __launch_bounds__(256) tbn_stats_kernel(const float* __restrict_
       const int r = (int)(v / ((int64_t)H * n));
       return (int64_t)r * Pw + (int64_t)sidx * pitch + c;
     };
-    // two points per iteration: both loads are issued before either is consumed
-    for (int64_t v = (int64_t)blockIdx.x * (256 / NCH) + slot; v < total; v += 2 * stride) {
-      float x[8], x2[8];
-      load8<FMT>(X, pos(v), chunk, x);
-      const bool two = v + stride < total;
-      if (two) load8<FMT>(X, pos(v + stride), chunk, x2);
+    // four points per iteration, all loads issued before the first is consumed (the grid stays small: every CTA ends with
+    // same-address double atomics, which serialise at ~ 27 clk each)
+    for (int64_t v = (int64_t)blockIdx.x * (256 / NCH) + slot; v < total; v += 4 * stride) {
+      float x[4][8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { s[k] += x[k]; q[k] = fmaf(x[k], x[k], q[k]); }
-      if (two) {
+      for (int u = 0; u < 4; ++u) {
+        if (v + u * stride < total) load8<FMT>(X, pos(v + u * stride), chunk, x[u]);
+        else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s[k] += x2[k]; q[k] = fmaf(x2[k], x2[k], q[k]); }
+          for (int k = 0; k < 8; ++k) x[u][k] = 0.f;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += x[u][k]; q[k] = fmaf(x[u][k], x[u][k], q[k]); }
     }
   }
   // lanes with the same chunk are NCH apart: fold them with shuffles, then one shared-memory atomic per warp and channel
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(256) tbn_stats_kernel(const float* __restrict_
 
 // sums[kCountSlot] carries the element count when the sums are all-reduced over the ranks (synchronised BatchNorm)
 constexpr int kCountSlot = 192;
+constexpr int kSumsStride = 256;          // doubles per reduction buffer (one per layer and direction: a single memset clears them all)
 __global__ void tset_count_kernel(double* __restrict__ sums, double count) { sums[kCountSlot] = count; }
 
 // all-reduce the local BatchNorm sums (+ count) over the ranks through the caller's hook; `cnt` then points at the global count
@@ -187,17 +196,28 @@ static int sync_sums(sc_ctx* ctx, double* sums, double count, const double** cnt
   return SC_OK;
 }
 
-__global__ void tbn_finalize_kernel(const double* __restrict__ sums, int C, double count, const double* __restrict__ cnt, float* __restrict__ mean,
-                                    float* __restrict__ istd, float* __restrict__ g_mean_slot, float* __restrict__ g_istd_slot) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (cnt) count = *cnt;
+// batch mean / inverse standard deviation of channel c from the reduction buffer (biased variance, eps 1e-4: Lasagne's BatchNormLayer)
+__device__ __forceinline__ void bn_moments(const double* __restrict__ sums, double count, int c, float& mean, float& istd) {
   const double m = sums[c * 2] / count;
   double var = sums[c * 2 + 1] / count - m * m;
   if (var < 0) var = 0;
-  const float is = (float)(1.0 / sqrt(var + (double)kBnEps));
-  mean[c] = (float)m; istd[c] = is;
-  g_mean_slot[c] = (float)m; g_istd_slot[c] = is;   // carried to the optimiser through the gradient buffer
+  mean = (float)m;
+  istd = (float)(1.0 / sqrt(var + (double)kBnEps));
+}
+// Head of the activation kernels: the moments of all channels -> shared memory (one double division / square root per channel
+// and CTA, then a barrier); the first CTA also publishes them for the backward pass and, through the gradient buffer, for the optimiser
+__device__ __forceinline__ void bn_moments_cta(const double* __restrict__ sums, double count, int C, float (&s_mu)[64], float (&s_is)[64],
+                                               float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ g_mean_slot,
+                                               float* __restrict__ g_istd_slot) {
+  if (threadIdx.x < 64) {
+    float m = 0.f, is = 0.f;
+    if (threadIdx.x < C) {
+      bn_moments(sums, count, threadIdx.x, m, is);
+      if (blockIdx.x == 0) { mean[threadIdx.x] = m; istd[threadIdx.x] = is; g_mean_slot[threadIdx.x] = m; g_istd_slot[threadIdx.x] = is; }
+    }
+    s_mu[threadIdx.x] = m; s_is[threadIdx.x] = is;
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -208,13 +228,18 @@ __global__ void tbn_finalize_kernel(const double* __restrict__ sums, int C, doub
 // ---------------------------------------------------------------------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_act_kernel(const float* __restrict__ X, int n, int C, int inPw, int inPitch,
-                                                                  const float* __restrict__ mean, const float* __restrict__ istd,
+                                                                  const double* __restrict__ sums, double count, const double* __restrict__ cnt,
+                                                                  float* __restrict__ mean, float* __restrict__ istd,
+                                                                  float* __restrict__ g_mean_slot, float* __restrict__ g_istd_slot,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ alpha, int pool,
                                                                   float* __restrict__ A, int oR, int oPitch, int oH,
                                                                   uint8_t* __restrict__ idx, uint16_t* __restrict__ AT, int CP) {
   constexpr int NCH = FMT / 8;
   __shared__ uint16_t tile[2][FMT][66];
+  __shared__ float s_mu[64], s_is[64];
+  if (cnt) count = *cnt;
+  bn_moments_cta(sums, count, C, s_mu, s_is, mean, istd, g_mean_slot, g_istd_slot);
   const int chunk = threadIdx.x % NCH, px = threadIdx.x / NCH;
   const int64_t oPw = (int64_t)n * oPitch, npix = (int64_t)oR * oPw;
   const int64_t q = (int64_t)blockIdx.x * 64 + px;
@@ -233,8 +258,8 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_act_kernel(const float* __
       for (int k = 0; k < 8; ++k) {
         const int ch = chunk * 8 + k;
         const bool on = ch < C;
-        const float g = on ? gamma[ch] * istd[ch] : 0.f;
-        sc_[k] = g; sh[k] = on ? beta[ch] - mean[ch] * g : 0.f; al[k] = on ? alpha[ch] : 0.f;
+        const float g = on ? gamma[ch] * s_is[ch] : 0.f;
+        sc_[k] = g; sh[k] = on ? beta[ch] - s_mu[ch] * g : 0.f; al[k] = on ? alpha[ch] : 0.f;
       }
       if (!pool) {
         float x[8];
@@ -288,17 +313,21 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_act_kernel(const float* __
 }
 
 // conv5 activation (valid 3x3 of the [7][n][8] F64CH map) -> F5 [n][540] in (c, h, w) order with the l1drop mask applied
-__global__ void tact5_flatten_kernel(const float* __restrict__ X4, int n, const float* __restrict__ mean, const float* __restrict__ istd,
+__global__ void tact5_flatten_kernel(const float* __restrict__ X4, int n, const double* __restrict__ sums, double count, const double* __restrict__ cnt,
+                                     float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ g_mean_slot, float* __restrict__ g_istd_slot,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha,
                                      const uint8_t* __restrict__ mask /*+ b*540, row stride 2700*/, float* __restrict__ F5) {
+  __shared__ float s_mu[64], s_is[64];
+  if (cnt) count = *cnt;
+  bn_moments_cta(sums, count, 60, s_mu, s_is, mean, istd, g_mean_slot, g_istd_slot);
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)n * 540) return;
   const int i = (int)(e / 540), k = (int)(e - (int64_t)i * 540);
   const int c = k / 9, r = k - c * 9, h = r / 3, w = r - h * 3;
   const __nv_bfloat16* px = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const char*>(X4) + ((int64_t)h * n * 8 + (int64_t)i * 8 + w) * 256);
   const float x = __bfloat162float(px[c]) + __bfloat162float(px[64 + c]);
-  const float g = gamma[c] * istd[c];
-  const float y = prelu(fmaf(x, g, beta[c] - mean[c] * g), alpha[c]);
+  const float g = gamma[c] * s_is[c];
+  const float y = prelu(fmaf(x, g, beta[c] - s_mu[c] * g), alpha[c]);
   F5[e] = mask[(int64_t)i * 2700 + k] ? 2.f * y : 0.f;
 }
 
@@ -391,11 +420,19 @@ for (int64_t v = (int64_t)blockIdx.x * (256 / NCH) + slot; v < total; v += (int6
     atomicAdd(&sums[threadIdx.x * 3 + 2], (double)red[threadIdx.x][2]);
   }
 }
+// The beta / gamma / slope gradients are the three per-channel sums of pass 1 -- the LOCAL sums: the gradient all-reduce adds the
+// ranks.  Without a synchronised-BatchNorm hook the first CTA of the pass-2 kernel writes them (gbeta != nullptr); with a hook the
+// sums are all-reduced in place before pass 2, so this one-CTA kernel copies them out first.
+__device__ __forceinline__ void bn_publish_grads(const double* __restrict__ sums, int C, float* __restrict__ gbeta, float* __restrict__ ggamma,
+                                                 float* __restrict__ galpha) {
+  if (gbeta && blockIdx.x == 0 && threadIdx.x < C) {
+    const int c = threadIdx.x;
+    gbeta[c] = (float)sums[c * 3]; ggamma[c] = (float)sums[c * 3 + 1]; galpha[c] = (float)sums[c * 3 + 2];
+  }
+}
 __global__ void tbn_bwd_params_kernel(const double* __restrict__ sums, int C, float* __restrict__ gbeta, float* __restrict__ ggamma,
                                       float* __restrict__ galpha) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  gbeta[c] = (float)sums[c * 3]; ggamma[c] = (float)sums[c * 3 + 1]; galpha[c] = (float)sums[c * 3 + 2];
+  bn_publish_grads(sums, C, gbeta, ggamma, galpha);
 }
 
 // pass 2 over ALL positions of the conv-output map (64 consecutive positions per CTA):
@@ -412,10 +449,12 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float*
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      const float* __restrict__ alpha, const double* __restrict__ sums, double count,
                                                                      const double* __restrict__ cnt,
+                                                                     float* __restrict__ gbeta, float* __restrict__ ggamma, float* __restrict__ galpha,
                                                                      float* __restrict__ frame, uint16_t* __restrict__ DT, int CP,
                                                                      float* __restrict__ planar, int pld) {
   constexpr int NCH = FMT / 8;
   if (cnt) count = *cnt;
+  bn_publish_grads(sums, C, gbeta, ggamma, galpha);
   __shared__ uint16_t tile[2][FMT][68];     // columns 0..63: this CTA's positions; 64, 65: the two positions to their left
   const int chunk = threadIdx.x % NCH, px = threadIdx.x / NCH;
   const int64_t npix = (int64_t)R * Pw;
@@ -503,9 +542,11 @@ __global__ void __launch_bounds__(256) tbn_bwd_conv1_kernel(const float* __restr
                                                             int n, const float* __restrict__ mean, const float* __restrict__ istd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ alpha, const double* __restrict__ sums, double count,
-                                                            const double* __restrict__ cnt, float* __restrict__ gW) {
+                                                            const double* __restrict__ cnt, float* __restrict__ gbeta, float* __restrict__ ggamma,
+                                                            float* __restrict__ galpha, float* __restrict__ gW) {
   constexpr int C = 20, H = 30;
   if (cnt) count = *cnt;
+  bn_publish_grads(sums, C, gbeta, ggamma, galpha);
   __shared__ float red[24][9];
   for (int i = threadIdx.x; i < 24 * 9; i += 256) (&red[0][0])[i] = 0.f;
   __syncthreads();
@@ -782,7 +823,7 @@ size_t tc_branch_bytes(int n) {
   b += 2 * al(big);                                                // frame, dA
   b += al((size_t)30 * n * 32 * 3 * 2 * 32 * 2);                   // DT: three shifted copies (largest: conv2, 3 x 2 x 32 rows)
   b += al((size_t)n * 20 * 30 * 32 * 4);                           // planar fp32 dX of conv1
-  b += 1024 * 4;
+  b += al(10 * kSumsStride * 8) + 1024 * 4;                        // BatchNorm reduction buffers
   return b;
 }
 
@@ -810,7 +851,7 @@ int tc_carve_branch(TcBranchBuf& T, char* base, int n) {
   T.dA = reinterpret_cast<float*>(take(big));
   T.DT = reinterpret_cast<uint16_t*>(take((size_t)30 * n * 32 * 3 * 2 * 32 * 2));
   T.dX0 = reinterpret_cast<float*>(take((size_t)n * 20 * 30 * 32 * 4));
-  T.sums = reinterpret_cast<double*>(take(256 * 8));            // [64][3] sums + the count slot
+  T.sums = reinterpret_cast<double*>(take(10 * kSumsStride * 8));   // per layer, forward (l) and backward (5 + l): [64][3] sums + the count slot
   return (int)0;
 }
 
@@ -856,14 +897,21 @@ int tc_branch_forward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pat
   const BranchOff& Ob = O.br[b];
   float* P = ctx->params;
   float* G = ctx->grads;
-  for (int l = 1; l < 5; ++l)
-    for (int d = 0; d < 2; ++d) {
-      const SweepW& S = ctx->train_sw[b][l][d];
-      const int ne = kTL[l].cout * kTL[l].cin * 9;
-      derive_panels_kernel<<<(ne + 255) / 256, 256, 0, s>>>(P + Ob.convW[l], kTL[l].cout, kTL[l].cin, d, S.ksteps, S.bn,
-                                                            reinterpret_cast<uint16_t*>(S.panels), reinterpret_cast<uint16_t*>(S.panels_pair));
-      ctx->launches++;
-    }
+  {
+    PanelJobs jobs;
+    int most = 0;
+    for (int l = 1; l < 5; ++l)
+      for (int d = 0; d < 2; ++d) {
+        const SweepW& S = ctx->train_sw[b][l][d];
+        jobs.j[(l - 1) * 2 + d] = {P + Ob.convW[l], kTL[l].cout, kTL[l].cin, d, S.ksteps, S.bn, reinterpret_cast<uint16_t*>(S.panels),
+                                   reinterpret_cast<uint16_t*>(S.panels_pair)};
+        const int ne = kTL[l].cout * kTL[l].cin * 9;
+        most = ne > most ? ne : most;
+      }
+    derive_panels_kernel<<<dim3((most + 255) / 256, 8), 256, 0, s>>>(jobs);
+    ctx->launches++;
+  }
+  SC_CUDA(cudaMemsetAsync(T.sums, 0, 10 * kSumsStride * sizeof(double), s));     // every BatchNorm reduction buffer of the step
   for (int l = 0; l < 5; ++l) {
     const TLayer& L = kTL[l];
     const int Pw = n * L.pitch;
@@ -876,26 +924,29 @@ int tc_branch_forward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pat
       SC_TRY(launch_conv_sweep(ctx, ctx->train_sw[b][l][0], l, T.A[l - 1], Li.fmt == 32 ? 1 : 0, T.X[l], L.fmt == 32 ? 1 : 0, Pw, L.R, L.H, 1, 0,
                                PC_TRAIN_FWD, s));
     }
-    SC_CUDA(cudaMemsetAsync(T.sums, 0, 64 * 3 * sizeof(double), s));
+    double* sums = T.sums + l * kSumsStride;
     const int64_t vpix = (int64_t)L.H * n * L.H;
-    if (L.fmt == 32) tbn_stats_kernel<32><<<cap_grid(ctx, (vpix + 63) / 64 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, T.sums);
-    else tbn_stats_kernel<64><<<cap_grid(ctx, (vpix + 31) / 32 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, T.sums);
+    if (L.fmt == 32) tbn_stats_kernel<32><<<cap_grid(ctx, (vpix + 63) / 64 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, sums);
+    else tbn_stats_kernel<64><<<cap_grid(ctx, (vpix + 31) / 32 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, sums);
     const double* cnt;
-    SC_TRY(sync_sums(ctx, T.sums, (double)vpix, &cnt, s));
-    tbn_finalize_kernel<<<1, 64, 0, s>>>(T.sums, L.cout, (double)vpix, cnt, T.mean[l], T.istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3]);
-    ctx->launches += 2;
+    SC_TRY(sync_sums(ctx, sums, (double)vpix, &cnt, s));
+    ctx->launches++;
+    // the activation kernels derive mean / inv-std from the sums themselves; their first CTA publishes them
     if (l < 4) {
       const int64_t opix = (int64_t)L.oR * n * L.oPitch;
       const unsigned grid = (unsigned)((opix + 63) / 64);
       if (L.fmt == 32)
-        tbn_act_kernel<32><<<grid, 256, 0, s>>>(T.X[l], n, L.cout, Pw, L.pitch, T.mean[l], T.istd[l], P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l],
-                                                L.pool, T.A[l], L.oR, L.oPitch, L.oH, T.idx[l], T.AT[l], pad8(L.cout));
+        tbn_act_kernel<32><<<grid, 256, 0, s>>>(T.X[l], n, L.cout, Pw, L.pitch, sums, (double)vpix, cnt, T.mean[l], T.istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3],
+                                                P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], L.pool, T.A[l], L.oR, L.oPitch, L.oH, T.idx[l], T.AT[l],
+                                                pad8(L.cout));
       else
-        tbn_act_kernel<64><<<grid, 512, 0, s>>>(T.X[l], n, L.cout, Pw, L.pitch, T.mean[l], T.istd[l], P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l],
-                                                L.pool, T.A[l], L.oR, L.oPitch, L.oH, T.idx[l], T.AT[l], pad8(L.cout));
+        tbn_act_kernel<64><<<grid, 512, 0, s>>>(T.X[l], n, L.cout, Pw, L.pitch, sums, (double)vpix, cnt, T.mean[l], T.istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3],
+                                                P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], L.pool, T.A[l], L.oR, L.oPitch, L.oH, T.idx[l], T.AT[l],
+                                                pad8(L.cout));
     } else {
-      tact5_flatten_kernel<<<(unsigned)(((int64_t)n * 540 + 255) / 256), 256, 0, s>>>(T.X[4], n, T.mean[4], T.istd[4], P + Ob.bn[4][1], P + Ob.bn[4][0],
-                                                                                     P + Ob.alpha[4], masks + b * 540, F5);
+      tact5_flatten_kernel<<<(unsigned)(((int64_t)n * 540 + 255) / 256), 256, 0, s>>>(T.X[4], n, sums, (double)vpix, cnt, T.mean[4], T.istd[4], G + Ob.bn[4][2],
+                                                                                     G + Ob.bn[4][3], P + Ob.bn[4][1], P + Ob.bn[4][0], P + Ob.alpha[4],
+                                                                                     masks + b * 540, F5);
     }
     ctx->launches++;
   }
@@ -913,18 +964,19 @@ static int bwd_layer(sc_ctx* ctx, int b, int l, const TcBranchBuf& T, const floa
   const int Pw = n * L.pitch;
   const int64_t vpix = (int64_t)L.H * n * L.H;
   constexpr int NCH = FMT / 8;
-  SC_CUDA(cudaMemsetAsync(T.sums, 0, 64 * 3 * sizeof(double), s));
+  double* sums = T.sums + (5 + l) * kSumsStride;
   tbn_bwd_reduce_kernel<FMT, DFMT><<<cap_grid(ctx, (vpix * NCH + 255) / 256 / 4 + 1, 2), 256, 0, s>>>(
       T.X[l], dA, T.idx[l], dF5, dF5_ld, mask, n, L.cout, L.H, Pw, L.pitch, L.pool, dPw, dPitch, T.mean[l], T.istd[l], P + Ob.bn[l][1], P + Ob.bn[l][0],
-      P + Ob.alpha[l], T.sums);
-  tbn_bwd_params_kernel<<<1, 64, 0, s>>>(T.sums, L.cout, G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l]);   // LOCAL sums: the gradient all-reduce adds the ranks
+      P + Ob.alpha[l], sums);
+  const bool hook = ctx->ar_hook != nullptr;     // synchronised BatchNorm: the LOCAL sums are the parameter gradients, copy them out before the all-reduce
+  if (hook) { tbn_bwd_params_kernel<<<1, 64, 0, s>>>(sums, L.cout, G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l]); ctx->launches++; }
   const double* cnt;
-  SC_TRY(sync_sums(ctx, T.sums, (double)vpix, &cnt, s));
+  SC_TRY(sync_sums(ctx, sums, (double)vpix, &cnt, s));
   const int64_t npix = (int64_t)L.R * Pw;
   tbn_bwd_dx_kernel<FMT, DFMT><<<(unsigned)((npix + 63) / 64), 64 * NCH, 0, s>>>(
       T.X[l], dA, T.idx[l], dF5, dF5_ld, mask, n, L.cout, L.H, L.R, Pw, L.pitch, L.pool, dPw, dPitch, T.mean[l], T.istd[l], P + Ob.bn[l][1], P + Ob.bn[l][0],
-      P + Ob.alpha[l], T.sums, (double)vpix, cnt, frame, DT, pad8(L.cout), planar, 32);
-  ctx->launches += 3;
+      P + Ob.alpha[l], sums, (double)vpix, cnt, hook ? nullptr : G + Ob.bn[l][0], G + Ob.bn[l][1], G + Ob.alpha[l], frame, DT, pad8(L.cout), planar, 32);
+  ctx->launches += 2;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
 }
@@ -947,17 +999,20 @@ int tc_branch_backward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pa
       // conv1: reduction pass, then dx and the weight gradient in one fused pass (no dgrad below conv1)
       float* P = ctx->params;
       const int64_t vpix = (int64_t)30 * n * 30;
-      SC_CUDA(cudaMemsetAsync(T.sums, 0, 64 * 3 * sizeof(double), s));
+      double* sums = T.sums + 5 * kSumsStride;
       tbn_bwd_reduce_kernel<32, 32><<<cap_grid(ctx, (vpix * 4 + 255) / 256 / 4 + 1, 2), 256, 0, s>>>(
           T.X[0], T.dA, nullptr, nullptr, 0, nullptr, n, 20, 30, Pw, 32, 0, Pw, 32, T.mean[0], T.istd[0], P + Ob.bn[0][1], P + Ob.bn[0][0],
-          P + Ob.alpha[0], T.sums);
-      tbn_bwd_params_kernel<<<1, 64, 0, s>>>(T.sums, 20, G + Ob.bn[0][0], G + Ob.bn[0][1], G + Ob.alpha[0]);
+          P + Ob.alpha[0], sums);
+      const bool hook = ctx->ar_hook != nullptr;
+      if (hook) { tbn_bwd_params_kernel<<<1, 64, 0, s>>>(sums, 20, G + Ob.bn[0][0], G + Ob.bn[0][1], G + Ob.alpha[0]); ctx->launches++; }
       const double* cnt;
-      SC_TRY(sync_sums(ctx, T.sums, (double)vpix, &cnt, s));
+      SC_TRY(sync_sums(ctx, sums, (double)vpix, &cnt, s));
       ProfScope prof(ctx, PC_TRAIN_BWD, s);
       tbn_bwd_conv1_kernel<<<cap_grid(ctx, (vpix + 63) / 64 / 8 + 1, 2), 256, 0, s>>>(T.X[0], T.dA, patches, n, T.mean[0], T.istd[0], P + Ob.bn[0][1],
-                                                                                    P + Ob.bn[0][0], P + Ob.alpha[0], T.sums, (double)vpix, cnt, G + Ob.convW[0]);
-      ctx->launches += 3;
+                                                                                    P + Ob.bn[0][0], P + Ob.alpha[0], sums, (double)vpix, cnt,
+                                                                                    hook ? nullptr : G + Ob.bn[0][0], G + Ob.bn[0][1], G + Ob.alpha[0],
+                                                                                    G + Ob.convW[0]);
+      ctx->launches += 2;
       break;
     }
     const TLayer& Li = kTL[l - 1];
