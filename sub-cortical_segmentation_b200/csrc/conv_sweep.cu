@@ -840,6 +840,11 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   int nseg = (4 * ctx->sm_count + a.nstrips * dil - 1) / (a.nstrips * dil);
   int L = (nq + nseg - 1) / nseg;
   if (L < 12) L = 12;
+  if (a.nstrips * dil * ((nq + 11) / 12) < ctx->sm_count) {            // small maps (training batches): 12-row items would leave SMs idle,
+    nseg = (ctx->sm_count + a.nstrips * dil - 1) / (a.nstrips * dil);  // so the rows are cut finer (down to 2 per item) to fill the machine once
+    L = (nq + nseg - 1) / nseg;
+    if (L < 2) L = 2;
+  }
   if (L > 96) L = 96;
   if (pool == 2) L = (L + 1) & ~1;                                      // row pairs of the stride-2 pool stay inside an item
   nseg = (nq + L - 1) / L;
@@ -910,6 +915,11 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     nseg = (4 * pairs_max + nsp * dil - 1) / (nsp * dil);
     L = (nq + nseg - 1) / nseg;
     if (L < 12) L = 12;
+    if (nsp * dil * ((nq + 11) / 12) < pairs_max) {
+      nseg = (pairs_max + nsp * dil - 1) / (nsp * dil);
+      L = (nq + nseg - 1) / nseg;
+      if (L < 2) L = 2;
+    }
     if (L > 96) L = 96;
     if (pool == 2) L = (L + 1) & ~1;
     nseg = (nq + L - 1) / L;
