@@ -254,12 +254,21 @@ def bench_train(ctx, torch, dist, rank, world, peaks, steps=20, warmup=5):
             fused_ms = float(t) / steps
         per = float(ms) / steps
         tfl = gb * FLOP_TRAIN_SAMPLE / (per * 1e-3) / 1e12
+        hbm = None           # the step is bound by the element-wise BatchNorm passes: DRAM bytes per step from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "r2_train_traffic.json")
+        if os.path.exists(tpath):
+            byt = json.load(open(tpath))["dram_bytes_per_step"].get(str(per_gpu))
+            if byt:
+                gbs = byt / (per * 1e-3) / 1e9
+                hbm = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                       "traffic": byt, "note": "per GPU; DRAM bytes of one step measured with ncu (profiles/r2_train_traffic_1024.txt)"}
         out[name] = {"global_batch": gb, "per_gpu_batch": per_gpu, "ms_per_step": per, "samples_per_s": gb / (per * 1e-3),
                      "e2e_samples_per_s": gb / (float(ms2) / steps * 1e-3), "h2d_bytes_per_step": int(per_gpu * (3 * 4096 + 60 + 1)),
                      "allreduce_ms": ar_ms, "allreduce_bytes": 883455 * 4, "ms_per_step_fused_allreduce_adam": fused_ms,
                      "samples_per_s_fused": (gb / (fused_ms * 1e-3)) if fused_ms else None, "gpu_launches_per_step": launches, "loss": float(loss.item()),
                      "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tflops"] * world, "unit": "TFLOP/s",
-                                  "frac": tfl / (peaks["tflops"] * world), "flops_per_sample": FLOP_TRAIN_SAMPLE}}
+                                  "frac": tfl / (peaks["tflops"] * world), "flops_per_sample": FLOP_TRAIN_SAMPLE},
+                     "roofline_hbm": hbm}
     out["scaling"] = {"global_batch_256": "strong (256 / N samples per GPU)", "per_gpu_batch_1024": "weak"}
     out["bn"] = "per-GPU batch statistics"
     return out
