@@ -169,6 +169,10 @@ int sc_set_option(sc_ctx* ctx, const char* key, int64_t value) {
     if (value >= 0 && !ctx->tc_timing_buf) SC_CUDA(cudaMalloc(&ctx->tc_timing_buf, sizeof(unsigned long long) * 8 * 1024));
     return SC_OK;
   }
+  if (!strcmp(key, "tc_skip")) {
+    ctx->tc_skip = value != 0;
+    return SC_OK;
+  }
   if (!strcmp(key, "tc_compact")) {
     ctx->tc_compact = value != 0;
     return SC_OK;

@@ -192,6 +192,7 @@ struct sc_ctx {
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
+  int tc_skip = 1;               // dense path with a sparse candidate mask: the conv sweeps skip the items no candidate needs
   int tc_compact = 1;            // dense path with a candidate mask: the FC head runs on the compacted candidate rows only
   int32_t* h_slab_cnt = nullptr; // pinned: candidates per slab
   unsigned char* tile_flags = nullptr;   // d1 with a row map: per-tile "has a candidate" flags (device, grow-only)
@@ -346,8 +347,15 @@ int launch_conv1_wide(sc_ctx* ctx, const float* vol, const ViewGeo& g, int ns, c
                       cudaStream_t st);
 // conv_sweep.cu : strip-sweep 3x3 dilated conv (+ fused stride-1 max-pool) over wide-row maps.
 // in_fmt / out_fmt: 1 = 128 B pixels (32 bf16 hi | 32 lo), 0 = 256 B pixels (64 hi | 64 lo)
+// Sparse candidate masks: an output position (row r, slice s, col c) of a layer is needed only if a candidate voxel (i, j) of slice s
+// has r - reach <= i <= r and c - reach <= j <= c (reach = rows_out - br: the receptive-field extent downstream of the layer).
+// occ[i * ns + s]: bit jb set when row i of slice s holds a candidate in columns [32 jb, 32 jb + 32) (launch_view_occupancy);
+// the sweep then skips the items (strip x row segment) no candidate needs.  flags: scratch of >= the number of items bytes.
+struct SweepSkip { const uint32_t* occ; int br, bc, ns, C1; uint8_t* flags; };
+int launch_view_occupancy(sc_ctx* ctx, const uint8_t* cand, const ViewGeo& g, uint32_t* occ, cudaStream_t st);
 int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
-                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx = 0, int in_dy = 0);
+                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx = 0, int in_dy = 0,
+                      const SweepSkip* skip = nullptr);
 
 // patch_forward.cu
 int launch_branch_patches(sc_ctx* ctx, int branch, const float* patches, int64_t n, float* c5_out /*[n][540]*/,

@@ -37,6 +37,7 @@ struct SweepArgs {
                           // -2 for the full correlation of a dgrad (what lies outside the map is zero-filled by the TMA unit)
   const float* scale; const float* shift; const float* alpha;
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
+  const uint8_t* item_on;    // sparse candidate masks: item t is computed only if item_on[t] != 0 (nullptr: every item)
 };
 
 __device__ __forceinline__ void sweep_mma(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t elected) {
@@ -157,7 +158,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         int w0, q, n0, Lc;
         decode(item, w0, q, n0, Lc);
-        if (Lc <= 0) continue;
+        if (Lc <= 0 || (a.item_on && !a.item_on[item])) continue;
         const int nload = Lc + (POOL == 1 ? 1 : 0) + 2;
         for (int m = 0; m < nload; ++m, ++g) {
           const uint32_t s = g % a.stages, use = g / a.stages;
@@ -190,7 +191,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
-      if (Lc <= 0) continue;
+      if (Lc <= 0 || (a.item_on && !a.item_on[item])) continue;
       const int nrow = Lc + (POOL == 1 ? 1 : 0);
       for (int m = 0; m < nrow; ++m, ++t) {
         const uint32_t b = t & 1;
@@ -270,7 +271,7 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
-      if (Lc <= 0) continue;
+      if (Lc <= 0 || (a.item_on && !a.item_on[item])) continue;
       const int nrow = Lc + (POOL == 1 ? 1 : 0);
       float hprev[CW];
 #pragma unroll
@@ -494,7 +495,7 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       for (int item = pair; item < a.n_items; item += npairs) {
         int w0, q, n0, Lc;
         decode(item, w0, q, n0, Lc);
-        if (Lc <= 0) continue;
+        if (Lc <= 0 || (a.item_on && !a.item_on[item])) continue;
         const int nload = Lc + (POOL == 1 ? 1 : 0) + 2;
         for (int m = 0; m < nload; ++m, ++g) {
           const uint32_t s = g % a.stages, use = g / a.stages;
@@ -523,7 +524,7 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       for (int item = pair; item < a.n_items; item += npairs) {
         int w0, q, n0, Lc;
         decode(item, w0, q, n0, Lc);
-        if (Lc <= 0) continue;
+        if (Lc <= 0 || (a.item_on && !a.item_on[item])) continue;
         const int nrow = Lc + (POOL == 1 ? 1 : 0);
         for (int m = 0; m < nrow; ++m, ++t) {
           const uint32_t b = t & 1;
@@ -593,7 +594,7 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     for (int item = pair; item < a.n_items; item += npairs) {
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
-      if (Lc <= 0) continue;
+      if (Lc <= 0 || (a.item_on && !a.item_on[item])) continue;
       const int nrow = Lc + (POOL == 1 ? 1 : 0);
       float hprev[CW];
 #pragma unroll
@@ -825,8 +826,84 @@ static int launch_sweep_t(sc_ctx* ctx, const CUtensorMap& mapA, const CUtensorMa
   return SC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Sparse candidate masks (crop mode, brain masks): which items of a sweep does any candidate need?
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) view_occupancy_kernel(const uint8_t* __restrict__ cand, ViewGeo g, uint32_t* __restrict__ occ) {
+  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);       // one warp per (row, slice)
+  if (w >= (int64_t)g.br * g.ns) return;
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(w / g.ns), sl = (int)(w - (int64_t)i * g.ns);
+  const uint8_t* base = cand + (int64_t)(g.s0 + sl) * g.ss + (int64_t)(g.r0 + i) * g.rs + (int64_t)g.c0 * g.cs;
+  uint32_t bits = 0;
+  for (int jb = 0; jb * 32 < g.bc; ++jb) {
+    const int j = jb * 32 + lane;
+    const bool on = j < g.bc && base[(int64_t)j * g.cs] != 0;
+    if (__any_sync(0xffffffffu, on)) bits |= 1u << jb;
+  }
+  if (lane == 0) occ[w] = bits;
+}
+
+int launch_view_occupancy(sc_ctx* ctx, const uint8_t* cand, const ViewGeo& g, uint32_t* occ, cudaStream_t st) {
+  SC_CHECK(g.bc <= 1024, SC_ERR_ARG, "sweep skip: more than 1024 columns per slice");
+  const int64_t warps = (int64_t)g.br * g.ns;
+  view_occupancy_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(cand, g, occ);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// one warp per item (strip or strip pair x dilation class x row segment): same decoding as the sweep kernels
+__global__ void __launch_bounds__(256) sweep_item_flags_kernel(const uint32_t* __restrict__ occ, int br, int bc, int ns, int C1, int reach, int n_items,
+                                                               int nstr, int dil, int L, int R, int item_w, int Pw, uint8_t* __restrict__ flags) {
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  const int lane = threadIdx.x & 31;
+  const int strip = item % nstr, rest = item / nstr;
+  const int q = rest % dil, seg = rest / dil;
+  const int Nq = (R - q + dil - 1) / dil;
+  const int n0 = seg * L;
+  const int Lc = Nq - n0 < L ? Nq - n0 : L;
+  bool any = false;
+  if (Lc > 0) {
+    const int rlo = q + dil * n0, rhi = q + dil * (n0 + Lc - 1);
+    const int ilo = rlo - reach > 0 ? rlo - reach : 0, ihi = rhi < br - 1 ? rhi : br - 1;
+    const int w0 = strip * item_w;
+    int w1 = w0 + item_w - 1;
+    if (w1 > Pw - 1) w1 = Pw - 1;
+    if (w0 <= w1 && ilo <= ihi) {
+      const int sa = w0 / C1, sb = w1 / C1;
+      const int nrow = ihi - ilo + 1;
+      for (int e = lane; e < nrow * (sb - sa + 1); e += 32) {
+        const int sl = sa + e / nrow, i = ilo + e % nrow;
+        if (sl >= ns) continue;
+        const int clo = w0 - sl * C1 > 0 ? w0 - sl * C1 : 0;
+        const int chi = w1 - sl * C1 < C1 - 1 ? w1 - sl * C1 : C1 - 1;
+        const int jlo = clo - reach > 0 ? clo - reach : 0, jhi = chi < bc - 1 ? chi : bc - 1;
+        if (jlo > jhi) continue;
+        const int b0 = jlo >> 5, b1 = jhi >> 5;
+        const uint32_t colmask = (b1 - b0 == 31 ? 0xffffffffu : ((1u << (b1 - b0 + 1)) - 1u)) << b0;
+        if (occ[(int64_t)i * ns + sl] & colmask) any = true;
+      }
+    }
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) flags[item] = any ? 1 : 0;
+}
+
+// fills skip->flags for the item decomposition in `a` (nstr strips or strip pairs of item_w wide columns each)
+static int launch_item_flags(sc_ctx* ctx, const SweepSkip* skip, SweepArgs& a, int nstr, int item_w, int dil, int rows_out, cudaStream_t st) {
+  if (!skip) return SC_OK;
+  sweep_item_flags_kernel<<<(unsigned)((a.n_items + 7) / 8), 256, 0, st>>>(skip->occ, skip->br, skip->bc, skip->ns, skip->C1, rows_out - skip->br,
+                                                                         a.n_items, nstr, dil, a.L, a.R, item_w, a.Pw, skip->flags);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  a.item_on = skip->flags;
+  return SC_OK;
+}
+
 int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
-                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx, int in_dy) {
+                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx, int in_dy, const SweepSkip* skip) {
   TcState* s = reinterpret_cast<TcState*>(ctx->tc_state);
   SC_CHECK(s != nullptr, SC_ERR_UNSUPPORTED, "tcgen05 back-end not initialised");
   if (Pw <= 0 || R <= 0) return SC_OK;
@@ -846,10 +923,12 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     if (L < 2) L = 2;
   }
   if (L > 96) L = 96;
+  if (skip && L > 32) L = 32;                                           // sparse candidate mask: finer items skip more
   if (pool == 2) L = (L + 1) & ~1;                                      // row pairs of the stride-2 pool stay inside an item
   nseg = (nq + L - 1) / L;
   a.L = L; a.nseg = nseg;
   a.n_items = a.nstrips * dil * nseg;
+  a.item_on = nullptr;
   SC_CHECK(pool != 2 || dil == 1, SC_ERR_ARG, "conv_sweep: the stride-2 pool needs dilation 1");
   a.npanels = w.npanels;
   a.in_dx = in_dx; a.in_dy = in_dy;
@@ -921,6 +1000,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
       if (L < 2) L = 2;
     }
     if (L > 96) L = 96;
+    if (skip && L > 32) L = 32;
     if (pool == 2) L = (L + 1) & ~1;
     nseg = (nq + L - 1) / L;
     a.L = L; a.nseg = nseg;
@@ -944,6 +1024,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "conv_sweep: cuTensorMapEncodeTiled(W pair) failed with %d", (int)r);
     const int npairs = a.n_items < pairs_max ? a.n_items : pairs_max;
+    SC_TRY(launch_item_flags(ctx, skip, a, nsp, 2 * a.strip_w, dil, rows_out, st));
     ProfScope prof(ctx, prof_cls, st);
     if (dil == 1 && pool == 2) {
       auto kern = conv_sweep_pair_kernel<3, 1, 2>;
@@ -973,6 +1054,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     SC_CUDA(cudaGetLastError());
     return SC_OK;
   }
+  SC_TRY(launch_item_flags(ctx, skip, a, a.nstrips, a.strip_w, dil, rows_out, st));
   ProfScope prof(ctx, prof_cls, st);
   if (w.ksteps == 2 && dil == 1 && pool == 2 && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 2, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // patch maps: conv2 + 2x2/2 pool
   if (w.ksteps == 2 && dil == 1 && pool == 1 && i32 && o32 && w.bn == 32) return launch_sweep_t<2, 1, 1, 8, true, true>(ctx, mapA, mapW, mapO, a, smem, st);     // conv2 + pool1

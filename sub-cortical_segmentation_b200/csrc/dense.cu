@@ -379,7 +379,12 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   const size_t nbox = (size_t)bx * plane;
   const size_t cmp_blocks = (size_t)nslabs * ((rows_max + 2047) / 2048);
   const size_t cmp_bytes = compact ? align256(nbox * 4) * 2 + align256(cmp_blocks * 8 + 16) + align256((size_t)nslabs * 4) : 0;
-  const size_t total = a5_bytes + scratch_bytes + feat_bytes + h1_bytes + h2_bytes + cmp_bytes;
+  // sparse masks: per-view candidate occupancy (one 32-bit word per (row, slice)) + the item flags of one sweep launch
+  size_t occ_off[3], skip_bytes = 0;
+  for (int v = 0; v < 3; ++v) { occ_off[v] = skip_bytes; skip_bytes += compact ? align256((size_t)vg[v].br * vg[v].ns * 4) : 0; }
+  const size_t flags_off = skip_bytes;
+  if (compact) skip_bytes += align256((size_t)1 << 20);
+  const size_t total = a5_bytes + scratch_bytes + feat_bytes + h1_bytes + h2_bytes + cmp_bytes + skip_bytes;
   SC_TRY(ensure_ws(ctx->ws, total));
   char* wsb = reinterpret_cast<char*>(ctx->ws.ptr);
   float* a5[3] = {reinterpret_cast<float*>(wsb + a5_off[0]), reinterpret_cast<float*>(wsb + a5_off[1]),
@@ -392,6 +397,7 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   int32_t* rowvox = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(rowmap) + align256(nbox * 4));
   int32_t* cmp_scratch = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(rowvox) + align256(nbox * 4));
   int32_t* d_slab_cnt = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(cmp_scratch) + align256(cmp_blocks * 8 + 16));
+  char* skip_base = wsb + (total - skip_bytes);
   if (compact) {
     // enqueue the scan first: its (tiny) result is on the host long before phase 1 has been launched
     if (!ctx->h_slab_cnt) {
@@ -402,6 +408,21 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     SC_TRY(launch_slab_compact(ctx, cand, boxg, bx, slab, rowmap, rowvox, d_slab_cnt, cmp_scratch, st));
     SC_CUDA(cudaMemcpyAsync(ctx->h_slab_cnt, d_slab_cnt, (size_t)nslabs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SC_CUDA(cudaEventRecord(ctx->compact_ev, st));
+    // the candidate count decides both the compaction of the FC head and whether the sweeps skip items: one short wait here
+    SC_CUDA(cudaEventSynchronize(ctx->compact_ev));
+    int64_t ncand = 0;
+    for (int i = 0; i < nslabs; ++i) ncand += ctx->h_slab_cnt[i];
+    if (ncand * 10 >= (int64_t)nbox * 9) compact = false;     // (nearly) every voxel is a candidate: the dense rows are cheaper
+  }
+  // sparse mask: the sweeps only compute the items (strip x row segment) within the receptive-field reach of a candidate
+  SweepSkip skips[3];
+  const bool skip_on = compact && ctx->tc_skip;
+  if (skip_on) {
+    for (int v = 0; v < 3; ++v) {
+      uint32_t* occ = reinterpret_cast<uint32_t*>(skip_base + occ_off[v]);
+      SC_TRY(launch_view_occupancy(ctx, cand, vg[v], occ, st));
+      skips[v] = {occ, vg[v].br, vg[v].bc, vg[v].ns, vg[v].bc + 29, reinterpret_cast<uint8_t*>(skip_base + flags_off)};
+    }
   }
 
   // ---- phase 1: conv1..conv5 per view, slices in groups ------------------------------------
@@ -428,10 +449,11 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
       float* m1 = carve(cur, 32); float* mp1 = carve(cur, 32);
       float* m3 = carve(cur, 64); float* mp2 = carve(cur, 64);
       SC_TRY(launch_conv1_wide(ctx, vol, g, g.ns, W.c1_host, m1, R1, C1, st));
-      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, Pw, R1, g.br + 26, 1, 1, PC_CONV2, st));     // conv2 + pool1
-      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, Pw, R1, g.br + 22, 2, 0, PC_CONV3, st));     // conv3
-      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, m3, 0, mp2, 0, Pw, R1, g.br + 16, 2, 1, PC_CONV4, st));     // conv4 + pool2 (CTA pairs)
-      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, mp2, 0, a5[v], 0, Pw, R1, g.br + 8, 4, 0, PC_CONV5, st));   // conv5 (CTA pairs)
+      const SweepSkip* sk = skip_on ? &skips[v] : nullptr;
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[1], 1, m1, 1, mp1, 1, Pw, R1, g.br + 26, 1, 1, PC_CONV2, st, 0, 0, sk));     // conv2 + pool1
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[2], 2, mp1, 1, m3, 0, Pw, R1, g.br + 22, 2, 0, PC_CONV3, st, 0, 0, sk));     // conv3
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[3], 3, m3, 0, mp2, 0, Pw, R1, g.br + 16, 2, 1, PC_CONV4, st, 0, 0, sk));     // conv4 + pool2 (CTA pairs)
+      SC_TRY(launch_conv_sweep(ctx, W.conv_sw[4], 4, mp2, 0, a5[v], 0, Pw, R1, g.br + 8, 4, 0, PC_CONV5, st, 0, 0, sk));   // conv5 (CTA pairs)
       SC_CUDA(cudaGetLastError());
     }
     for (int sb = 0; sb < g.ns && !tc; sb += group) {
@@ -474,12 +496,6 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   }
   int atlas_waited = 0;                                // chunked upload: chunks of x-planes this stream has already waited for
   OutGeo og = {b[0], b[2], b[4], by, bz, Y, Z};
-  if (compact) {
-    SC_CUDA(cudaEventSynchronize(ctx->compact_ev));
-    int64_t ncand = 0;
-    for (int i = 0; i < nslabs; ++i) ncand += ctx->h_slab_cnt[i];
-    if (ncand * 10 >= (int64_t)nbox * 9) compact = false;     // (nearly) every voxel is a candidate: the dense rows are cheaper
-  }
   // tensor-core mode: columns 272..319 of the split h2 rows are never written by fc_2 and must not hold NaN patterns
   if (tc) SC_CUDA(cudaMemsetAsync(h2, 0, h2_bytes, st));
   for (int ix0 = 0; ix0 < bx; ix0 += slab) {
