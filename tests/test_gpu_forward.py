@@ -202,6 +202,43 @@ def test_dense_candidate_compaction(ctx, density):
     assert float((out[0][1][sel] == out[1][1][sel]).float().mean()) >= 0.9999
 
 
+def test_sparse_mask_sweep_item_skipping(ctx):
+    """Sparse candidate masks: the conv sweeps skip the items (strip x row segment) outside the receptive-field reach of every
+    candidate.  Candidates in blobs, on faces and in the corners of the volume get bit-identical probabilities with and without the
+    skipping, although the workspace still holds the maps of ANOTHER volume in the skipped regions."""
+    if ctx.counter("gemm") != 1:
+        pytest.skip("tcgen05 back-end not selected")
+    g = torch.Generator(device="cuda").manual_seed(33)
+    shape = (150, 120, 140)
+    other = torch.randn(shape, device="cuda", generator=g) * 5
+    vol = torch.randn(shape, device="cuda", generator=g)
+    atlas = torch.rand(shape + (15,), device="cuda", generator=g) ** 6
+    atlas = atlas / atlas.sum(-1, keepdim=True)
+    cand = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+    cand[60:75, 40:52, 100:118] = 1                          # a blob
+    cand[5:9, 100:110, 3:30] = 1                             # a slab near three faces
+    for c in ((0, 0, 0), (149, 119, 139), (0, 119, 0), (149, 0, 139), (75, 0, 70), (0, 60, 139), (149, 60, 0), (33, 77, 99)):
+        cand[c] = 1                                          # isolated voxels: corners, faces, interior
+    out = []
+    for skip in (1, 0):
+        lab0 = torch.zeros(shape, dtype=torch.uint8, device="cuda")
+        ctx.segment_volume(other, atlas, label_vol=lab0)     # fills the workspace with the maps of a different volume
+        ctx.set_option("tc_skip", skip)
+        prob = torch.full(shape + (15,), -1.0, dtype=torch.float32, device="cuda")
+        lab = torch.full(shape, 99, dtype=torch.uint8, device="cuda")
+        ctx.segment_volume(vol, atlas, cand_mask=cand, label_vol=lab, proba_vol=prob)
+        out.append((prob, lab))
+    ctx.set_option("tc_skip", 1)
+    sel = cand.bool()
+    assert bool((out[0][1][~sel] == 99).all()) and bool((out[0][0][~sel] == -1.0).all())
+    assert torch.equal(out[0][0][sel], out[1][0][sel]) and torch.equal(out[0][1][sel], out[1][1][sel])
+    # and against the patchwise path (a different formulation of the same function)
+    xyz = torch.nonzero(sel).to(torch.int32)[::7].contiguous()
+    pp, _ = ctx.forward_from_volume(vol, atlas, xyz)
+    got = out[0][0][xyz[:, 0].long(), xyz[:, 1].long(), xyz[:, 2].long()]
+    assert float((got - pp).abs().max()) < 2e-4
+
+
 def test_dense_equals_patchwise_at_scale(ctx):
     """Size-independent property at a larger size: the dense path and the patchwise path are the
     same function of (volume, atlas, voxel)."""
