@@ -192,6 +192,7 @@ struct sc_ctx {
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
+  int train_fused_stats = 1;     // training forward: BatchNorm statistics accumulated in the sweep epilogues (off: a separate pass over the stored maps)
   int tc_skip = 1;               // dense path with a sparse candidate mask: the conv sweeps skip the items no candidate needs
   int tc_compact = 1;            // dense path with a candidate mask: the FC head runs on the compacted candidate rows only
   int32_t* h_slab_cnt = nullptr; // pinned: candidates per slab
@@ -351,11 +352,14 @@ int launch_conv1_wide(sc_ctx* ctx, const float* vol, const ViewGeo& g, int ns, c
 // has r - reach <= i <= r and c - reach <= j <= c (reach = rows_out - br: the receptive-field extent downstream of the layer).
 // occ[i * ns + s]: bit jb set when row i of slice s holds a candidate in columns [32 jb, 32 jb + 32) (launch_view_occupancy);
 // the sweep then skips the items (strip x row segment) no candidate needs.  flags: scratch of >= the number of items bytes.
+// training forward: per-channel sum / sum of squares of the raw conv output over the valid H x H region of every patch, accumulated
+// into sums[c][2] (doubles) by the sweep's epilogue -- the BatchNorm statistics without a separate pass over the map
+struct SweepStats { double* sums; int H, pitch; };
 struct SweepSkip { const uint32_t* occ; int br, bc, ns, C1; uint8_t* flags; };
 int launch_view_occupancy(sc_ctx* ctx, const uint8_t* cand, const ViewGeo& g, uint32_t* occ, cudaStream_t st);
 int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
                       int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx = 0, int in_dy = 0,
-                      const SweepSkip* skip = nullptr);
+                      const SweepSkip* skip = nullptr, const struct SweepStats* stats = nullptr);
 
 // patch_forward.cu
 int launch_branch_patches(sc_ctx* ctx, int branch, const float* patches, int64_t n, float* c5_out /*[n][540]*/,

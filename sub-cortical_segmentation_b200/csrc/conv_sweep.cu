@@ -38,6 +38,8 @@ struct SweepArgs {
   const float* scale; const float* shift; const float* alpha;
   unsigned long long* dbg;   // optional per-CTA cycle counters [8] (sc_set_option "tc_timing"): where each role waits
   const uint8_t* item_on;    // sparse candidate masks: item t is computed only if item_on[t] != 0 (nullptr: every item)
+  double* stats;             // training forward (DIL = 1, no pool): per-channel sum / sum of squares of the raw output over the valid
+  int st_H, st_pitch;        // region (row < st_H, (wide column mod st_pitch) < st_H; st_pitch a power of two) accumulated into stats[c][2]
 };
 
 __device__ __forceinline__ void sweep_mma(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t elected) {
@@ -68,6 +70,29 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+// BatchNorm batch statistics fused into the training forward sweeps: every epilogue thread keeps the sums of its pixel column,
+// folded at the end of the kernel: warp shuffles -> shared memory across the four lane quarters -> one double atomic per CTA,
+// channel and moment (the per-CTA global atomics hit the same few addresses: ~ 27 clk each, so there must be few of them)
+template <int CW>
+__device__ __forceinline__ void sweep_stats_flush(float (&st_s)[CW], float (&st_q)[CW], float* s_red /*[16 warps][2 * CW]*/, int ew, int c0,
+                                                  bool real, int lane, double* stats) {
+#pragma unroll
+  for (int k = 0; k < CW; ++k)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { st_s[k] += __shfl_xor_sync(0xffffffffu, st_s[k], o); st_q[k] += __shfl_xor_sync(0xffffffffu, st_q[k], o); }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < CW; ++k) { s_red[ew * 2 * CW + k] = st_s[k]; s_red[ew * 2 * CW + CW + k] = st_q[k]; }
+  }
+  asm volatile("bar.sync 7, 512;" ::: "memory");      // its own barrier: 5 and 6 belong to the row loop, which slower warps may still be in
+  if ((ew & 3) == 0 && real && lane < 2 * CW) {  // first warp of every column group: lane -> (moment, channel)
+    const int base = ew * 2 * CW + lane;         // the group's four warps (one per TMEM lane quarter) are ew, ew + 1, ew + 2, ew + 3
+    const float tot = s_red[base] + s_red[base + 2 * CW] + s_red[base + 4 * CW] + s_red[base + 6 * CW];
+    const int mom = lane / CW, ch = c0 + (lane - mom * CW);
+    if (ch < 64) atomicAdd(&stats[ch * 2 + mom], (double)tot);
+  }
+}
+
 template <int CW>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[CW]) {
   if constexpr (CW == 16) tmem_ld16(taddr, r); else tmem_ld8(taddr, r);
@@ -268,6 +293,10 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint32_t t = 0, e = 0;                   // conv rows consumed, rows emitted
     long long w_tfull = 0;
     const long long tstart = a.dbg ? clock64() : 0;
+    constexpr bool STATS = POOL == 0 && DIL == 1;   // the instantiations the training forward uses
+    float st_s[STATS ? CW : 1], st_q[STATS ? CW : 1];
+#pragma unroll
+    for (int k = 0; k < (STATS ? CW : 1); ++k) st_s[k] = st_q[k] = 0.f;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
@@ -348,6 +377,15 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (!(m & 1)) continue;                  // block-uniform
           r_out >>= 1;
         }
+        if constexpr (STATS) {
+          if (a.stats && real) {
+            const int wpx = w0 + px;
+            if (wpx < a.Pw && (wpx & (a.st_pitch - 1)) < a.st_H && r_out < a.st_H) {
+#pragma unroll
+              for (int k = 0; k < CW; ++k) { st_s[k] += v[k]; st_q[k] = fmaf(v[k], v[k], st_q[k]); }
+            }
+          }
+        }
         // ---- emit row r_out: pieces -> swizzled output tile -> TMA store
         uint8_t* ob = sOut + (e % (uint32_t)a.out_bufs) * OB_BYTES;
         if (a.out_bufs == 1) {                      // single tile: wait until the previous store has read it
@@ -377,6 +415,9 @@ conv_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if constexpr (STATS) {
+      if (a.stats) sweep_stats_flush<CW>(st_s, st_q, s_xch, ew, c0, real, lane, a.stats);
+    }
     if (a.dbg && threadIdx.x == 64) {
       a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull; a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - tstart);
       a.dbg[blockIdx.x * 8 + 7] = t;
@@ -591,6 +632,10 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     const uint32_t sw = (uint32_t)(trow & 7);
     const uint32_t hi_chunk = (uint32_t)(c0 >> 3);
     uint32_t t = 0, e = 0;
+    constexpr bool STATS = POOL == 0 && DIL == 1;
+    float st_s[STATS ? CW : 1], st_q[STATS ? CW : 1];
+#pragma unroll
+    for (int k = 0; k < (STATS ? CW : 1); ++k) st_s[k] = st_q[k] = 0.f;
     for (int item = pair; item < a.n_items; item += npairs) {
       int w0, q, n0, Lc;
       decode(item, w0, q, n0, Lc);
@@ -667,6 +712,15 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           if (!(m & 1)) continue;                  // block-uniform
           r_out >>= 1;
         }
+        if constexpr (STATS) {
+          if (a.stats && real) {
+            const int wpx = w0 + px;
+            if (wpx < a.Pw && (wpx & (a.st_pitch - 1)) < a.st_H && r_out < a.st_H) {
+#pragma unroll
+              for (int k = 0; k < CW; ++k) { st_s[k] += v[k]; st_q[k] = fmaf(v[k], v[k], st_q[k]); }
+            }
+          }
+        }
         uint8_t* ob = sOut + (e % (uint32_t)a.out_bufs) * OB_BYTES;
         if (a.out_bufs == 1) {
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -695,6 +749,9 @@ conv_sweep_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if constexpr (STATS) {
+      if (a.stats) sweep_stats_flush<CW>(st_s, st_q, s_xch, ew, c0, real, lane, a.stats);
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -903,7 +960,8 @@ static int launch_item_flags(sc_ctx* ctx, const SweepSkip* skip, SweepArgs& a, i
 }
 
 int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, int in_fmt, float* out, int out_fmt,
-                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx, int in_dy, const SweepSkip* skip) {
+                      int Pw, int R, int rows_out, int dil, int pool, int prof_cls, cudaStream_t st, int in_dx, int in_dy, const SweepSkip* skip,
+                      const SweepStats* stats) {
   TcState* s = reinterpret_cast<TcState*>(ctx->tc_state);
   SC_CHECK(s != nullptr, SC_ERR_UNSUPPORTED, "tcgen05 back-end not initialised");
   if (Pw <= 0 || R <= 0) return SC_OK;
@@ -929,6 +987,11 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
   a.L = L; a.nseg = nseg;
   a.n_items = a.nstrips * dil * nseg;
   a.item_on = nullptr;
+  a.stats = nullptr; a.st_H = 0; a.st_pitch = 1;
+  if (stats) {
+    SC_CHECK(dil == 1 && !pool && (stats->pitch & (stats->pitch - 1)) == 0, SC_ERR_ARG, "conv_sweep: fused statistics need dil 1, no pool, a power-of-two pitch");
+    a.stats = stats->sums; a.st_H = stats->H; a.st_pitch = stats->pitch;
+  }
   SC_CHECK(pool != 2 || dil == 1, SC_ERR_ARG, "conv_sweep: the stride-2 pool needs dilation 1");
   a.npanels = w.npanels;
   a.in_dx = in_dx; a.in_dy = in_dy;
@@ -1006,7 +1069,7 @@ int launch_conv_sweep(sc_ctx* ctx, const SweepW& w, int layer, const float* in, 
     a.L = L; a.nseg = nseg;
     a.n_items = nsp * dil * nseg;
     const int wp_bytes = w.npanels * w.bn * 128;
-    const int fixed_p = 1024 + ((wp_bytes + 1023) & ~1023) + 256 + 192 * 4 + (pool ? 2 * 4 * 4 * 2 * 16 * 4 : 0);
+    const int fixed_p = 1024 + ((wp_bytes + 1023) & ~1023) + 256 + 192 * 4 + ((pool || stats) ? 2 * 4 * 4 * 2 * 16 * 4 : 0);
     a.out_bufs = 2;
     a.stages = (227 * 1024 - fixed_p - 2 * ob_bytes) / slot;
     if (a.stages < 4) { a.out_bufs = 1; a.stages = (227 * 1024 - fixed_p - ob_bytes) / slot; }

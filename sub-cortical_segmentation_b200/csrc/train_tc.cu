@@ -915,22 +915,32 @@ int tc_branch_forward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pat
   for (int l = 0; l < 5; ++l) {
     const TLayer& L = kTL[l];
     const int Pw = n * L.pitch;
-    if (l == 0) {
-      ProfScope prof(ctx, PC_TRAIN_FWD, s);
-      tconv1_kernel<<<cap_grid(ctx, ((int64_t)30 * n * 32 + 255) / 256, 8), 256, 0, s>>>(patches, n, wf0, T.X[0]);
-      ctx->launches++;
-    } else {
-      const TLayer& Li = kTL[l - 1];
-      SC_TRY(launch_conv_sweep(ctx, ctx->train_sw[b][l][0], l, T.A[l - 1], Li.fmt == 32 ? 1 : 0, T.X[l], L.fmt == 32 ? 1 : 0, Pw, L.R, L.H, 1, 0,
-                               PC_TRAIN_FWD, s));
-    }
     double* sums = T.sums + l * kSumsStride;
     const int64_t vpix = (int64_t)L.H * n * L.H;
-    if (L.fmt == 32) tbn_stats_kernel<32><<<cap_grid(ctx, (vpix + 63) / 64 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, sums);
-    else tbn_stats_kernel<64><<<cap_grid(ctx, (vpix + 31) / 32 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, sums);
+    if (l == 0) {
+      {
+        ProfScope prof(ctx, PC_TRAIN_FWD, s);
+        tconv1_kernel<<<cap_grid(ctx, ((int64_t)30 * n * 32 + 255) / 256, 8), 256, 0, s>>>(patches, n, wf0, T.X[0]);
+      }
+      tbn_stats_kernel<32><<<cap_grid(ctx, (vpix + 63) / 64 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, sums);
+      ctx->launches += 2;
+    } else {
+      // conv2..conv5: the sweep's epilogue accumulates the batch statistics of its raw output (no separate pass over the map)
+      const TLayer& Li = kTL[l - 1];
+      // With a synchronised-BatchNorm hook the statistics come from a separate pass over the STORED map instead (double sums of
+      // identical values: N ranks then reproduce one rank up to the order of a handful of double additions).
+      const SweepStats st = {sums, L.H, L.pitch};
+      const bool fuse = ctx->train_fused_stats && !ctx->ar_hook;
+      SC_TRY(launch_conv_sweep(ctx, ctx->train_sw[b][l][0], l, T.A[l - 1], Li.fmt == 32 ? 1 : 0, T.X[l], L.fmt == 32 ? 1 : 0, Pw, L.R, L.H, 1, 0,
+                               PC_TRAIN_FWD, s, 0, 0, nullptr, fuse ? &st : nullptr));
+      if (!fuse) {
+        if (L.fmt == 32) tbn_stats_kernel<32><<<cap_grid(ctx, (vpix + 63) / 64 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, sums);
+        else tbn_stats_kernel<64><<<cap_grid(ctx, (vpix + 31) / 32 / 4 + 1, 2), 256, 0, s>>>(T.X[l], n, L.cout, L.H, Pw, L.pitch, sums);
+        ctx->launches++;
+      }
+    }
     const double* cnt;
     SC_TRY(sync_sums(ctx, sums, (double)vpix, &cnt, s));
-    ctx->launches++;
     // the activation kernels derive mean / inv-std from the sums themselves; their first CTA publishes them
     if (l < 4) {
       const int64_t opix = (int64_t)L.oR * n * L.oPitch;
