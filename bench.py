@@ -596,7 +596,7 @@ def main():
     pad = {"gemm_d1": 3 * (576 / 540.0) * (192 / 180.0), "gemm_fc1": 3 * (576 / 540.0) * (576 / 540.0),
            "gemm_fc2": 3 * (576 / 555.0) * (288 / 270.0)}.get(dom)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")     # dram bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")     # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath) and size == 256 and backend.startswith("tcgen05"):
         traffic = json.load(open(tpath))["bytes_per_launch"].get(dom)
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
