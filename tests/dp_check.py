@@ -113,7 +113,10 @@ def check_sync_bn(ctx, rank, world, n=48):
                 g = g / world                       # the statistics slots carry one (identical) copy per rank
             l2 = np.linalg.norm(g - a) / max(np.linalg.norm(a), 1e-6)
             worst = max(worst, l2)
-            assert l2 < 1e-2, "sync-BN %s[%d]: relative L2 err %g" % (name, k, l2)
+            # one PReLU / max-pool decision taken the other way (a pre-activation within rounding of a kink) moves one of ~ 4e4
+            # random-sign terms of a weight gradient: ~ 0.5 % of its norm; a few such flips are tolerated, unsynchronised
+            # statistics would show up as tens of per cent
+            assert l2 < 3e-2, "sync-BN %s[%d]: relative L2 err %g" % (name, k, l2)
     return worst
 
 
