@@ -456,6 +456,19 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float*
   if (cnt) count = *cnt;
   bn_publish_grads(sums, C, gbeta, ggamma, galpha);
   __shared__ uint16_t tile[2][FMT][68];     // columns 0..63: this CTA's positions; 64, 65: the two positions to their left
+  // per-channel constants once per CTA: the two double divisions per channel cost more than the rest of a thread's work (issuing the
+  // map loads before this barrier was tried: the longer live ranges cost more occupancy than the overlap gains)
+  __shared__ float s_k[64][5];              // mean, istd, gamma, beta, alpha
+  __shared__ float s_m[64][2];              // sum(dy) / m, sum(dy xhat) / m
+  if (threadIdx.x < 64) {
+    const int ch = threadIdx.x;
+    const bool on = ch < C;
+    s_k[ch][0] = on ? mean[ch] : 0.f; s_k[ch][1] = on ? istd[ch] : 0.f; s_k[ch][2] = on ? gamma[ch] : 0.f;
+    s_k[ch][3] = on ? beta[ch] : 0.f; s_k[ch][4] = on ? alpha[ch] : 0.f;
+    s_m[ch][0] = on ? (float)(sums[ch * 3] / count) : 0.f;
+    s_m[ch][1] = on ? (float)(sums[ch * 3 + 1] / count) : 0.f;
+  }
+  __syncthreads();
   const int chunk = threadIdx.x % NCH, px = threadIdx.x / NCH;
   const int64_t npix = (int64_t)R * Pw;
   const int64_t q0 = (int64_t)blockIdx.x * 64;
@@ -474,11 +487,11 @@ __global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float*
     for (int k = 0; k < 8; ++k) {
       const int ch = chunk * 8 + k;
       if (ch < C) {
-        const float is = istd[ch], ga = gamma[ch];
-        const float xh = (x[k] - mean[ch]) * is;
-        const float yv = fmaf(xh, ga, beta[ch]);
-        const float dy = yv > 0.f ? g[k] : alpha[ch] * g[k];
-        dx[k] = ga * is * (dy - (float)(sums[ch * 3] / count) - xh * (float)(sums[ch * 3 + 1] / count));
+        const float is = s_k[ch][1], ga = s_k[ch][2];
+        const float xh = (x[k] - s_k[ch][0]) * is;
+        const float yv = fmaf(xh, ga, s_k[ch][3]);
+        const float dy = yv > 0.f ? g[k] : s_k[ch][4] * g[k];
+        dx[k] = ga * is * (dy - s_m[ch][0] - xh * s_m[ch][1]);
       }
     }
     return true;
