@@ -227,7 +227,7 @@ __device__ __forceinline__ void bn_moments_cta(const double* __restrict__ sums, 
 // One CTA = 64 consecutive positions of the OUTPUT map x all channel chunks.
 // ---------------------------------------------------------------------------------------------------------------
 template <int FMT>
-__global__ void __launch_bounds__(64 * (FMT / 8)) tbn_act_kernel(const float* __restrict__ X, int n, int C, int inPw, int inPitch,
+__global__ void __launch_bounds__(64 * (FMT / 8), FMT == 32 ? 5 : 2) tbn_act_kernel(const float* __restrict__ X, int n, int C, int inPw, int inPitch,
                                                                   const double* __restrict__ sums, double count, const double* __restrict__ cnt,
                                                                   float* __restrict__ mean, float* __restrict__ istd,
                                                                   float* __restrict__ g_mean_slot, float* __restrict__ g_istd_slot,
@@ -442,7 +442,7 @@ __global__ void tbn_bwd_params_kernel(const double* __restrict__ sums, int C, fl
 //                     (DT_k[p] = dx[p - k]), zeros outside the valid region = the wgrad operand of filter column k
 //   planar  (l == 0): fp32 [n][C][H][ld] for the CUDA-core conv1 wgrad
 template <int FMT, int DFMT>
-__global__ void __launch_bounds__(64 * (FMT / 8)) tbn_bwd_dx_kernel(const float* __restrict__ X, const float* __restrict__ dA, const uint8_t* __restrict__ idx,
+__global__ void __launch_bounds__(64 * (FMT / 8), FMT == 32 ? 6 : 3) tbn_bwd_dx_kernel(const float* __restrict__ X, const float* __restrict__ dA, const uint8_t* __restrict__ idx,
                                                                      const float* __restrict__ dF5, int dF5_ld, const uint8_t* __restrict__ mask,
                                                                      int n, int C, int H, int R, int Pw, int pitch, int pool, int dPw, int dPitch,
                                                                      const float* __restrict__ mean, const float* __restrict__ istd,
