@@ -403,7 +403,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime     # a rank that leaves a collective section early must cost minutes, not the default ten
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     peaks = load_peaks()
     size = args.size
     nvox = size ** 3
@@ -554,6 +555,7 @@ def main():
                 extra[name] = fn()
             except Exception as exc:
                 extra[name] = {"error": repr(exc)[:300]}
+                sys.stderr.write("bench.py: section %s failed on rank %d: %r\n" % (name, rank, exc))
         time.sleep(1.0)
         section("train", lambda: bench_train(ctx, torch, dist, rank, world, peaks))
         ctx.load_weights(nets.pack_params(pickle.load(open(WEIGHTS, "rb"), encoding="latin1")))   # the steps above moved the weights

@@ -32,6 +32,15 @@ def _committed():
         return nets.pack_params(pickle.load(f, encoding="latin1"))
 
 
+def _agree(errs, what):
+    """Collective: every rank learns whether ANY rank failed `what`, and all of them raise at the same point -- an assertion on one
+    rank alone would leave the others waiting in the next collective until the NCCL watchdog fires."""
+    flag = torch.tensor([1 if errs else 0], dtype=torch.int32, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()):
+        raise AssertionError("%s: %s" % (what, "; ".join(errs) if errs else "failed on another rank"))
+
+
 def check_sharded_inference(ctx, rank, world):
     g = torch.Generator(device="cuda").manual_seed(7)
     shape = (48, 40, 36)
@@ -42,11 +51,14 @@ def check_sharded_inference(ctx, rank, world):
     ctx.segment_volume(vol, atlas, label_vol=full)
     part = torch.full(shape, 255, dtype=torch.uint8, device="cuda")
     slab = parallel.segment_volume_sharded(ctx, vol, atlas, label_vol=part)
-    if slab is not None:
-        assert bool((part[slab[0]:slab[1]] == full[slab[0]:slab[1]]).all()), "sharded slab differs from the unsharded result"
+    errs = []
+    if slab is not None and not bool((part[slab[0]:slab[1]] == full[slab[0]:slab[1]]).all()):
+        errs.append("sharded slab differs from the unsharded result")
     touched = (part != 255).to(torch.int32)
     dist.all_reduce(touched)                       # test-only collective: every voxel written exactly once across ranks
-    assert bool((touched == 1).all()), "the slabs of the ranks do not tile the volume"
+    if not bool((touched == 1).all()):
+        errs.append("the slabs of the ranks do not tile the volume")
+    return errs
 
 
 def _batch(n, seed=3):
@@ -63,6 +75,7 @@ def check_dp_step(ctx, rank, world, n=32):
     d = [torch.from_numpy(a[idx]).cuda() for a in x] + [torch.from_numpy(at[idx]).cuda(), torch.from_numpy(y[idx]).cuda()]
     grads = ctx.grad_tensor()
     loss = None
+    errs = []
     for step in range(3):
         loss = ctx.train_forward_backward(*d, n_global=n, seed=100 + step)
         local_g = grads.clone()
@@ -71,14 +84,17 @@ def check_dp_step(ctx, rank, world, n=32):
         gathered = [torch.zeros_like(src) for _ in range(world)]
         dist.all_gather(gathered, src)
         total = torch.stack(gathered).sum(0).to(grads.device)
-        assert torch.allclose(grads, total, rtol=1e-5, atol=1e-7), "all-reduced gradient != sum of shard gradients"
+        if not torch.allclose(grads, total, rtol=1e-5, atol=1e-7):
+            errs.append("step %d: all-reduced gradient != sum of shard gradients" % step)
         ctx.adam_step(lr=1e-3, stat_scale=1.0 / world)
     p = ctx.param_tensor().clone()
     ref = p.clone()
     dist.broadcast(ref, 0)
-    assert torch.equal(p, ref), "parameters diverged across ranks"
-    assert bool(torch.isfinite(p).all()) and np.isfinite(float(loss))
-    return float(loss)
+    if not torch.equal(p, ref):
+        errs.append("parameters diverged across ranks")
+    if not (bool(torch.isfinite(p).all()) and np.isfinite(float(loss))):
+        errs.append("non-finite parameters or loss")
+    return float(loss), errs
 
 
 def check_sync_bn(ctx, rank, world, n=48):
@@ -103,21 +119,37 @@ def check_sync_bn(ctx, rank, world, n=48):
     parallel.allreduce_gradients(grads, loss)
     ctx.set_sync_bn(False)
     ctx.set_option("train_fused_stats", 1)
-    assert abs(float(loss) - loss_ref) < 2e-4 * max(1.0, abs(loss_ref)), (float(loss), loss_ref)
+    # every rank judges the same numbers: rank 0's single-device reference
+    ref_pack = torch.cat([g_ref, torch.tensor([loss_ref], device=g_ref.device)])
+    if dist.get_backend() == "nccl":
+        dist.broadcast(ref_pack, 0)
+    else:
+        h = ref_pack.cpu()
+        dist.broadcast(h, 0)
+        ref_pack = h.to(g_ref.device)
+    g_ref, loss_ref = ref_pack[:-1], float(ref_pack[-1])
+    errs = []
+    if not abs(float(loss) - loss_ref) < 2e-4 * max(1.0, abs(loss_ref)):
+        errs.append("sync-BN loss %r vs single-device %r" % (float(loss), loss_ref))
     G, R = nets.unpack_params(grads.cpu().numpy()), nets.unpack_params(g_ref.cpu().numpy())
-    worst = 0.0
+    l2s = []
     for name, arrs in R.items():
         for k, a in enumerate(arrs):
             g = G[name][k]
             if name.endswith("_bn") and k >= 2:
                 g = g / world                       # the statistics slots carry one (identical) copy per rank
-            l2 = np.linalg.norm(g - a) / max(np.linalg.norm(a), 1e-6)
-            worst = max(worst, l2)
-            # one PReLU / max-pool decision taken the other way (a pre-activation within rounding of a kink) moves one of ~ 4e4
-            # random-sign terms of a weight gradient: ~ 0.5 % of its norm; a few such flips are tolerated, unsynchronised
-            # statistics would show up as tens of per cent
-            assert l2 < 3e-2, "sync-BN %s[%d]: relative L2 err %g" % (name, k, l2)
-    return worst
+            l2s.append((float(np.linalg.norm(g - a) / max(np.linalg.norm(a), 1e-6)), "%s[%d]" % (name, k)))
+    # Synchronised statistics reproduce the single-device step to ~ 2e-5.  One PReLU / max-pool decision taken the other way (a
+    # pre-activation within rounding of a kink) moves one of ~ 4e4 random-sign terms of a weight gradient, ~ 0.5 % of its norm, in
+    # the tensors of ONE branch; unsynchronised statistics move EVERY convolutional tensor by per cents.  So: the bulk of the tensors
+    # must agree tightly, and none may be far off.
+    worst, worst_name = max(l2s)
+    median = float(np.median([v for v, _ in l2s]))
+    if not median < 1e-3:
+        errs.append("sync-BN: median relative L2 err of the gradient tensors %g" % median)
+    if not worst < 1e-1:
+        errs.append("sync-BN %s: relative L2 err %g" % (worst_name, worst))
+    return float(worst), errs
 
 
 def check_fused_adam(ctx, rank, world, n=32):
@@ -144,11 +176,14 @@ def check_fused_adam(ctx, rank, world, n=32):
         out.append(ctx.param_tensor().clone())
     ref = out[1].clone()
     dist.broadcast(ref, 0)
-    assert torch.equal(out[1], ref), "fused step: parameters differ across ranks"
+    errs = []
+    if not torch.equal(out[1], ref):
+        errs.append("fused step: parameters differ across ranks")
     # same update up to the summation order of the reduction (and the kink flips it can trigger in the following steps)
     rel = float((out[0] - out[1]).norm() / out[0].norm())
-    assert rel < 1e-4, "fused all-reduce + Adam differs from all_reduce + adam_step: relative L2 %g" % rel
-    return rel
+    if not rel < 1e-3:         # observed 5e-6 .. 6e-5; a kink flip in step 2 or 3 moves single parameters by the step size (1e-3 each)
+        errs.append("fused all-reduce + Adam differs from all_reduce + adam_step: relative L2 %g" % rel)
+    return rel, errs
 
 
 def check_fit_replicas(rank, world, device):
@@ -167,8 +202,11 @@ def check_fit_replicas(rank, world, device):
     p = net.ctx.param_tensor().clone()
     ref = p.clone()
     dist.broadcast(ref, 0)
-    assert torch.equal(p, ref), "Net.fit replicas diverged"
-    assert len(net.train_history_) == 2 and np.isfinite(net.train_history_[-1]['train_loss'])
+    errs = []
+    if not torch.equal(p, ref):
+        errs.append("Net.fit replicas diverged")
+    if not (len(net.train_history_) == 2 and np.isfinite(net.train_history_[-1]['train_loss'])):
+        errs.append("Net.fit history incomplete")
     if world > 1:
         y_bad = y.copy()
         if rank == world - 1:
@@ -178,25 +216,29 @@ def check_fit_replicas(rank, world, device):
         except ValueError:
             pass
         else:
-            raise AssertionError("a rank with a different training set was not detected")
+            errs.append("a rank with a different training set was not detected")
     net.ctx.close()
+    return errs
 
 
 def run_checks(ctx, rank, world, device, fit=True, fused=True):
-    """-> dict of results; raises AssertionError on the first failed check"""
+    """-> dict of results; raises AssertionError on the first failed check -- on EVERY rank, at the same point (_agree)"""
     ctx.load_weights(_committed())
     ctx.reset_optimizer()
-    check_sharded_inference(ctx, rank, world)
-    loss = check_dp_step(ctx, rank, world)
+    _agree(check_sharded_inference(ctx, rank, world), "sharded inference")
+    loss, errs = check_dp_step(ctx, rank, world)
+    _agree(errs, "data-parallel step")
     out = {"sharded_inference": "ok", "dp_step": "ok", "loss": loss}
     ctx.load_weights(_committed())
-    out["sync_bn_worst_rel_l2"] = check_sync_bn(ctx, rank, world)
+    out["sync_bn_worst_rel_l2"], errs = check_sync_bn(ctx, rank, world)
+    _agree(errs, "sync-BN")
     out["sync_bn"] = "ok"
     if fused:
-        out["fused_adam_rel_l2"] = check_fused_adam(ctx, rank, world)
+        out["fused_adam_rel_l2"], errs = check_fused_adam(ctx, rank, world)
+        _agree(errs, "fused all-reduce + Adam")
         out["fused_adam"] = "ok"
     if fit:
-        check_fit_replicas(rank, world, device)
+        _agree(check_fit_replicas(rank, world, device), "Net.fit replicas")
         out["fit_replicas"] = "ok"
     dist.barrier()
     return out
@@ -213,10 +255,11 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     device = 0 if same_device else local
     torch.cuda.set_device(device)
+    import datetime
     if backend == "nccl":
-        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device), timeout=datetime.timedelta(seconds=180))
     else:
-        dist.init_process_group(backend)
+        dist.init_process_group(backend, timeout=datetime.timedelta(seconds=180))
     ctx = _native.Context(device)
     res = run_checks(ctx, rank, world, device, fused="--no-fused" not in sys.argv)
     if rank == 0:
