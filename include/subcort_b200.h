@@ -100,7 +100,8 @@ SC_API int sc_import_volume(sc_ctx* ctx, const void* src_dev, int elem_bytes, co
                      void* dst_dev, void* stream);
 /* Crop mode (base.py:367-369): the atlas priors are only read at the candidate voxels, so only the candidates' bounding
  * box {x0,x1,y0,y1,z0,z1} of the HOST array (94 % of a scan's bytes are priors) is uploaded: strided DMA copies into
- * staging_dev (Fortran-ordered source: >= box voxels * channels * elem_bytes bytes; NULL for a C-ordered source) and a
+ * staging_dev (Fortran-ordered source: >= X * box_y * box_z * channels * elem_bytes bytes -- whole x rows are moved, the
+ * x range is cut on the device; NULL for a C-ordered source) and a
  * reorder into the box region of dst_dev, the full-size C-ordered [X][Y][Z][channels] device volume.  Voxels outside
  * the box keep whatever dst_dev held.  src_host should be page-locked (pageable memory makes the copies synchronous). */
 SC_API int sc_upload_volume_box(sc_ctx* ctx, const void* src_host, int elem_bytes, const int32_t dims[3], int channels,

@@ -225,7 +225,7 @@ class Context(object):
             out = torch.empty(full, dtype=tdt, device=dev)
         staging = None
         if fortran:
-            n = (box[1] - box[0]) * (box[3] - box[2]) * (box[5] - box[4]) * int(channels)
+            n = shape[0] * (box[3] - box[2]) * (box[5] - box[4]) * int(channels)        # whole x rows (contiguous runs of the y range)
             staging = torch.empty(n, dtype=tdt, device=dev)
         _check(self.lib.sc_upload_volume_box(self.h, ctypes.c_void_p(arr.ctypes.data), arr.dtype.itemsize, _dims(shape), int(channels),
                                              1 if fortran else 0, (_c_i32 * 6)(*[int(b) for b in box]), _ptr(staging), _ptr(out), _stream()))

@@ -232,10 +232,31 @@ def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=Non
     import torch
     t0 = time.time()
     shape = tuple(int(s) for s in t1.shape[:3])
-    raw, dt = ctx.upload_volume(t1)
     atlas = np.asarray(atlas)
     if atlas.dtype != np.float32:          # a scaled NIfTI comes back as float64: the priors are consumed as float32 (base.py:388)
         atlas = atlas.astype(np.float32, order='K')
+    main = torch.cuda.current_stream()
+    side = _side_stream(ctx.device)
+    atlas_ready = torch.cuda.Event()
+    d_atlas = None
+
+    def start_atlas_upload(box):
+        # The priors (94 % of the upload) are first needed by the FC head: they are uploaded and reordered on a side stream while
+        # the convolution phase runs -- enqueued behind the host-synchronous steps that precede it, whose small device -> host
+        # copies would otherwise queue up behind the gigabyte.  Crop mode reads the priors at the candidates only: just the
+        # bounding box of the dilated mask is uploaded (strided DMA from the host array).
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if box is not None:
+                d = ctx.upload_volume_box(atlas, box, channels=15)
+            else:
+                d, _ = ctx.upload_volume(atlas, channels=15)
+                d = d.view(torch.float32).view(shape + (15,))
+            atlas_ready.record(side)
+        return d
+
+    # T1 first: copies of one direction are served in issue order, and the convolution phase only waits for the T1 volume
+    raw, dt = ctx.upload_volume(t1)
     vol, mean, std = ctx.normalise_volume(raw, dt, shape)
     if crop_mask is not None:
         mraw, mdt = ctx.upload_volume(crop_mask)
@@ -243,23 +264,8 @@ def segment_arrays(ctx, t1, atlas, crop_mask=None, want_proba=False, timings=Non
     else:
         cand = ctx.candidate_mask(raw, dt, shape)                          # == image.astype('bool')
     box, n_cand = ctx.mask_bbox(cand)
-    # the priors (94 % of the upload) are first needed by the FC head: they are uploaded and reordered on a side stream while
-    # the convolution phase runs -- enqueued only now, behind the host-synchronous steps above, whose small device -> host
-    # copies would otherwise queue up behind the gigabyte.  Crop mode reads the priors at the candidates only: just the
-    # bounding box of the dilated mask is uploaded (strided DMA from the host array).
-    main = torch.cuda.current_stream()
-    side = _side_stream(ctx.device)
-    side.wait_stream(main)
-    atlas_ready = torch.cuda.Event()
-    d_atlas = None
     if box is not None:
-        with torch.cuda.stream(side):
-            if crop_mask is not None:
-                d_atlas = ctx.upload_volume_box(atlas, box, channels=15)
-            else:
-                d_atlas, _ = ctx.upload_volume(atlas, channels=15)
-                d_atlas = d_atlas.view(torch.float32).view(shape + (15,))
-            atlas_ready.record(side)
+        d_atlas = start_atlas_upload(box if crop_mask is not None else None)
     lab = torch.zeros(shape, dtype=torch.uint8, device=vol.device)
     prob = torch.zeros(shape + (15,), dtype=torch.float32, device=vol.device) if want_proba else None
     if box is not None:

@@ -490,10 +490,6 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
   }
 
   // ---- phase 2: d1 (x3) + FC head per slab of x-planes -------------------------------------
-  if (ctx->atlas_ready && ctx->atlas_chunks == 0) {   // host entry point: the atlas upload ran on a side stream during phase 1
-    SC_CUDA(cudaStreamWaitEvent(st, ctx->atlas_ready, 0));
-    ctx->atlas_ready = nullptr;
-  }
   int atlas_waited = 0;                                // chunked upload: chunks of x-planes this stream has already waited for
   OutGeo og = {b[0], b[2], b[4], by, bz, Y, Z};
   // tensor-core mode: columns 272..319 of the split h2 rows are never written by fc_2 and must not hold NaN patterns
@@ -555,6 +551,10 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     p.C = h1; p.ldc = kH1Ld; p.n_store = 540; p.out_split = tc ? 1 : 0;
     p.prof_cls = PC_GEMM_FC1;
     const bool atlas_fused = tc;   // the CTA-pair kernel writes the atlas columns in its epilogue
+    if (ctx->atlas_ready && ctx->atlas_chunks == 0) {   // an atlas upload on a side stream (sc_atlas_ready_event): the priors are first
+      SC_CUDA(cudaStreamWaitEvent(st, ctx->atlas_ready, 0));   // read here, after the conv phase and the first slab's d1 launches
+      ctx->atlas_ready = nullptr;
+    }
     if (atlas_fused) { p.atlas = atlas; p.ageo = og; p.ageo.x0 = b[0] + ix0; if (compact) p.rowvox = rowvox + slab_base; }
     SC_TRY(tc ? launch_gemm_tc(ctx, p, ctx->fc1, st) : launch_gemm(ctx, p, ctx->fc1, st));
     p.atlas = nullptr; p.rowvox = nullptr;
@@ -579,6 +579,10 @@ int segment_volume(sc_ctx* ctx, const float* vol, const int32_t* dims, const flo
     } else {
       SC_TRY(launch_out_softmax(ctx, h2, rows, proba_vol, nullptr, label_vol, cand, &og2, st));
     }
+  }
+  if (ctx->atlas_ready && ctx->atlas_chunks == 0) {     // no slab had a candidate: still join the upload before the caller goes on
+    SC_CUDA(cudaStreamWaitEvent(st, ctx->atlas_ready, 0));
+    ctx->atlas_ready = nullptr;
   }
   return SC_OK;
 }
