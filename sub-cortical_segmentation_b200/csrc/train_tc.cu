@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(64 * (FMT / 8), FMT == 32 ? 6 : 3) tbn_bwd_dx_
 // K = 9: CUDA cores).  gW[co][8 - t] += sum over pixels dx[co] * patch[r + ky][c + kx]; 72 accumulators per thread (8 channels
 // x 9 taps), folded with shuffles and shared-memory atomics.  conv1 has no dgrad, so dx is never written.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tbn_bwd_conv1_kernel(const float* __restrict__ X, const float* __restrict__ dA, const float* __restrict__ patches,
+__global__ void __launch_bounds__(256, 2) tbn_bwd_conv1_kernel(const float* __restrict__ X, const float* __restrict__ dA, const float* __restrict__ patches,
                                                             int n, const float* __restrict__ mean, const float* __restrict__ istd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ alpha, const double* __restrict__ sums, double count,
@@ -570,15 +570,18 @@ __global__ void __launch_bounds__(256) tbn_bwd_conv1_kernel(const float* __restr
   for (int k = 0; k < 8; ++k)
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+  // per-channel constants in shared memory (7 x 8 registers less per thread: two CTAs fit an SM instead of one)
+  __shared__ float s_c[24][8];              // mean, istd, gamma, beta, alpha, sum(dy) / m, sum(dy xhat) / m, gamma * istd
+  if (threadIdx.x < 24) {
+    const int ch = threadIdx.x;
+    const bool on = ch < C;
+    s_c[ch][0] = on ? mean[ch] : 0.f; s_c[ch][1] = on ? istd[ch] : 0.f; s_c[ch][2] = on ? gamma[ch] : 0.f;
+    s_c[ch][3] = on ? beta[ch] : 0.f; s_c[ch][4] = on ? alpha[ch] : 0.f;
+    s_c[ch][5] = on ? (float)(sums[ch * 3] / count) : 0.f; s_c[ch][6] = on ? (float)(sums[ch * 3 + 1] / count) : 0.f;
+    s_c[ch][7] = on ? gamma[ch] * istd[ch] : 0.f;
+  }
+  __syncthreads();
   if (chunk < 3) {
-    float mu[8], is[8], ga[8], be[8], al[8], m1[8], m2[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int ch = chunk * 8 + k;
-      const bool on = ch < C;
-      mu[k] = on ? mean[ch] : 0.f; is[k] = on ? istd[ch] : 0.f; ga[k] = on ? gamma[ch] : 0.f; be[k] = on ? beta[ch] : 0.f; al[k] = on ? alpha[ch] : 0.f;
-      m1[k] = on ? (float)(sums[ch * 3] / count) : 0.f; m2[k] = on ? (float)(sums[ch * 3 + 1] / count) : 0.f;
-    }
     const int64_t total = (int64_t)H * n * H;
     for (int64_t v = (int64_t)blockIdx.x * 64 + slot; v < total; v += (int64_t)gridDim.x * 64) {
       const int c = (int)(v % H);
@@ -596,10 +599,12 @@ __global__ void __launch_bounds__(256) tbn_bwd_conv1_kernel(const float* __restr
         for (int kx = 0; kx < 3; ++kx) w[ky * 3 + kx] = __ldg(src + ky * 32 + kx);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float xh = (x[k] - mu[k]) * is[k];
-        const float yv = fmaf(xh, ga[k], be[k]);
-        const float dy = yv > 0.f ? g[k] : al[k] * g[k];
-        const float dx = ga[k] * is[k] * (dy - m1[k] - xh * m2[k]);
+        const float4 c0 = *reinterpret_cast<const float4*>(&s_c[chunk * 8 + k][0]);     // mean, istd, gamma, beta
+        const float4 c1 = *reinterpret_cast<const float4*>(&s_c[chunk * 8 + k][4]);     // alpha, m1, m2, gamma * istd
+        const float xh = (x[k] - c0.x) * c0.y;
+        const float yv = fmaf(xh, c0.z, c0.w);
+        const float dy = yv > 0.f ? g[k] : c1.x * g[k];
+        const float dx = c0.z * c0.y * (dy - c1.y - xh * c1.z);
 #pragma unroll
         for (int t = 0; t < 9; ++t) acc[k][t] = fmaf(dx, w[t], acc[k][t]);
       }
