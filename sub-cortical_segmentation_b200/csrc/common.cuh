@@ -192,6 +192,7 @@ struct sc_ctx {
   void* tc_state = nullptr;      // tcgen05 back-end state (tensor-map encoder entry point)
   int tc_timing_cls = -1;        // ProfClass whose persistent launches record per-role wait cycles (debug)
   unsigned long long* tc_timing_buf = nullptr;   // [sm_count][8], overwritten by every instrumented launch
+  int train_wgrad_mn = 1;        // conv weight gradients from the pixel-major maps (MN-major operands) instead of planar transposed copies
   int train_fused_stats = 1;     // training forward: BatchNorm statistics accumulated in the sweep epilogues (off: a separate pass over the stored maps)
   int tc_skip = 1;               // dense path with a sparse candidate mask: the conv sweeps skip the items no candidate needs
   int tc_compact = 1;            // dense path with a candidate mask: the FC head runs on the compacted candidate rows only

@@ -22,6 +22,14 @@
 
 namespace sc {
 
+__device__ __forceinline__ void tmem_ld16_raw(uint32_t taddr, uint32_t (&r)[16]) {   // 32 lanes x 16 consecutive 32-bit columns (no wait)
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // split-map access: a pixel holds FMT channel slots as FMT bf16 "hi" then FMT bf16 "lo"; chunk = 8 channels = 16 B + 16 B
 // ---------------------------------------------------------------------------------------------------------------
@@ -522,6 +530,7 @@ __global__ void __launch_bounds__(64 * (FMT / 8), FMT == 32 ? 6 : 3) tbn_bwd_dx_
   split8(dx, h, l);
   if (q < npix) store8<FMT>(frame, q, chunk, h, l);
   to_tile(h, l, px);
+  if (!DT) return;       // wgrad reads the pixel-major frame itself (wgrad_mn_kernel): no planar copies
   if (px < 2) {          // the shifted copies of this CTA's 64 positions start one / two positions to the left: recompute those two
     float dh[8];
     int r2, s2, c2;
@@ -810,6 +819,184 @@ static int launch_wgrad_tc(sc_ctx* ctx, const uint16_t* AT, const uint16_t* DT, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// wgrad straight from the PIXEL-major split maps (no planar copies): both operands MN-major.
+//   gW[ty][tx][ci][co] = sum_p A[p + ty*Pw + tx][ci] * dX[p][co]
+// A TMA box of 64 bf16 x 64 pixels of a split map is, in shared memory, 64 K-rows (pixels) of 128 B holding 64 "MN" elements:
+// exactly the canonical MN-major SWIZZLE_128B operand (8-row groups 1024 B apart = SBO; further 64-element MN chunks LBO apart).
+// The 64 MN elements of a 128 B pixel (20-channel maps) are [32 hi | 32 lo]; a 256 B pixel gives a hi box and a lo box = M (or N) 128.
+// ONE MMA per k-step then produces all four hi/lo blocks of the product; the epilogue adds hi*hi + hi*lo + lo*hi and drops lo*lo.
+// A tap is a shift of the OUTER (pixel) TMA coordinate by ty*Pw + tx: any integer, so the three column taps need no shifted copies.
+//   blockIdx.y = filter row ty; the CTAs of a row split the pixel range (split-K) and add their partial sums atomically
+//   128 B input pixels: M = 128 stacks two column taps (tx, tx + 1); 256 B input pixels: M = 128 = hi | lo of one column tap
+// warp 0: TMA producer, warp 1: MMA issue, warps 2-5: epilogue
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradMnArgs {
+  int cin, cout;
+  int nbA, nbD;                  // boxes per pixel of the input map / the gradient map (1: 128 B pixels, 2: 256 B pixels = hi box + lo box)
+  int Pw;                        // wide-row pitch in pixels
+  int nkb;                       // 64-pixel blocks to reduce over
+  int stages;
+  float* gW;                     // [cout][cin][3][3] master-layout gradient (accumulated atomically)
+};
+constexpr int WG_BOX = 64 * 128;   // bytes of one box: 64 pixels x 128 B
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {   // MN-major, SWIZZLE_128B: LBO = one box, SBO = 8 pixel rows
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(WG_BOX >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_mn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapD, const WgradMnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int a_bytes = 3 * a.nbA * WG_BOX, d_bytes = a.nbD * WG_BOX;       // the three column taps of A, then the gradient
+  const int stage_bytes = a_bytes + d_bytes + (a.nbA == 1 ? WG_BOX : 0);  // 128 B pixels: the tap pair (2, 3) reads one box past the taps
+  const int ngroups = a.nbA == 1 ? 2 : 3;                                 // MMAs per k-step (accumulators)
+  const int N = 64 * a.nbD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + a.stages;
+  uint64_t* done = bars + 2 * a.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ty = blockIdx.y;
+  const int per = (a.nkb + gridDim.x - 1) / gridDim.x;
+  const int kb0 = blockIdx.x * per, kb1 = min(a.nkb, kb0 + per);
+  const int nk = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapD)) : "memory");
+        for (int i = 0; i < nk; ++i) {
+          const int s = i % a.stages, use = i / a.stages;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          mbar_expect_tx(&full[s], (uint32_t)(a_bytes + d_bytes));
+          uint8_t* sp = smem + s * stage_bytes;
+          const int p0 = (kb0 + i) * 64;
+          for (int tx = 0; tx < 3; ++tx)
+            for (int h = 0; h < a.nbA; ++h)      // column tap tx: the pixels p0 + ty * Pw + tx ... (zero fill beyond the map)
+              tma_load_2d(&mapA, &full[s], sp + (tx * a.nbA + h) * WG_BOX, h * 64, p0 + ty * a.Pw + tx);
+          for (int h = 0; h < a.nbD; ++h) tma_load_2d(&mapD, &full[s], sp + a_bytes + h * WG_BOX, h * 64, p0);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      const uint32_t leader = elect_one();
+      // D = F32, A = B = BF16, both MN-major (bits 15, 16), N = 64 * nbD, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % a.stages;
+        mbar_wait(&full[s], (i / a.stages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sp = smem_u32(smem + s * stage_bytes);
+        const uint64_t dd = umma_desc_mn(sp + a_bytes);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                         // 16 pixels = two 8-row groups = 2048 B per k-step
+          const uint64_t o = (uint64_t)(j * (2048 >> 4));
+          for (int g = 0; g < ngroups; ++g) {
+            const uint64_t ad = umma_desc_mn(sp + g * 2 * WG_BOX);     // 128 B pixels: taps (2g, 2g + 1); 256 B pixels: hi | lo of tap g
+            umma_bf16_elect(tmem_base + (uint32_t)(g * N), ad + o, dd + o, idesc, (i | j) != 0, leader);
+          }
+        }
+        if (leader) umma_commit(&empty[s]);
+        __syncwarp();
+      }
+      if (leader) umma_commit(done);
+      __syncwarp();
+    } else {
+      const int q = warp & 3;      // TMEM lane quarter this warp may read
+      mbar_wait(done, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = q * 32 + lane;
+      const int halfN = N >> 1;    // columns [0, halfN): hi parts of the gradient channels, [halfN, N): lo parts
+      for (int g = 0; g < ngroups; ++g) {
+        // accumulator row -> (column tap, input channel, hi / lo)
+        int tx, ci; bool lo_row;
+        if (a.nbA == 1) { tx = 2 * g + (row >> 6); const int r = row & 63; lo_row = r >= 32; ci = r & 31; }
+        else { tx = g; lo_row = row >= 64; ci = row & 63; }
+        const bool on = tx < 3 && ci < a.cin;
+        for (int c0 = 0; c0 < halfN; c0 += 16) {
+          uint32_t rh[16], rl[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * N + c0);
+          tmem_ld16_raw(taddr, rh);
+          tmem_ld16_raw(taddr + (uint32_t)halfN, rl);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (on) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int co = c0 + k;
+              // hi row: hi*hi + hi*lo; lo row: lo*hi only.  tap t of the correlation = element 8 - t of the (true-convolution) filter
+              const float v = lo_row ? __uint_as_float(rh[k]) : __uint_as_float(rh[k]) + __uint_as_float(rl[k]);
+              if (co < a.cout) atomicAdd(a.gW + ((int64_t)co * a.cin + ci) * 9 + (8 - (ty * 3 + tx)), v);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// A: the input activation map of the layer (fmtA = 32 / 64 channel slots per pixel), D: the zero-framed output gradient (fmtD)
+static int launch_wgrad_mn(sc_ctx* ctx, const float* A, int fmtA, const float* D, int fmtD, int cin, int cout, int Pw, int64_t npix, int rows_valid,
+                           float* gW, cudaStream_t st) {
+  TcState* s = reinterpret_cast<TcState*>(ctx->tc_state);
+  SC_CHECK(s != nullptr, SC_ERR_UNSUPPORTED, "tcgen05 back-end not initialised");
+  SC_CHECK(npix < (1ll << 31) && cin <= fmtA && cout <= fmtD, SC_ERR_ARG, "wgrad_mn: bad geometry");
+  WgradMnArgs a;
+  a.cin = cin; a.cout = cout; a.nbA = fmtA == 32 ? 1 : 2; a.nbD = fmtD == 32 ? 1 : 2; a.Pw = Pw; a.gW = gW;
+  a.nkb = (int)(((int64_t)rows_valid * Pw + 63) / 64);      // the gradient is zero beyond its valid rows
+  const int stage_bytes = (3 * a.nbA + a.nbD + (a.nbA == 1 ? 1 : 0)) * WG_BOX;
+  a.stages = (227 * 1024 - 2048) / stage_bytes;
+  if (a.stages > 6) a.stages = 6;
+  SC_CHECK(a.stages >= 2, SC_ERR_ARG, "wgrad_mn: stage does not fit (%d bytes)", stage_bytes);
+  const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16;
+  CUtensorMap mapA, mapD;
+  auto encode = [&](CUtensorMap* m, const float* base, int fmt) {
+    cuuint64_t dims[2] = {(cuuint64_t)(2 * fmt), (cuuint64_t)npix};          // bf16 elements per pixel (hi | lo), pixels
+    cuuint64_t strides[1] = {(cuuint64_t)fmt * 4};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t es[2] = {1, 1};
+    return s->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = encode(&mapA, A, fmtA);
+  SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "wgrad_mn: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  r = encode(&mapD, D, fmtD);
+  SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "wgrad_mn: cuTensorMapEncodeTiled(D) failed with %d", (int)r);
+  SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(wgrad_mn_kernel), 227 * 1024));
+  // split-K: three filter rows x gx CTAs, at least ~6 pixel blocks per CTA (the epilogue's atomics must not dominate)
+  int gx = (a.nkb + 5) / 6;
+  if (gx > ctx->sm_count / 3) gx = ctx->sm_count / 3;
+  if (gx < 1) gx = 1;
+  ProfScope prof(ctx, PC_TRAIN_BWD, st);
+  wgrad_mn_kernel<<<dim3(gx, 3), 192, smem, st>>>(mapA, mapD, a);
+  ctx->launches++;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // the convolutional part of the step for one branch
 // ---------------------------------------------------------------------------------------------------------------
 struct TLayer { int cin, cout, R, pitch, fmt, H, pool, oR, oPitch, oH; };
@@ -965,11 +1152,11 @@ int tc_branch_forward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pat
       const unsigned grid = (unsigned)((opix + 63) / 64);
       if (L.fmt == 32)
         tbn_act_kernel<32><<<grid, 256, 0, s>>>(T.X[l], n, L.cout, Pw, L.pitch, sums, (double)vpix, cnt, T.mean[l], T.istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3],
-                                                P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], L.pool, T.A[l], L.oR, L.oPitch, L.oH, T.idx[l], T.AT[l],
+                                                P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], L.pool, T.A[l], L.oR, L.oPitch, L.oH, T.idx[l], ctx->train_wgrad_mn ? nullptr : T.AT[l],
                                                 pad8(L.cout));
       else
         tbn_act_kernel<64><<<grid, 512, 0, s>>>(T.X[l], n, L.cout, Pw, L.pitch, sums, (double)vpix, cnt, T.mean[l], T.istd[l], G + Ob.bn[l][2], G + Ob.bn[l][3],
-                                                P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], L.pool, T.A[l], L.oR, L.oPitch, L.oH, T.idx[l], T.AT[l],
+                                                P + Ob.bn[l][1], P + Ob.bn[l][0], P + Ob.alpha[l], L.pool, T.A[l], L.oR, L.oPitch, L.oH, T.idx[l], ctx->train_wgrad_mn ? nullptr : T.AT[l],
                                                 pad8(L.cout));
     } else {
       tact5_flatten_kernel<<<(unsigned)(((int64_t)n * 540 + 255) / 256), 256, 0, s>>>(T.X[4], n, sums, (double)vpix, cnt, T.mean[4], T.istd[4], G + Ob.bn[4][2],
@@ -1014,15 +1201,16 @@ int tc_branch_backward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pa
                        cudaStream_t s) {
   const BranchOff& Ob = ctx->off.br[b];
   float* G = ctx->grads;
+  uint16_t* DT = ctx->train_wgrad_mn ? nullptr : T.DT;     // the MN-major wgrad reads the frame itself: no planar gradient copies
   for (int l = 4; l >= 0; --l) {
     const TLayer& L = kTL[l];
     const int Pw = n * L.pitch;
     // the incoming gradient: conv5 <- dF5; pooled layers <- the dgrad output at the pooled geometry; others same geometry
     const int dPw = L.pool ? n * L.oPitch : Pw, dPitch = L.pool ? L.oPitch : L.pitch;
-    if (l == 4) SC_TRY((bwd_layer<64, 64>(ctx, b, l, T, nullptr, dF5, dF5_ld, masks + b * 540, n, dPw, dPitch, T.frame, T.DT, nullptr, s)));
-    else if (l == 3) SC_TRY((bwd_layer<64, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, T.DT, nullptr, s)));
-    else if (l == 2) SC_TRY((bwd_layer<64, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, T.DT, nullptr, s)));
-    else if (l == 1) SC_TRY((bwd_layer<32, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, T.DT, nullptr, s)));
+    if (l == 4) SC_TRY((bwd_layer<64, 64>(ctx, b, l, T, nullptr, dF5, dF5_ld, masks + b * 540, n, dPw, dPitch, T.frame, DT, nullptr, s)));
+    else if (l == 3) SC_TRY((bwd_layer<64, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, DT, nullptr, s)));
+    else if (l == 2) SC_TRY((bwd_layer<64, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, DT, nullptr, s)));
+    else if (l == 1) SC_TRY((bwd_layer<32, 64>(ctx, b, l, T, T.dA, nullptr, 0, nullptr, n, dPw, dPitch, T.frame, DT, nullptr, s)));
     else {
       // conv1: reduction pass, then dx and the weight gradient in one fused pass (no dgrad below conv1)
       float* P = ctx->params;
@@ -1045,7 +1233,8 @@ int tc_branch_backward(sc_ctx* ctx, int b, const TcBranchBuf& T, const float* pa
     }
     const TLayer& Li = kTL[l - 1];
     const int64_t npix = (int64_t)L.R * Pw;
-    SC_TRY(launch_wgrad_tc(ctx, T.AT[l - 1], T.DT, L.cin, L.cout, pad8(L.cin), pad16(L.cout), Pw, npix, L.H, G + Ob.convW[l], s));
+    if (ctx->train_wgrad_mn) SC_TRY(launch_wgrad_mn(ctx, T.A[l - 1], Li.fmt, T.frame, L.fmt, L.cin, L.cout, Pw, npix, L.H, G + Ob.convW[l], s));
+    else SC_TRY(launch_wgrad_tc(ctx, T.AT[l - 1], T.DT, L.cin, L.cout, pad8(L.cin), pad16(L.cout), Pw, npix, L.H, G + Ob.convW[l], s));
     // dgrad: the gradient of this layer's input = sweep over the zero-framed dx with the raw taps; valid Li.oH x Li.oH
     SC_TRY(launch_conv_sweep(ctx, ctx->train_sw[b][l][1], l, T.frame, L.fmt == 32 ? 1 : 0, T.dA, (l == 1) ? 1 : 0, Pw, L.R, Li.oH, 1, 0,
                              PC_TRAIN_BWD, s, -2, -2));
