@@ -294,18 +294,21 @@ __global__ void __launch_bounds__(64 * (FMT / 8), FMT == 32 ? 5 : 2) tbn_act_ker
     uint4 h, l;
     split8(a, h, l);
     store8<FMT>(A, q, chunk, h, l);
-    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+    if (AT) {
+      const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      tile[0][chunk * 8 + 2 * k][px] = (uint16_t)(hh[k] & 0xffffu); tile[0][chunk * 8 + 2 * k + 1][px] = (uint16_t)(hh[k] >> 16);
-      tile[1][chunk * 8 + 2 * k][px] = (uint16_t)(ll[k] & 0xffffu); tile[1][chunk * 8 + 2 * k + 1][px] = (uint16_t)(ll[k] >> 16);
+      for (int k = 0; k < 4; ++k) {
+        tile[0][chunk * 8 + 2 * k][px] = (uint16_t)(hh[k] & 0xffffu); tile[0][chunk * 8 + 2 * k + 1][px] = (uint16_t)(hh[k] >> 16);
+        tile[1][chunk * 8 + 2 * k][px] = (uint16_t)(ll[k] & 0xffffu); tile[1][chunk * 8 + 2 * k + 1][px] = (uint16_t)(ll[k] >> 16);
+      }
     }
-  } else {
+  } else if (AT) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { tile[0][chunk * 8 + k][px] = 0; tile[1][chunk * 8 + k][px] = 0; }
   }
+  if (!AT) return;       // the MN-major wgrad reads the pixel-major map itself: no planar transposed copy
   __syncthreads();
-  if (AT) {
+  {
     // rows of 64 positions (128 B) per channel: one warp per row, lane = two positions
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int64_t q0 = (int64_t)blockIdx.x * 64;
@@ -529,8 +532,8 @@ __global__ void __launch_bounds__(64 * (FMT / 8), FMT == 32 ? 6 : 3) tbn_bwd_dx_
   uint4 h, l;
   split8(dx, h, l);
   if (q < npix) store8<FMT>(frame, q, chunk, h, l);
-  to_tile(h, l, px);
   if (!DT) return;       // wgrad reads the pixel-major frame itself (wgrad_mn_kernel): no planar copies
+  to_tile(h, l, px);
   if (px < 2) {          // the shifted copies of this CTA's 64 positions start one / two positions to the left: recompute those two
     float dh[8];
     int r2, s2, c2;
@@ -834,22 +837,27 @@ struct WgradMnArgs {
   int cin, cout;
   int nbA, nbD;                  // boxes per pixel of the input map / the gradient map (1: 128 B pixels, 2: 256 B pixels = hi box + lo box)
   int Pw;                        // wide-row pitch in pixels
-  int nkb;                       // 64-pixel blocks to reduce over
+  int kp;                        // pixels per pipeline stage (multiple of 16, <= 192): one TMA box of kp (+ 2) pixel rows per hi / lo half
+  int win_bytes, box_bytes;      // shared-memory bytes reserved per input window ((kp + 2) x 128 B, 1024-aligned) / per gradient box (kp x 128 B)
+  int nkb;                       // kp-pixel blocks to reduce over
   int stages;
   float* gW;                     // [cout][cin][3][3] master-layout gradient (accumulated atomically)
 };
-constexpr int WG_BOX = 64 * 128;   // bytes of one box: 64 pixels x 128 B
 
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {   // MN-major, SWIZZLE_128B: LBO = one box, SBO = 8 pixel rows
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(WG_BOX >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// MN-major, SWIZZLE_128B: SBO = 8 pixel rows (1024 B); LBO = distance of the second 64-element MN chunk
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 __global__ void __launch_bounds__(192, 1)
 wgrad_mn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapD, const WgradMnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int a_bytes = 3 * a.nbA * WG_BOX, d_bytes = a.nbD * WG_BOX;       // the three column taps of A, then the gradient
-  const int stage_bytes = a_bytes + d_bytes + (a.nbA == 1 ? WG_BOX : 0);  // 128 B pixels: the tap pair (2, 3) reads one box past the taps
+  // per stage: the input window of kp + 2 pixels (one box per hi / lo half) serves the three column taps -- a tap is a start address
+  // shifted by whole 128 B pixel rows (the swizzle follows the absolute address bits) -- then the gradient boxes
+  const int WG_WIN = a.win_bytes, WG_BOX = a.box_bytes;
+  const int a_bytes = a.nbA * WG_WIN, d_bytes = a.nbD * WG_BOX;
+  const int stage_bytes = a_bytes + d_bytes;
   const int ngroups = a.nbA == 1 ? 2 : 3;                                 // MMAs per k-step (accumulators)
   const int N = 64 * a.nbD;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
@@ -885,12 +893,11 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int i = 0; i < nk; ++i) {
           const int s = i % a.stages, use = i / a.stages;
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-          mbar_expect_tx(&full[s], (uint32_t)(a_bytes + d_bytes));
+          mbar_expect_tx(&full[s], (uint32_t)(a.nbA * (a.kp + 2) * 128 + d_bytes));
           uint8_t* sp = smem + s * stage_bytes;
-          const int p0 = (kb0 + i) * 64;
-          for (int tx = 0; tx < 3; ++tx)
-            for (int h = 0; h < a.nbA; ++h)      // column tap tx: the pixels p0 + ty * Pw + tx ... (zero fill beyond the map)
-              tma_load_2d(&mapA, &full[s], sp + (tx * a.nbA + h) * WG_BOX, h * 64, p0 + ty * a.Pw + tx);
+          const int p0 = (kb0 + i) * a.kp;
+          for (int h = 0; h < a.nbA; ++h)        // pixels p0 + ty * Pw ... + kp + 1 (zero fill beyond the map)
+            tma_load_2d(&mapA, &full[s], sp + h * WG_WIN, h * 64, p0 + ty * a.Pw);
           for (int h = 0; h < a.nbD; ++h) tma_load_2d(&mapD, &full[s], sp + a_bytes + h * WG_BOX, h * 64, p0);
         }
       }
@@ -904,12 +911,15 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         mbar_wait(&full[s], (i / a.stages) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sp = smem_u32(smem + s * stage_bytes);
-        const uint64_t dd = umma_desc_mn(sp + a_bytes);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {                         // 16 pixels = two 8-row groups = 2048 B per k-step
+        const uint64_t dd = umma_desc_mn(sp + a_bytes, WG_BOX);
+        const int nks = a.kp >> 4;
+#pragma unroll 4
+        for (int j = 0; j < nks; ++j) {                       // 16 pixels = two 8-row groups = 2048 B per k-step
           const uint64_t o = (uint64_t)(j * (2048 >> 4));
           for (int g = 0; g < ngroups; ++g) {
-            const uint64_t ad = umma_desc_mn(sp + g * 2 * WG_BOX);     // 128 B pixels: taps (2g, 2g + 1); 256 B pixels: hi | lo of tap g
+            // 256 B pixels: M = hi box | lo box of column tap g (start shifted by g rows)
+            // 128 B pixels: M = column taps (2g, 2g + 1): the second chunk is the same window one pixel row further
+            const uint64_t ad = a.nbA == 2 ? umma_desc_mn(sp + g * 128, WG_WIN) : umma_desc_mn(sp + 2 * g * 128, 128);
             umma_bf16_elect(tmem_base + (uint32_t)(g * N), ad + o, dd + o, idesc, (i | j) != 0, leader);
           }
         }
@@ -965,28 +975,32 @@ static int launch_wgrad_mn(sc_ctx* ctx, const float* A, int fmtA, const float* D
   SC_CHECK(npix < (1ll << 31) && cin <= fmtA && cout <= fmtD, SC_ERR_ARG, "wgrad_mn: bad geometry");
   WgradMnArgs a;
   a.cin = cin; a.cout = cout; a.nbA = fmtA == 32 ? 1 : 2; a.nbD = fmtD == 32 ? 1 : 2; a.Pw = Pw; a.gW = gW;
-  a.nkb = (int)(((int64_t)rows_valid * Pw + 63) / 64);      // the gradient is zero beyond its valid rows
-  const int stage_bytes = (3 * a.nbA + a.nbD + (a.nbA == 1 ? 1 : 0)) * WG_BOX;
+  // pixels per stage: long enough to amortise the per-stage hand-offs, short enough for >= 3 stages
+  a.kp = (a.nbA == 1 && a.nbD == 1) ? 192 : 128;
+  a.win_bytes = ((a.kp + 2) * 128 + 1023) & ~1023;
+  a.box_bytes = a.kp * 128;
+  a.nkb = (int)(((int64_t)rows_valid * Pw + a.kp - 1) / a.kp);      // the gradient is zero beyond its valid rows
+  const int stage_bytes = a.nbA * a.win_bytes + a.nbD * a.box_bytes;
   a.stages = (227 * 1024 - 2048) / stage_bytes;
   if (a.stages > 6) a.stages = 6;
   SC_CHECK(a.stages >= 2, SC_ERR_ARG, "wgrad_mn: stage does not fit (%d bytes)", stage_bytes);
   const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16;
   CUtensorMap mapA, mapD;
-  auto encode = [&](CUtensorMap* m, const float* base, int fmt) {
+  auto encode = [&](CUtensorMap* m, const float* base, int fmt, int box_px) {
     cuuint64_t dims[2] = {(cuuint64_t)(2 * fmt), (cuuint64_t)npix};          // bf16 elements per pixel (hi | lo), pixels
     cuuint64_t strides[1] = {(cuuint64_t)fmt * 4};
-    cuuint32_t box[2] = {64, 64};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_px};
     cuuint32_t es[2] = {1, 1};
     return s->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
-  CUresult r = encode(&mapA, A, fmtA);
+  CUresult r = encode(&mapA, A, fmtA, a.kp + 2);        // kp pixels + the two further ones the column taps 1, 2 reach
   SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "wgrad_mn: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
-  r = encode(&mapD, D, fmtD);
+  r = encode(&mapD, D, fmtD, a.kp);
   SC_CHECK(r == CUDA_SUCCESS, SC_ERR_CUDA, "wgrad_mn: cuTensorMapEncodeTiled(D) failed with %d", (int)r);
   SC_TRY(ensure_smem_attr(ctx, reinterpret_cast<const void*>(wgrad_mn_kernel), 227 * 1024));
-  // split-K: three filter rows x gx CTAs, at least ~6 pixel blocks per CTA (the epilogue's atomics must not dominate)
-  int gx = (a.nkb + 5) / 6;
+  // split-K: three filter rows x gx CTAs, at least ~3 stages of pixels per CTA (the epilogue's atomics must not dominate)
+  int gx = (a.nkb + 2) / 3;
   if (gx > ctx->sm_count / 3) gx = ctx->sm_count / 3;
   if (gx < 1) gx = 1;
   ProfScope prof(ctx, PC_TRAIN_BWD, st);
