@@ -7,14 +7,14 @@
 //                                 statistics need a grid-wide reduction before the activation)
 //       dgrad    conv2..conv5   = the same sweep over the zero-framed output gradient with the raw (un-flipped) taps and
 //                                 the channel roles swapped
-//       wgrad    conv2..conv5   = wgrad_tc_kernel below: an implicit GEMM whose K dimension is the PIXEL axis
-//                                 (gW[tap][ci][co] = sum_p A[p + shift(tap)][ci] * dX[p][co]); both operands are read
-//                                 from channel-major ("planar transposed") bf16 hi/lo copies that the element-wise
-//                                 kernels write next to the pixel-major maps.  A filter ROW is a shift of the TMA start
-//                                 coordinate by the wide-row pitch (a multiple of 16 bytes); a filter COLUMN would be a
-//                                 2-byte shift, which TMA cannot address (the innermost coordinate must stay 16-byte
-//                                 aligned: measured, "illegal instruction"), so the gradient is stored three times,
-//                                 shifted by 0, 1 and 2 pixels.  The three filter rows are stacked along M
+//       wgrad    conv2..conv5   = wgrad_mn_kernel below: an implicit GEMM whose K dimension is the PIXEL axis
+//                                 (gW[tap][ci][co] = sum_p A[p + shift(tap)][ci] * dX[p][co]) with both operands MN-major, read
+//                                 straight from the pixel-major maps (a TMA box of a map IS the canonical MN-major operand; a tap
+//                                 is a shift of the outer TMA coordinate / a row-shifted descriptor start).  Its predecessor
+//                                 wgrad_tc_kernel (sc_set_option "train_wgrad_mn" = 0) reads K-major operands from channel-major
+//                                 ("planar transposed") bf16 hi/lo copies that the element-wise kernels then write next to the
+//                                 pixel-major maps -- the gradient three times, shifted by 0, 1 and 2 pixels, because a filter
+//                                 COLUMN would be a 2-byte shift of the innermost TMA coordinate, which must stay 16-byte aligned
 //   * every product is the bf16x3 split (xl*wh + xh*wl + xh*wh, fp32 accumulate in TMEM), like inference
 //   * BatchNorm statistics / activation / pooling and their backward passes are element-wise kernels over the split maps
 // conv1 (K = 9) stays on CUDA cores.  The dense layers are in train_dense.cu.
