@@ -912,16 +912,21 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sp = smem_u32(smem + s * stage_bytes);
         const uint64_t dd = umma_desc_mn(sp + a_bytes, WG_BOX);
+        // 256 B pixels: M = hi box | lo box of column tap g (start shifted by g rows)
+        // 128 B pixels: M = column taps (2g, 2g + 1): the second chunk is the same window one pixel row further
+        // (descriptors once per stage: the issue loop itself is two or three MMAs and one 64-bit add per k-step)
+        const uint64_t ad0 = a.nbA == 2 ? umma_desc_mn(sp, WG_WIN) : umma_desc_mn(sp, 128);
+        const uint64_t ad1 = a.nbA == 2 ? umma_desc_mn(sp + 128, WG_WIN) : umma_desc_mn(sp + 256, 128);
+        const uint64_t ad2 = umma_desc_mn(sp + 256, WG_WIN);
+        const uint32_t third = (leader && ngroups == 3) ? 1u : 0u;
         const int nks = a.kp >> 4;
+        uint64_t o = 0;
 #pragma unroll 4
-        for (int j = 0; j < nks; ++j) {                       // 16 pixels = two 8-row groups = 2048 B per k-step
-          const uint64_t o = (uint64_t)(j * (2048 >> 4));
-          for (int g = 0; g < ngroups; ++g) {
-            // 256 B pixels: M = hi box | lo box of column tap g (start shifted by g rows)
-            // 128 B pixels: M = column taps (2g, 2g + 1): the second chunk is the same window one pixel row further
-            const uint64_t ad = a.nbA == 2 ? umma_desc_mn(sp + g * 128, WG_WIN) : umma_desc_mn(sp + 2 * g * 128, 128);
-            umma_bf16_elect(tmem_base + (uint32_t)(g * N), ad + o, dd + o, idesc, (i | j) != 0, leader);
-          }
+        for (int j = 0; j < nks; ++j, o += (uint64_t)(2048 >> 4)) {      // 16 pixels = two 8-row groups = 2048 B per k-step
+          const uint32_t acc = (i | j) != 0;
+          umma_bf16_elect(tmem_base, ad0 + o, dd + o, idesc, acc, leader);
+          umma_bf16_elect(tmem_base + (uint32_t)N, ad1 + o, dd + o, idesc, acc, leader);
+          umma_bf16_elect(tmem_base + (uint32_t)(2 * N), ad2 + o, dd + o, idesc, acc, third);
         }
         if (leader) umma_commit(&empty[s]);
         __syncwarp();
